@@ -1,0 +1,919 @@
+// ekf.cu — EKF-SLAM hot path for sm_100a: predict, heading update, Mahalanobis gating,
+// Kalman gain (sparse H), in-place symmetric covariance update over the upper triangle,
+// in-place augmentation, plus the cslam_ekf_* C ABI (include/cslam.h).
+//
+// Data layout in HBM:
+//   X      : 2 x n_cap doubles (ping-pong so gain/heading kernels never read what they write)
+//   P      : n_cap x ld doubles, row-major, ld = n_cap rounded up to 16 doubles (128 B rows);
+//            ONLY the upper triangle (j >= i) is authoritative — the update streams
+//            8*n*(n+1) bytes instead of 16*n^2.
+//   A (W1) : r x lda doubles, column-major over state rows (one contiguous n-vector per
+//            update rank), r <= 64 — the scaled gain panel of slam.h:257.
+#include <limits>
+#include <new>
+
+#include "common.cuh"
+
+namespace cslam {
+
+// ------------------------------------------------------------------------------------
+// Handle
+// ------------------------------------------------------------------------------------
+constexpr int kMaxRank = 2 * CSLAM_MAX_BATCH_OBS;  // 64
+
+struct BatchSmall {  // device-resident scratch of the joint update (EKF.cpp:93-129)
+    double hu[CSLAM_MAX_BATCH_OBS][2][3];
+    double lu[CSLAM_MAX_BATCH_OBS][2][2];
+    double V[kMaxRank];
+    double G[kMaxRank * kMaxRank];  // row-major r x r: L^-1 (literal) or L^-T (Q1 intended)
+    double u[kMaxRank];             // G * G^T * V
+    int f[CSLAM_MAX_BATCH_OBS];
+};
+
+struct GateScratch {
+    double* part_nd = nullptr;   // [blocks][m]
+    double* part_out = nullptr;  // [blocks][m]
+    int* part_j = nullptr;       // [blocks][m]
+    int* d_jbest = nullptr;      // [CSLAM_MAX_OBS]
+    double* d_nbest = nullptr;
+    double* d_outer = nullptr;
+    int max_blocks = 0;
+};
+
+}  // namespace cslam
+
+struct cslam_ekf {
+    int device = 0;
+    unsigned flags = 0;
+    int cap_landmarks = 0;
+    int n_cap = 0;
+    size_t ld = 0;   // leading dimension of P (doubles)
+    size_t lda = 0;  // leading dimension of A / PHT panels (doubles)
+    int n = 3;
+    int cur = 0;  // which X buffer is current
+    double* X[2] = {nullptr, nullptr};
+    double* P = nullptr;
+    double* A = nullptr;    // [kMaxRank][lda]
+    double* PHT = nullptr;  // [kMaxRank][lda]
+    cslam::BatchSmall* small = nullptr;
+    int* status = nullptr;        // device: #skipped updates
+    unsigned* ticket = nullptr;   // device: last-block tickets (predict, gate)
+    cslam::GateScratch gate;
+    void* pinned = nullptr;  // host staging
+    size_t pinned_bytes = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+};
+
+namespace cslam {
+
+// ------------------------------------------------------------------------------------
+// Kernels
+// ------------------------------------------------------------------------------------
+
+// EKF.cpp:406-455 predict.  Rows 0..2 of P for columns [3, 3+width) get Gv * (.) — with
+// Gv = [[1,0,a],[0,1,b],[0,0,1]] that is row0 += a*row2, row1 += b*row2.  The mirrored
+// columns (EKF.cpp:443) live in the lower triangle and are not stored.  The block that
+// draws the last ticket updates Pvv and the pose, after every block has read the old phi.
+__global__ void __launch_bounds__(256) k_predict(double* __restrict__ X, double* __restrict__ P, size_t ld, int n,
+                                                 double v, double swa, double q00, double q01, double q10,
+                                                 double q11, double wb, double dt, int width,
+                                                 unsigned* __restrict__ ticket) {
+    const double phi = X[2];
+    const double s = sin(swa + phi), c = cos(swa + phi);
+    const double g02 = -v * dt * s, g12 = v * dt * c;
+    const int col = 3 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (col < 3 + width) {
+        const double p0 = P[col], p1 = P[ld + col], p2 = P[2 * ld + col];
+        P[col] = p0 + g02 * p2;
+        P[ld + col] = p1 + g12 * p2;
+    }
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!is_last || threadIdx.x != 0) return;
+    *ticket = 0;
+    // Pvv <- Gv Pvv Gv^T + Gu Q Gu^T   (EKF.cpp:439)
+    double Pv[3][3];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) Pv[i][j] = psym(P, ld, i, j);
+    const double Gv[3][3] = {{1, 0, g02}, {0, 1, g12}, {0, 0, 1}};
+    const double Gu[3][2] = {{dt * c, -v * dt * s}, {dt * s, v * dt * c}, {dt * sin(swa) / wb, v * dt * cos(swa) / wb}};
+    const double Q[2][2] = {{q00, q01}, {q10, q11}};
+    double GP[3][3], GQ[3][2];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            double a = 0;
+            for (int k = 0; k < 3; k++) a += Gv[i][k] * Pv[k][j];
+            GP[i][j] = a;
+        }
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 2; j++) {
+            double a = 0;
+            for (int k = 0; k < 2; k++) a += Gu[i][k] * Q[k][j];
+            GQ[i][j] = a;
+        }
+    for (int i = 0; i < 3; i++)
+        for (int j = i; j < 3; j++) {
+            double a = 0, b = 0;
+            for (int k = 0; k < 3; k++) a += GP[i][k] * Gv[j][k];
+            for (int k = 0; k < 2; k++) b += GQ[i][k] * Gu[j][k];
+            P[(size_t)i * ld + j] = a + b;
+        }
+    X[0] = X[0] + v * dt * c;
+    X[1] = X[1] + v * dt * s;
+    X[2] = pi2pi(phi + v * dt * sin(swa) / wb);
+}
+
+// EKF.cpp:328-352 + slam.h:700-725 with H = e_2^T.  Column 2 of P is (P[0][2], P[1][2],
+// row 2 from the diagonal on).  Writes Xout = Xin + W*v and the rank-1 panel a = p/sqrt(S):
+// for symmetric P the Joseph form C P C^T + W R W^T equals P - p p^T / S.
+__global__ void __launch_bounds__(256) k_heading_gain(const double* __restrict__ Xin, double* __restrict__ Xout,
+                                                      const double* __restrict__ P, size_t ld, int n,
+                                                      double phi_meas, double R, double* __restrict__ A) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double v = pi2pi(phi_meas - Xin[2]);
+    const double S = P[2 * ld + 2] + R;
+    const double SI = 1.0 / S;
+    const double p = i < 2 ? P[(size_t)i * ld + 2] : P[2 * ld + i];
+    Xout[i] = Xin[i] + (p * SI) * v;
+    A[i] = p / sqrt(S);
+}
+
+// Per-observation prologue of slam.h:235-266 using the sparse H (robot block + one landmark
+// block): only the 5x5 sub-block of P at columns {0,1,2,f,f+1} enters S.
+struct GainSmall {
+    double H[2][5];
+    double G[2][2];
+    double V[2];
+    int ok;
+};
+__device__ void gain_prologue(const double* __restrict__ X, const double* __restrict__ P, size_t ld, int f,
+                              double zr, double zb, const double R[4], unsigned flags, GainSmall& g) {
+    const int cols[5] = {0, 1, 2, f, f + 1};
+    const ObsLin o = observe_lin(X[0], X[1], X[2], X[f], X[f + 1]);
+    for (int a = 0; a < 2; a++) {
+        for (int c = 0; c < 3; c++) g.H[a][c] = o.hu[a][c];
+        g.H[a][3] = o.lu[a][0];
+        g.H[a][4] = o.lu[a][1];
+    }
+    g.V[0] = zr - o.zr;
+    g.V[1] = pi2pi(zb - o.zb);
+    double Pc[5][5];
+    for (int a = 0; a < 5; a++)
+        for (int b = a; b < 5; b++) Pc[a][b] = Pc[b][a] = P[(size_t)cols[a] * ld + cols[b]];
+    double PHTc[5][2];
+    for (int a = 0; a < 5; a++)
+        for (int k = 0; k < 2; k++) {
+            double s = 0;
+            for (int b = 0; b < 5; b++) s += Pc[a][b] * g.H[k][b];
+            PHTc[a][k] = s;
+        }
+    double S[2][2];
+    for (int k = 0; k < 2; k++)
+        for (int l = 0; l < 2; l++) {
+            double s = 0;
+            for (int a = 0; a < 5; a++) s += g.H[k][a] * PHTc[a][l];
+            S[k][l] = s + R[k + 2 * l];
+        }
+    // makeSymmetric (slam.h:247), LLT (slam.h:417-423), SCHOL.inverse() through PartialPivLU
+    // (slam.h:251) — op for op as oracle::cholesky_update; failure -> zero gain (slam.h:252-255).
+    double Ss[2][2], L[2][2], Li[2][2];
+    for (int k = 0; k < 2; k++)
+        for (int l = 0; l < 2; l++) Ss[k][l] = (S[k][l] + S[l][k]) * 0.5;
+    int ok = chol_lower<2>(Ss, L) ? 1 : 0;
+    inv_lu<2>(L, Li);
+    for (int k = 0; k < 2; k++)
+        for (int l = 0; l < 2; l++) ok = ok && isfinite(Li[k][l]);
+    double G00 = 0, G01 = 0, G10 = 0, G11 = 0;
+    if (ok) {
+        if (flags & CSLAM_FLAG_Q1_METRIC_S) {  // G = L^-T
+            G00 = Li[0][0]; G01 = Li[1][0]; G10 = Li[0][1]; G11 = Li[1][1];
+        } else {  // literal: G = L^-1
+            G00 = Li[0][0]; G01 = Li[0][1]; G10 = Li[1][0]; G11 = Li[1][1];
+        }
+    }
+    g.G[0][0] = G00; g.G[0][1] = G01; g.G[1][0] = G10; g.G[1][1] = G11;
+    g.ok = ok;
+}
+
+// slam.h:243,257-259 for one observation: PHT = P H^T (5 columns of P), W1 = PHT G,
+// W = W1 G^T, Xout = Xin + W V; the rank-2 panel A = W1 feeds k_cov_update.
+__global__ void __launch_bounds__(256) k_gain_single(const double* __restrict__ Xin, double* __restrict__ Xout,
+                                                     const double* __restrict__ P, size_t ld, int n, double zr,
+                                                     double zb, int idf, double r00, double r10, double r01,
+                                                     double r11, unsigned flags, double* __restrict__ A, size_t lda,
+                                                     int* __restrict__ status) {
+    __shared__ GainSmall g;
+    const int f = 3 + 2 * (idf - 1);
+    if (threadIdx.x == 0) {
+        const double R[4] = {r00, r10, r01, r11};
+        gain_prologue(Xin, P, ld, f, zr, zb, R, flags, g);
+        if (!g.ok && blockIdx.x == 0) atomicAdd(status, 1);
+    }
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    // P(i, c) for c in {0,1,2,f,f+1}: row i where i <= c (strided in i), row c otherwise (coalesced in i)
+    const double p0 = i <= 0 ? P[(size_t)i * ld + 0] : P[0 * ld + i];
+    const double p1 = i <= 1 ? P[(size_t)i * ld + 1] : P[1 * ld + i];
+    const double p2 = i <= 2 ? P[(size_t)i * ld + 2] : P[2 * ld + i];
+    const double p3 = i <= f ? P[(size_t)i * ld + f] : P[(size_t)f * ld + i];
+    const double p4 = i <= f + 1 ? P[(size_t)i * ld + f + 1] : P[(size_t)(f + 1) * ld + i];
+    double pht[2];
+    for (int k = 0; k < 2; k++)
+        pht[k] = (((p0 * g.H[k][0] + p1 * g.H[k][1]) + p2 * g.H[k][2]) + p3 * g.H[k][3]) + p4 * g.H[k][4];
+    const double w1_0 = pht[0] * g.G[0][0] + pht[1] * g.G[1][0];
+    const double w1_1 = pht[0] * g.G[0][1] + pht[1] * g.G[1][1];
+    const double w_0 = w1_0 * g.G[0][0] + w1_1 * g.G[0][1];
+    const double w_1 = w1_0 * g.G[1][0] + w1_1 * g.G[1][1];
+    Xout[i] = Xin[i] + (w_0 * g.V[0] + w_1 * g.V[1]);
+    A[i] = w1_0;
+    A[lda + i] = w1_1;
+}
+
+// slam.h:260  P <- P - W1 W1^T over the UPPER TRIANGLE only, in place, FP64.
+// One CTA per T x T tile of the triangle (tiles with tc >= tr); thread = one 16-byte column
+// pair x T/RG rows, all loads of a batch issued before the first use so that every SM keeps
+// tens of KB in flight; the panel rows of the tile are staged in shared memory (broadcast
+// reads), the two panel columns a thread owns stay in registers.  Elements below the
+// diagonal inside diagonal tiles are neither loaded nor stored.  diag_eps implements
+// slam.h:719 (P += I * FLT_MIN) for the heading update.
+template <int R, int T>
+__global__ void __launch_bounds__(256) k_cov_update(double* __restrict__ P, size_t ld, int n,
+                                                    const double* __restrict__ A, size_t lda, int nt,
+                                                    double diag_eps) {
+    constexpr int CP = T / 2;       // column pairs per tile
+    constexpr int RG = 256 / CP;    // row groups
+    constexpr int RPT = T / RG;     // rows per thread
+    constexpr int BATCH = RPT > 8 ? 8 : RPT;
+    __shared__ double sAr[R][T];
+
+    // triangular tile index -> (tr, tc), row-major over the upper triangle
+    const long long t = blockIdx.x;
+    int tr = (int)floor(((2.0 * nt + 1.0) - sqrt((2.0 * nt + 1.0) * (2.0 * nt + 1.0) - 8.0 * (double)t)) * 0.5);
+    while ((long long)tr * nt - (long long)tr * (tr - 1) / 2 > t) tr--;
+    while ((long long)(tr + 1) * nt - (long long)(tr + 1) * tr / 2 <= t) tr++;
+    const int tc = tr + (int)(t - ((long long)tr * nt - (long long)tr * (tr - 1) / 2));
+
+    const int i0 = tr * T, j0 = tc * T;
+    for (int idx = threadIdx.x; idx < R * T; idx += 256) {
+        const int k = idx / T, ii = idx % T;
+        sAr[k][ii] = (i0 + ii < n) ? A[(size_t)k * lda + i0 + ii] : 0.0;
+    }
+    const int cp = threadIdx.x % CP, rg = threadIdx.x / CP;
+    const int j = j0 + 2 * cp;
+    double aj0[R], aj1[R];
+#pragma unroll
+    for (int k = 0; k < R; k++) {
+        aj0[k] = (j < n) ? A[(size_t)k * lda + j] : 0.0;
+        aj1[k] = (j + 1 < n) ? A[(size_t)k * lda + j + 1] : 0.0;
+    }
+    __syncthreads();
+    if (j >= n) return;
+    const bool diag_tile = (tr == tc);
+#pragma unroll 1
+    for (int b0 = 0; b0 < RPT; b0 += BATCH) {
+        double2 v[BATCH];
+#pragma unroll
+        for (int b = 0; b < BATCH; b++) {
+            const int ii = rg + (b0 + b) * RG;
+            const int i = i0 + ii;
+            const bool act = (i < n) && (!diag_tile || j + 1 >= i);
+            if (act) v[b] = ld128(P + (size_t)i * ld + j);
+        }
+#pragma unroll
+        for (int b = 0; b < BATCH; b++) {
+            const int ii = rg + (b0 + b) * RG;
+            const int i = i0 + ii;
+            const bool act = (i < n) && (!diag_tile || j + 1 >= i);
+            if (act) {
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int k = 0; k < R; k++) {
+                    const double ai = sAr[k][ii];
+                    s0 += ai * aj0[k];
+                    s1 += ai * aj1[k];
+                }
+                double2 o = v[b];
+                if (j >= i) o.x = o.x - s0;
+                if (j + 1 < n) o.y = o.y - s1;
+                if (j == i) o.x += diag_eps;
+                if (j + 1 == i) o.y += diag_eps;
+                st128(P + (size_t)i * ld + j, o);
+            }
+        }
+    }
+}
+
+// General-rank variant (r <= 64, any r) for the joint update; FP64 FMA, panels in shared
+// memory.  The DMMA kernel in ekf_dmma.cu replaces it for large maps.
+template <int T>
+__global__ void __launch_bounds__(256) k_cov_update_rank(double* __restrict__ P, size_t ld, int n,
+                                                         const double* __restrict__ A, size_t lda, int r, int nt) {
+    constexpr int CP = T / 2, RG = 256 / CP, RPT = T / RG;
+    extern __shared__ double smem[];
+    double* sAr = smem;          // [r][T]
+    double* sAc = smem + r * T;  // [r][T]
+    const long long t = blockIdx.x;
+    int tr = (int)floor(((2.0 * nt + 1.0) - sqrt((2.0 * nt + 1.0) * (2.0 * nt + 1.0) - 8.0 * (double)t)) * 0.5);
+    while ((long long)tr * nt - (long long)tr * (tr - 1) / 2 > t) tr--;
+    while ((long long)(tr + 1) * nt - (long long)(tr + 1) * tr / 2 <= t) tr++;
+    const int tc = tr + (int)(t - ((long long)tr * nt - (long long)tr * (tr - 1) / 2));
+    const int i0 = tr * T, j0 = tc * T;
+    for (int idx = threadIdx.x; idx < r * T; idx += 256) {
+        const int k = idx / T, ii = idx % T;
+        sAr[idx] = (i0 + ii < n) ? A[(size_t)k * lda + i0 + ii] : 0.0;
+        sAc[idx] = (j0 + ii < n) ? A[(size_t)k * lda + j0 + ii] : 0.0;
+    }
+    __syncthreads();
+    const int cp = threadIdx.x % CP, rg = threadIdx.x / CP;
+    const int j = j0 + 2 * cp;
+    if (j >= n) return;
+    double s0[RPT], s1[RPT];
+#pragma unroll
+    for (int b = 0; b < RPT; b++) s0[b] = s1[b] = 0.0;
+    for (int k = 0; k < r; k++) {
+        const double a0 = sAc[k * T + 2 * cp], a1 = sAc[k * T + 2 * cp + 1];
+#pragma unroll
+        for (int b = 0; b < RPT; b++) {
+            const double ai = sAr[k * T + rg + b * RG];
+            s0[b] += ai * a0;
+            s1[b] += ai * a1;
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < RPT; b++) {
+        const int i = i0 + rg + b * RG;
+        if (i < n && j + 1 >= i) {
+            double2 o = ld128(P + (size_t)i * ld + j);
+            if (j >= i) o.x -= s0[b];
+            if (j + 1 < n) o.y -= s1[b];
+            st128(P + (size_t)i * ld + j, o);
+        }
+    }
+}
+
+// EKF.cpp:28-91 addOneNewFeature without the copy/resize: the two new columns (rows
+// 0..len-1) and the new 2x2 diagonal block are written inside the pre-allocated P.
+//   P[i][len+k] = (Gv * P[0:3, i])_k ;  P[len:len+2, len:len+2] = Gv Pvv Gv^T + Gz R Gz^T
+__global__ void __launch_bounds__(256) k_augment(double* __restrict__ X, double* __restrict__ P, size_t ld,
+                                                 int len, double r, double b, double r00, double r10, double r01,
+                                                 double r11) {
+    const double phi = X[2];
+    const double s = sin(phi + b), c = cos(phi + b);
+    const double g02 = -r * s, g12 = r * c;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < len) {
+        const double p0 = psym(P, ld, 0, i), p1 = psym(P, ld, 1, i), p2 = psym(P, ld, 2, i);
+        P[(size_t)i * ld + len] = p0 + g02 * p2;
+        P[(size_t)i * ld + len + 1] = p1 + g12 * p2;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        X[len] = X[0] + r * c;
+        X[len + 1] = X[1] + r * s;
+        double Pv[3][3];
+        for (int a = 0; a < 3; a++)
+            for (int d = 0; d < 3; d++) Pv[a][d] = psym(P, ld, a, d);
+        const double Gv[2][3] = {{1, 0, g02}, {0, 1, g12}};
+        const double Gz[2][2] = {{c, -r * s}, {s, r * c}};
+        const double R[2][2] = {{r00, r01}, {r10, r11}};
+        double GP[2][3], GR[2][2];
+        for (int a = 0; a < 2; a++)
+            for (int d = 0; d < 3; d++) {
+                double acc = 0;
+                for (int k = 0; k < 3; k++) acc += Gv[a][k] * Pv[k][d];
+                GP[a][d] = acc;
+            }
+        for (int a = 0; a < 2; a++)
+            for (int d = 0; d < 2; d++) {
+                double acc = 0;
+                for (int k = 0; k < 2; k++) acc += Gz[a][k] * R[k][d];
+                GR[a][d] = acc;
+            }
+        for (int a = 0; a < 2; a++)
+            for (int d = a; d < 2; d++) {
+                double x = 0, y = 0;
+                for (int k = 0; k < 3; k++) x += GP[a][k] * Gv[d][k];
+                for (int k = 0; k < 2; k++) y += GR[a][k] * Gz[d][k];
+                P[(size_t)(len + a) * ld + len + d] = x + y;
+            }
+    }
+}
+
+// ---------------------------------------------------------------- joint (batch) update ----
+
+struct ObsPack {  // kernel-parameter transport of one scan (no H2D copy)
+    double z[2 * CSLAM_MAX_OBS];
+    int idf[CSLAM_MAX_OBS];
+    int m;
+    double R[4];
+};
+
+// EKF.cpp:108-121: every observation linearised at the SAME prior X.
+__global__ void k_batch_prep(const double* __restrict__ X, ObsPack ob, BatchSmall* __restrict__ sm) {
+    const int k = threadIdx.x;
+    if (k >= ob.m) return;
+    const int f = 3 + 2 * (ob.idf[k] - 1);
+    const ObsLin o = observe_lin(X[0], X[1], X[2], X[f], X[f + 1]);
+    for (int a = 0; a < 2; a++) {
+        for (int c = 0; c < 3; c++) sm->hu[k][a][c] = o.hu[a][c];
+        sm->lu[k][a][0] = o.lu[a][0];
+        sm->lu[k][a][1] = o.lu[a][1];
+    }
+    sm->f[k] = f;
+    sm->V[2 * k] = ob.z[2 * k] - o.zr;
+    sm->V[2 * k + 1] = pi2pi(ob.z[2 * k + 1] - o.zb);
+}
+
+// slam.h:243 PHT = P H^T with the stacked sparse H: 3 + 2m columns of P per state row.
+__global__ void __launch_bounds__(128) k_batch_pht(const double* __restrict__ P, size_t ld, int n, int m,
+                                                   const BatchSmall* __restrict__ sm, double* __restrict__ PHT,
+                                                   size_t lda) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;
+    if (i >= n) return;
+    const int f = sm->f[k];
+    const double p0 = psym(P, ld, i, 0), p1 = psym(P, ld, i, 1), p2 = psym(P, ld, i, 2);
+    const double p3 = psym(P, ld, i, f), p4 = psym(P, ld, i, f + 1);
+    for (int a = 0; a < 2; a++)
+        PHT[(size_t)(2 * k + a) * lda + i] =
+            (((p0 * sm->hu[k][a][0] + p1 * sm->hu[k][a][1]) + p2 * sm->hu[k][a][2]) + p3 * sm->lu[k][a][0]) +
+            p4 * sm->lu[k][a][1];
+}
+
+// slam.h:244-255: S = H PHT + RR, symmetrise, lower Cholesky, L^-1, finiteness check,
+// G = L^-1 (literal) or L^-T (Q1), u = G G^T V.  One CTA, r <= 64, everything in shared memory.
+__global__ void __launch_bounds__(256) k_batch_chol(const double* __restrict__ PHT, size_t lda, int m, double r00,
+                                                    double r10, double r01, double r11, unsigned flags,
+                                                    BatchSmall* __restrict__ sm, int* __restrict__ status) {
+    const int r = 2 * m;
+    extern __shared__ double chol_smem[];
+    double(*S)[kMaxRank + 1] = reinterpret_cast<double(*)[kMaxRank + 1]>(chol_smem);
+    double(*Li)[kMaxRank + 1] = reinterpret_cast<double(*)[kMaxRank + 1]>(chol_smem + kMaxRank * (kMaxRank + 1));
+    __shared__ double tvec[kMaxRank];
+    __shared__ int ok;
+    const double R[2][2] = {{r00, r01}, {r10, r11}};
+    for (int idx = threadIdx.x; idx < r * r; idx += blockDim.x) {
+        const int a = idx / r, b = idx % r;
+        const int k = a / 2, al = a % 2;
+        const int f = sm->f[k];
+        double s = 0;
+        for (int c = 0; c < 3; c++) s += sm->hu[k][al][c] * PHT[(size_t)b * lda + c];
+        s += sm->lu[k][al][0] * PHT[(size_t)b * lda + f];
+        s += sm->lu[k][al][1] * PHT[(size_t)b * lda + f + 1];
+        if (a / 2 == b / 2) s += R[al][b % 2];
+        S[a][b] = s;
+    }
+    if (threadIdx.x == 0) ok = 1;
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < r * r; idx += blockDim.x) {
+        const int a = idx / r, b = idx % r;
+        if (a > b) {
+            const double v = (S[a][b] + S[b][a]) * 0.5;
+            Li[a][b] = v;  // temp
+        }
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < r * r; idx += blockDim.x) {
+        const int a = idx / r, b = idx % r;
+        if (a > b) S[a][b] = S[b][a] = Li[a][b];
+    }
+    __syncthreads();
+    // right-looking Cholesky on the lower triangle of S (in place)
+    for (int j = 0; j < r; j++) {
+        if (threadIdx.x == 0) {
+            const double d = S[j][j];
+            if (!(d > 0.0)) ok = 0;
+            S[j][j] = sqrt(d);
+        }
+        __syncthreads();
+        if (!ok) break;
+        const double ljj = S[j][j];
+        for (int i = j + 1 + threadIdx.x; i < r; i += blockDim.x) S[i][j] = S[i][j] / ljj;
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < (r - j - 1) * (r - j - 1); idx += blockDim.x) {
+            const int i = j + 1 + idx / (r - j - 1), c = j + 1 + idx % (r - j - 1);
+            if (c <= i) S[i][c] -= S[i][j] * S[c][j];
+        }
+        __syncthreads();
+    }
+    // Li = L^-1 by forward substitution, one thread per column
+    if (ok) {
+        for (int c = threadIdx.x; c < r; c += blockDim.x) {
+            for (int i = 0; i < r; i++) {
+                if (i < c) { Li[i][c] = 0.0; continue; }
+                double s = (i == c) ? 1.0 : 0.0;
+                for (int k = c; k < i; k++) s -= S[i][k] * Li[k][c];
+                Li[i][c] = s / S[i][i];
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && ok) {
+        for (int i = 0; i < r && ok; i++)
+            for (int c = 0; c <= i; c++)
+                if (!isfinite(Li[i][c])) { ok = 0; break; }
+    }
+    __syncthreads();
+    if (!ok && threadIdx.x == 0) atomicAdd(status, 1);
+    // G and u
+    for (int idx = threadIdx.x; idx < r * r; idx += blockDim.x) {
+        const int a = idx / r, b = idx % r;
+        double g = 0.0;
+        if (ok) g = (flags & CSLAM_FLAG_Q1_METRIC_S) ? Li[b][a] : Li[a][b];
+        sm->G[a * r + b] = g;
+    }
+    __syncthreads();
+    // t = G^T V ; u = G t
+    for (int l = threadIdx.x; l < r; l += blockDim.x) {
+        double s = 0;
+        for (int k = 0; k < r; k++) s += sm->G[k * r + l] * sm->V[k];
+        tvec[l] = s;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < r; k += blockDim.x) {
+        double s = 0;
+        for (int l = 0; l < r; l++) s += sm->G[k * r + l] * tvec[l];
+        sm->u[k] = s;
+    }
+}
+
+// slam.h:257-259: W1 = PHT G (panel A), Xout = Xin + PHT u  (= X + W1 G^T V).
+// grid.y selects a chunk of 8 output ranks so accumulators stay in registers.
+__global__ void __launch_bounds__(128) k_batch_w1(const double* __restrict__ PHT, size_t lda, int n, int r,
+                                                  const BatchSmall* __restrict__ sm, const double* __restrict__ Xin,
+                                                  double* __restrict__ Xout, double* __restrict__ A) {
+    __shared__ double sG[kMaxRank][8];
+    __shared__ double su[kMaxRank];
+    const int l0 = blockIdx.y * 8;
+    for (int idx = threadIdx.x; idx < r * 8; idx += blockDim.x) {
+        const int k = idx / 8, l = idx % 8;
+        sG[k][l] = (l0 + l < r) ? sm->G[k * r + l0 + l] : 0.0;
+    }
+    for (int k = threadIdx.x; k < r; k += blockDim.x) su[k] = sm->u[k];
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double dx = 0;
+    for (int k = 0; k < r; k++) {
+        const double p = PHT[(size_t)k * lda + i];
+#pragma unroll
+        for (int l = 0; l < 8; l++) acc[l] += p * sG[k][l];
+        dx += p * su[k];
+    }
+#pragma unroll
+    for (int l = 0; l < 8; l++)
+        if (l0 + l < r) A[(size_t)(l0 + l) * lda + i] = acc[l];
+    if (blockIdx.y == 0) Xout[i] = Xin[i] + dx;
+}
+
+// gating kernel lives in gate.cu (separate TU, compiled with -fmad=false)
+int launch_gate(const double* X, const double* P, size_t ld, int nf, const double* Z, int m, const double R[4],
+                double gate1, double gate2, double* part_nd, double* part_out, int* part_j, unsigned* ticket,
+                int* jbest, double* nbest, double* outer, cudaStream_t stream);
+
+// ------------------------------------------------------------------------ accessors ----
+__global__ void k_gather_block(const double* __restrict__ P, size_t ld, int r0, int c0, int nr, int nc,
+                               double* __restrict__ out) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)nr * nc) return;
+    const int i = r0 + (int)(idx / nc), j = c0 + (int)(idx % nc);
+    out[idx] = psym(P, ld, i, j);
+}
+__global__ void k_scatter_upper(double* __restrict__ P, size_t ld, int n, const double* __restrict__ in) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)n * n) return;
+    const int i = (int)(idx / n), j = (int)(idx % n);
+    if (j >= i) P[(size_t)i * ld + j] = in[idx];
+}
+
+// defined in ekf_dmma.cu: tensor-core (FP64 DMMA) rank-r update for large maps
+int launch_cov_update_dmma(double* P, size_t ld, int n, const double* A, size_t lda, int r, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------
+// Host-side launch helpers
+// ------------------------------------------------------------------------------------
+static inline long long tri_tiles(int nt) { return (long long)nt * (nt + 1) / 2; }
+
+template <int R>
+static int launch_cov_update(cslam_ekf* h, double diag_eps) {
+    const int n = h->n;
+    if (n >= 2048) {
+        const int nt = (n + 127) / 128;
+        k_cov_update<R, 128><<<(unsigned)tri_tiles(nt), 256, 0, h->stream>>>(h->P, h->ld, n, h->A, h->lda, nt,
+                                                                              diag_eps);
+    } else {
+        const int nt = (n + 63) / 64;
+        k_cov_update<R, 64><<<(unsigned)tri_tiles(nt), 256, 0, h->stream>>>(h->P, h->ld, n, h->A, h->lda, nt,
+                                                                             diag_eps);
+    }
+    CSLAM_CUDA(cudaGetLastError());
+    return CSLAM_OK;
+}
+
+static int launch_cov_update_rank(cslam_ekf* h, int r) {
+    const int n = h->n;
+    // large maps: FP64 tensor-core kernel; small maps: plain FMA kernel
+    if (n >= 1024) return launch_cov_update_dmma(h->P, h->ld, n, h->A, h->lda, r, h->stream);
+    const int nt = (n + 63) / 64;
+    const size_t smem = (size_t)2 * r * 64 * sizeof(double);
+    k_cov_update_rank<64><<<(unsigned)tri_tiles(nt), 256, smem, h->stream>>>(h->P, h->ld, n, h->A, h->lda, r, nt);
+    CSLAM_CUDA(cudaGetLastError());
+    return CSLAM_OK;
+}
+
+static int check_handle(const cslam_ekf* h) {
+    CSLAM_REQUIRE(h != nullptr, CSLAM_ERR_BAD_ARG, "null handle");
+    CSLAM_CUDA(cudaSetDevice(h->device));
+    return CSLAM_OK;
+}
+
+}  // namespace cslam
+
+using namespace cslam;
+
+// ------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------
+extern "C" {
+
+int cslam_ekf_create(cslam_ekf_t** out, int capacity_landmarks, int device, unsigned flags) {
+    CSLAM_REQUIRE(out != nullptr, CSLAM_ERR_BAD_ARG, "out is null");
+    CSLAM_REQUIRE(capacity_landmarks >= 0 && capacity_landmarks <= 500000, CSLAM_ERR_BAD_ARG,
+                  "capacity_landmarks out of range");
+    *out = nullptr;
+    int count = 0;
+    CSLAM_CUDA(cudaGetDeviceCount(&count));
+    CSLAM_REQUIRE(device >= 0 && device < count, CSLAM_ERR_CUDA, "no such CUDA device (no CPU fallback exists)");
+    CSLAM_CUDA(cudaSetDevice(device));
+    cslam_ekf* h = new (std::nothrow) cslam_ekf();
+    CSLAM_REQUIRE(h != nullptr, CSLAM_ERR_BAD_ARG, "out of host memory");
+    h->device = device;
+    h->flags = flags;
+    h->cap_landmarks = capacity_landmarks;
+    h->n_cap = 3 + 2 * capacity_landmarks;
+    h->ld = ((size_t)h->n_cap + 1 + 15) / 16 * 16;  // >= n_cap + 1 so the last column pair stays in-row
+    h->lda = h->ld;
+    h->n = 3;
+    auto fail = [&](int code) {
+        cslam_ekf_destroy(h);
+        return code;
+    };
+    const size_t pbytes = (size_t)h->n_cap * h->ld * sizeof(double);
+#define TRY(call)                                                                            \
+    do {                                                                                     \
+        cudaError_t e__ = (call);                                                            \
+        if (e__ != cudaSuccess) {                                                            \
+            set_last_error("cslam_ekf_create: %s -> %s", #call, cudaGetErrorString(e__));    \
+            return fail(CSLAM_ERR_CUDA);                                                     \
+        }                                                                                    \
+    } while (0)
+    TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->own_stream = true;
+    TRY(cudaMalloc(&h->X[0], h->ld * sizeof(double)));
+    TRY(cudaMalloc(&h->X[1], h->ld * sizeof(double)));
+    TRY(cudaMalloc(&h->P, pbytes));
+    TRY(cudaMalloc(&h->A, (size_t)kMaxRank * h->lda * sizeof(double)));
+    TRY(cudaMalloc(&h->PHT, (size_t)kMaxRank * h->lda * sizeof(double)));
+    TRY(cudaMalloc(&h->small, sizeof(BatchSmall)));
+    TRY(cudaMalloc(&h->status, sizeof(int)));
+    TRY(cudaMalloc(&h->ticket, 4 * sizeof(unsigned)));
+    h->gate.max_blocks = (capacity_landmarks + 255) / 256 + 1;
+    TRY(cudaMalloc(&h->gate.part_nd, (size_t)h->gate.max_blocks * CSLAM_MAX_OBS * sizeof(double)));
+    TRY(cudaMalloc(&h->gate.part_out, (size_t)h->gate.max_blocks * CSLAM_MAX_OBS * sizeof(double)));
+    TRY(cudaMalloc(&h->gate.part_j, (size_t)h->gate.max_blocks * CSLAM_MAX_OBS * sizeof(int)));
+    TRY(cudaMalloc(&h->gate.d_jbest, CSLAM_MAX_OBS * sizeof(int)));
+    TRY(cudaMalloc(&h->gate.d_nbest, CSLAM_MAX_OBS * sizeof(double)));
+    TRY(cudaMalloc(&h->gate.d_outer, CSLAM_MAX_OBS * sizeof(double)));
+    h->pinned_bytes = std::max<size_t>(h->ld * sizeof(double), 1 << 16);
+    TRY(cudaMallocHost(&h->pinned, h->pinned_bytes));
+    TRY(cudaMemsetAsync(h->X[0], 0, h->ld * sizeof(double), h->stream));
+    TRY(cudaMemsetAsync(h->X[1], 0, h->ld * sizeof(double), h->stream));
+    TRY(cudaMemsetAsync(h->P, 0, pbytes, h->stream));
+    TRY(cudaMemsetAsync(h->A, 0, (size_t)kMaxRank * h->lda * sizeof(double), h->stream));
+    TRY(cudaMemsetAsync(h->PHT, 0, (size_t)kMaxRank * h->lda * sizeof(double), h->stream));
+    TRY(cudaMemsetAsync(h->status, 0, sizeof(int), h->stream));
+    TRY(cudaMemsetAsync(h->ticket, 0, 4 * sizeof(unsigned), h->stream));
+    TRY(cudaStreamSynchronize(h->stream));
+#undef TRY
+    *out = h;
+    return CSLAM_OK;
+}
+
+int cslam_ekf_destroy(cslam_ekf_t* h) {
+    if (!h) return CSLAM_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->X[0]); cudaFree(h->X[1]); cudaFree(h->P); cudaFree(h->A); cudaFree(h->PHT);
+    cudaFree(h->small); cudaFree(h->status); cudaFree(h->ticket);
+    cudaFree(h->gate.part_nd); cudaFree(h->gate.part_out); cudaFree(h->gate.part_j);
+    cudaFree(h->gate.d_jbest); cudaFree(h->gate.d_nbest); cudaFree(h->gate.d_outer);
+    if (h->pinned) cudaFreeHost(h->pinned);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return CSLAM_OK;
+}
+
+int cslam_ekf_set_stream(cslam_ekf_t* h, void* cuda_stream) {
+    if (int rc = check_handle(h)) return rc;
+    CSLAM_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    h->stream = static_cast<cudaStream_t>(cuda_stream);
+    h->own_stream = false;
+    return CSLAM_OK;
+}
+
+int cslam_ekf_sync(cslam_ekf_t* h, int* skipped_updates) {
+    if (int rc = check_handle(h)) return rc;
+    if (skipped_updates) {
+        CSLAM_CUDA(cudaMemcpyAsync(h->pinned, h->status, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CSLAM_CUDA(cudaStreamSynchronize(h->stream));
+        *skipped_updates = *static_cast<int*>(h->pinned);
+    } else {
+        CSLAM_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    return CSLAM_OK;
+}
+
+int cslam_ekf_n(const cslam_ekf_t* h) { return h ? h->n : -1; }
+int cslam_ekf_num_landmarks(const cslam_ekf_t* h) { return h ? (h->n - 3) / 2 : -1; }
+int cslam_ekf_capacity(const cslam_ekf_t* h) { return h ? h->cap_landmarks : -1; }
+
+int cslam_ekf_predict(cslam_ekf_t* h, double v, double swa, const double Q[4], double wb, double dt) {
+    if (int rc = check_handle(h)) return rc;
+    CSLAM_REQUIRE(Q != nullptr, CSLAM_ERR_BAD_ARG, "Q is null");
+    const int n = h->n;
+    int width = 0;
+    if (n > 3) width = (h->flags & CSLAM_FLAG_Q2_FULL_WIDTH) ? n - 3 : n - 4;  // Q2, EKF.cpp:442
+    const int blocks = std::max(1, (width + 255) / 256);
+    k_predict<<<blocks, 256, 0, h->stream>>>(h->X[h->cur], h->P, h->ld, n, v, swa, Q[0], Q[2], Q[1], Q[3], wb, dt,
+                                             width, h->ticket);
+    CSLAM_CUDA(cudaGetLastError());
+    return CSLAM_OK;
+}
+
+int cslam_ekf_observe_heading(cslam_ekf_t* h, double phi, int use_heading) {
+    if (int rc = check_handle(h)) return rc;
+    if (!use_heading) return CSLAM_OK;  // EKF.cpp:332-335
+    const int n = h->n;
+    const double sigma = 0.01F * kPi / 180.0F;  // EKF.cpp:337
+    k_heading_gain<<<(n + 255) / 256, 256, 0, h->stream>>>(h->X[h->cur], h->X[h->cur ^ 1], h->P, h->ld, n, phi,
+                                                           sigma * sigma, h->A);
+    CSLAM_CUDA(cudaGetLastError());
+    h->cur ^= 1;
+    return launch_cov_update<1>(h, kFltMin);
+}
+
+int cslam_ekf_gate(cslam_ekf_t* h, const double* Z, int m, const double R[4], double gate1, double gate2,
+                   int32_t* jbest, uint8_t* is_new, double* nbest, double* outer) {
+    if (int rc = check_handle(h)) return rc;
+    CSLAM_REQUIRE(m >= 0, CSLAM_ERR_BAD_ARG, "m < 0");
+    CSLAM_REQUIRE(m == 0 || (Z && R && jbest), CSLAM_ERR_BAD_ARG, "null argument");
+    const int nf = (h->n - 3) / 2;
+    for (int base = 0; base < m; base += CSLAM_MAX_OBS) {
+        const int mc = std::min(CSLAM_MAX_OBS, m - base);
+        if (int rc = launch_gate(h->X[h->cur], h->P, h->ld, nf, Z + 2 * base, mc, R, gate1, gate2, h->gate.part_nd,
+                                 h->gate.part_out, h->gate.part_j, h->ticket + 1, h->gate.d_jbest, h->gate.d_nbest,
+                                 h->gate.d_outer, h->stream))
+            return rc;
+        char* pin = static_cast<char*>(h->pinned);
+        int* pj = reinterpret_cast<int*>(pin);
+        double* pn = reinterpret_cast<double*>(pin + 1024);
+        double* po = reinterpret_cast<double*>(pin + 2048);
+        CSLAM_CUDA(cudaMemcpyAsync(pj, h->gate.d_jbest, mc * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CSLAM_CUDA(cudaMemcpyAsync(pn, h->gate.d_nbest, mc * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CSLAM_CUDA(cudaMemcpyAsync(po, h->gate.d_outer, mc * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CSLAM_CUDA(cudaStreamSynchronize(h->stream));
+        for (int i = 0; i < mc; i++) {
+            jbest[base + i] = pj[i];
+            if (is_new) is_new[base + i] = (pj[i] == 0 && po[i] > gate2) ? 1 : 0;  // EKF.cpp:287-295
+            if (nbest) nbest[base + i] = pn[i];
+            if (outer) outer[base + i] = po[i];
+        }
+    }
+    return CSLAM_OK;
+}
+
+int cslam_ekf_update(cslam_ekf_t* h, const double* Z, const int32_t* idf, int m, const double R[4], int batch) {
+    if (int rc = check_handle(h)) return rc;
+    CSLAM_REQUIRE(m >= 0, CSLAM_ERR_BAD_ARG, "m < 0");
+    if (m == 0) return CSLAM_OK;  // test/main.cpp:188 calls update with an empty ZF
+    CSLAM_REQUIRE(Z && idf && R, CSLAM_ERR_BAD_ARG, "null argument");
+    const int n = h->n, nf = (n - 3) / 2;
+    for (int i = 0; i < m; i++)
+        CSLAM_REQUIRE(idf[i] >= 1 && idf[i] <= nf, CSLAM_ERR_BAD_ARG, "idf out of range (1-based map slots)");
+    if (!batch) {
+        for (int i = 0; i < m; i++) {
+            k_gain_single<<<(n + 255) / 256, 256, 0, h->stream>>>(h->X[h->cur], h->X[h->cur ^ 1], h->P, h->ld, n,
+                                                                  Z[2 * i], Z[2 * i + 1], idf[i], R[0], R[1], R[2],
+                                                                  R[3], h->flags, h->A, h->lda, h->status);
+            CSLAM_CUDA(cudaGetLastError());
+            h->cur ^= 1;
+            if (int rc = launch_cov_update<2>(h, 0.0)) return rc;
+        }
+        return CSLAM_OK;
+    }
+    CSLAM_REQUIRE(m <= CSLAM_MAX_BATCH_OBS, CSLAM_ERR_UNSUPPORTED, "joint update supports at most 32 observations");
+    ObsPack ob;
+    memset(&ob, 0, sizeof(ob));
+    memcpy(ob.z, Z, sizeof(double) * 2 * m);
+    memcpy(ob.idf, idf, sizeof(int) * m);
+    ob.m = m;
+    memcpy(ob.R, R, sizeof(double) * 4);
+    const int r = 2 * m;
+    k_batch_prep<<<1, CSLAM_MAX_BATCH_OBS, 0, h->stream>>>(h->X[h->cur], ob, h->small);
+    k_batch_pht<<<dim3((n + 127) / 128, m), 128, 0, h->stream>>>(h->P, h->ld, n, m, h->small, h->PHT, h->lda);
+    const int chol_smem = 2 * kMaxRank * (kMaxRank + 1) * (int)sizeof(double);
+    CSLAM_CUDA(cudaFuncSetAttribute(k_batch_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, chol_smem));
+    k_batch_chol<<<1, 256, chol_smem, h->stream>>>(h->PHT, h->lda, m, R[0], R[1], R[2], R[3], h->flags, h->small,
+                                           h->status);
+    k_batch_w1<<<dim3((n + 127) / 128, (r + 7) / 8), 128, 0, h->stream>>>(h->PHT, h->lda, n, r, h->small,
+                                                                           h->X[h->cur], h->X[h->cur ^ 1], h->A);
+    CSLAM_CUDA(cudaGetLastError());
+    h->cur ^= 1;
+    return launch_cov_update_rank(h, r);
+}
+
+int cslam_ekf_augment(cslam_ekf_t* h, const double* Z, int m, const double R[4]) {
+    if (int rc = check_handle(h)) return rc;
+    CSLAM_REQUIRE(m >= 0, CSLAM_ERR_BAD_ARG, "m < 0");
+    if (m == 0) return CSLAM_OK;
+    CSLAM_REQUIRE(Z && R, CSLAM_ERR_BAD_ARG, "null argument");
+    CSLAM_REQUIRE(h->n + 2 * m <= h->n_cap, CSLAM_ERR_CAPACITY, "landmark capacity exceeded");
+    for (int i = 0; i < m; i++) {
+        const int len = h->n;
+        k_augment<<<(len + 255) / 256, 256, 0, h->stream>>>(h->X[h->cur], h->P, h->ld, len, Z[2 * i], Z[2 * i + 1],
+                                                            R[0], R[1], R[2], R[3]);
+        CSLAM_CUDA(cudaGetLastError());
+        h->n += 2;
+    }
+    return CSLAM_OK;
+}
+
+int cslam_ekf_get_state(cslam_ekf_t* h, double* X, int max_n) {
+    if (int rc = check_handle(h)) return rc;
+    CSLAM_REQUIRE(X != nullptr && max_n >= h->n, CSLAM_ERR_BAD_ARG, "buffer too small");
+    CSLAM_CUDA(cudaMemcpyAsync(h->pinned, h->X[h->cur], h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CSLAM_CUDA(cudaStreamSynchronize(h->stream));
+    memcpy(X, h->pinned, h->n * sizeof(double));
+    return CSLAM_OK;
+}
+
+int cslam_ekf_get_cov_block(cslam_ekf_t* h, int r0, int c0, int nr, int nc, double* out) {
+    if (int rc = check_handle(h)) return rc;
+    CSLAM_REQUIRE(out && r0 >= 0 && c0 >= 0 && nr >= 0 && nc >= 0 && r0 + nr <= h->n && c0 + nc <= h->n,
+                  CSLAM_ERR_BAD_ARG, "block out of range");
+    if (nr == 0 || nc == 0) return CSLAM_OK;
+    double* tmp = nullptr;
+    const size_t cnt = (size_t)nr * nc;
+    CSLAM_CUDA(cudaMalloc(&tmp, cnt * sizeof(double)));
+    k_gather_block<<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(h->P, h->ld, r0, c0, nr, nc, tmp);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(out, tmp, cnt * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(tmp);
+    CSLAM_CUDA(e);
+    return CSLAM_OK;
+}
+
+int cslam_ekf_reset(cslam_ekf_t* h, const double* X, int n, const double* P) {
+    if (int rc = check_handle(h)) return rc;
+    CSLAM_REQUIRE(X && n >= 3 && n <= h->n_cap && ((n - 3) % 2 == 0), CSLAM_ERR_BAD_ARG, "bad state size");
+    CSLAM_CUDA(cudaStreamSynchronize(h->stream));
+    CSLAM_CUDA(cudaMemset(h->X[0], 0, h->ld * sizeof(double)));
+    CSLAM_CUDA(cudaMemset(h->X[1], 0, h->ld * sizeof(double)));
+    CSLAM_CUDA(cudaMemcpy(h->X[0], X, n * sizeof(double), cudaMemcpyHostToDevice));
+    h->cur = 0;
+    h->n = n;
+    CSLAM_CUDA(cudaMemset(h->P, 0, (size_t)h->n_cap * h->ld * sizeof(double)));
+    CSLAM_CUDA(cudaMemset(h->status, 0, sizeof(int)));
+    if (P) {
+        double* tmp = nullptr;
+        const size_t cnt = (size_t)n * n;
+        CSLAM_CUDA(cudaMalloc(&tmp, cnt * sizeof(double)));
+        cudaError_t e = cudaMemcpy(tmp, P, cnt * sizeof(double), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) {
+            k_scatter_upper<<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(h->P, h->ld, n, tmp);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        cudaFree(tmp);
+        CSLAM_CUDA(e);
+    }
+    return CSLAM_OK;
+}
+
+int cslam_ekf_device_ptrs(cslam_ekf_t* h, void** dX, void** dP, size_t* ld) {
+    if (int rc = check_handle(h)) return rc;
+    if (dX) *dX = h->X[h->cur];
+    if (dP) *dP = h->P;
+    if (ld) *ld = h->ld;
+    return CSLAM_OK;
+}
+
+}  // extern "C"

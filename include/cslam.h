@@ -1,0 +1,159 @@
+/* cslam.h — C ABI of the B200-native SLAM filter hot path (libcslam.so).
+ *
+ * This is the drop-in boundary for conan-slam's filter layer.  The reference has no
+ * FFI: its boundary is the abstract C++ class `Slam` (slam/include/slam.h:56-977) that
+ * test/main.cpp drives through std::shared_ptr<Slam> (test/main.cpp:89,204).  Each entry
+ * point below names the `Slam` virtual it replaces (file:line under /root/reference).
+ * The C++ adaptor (conan_slam_b200/host/slam_gpu.hpp) and the Python mirror
+ * (conan_slam_b200/ekf.py, pf.py) re-expose these under the reference's own method names.
+ *
+ * Conventions (identical to the reference unless stated):
+ *   - state X = [x, y, phi, l1x, l1y, ...]  (EKF.cpp:356-357), n = 3 + 2*N, FP64 on the device
+ *   - landmark ids `idf` are 1-BASED map slots (EKF.cpp:356-357; table values EKF.cpp:212-226)
+ *   - Z is 2 x m column-major = interleaved (range_i, bearing_i) pairs, radians
+ *   - R, Q are 2 x 2 (4 doubles; symmetric, so row/column-major coincide)
+ *   - resampled `keep` indices are 0-based int32
+ *   - all state lives on the GPU behind the handle; host buffers are caller-owned
+ *   - one handle = one CUDA stream; calls on a handle must be externally serialised
+ *   - functions return CSLAM_OK or an error code and never throw; cslam_last_error()
+ *     gives the message.  Numerically skipped updates (reference: slam.h:252-255 zero-gain
+ *     path) are counted on the device and reported by cslam_*_sync().
+ *   - there is NO CPU fallback: without a usable CUDA device every compute call fails
+ *     with CSLAM_ERR_CUDA.
+ */
+#ifndef CSLAM_H
+#define CSLAM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSLAM_VERSION 100
+
+#define CSLAM_OK              0
+#define CSLAM_ERR_BAD_ARG     1
+#define CSLAM_ERR_CAPACITY    2
+#define CSLAM_ERR_CUDA        3
+#define CSLAM_ERR_NCCL        4
+#define CSLAM_ERR_UNSUPPORTED 5
+
+/* Quirk switches.  0 reproduces the reference literally; each
+ * bit selects the intended behaviour for ONE quirk.  Same values as oracle/slam_oracle.hpp. */
+#define CSLAM_FLAG_REF_LITERAL   0u
+#define CSLAM_FLAG_Q1_METRIC_S   (1u << 0) /* gain metric S=LL^T instead of L^T L      slam.h:250-260 */
+#define CSLAM_FLAG_Q2_FULL_WIDTH (1u << 1) /* predict all cross-cov columns           EKF.cpp:442-443 */
+#define CSLAM_FLAG_Q5_RETURN_ZN  (1u << 2) /* dataAssociate returns new features      EKF.cpp:308-325 */
+#define CSLAM_FLAG_Q9_METRIC_S   (1u << 3) /* gaussEvaluate exponent uses S^-1        PF.cpp:287-300  */
+#define CSLAM_FLAG_Q10_SEARCH    (1u << 4) /* resample Keep[c]=min{i:sel[c]<cumW[i]}  PF.cpp:566-574  */
+#define CSLAM_FLAG_INTENDED      0x1Fu
+
+/* Largest number of observations one update/gate/augment call accepts (they travel as
+ * kernel parameters, no H2D copy); a joint (batch) update accepts at most 32 (rank 64). */
+#define CSLAM_MAX_OBS       64
+#define CSLAM_MAX_BATCH_OBS 32
+
+typedef struct cslam_ekf cslam_ekf_t;
+typedef struct cslam_pf cslam_pf_t;
+
+const char* cslam_last_error(void);
+int cslam_version(void);
+int cslam_device_count(int* count);
+
+/* ------------------------------------------------------------------ EKF-SLAM ---- */
+
+/* Replaces `new EKF(LM, WP)` (EKF.cpp:3-7) + the driver-owned X(3)=0, P(3x3)=0
+ * (test/main.cpp:107-108).  Pre-allocates X and the joint covariance for
+ * `capacity_landmarks` landmarks (n_cap = 3 + 2*capacity; P is n_cap x ld FP64,
+ * row-major, upper triangle authoritative) so augmentation never reallocates. */
+int cslam_ekf_create(cslam_ekf_t** out, int capacity_landmarks, int device, unsigned flags);
+int cslam_ekf_destroy(cslam_ekf_t* h);
+/* Run this handle's kernels on a caller-provided cudaStream_t (e.g. a torch stream). */
+int cslam_ekf_set_stream(cslam_ekf_t* h, void* cuda_stream);
+/* Wait for the stream; *skipped_updates (nullable) = updates skipped as non-SPD since create/reset. */
+int cslam_ekf_sync(cslam_ekf_t* h, int* skipped_updates);
+int cslam_ekf_n(const cslam_ekf_t* h);             /* state dimension n = X.rows()            */
+int cslam_ekf_num_landmarks(const cslam_ekf_t* h); /* (n-3)/2                                  */
+int cslam_ekf_capacity(const cslam_ekf_t* h);
+
+/* Slam::predict(X,P,v,swa,Q,wb,dt)                      slam.h:841-847 -> EKF.cpp:406-455 */
+int cslam_ekf_predict(cslam_ekf_t* h, double v, double swa, const double Q[4], double wb, double dt);
+/* Slam::observeHeading(X,P,phi,useHeading)              slam.h:788 -> EKF.cpp:328-352 -> slam.h:700-725 */
+int cslam_ekf_observe_heading(cslam_ekf_t* h, double phi, int use_heading);
+/* Slam::dataAssociate(X,P,Z,R,gate1,gate2)              slam.h:482-487 -> EKF.cpp:235-326 (+131-144)
+ * Per observation i: jbest[i] = 1-based nearest in-gate landmark (0 = none, lowest j wins ties),
+ * is_new[i] = (jbest==0 && min_j nis > gate2).  nbest/outer are optional (nullable):
+ * nbest[i] = nd of jbest (inf if none); outer[i] = min_j nis_j — equal to the reference's
+ * `outer` whenever the reference consults it, i.e. when jbest==0. */
+int cslam_ekf_gate(cslam_ekf_t* h, const double* Z, int m, const double R[4], double gate1, double gate2,
+                   int32_t* jbest, uint8_t* is_new, double* nbest, double* outer);
+/* Slam::update(X,P,Z,R,idf,batch)                       slam.h:938-943 -> EKF.cpp:481-496
+ *   batch=0: singleUpdate EKF.cpp:457-479 (re-linearised per observation)
+ *   batch=1: batchUpdate  EKF.cpp:93-129  (one joint rank-2m update; m <= CSLAM_MAX_BATCH_OBS)
+ * both through Slam::choleskyUpdate slam.h:235-266.  Asynchronous. m == 0 is a no-op. */
+int cslam_ekf_update(cslam_ekf_t* h, const double* Z, const int32_t* idf, int m, const double R[4], int batch);
+/* Slam::augment(X,P,Z,R)                                slam.h:190-191 -> EKF.cpp:9-26 -> :28-91 */
+int cslam_ekf_augment(cslam_ekf_t* h, const double* Z, int m, const double R[4]);
+
+/* State / covariance accessors (the driver owns X and P in the reference; here they are
+ * read back on request).  get_cov_block returns a dense row-major nr x nc block with the
+ * lower triangle mirrored from the authoritative upper one. */
+int cslam_ekf_get_state(cslam_ekf_t* h, double* X, int max_n);
+int cslam_ekf_get_cov_block(cslam_ekf_t* h, int r0, int c0, int nr, int nc, double* out);
+/* Load a state (tests / benchmarks / checkpoint restore): X has n entries, P is a dense
+ * row-major n x n matrix (only j >= i is read) or NULL for zeros. */
+int cslam_ekf_reset(cslam_ekf_t* h, const double* X, int n, const double* P);
+/* Device pointers for zero-copy consumers (bench, visualisers): X (n doubles), P (row-major, ld). */
+int cslam_ekf_device_ptrs(cslam_ekf_t* h, void** dX, void** dP, size_t* ld);
+
+/* -------------------------------------------------------- particle filter (FastSLAM) ---- */
+
+/* Replaces `new PF(LM, WP)` + Slam::initializeParticles(n) (slam.h:688 -> PF.cpp:319-341):
+ * w = 1/P, X = 0, P = 0, no features.  SoA over particles on the device. */
+int cslam_pf_create(cslam_pf_t** out, int num_particles, int capacity_landmarks, int device, unsigned flags);
+int cslam_pf_destroy(cslam_pf_t* h);
+int cslam_pf_set_stream(cslam_pf_t* h, void* cuda_stream);
+int cslam_pf_sync(cslam_pf_t* h, int* skipped_updates);
+int cslam_pf_num_particles(const cslam_pf_t* h);
+int cslam_pf_num_features(const cslam_pf_t* h);
+
+/* Slam::predict(Particle_t&,v,swa,Q,wb,dt) for every particle     slam.h:858-863 -> PF.cpp:419-471 */
+int cslam_pf_predict(cslam_pf_t* h, double v, double swa, const double Q[4], double wb, double dt);
+/* Slam::observeHeading(Particle_t&,phi,use) for every particle     slam.h:796 -> PF.cpp:382-417 */
+int cslam_pf_observe_heading(cslam_pf_t* h, double phi, int use_heading);
+/* Slam::sampleProposal(Particle_t&,Z,idf,R) for every particle     slam.h:881-884 -> PF.cpp:502-544.
+ * xi: 3 standard-normal draws per particle, [p][3] (the values slam.h:753-764 would take
+ * from Boost — an input).  xi_on_device != 0: xi is a device pointer. */
+int cslam_pf_sample_proposal(cslam_pf_t* h, const double* Z, const int32_t* idf, int m, const double R[4],
+                             const double* xi, int xi_on_device);
+/* Slam::featureUpdate(Particle_t&,Z,idf,R) for every particle      slam.h:549-552 -> PF.cpp:222-277 */
+int cslam_pf_feature_update(cslam_pf_t* h, const double* Z, const int32_t* idf, int m, const double R[4]);
+/* Slam::resampleParticles(particles,numEffective,on)               slam.h:871-872 -> PF.cpp:473-500
+ *   -> stratifiedResample PF.cpp:546-577 (+ stratifiedRandom :579-596).
+ * u: one deviate per slot (an input).  keep (nullable, host, P int32) receives the
+ * selected 0-based source index per slot; *neff the effective particle count; *resampled
+ * whether the gather-copy ran (neff < num_effective && resample_on). */
+int cslam_pf_resample(cslam_pf_t* h, const double* u, int u_on_device, double num_effective, int resample_on,
+                      int32_t* keep, double* neff, int* resampled);
+/* Slam::addOneNewFeature(Particle_t&,Z,R) for every particle       slam.h:134 -> PF.cpp:9-60 */
+int cslam_pf_add_features(cslam_pf_t* h, const double* Z, int m, const double R[4]);
+/* particles[i].X = multivariateNormalGaussianDistribution(X,P,1); P = 0   test/main.cpp:319-325 */
+int cslam_pf_sample_pose(cslam_pf_t* h, const double* xi, int xi_on_device);
+
+/* Accessors: weights (P), poses ([p][3]), pose covariances ([p][9] row-major),
+ * features of one particle (XF [f][2], PF [f][4] row-major 2x2). */
+int cslam_pf_get_weights(cslam_pf_t* h, double* w);
+int cslam_pf_get_poses(cslam_pf_t* h, double* X);
+int cslam_pf_get_pose_covs(cslam_pf_t* h, double* Pv);
+int cslam_pf_get_features(cslam_pf_t* h, int particle, double* XF, double* PF);
+int cslam_pf_set_weights(cslam_pf_t* h, const double* w);
+int cslam_pf_set_poses(cslam_pf_t* h, const double* X, const double* Pv);
+/* Slam::extractStatesFromParticles (slam.h:493-511): pose of the MINIMUM-weight particle (Q13). */
+int cslam_pf_extract_state(cslam_pf_t* h, double X[3], int* index);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSLAM_H */

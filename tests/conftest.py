@@ -1,0 +1,47 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def _has_gpu():
+    try:
+        import ctypes as C
+
+        from conan_slam_b200 import _lib
+        lib = _lib.load_library()
+        n = C.c_int(0)
+        return lib.cslam_device_count(C.byref(n)) == 0 and n.value > 0
+    except Exception:
+        return False
+
+
+@pytest.fixture(scope="session")
+def gpu_available():
+    return _has_gpu()
+
+
+def pytest_collection_modifyitems(config, items):
+    # -m gpu tests must FAIL (not skip) if the library is missing on a GPU box; on a box with no
+    # GPU at all they are skipped so that a plain `pytest tests` stays usable.
+    if _has_gpu():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device visible")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _build_oracle():
+    import oracle_py
+    oracle_py.build_oracle()

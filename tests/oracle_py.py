@@ -1,0 +1,328 @@
+"""ctypes face of oracle/liboracle_slam.so (the CPU restatement of the reference).
+
+TEST INFRASTRUCTURE: imported only by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The classes mirror conan_slam_b200.EKF / PF method
+for method so a parity test reads `for f in (oracle, gpu): f.predict(...)`.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_SO = os.path.join(ORACLE_DIR, "liboracle_slam.so")
+
+FLAG_INTENDED = 0x1F
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_u8 = C.POINTER(C.c_uint8)
+_LIB = None
+
+
+def build_oracle(force=False):
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("slam_oracle.hpp", "oracle_capi.cpp", "oracle_bench.cpp", "Makefile")]
+    stale = (not os.path.exists(ORACLE_SO)) or any(os.path.getmtime(s) > os.path.getmtime(ORACLE_SO) for s in srcs)
+    if force or stale:
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "-s", "liboracle_slam.so"])
+    return ORACLE_SO
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        build_oracle()
+        L = C.CDLL(ORACLE_SO)
+        L.orc_ekf_create.restype = C.c_void_p
+        L.orc_ekf_create.argtypes = [C.c_uint]
+        L.orc_pf_create.restype = C.c_void_p
+        L.orc_pf_create.argtypes = [C.c_int, C.c_uint]
+        L.orc_pi2pi.restype = C.c_double
+        L.orc_pi2pi.argtypes = [C.c_double]
+        L.orc_pi2pi_f.restype = C.c_float
+        L.orc_pi2pi_f.argtypes = [C.c_float]
+        _LIB = L
+    return _LIB
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return a.ctypes.data_as(_ip)
+
+
+def _zflat(Z):
+    Z = np.asarray(Z, dtype=np.float64)
+    if Z.size == 0:
+        return np.zeros(0), 0
+    Z = Z.reshape(2, -1)
+    return np.ascontiguousarray(Z.T).reshape(-1), Z.shape[1]
+
+
+def _m2(M):
+    return np.ascontiguousarray(np.asarray(M, dtype=np.float64).reshape(2, 2).T).reshape(-1)
+
+
+class OracleEKF:
+    def __init__(self, flags=0):
+        self.L = lib()
+        self.h = C.c_void_p(self.L.orc_ekf_create(flags))
+        self.flags = flags
+
+    def __del__(self):
+        try:
+            self.L.orc_ekf_destroy(self.h)
+        except Exception:
+            pass
+
+    @property
+    def n(self):
+        return self.L.orc_ekf_n(self.h)
+
+    @property
+    def num_landmarks(self):
+        return (self.n - 3) // 2
+
+    def reset(self, X, P=None):
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        if P is not None:
+            P = np.ascontiguousarray(P, dtype=np.float64)
+        self.L.orc_ekf_reset(self.h, _d(X), X.shape[0], _d(P) if P is not None else None)
+
+    @property
+    def X(self):
+        out = np.empty(self.n)
+        self.L.orc_ekf_get_state(self.h, _d(out))
+        return out
+
+    @property
+    def P(self):
+        n = self.n
+        out = np.empty((n, n))
+        self.L.orc_ekf_get_cov(self.h, _d(out))
+        return out
+
+    def predict(self, v, swa, Q, wb, dt):
+        q = _m2(Q)
+        self.L.orc_ekf_predict(self.h, C.c_double(v), C.c_double(swa), _d(q), C.c_double(wb), C.c_double(dt))
+
+    def observeHeading(self, phi, useHeading=False, dense=False):
+        self.L.orc_ekf_observe_heading(self.h, C.c_double(phi), int(bool(useHeading)), int(bool(dense)))
+
+    def update(self, Z, R, idf, batch=False):
+        z, m = _zflat(Z)
+        if m == 0:
+            return 0
+        idf = np.ascontiguousarray(idf, dtype=np.int32)
+        r = _m2(R)
+        return self.L.orc_ekf_update(self.h, _d(z), _i(idf), m, _d(r), int(bool(batch)))
+
+    def augment(self, Z, R):
+        z, m = _zflat(Z)
+        if m == 0:
+            return
+        r = _m2(R)
+        self.L.orc_ekf_augment(self.h, _d(z), m, _d(r))
+
+    def gate(self, Z, R, gate1, gate2, dense=False):
+        z, m = _zflat(Z)
+        r = _m2(R)
+        jbest = np.zeros(m, dtype=np.int32)
+        is_new = np.zeros(m, dtype=np.uint8)
+        nbest = np.zeros(m)
+        outer = np.zeros(m)
+        idf = np.zeros(max(m, 1), dtype=np.int32)
+        zn = C.c_int(0)
+        na = self.L.orc_ekf_gate(self.h, _d(z), m, _d(r), C.c_double(gate1), C.c_double(gate2), int(bool(dense)),
+                                 _i(jbest), is_new.ctypes.data_as(_u8), _d(nbest), _d(outer), _i(idf), C.byref(zn))
+        return jbest, is_new, nbest, outer, idf[:na].copy(), zn.value
+
+    def dataAssociateTable(self, idz, table):
+        idz = np.ascontiguousarray(idz, dtype=np.int32)
+        m = idz.shape[0]
+        zf = np.zeros(max(m, 1), dtype=np.int32)
+        zn = np.zeros(max(m, 1), dtype=np.int32)
+        idf = np.zeros(max(m, 1), dtype=np.int32)
+        nzf, nzn = C.c_int(0), C.c_int(0)
+        self.L.orc_ekf_table(self.h, _i(idz), m, _i(table), table.shape[0], _i(zf), _i(idf), C.byref(nzf), _i(zn),
+                             C.byref(nzn))
+        return zf[:nzf.value].copy(), idf[:nzf.value].copy(), zn[:nzn.value].copy()
+
+
+class OraclePF:
+    def __init__(self, num_particles, flags=0):
+        self.L = lib()
+        self.np_ = int(num_particles)
+        self.h = C.c_void_p(self.L.orc_pf_create(self.np_, flags))
+
+    def __del__(self):
+        try:
+            self.L.orc_pf_destroy(self.h)
+        except Exception:
+            pass
+
+    @property
+    def num_particles(self):
+        return self.np_
+
+    @property
+    def num_features(self):
+        return self.L.orc_pf_num_features(self.h)
+
+    def predict(self, v, swa, Q, wb, dt):
+        q = _m2(Q)
+        self.L.orc_pf_predict(self.h, C.c_double(v), C.c_double(swa), _d(q), C.c_double(wb), C.c_double(dt))
+
+    def observeHeading(self, phi, useHeading=False):
+        self.L.orc_pf_observe_heading(self.h, C.c_double(phi), int(bool(useHeading)))
+
+    def sampleProposal(self, Z, idf, R, xi):
+        z, m = _zflat(Z)
+        idf = np.ascontiguousarray(idf, dtype=np.int32)
+        xi = np.ascontiguousarray(xi, dtype=np.float64).reshape(-1)
+        r = _m2(R)
+        self.L.orc_pf_sample_proposal(self.h, _d(z), _i(idf), m, _d(r), _d(xi))
+
+    def featureUpdate(self, Z, idf, R):
+        z, m = _zflat(Z)
+        idf = np.ascontiguousarray(idf, dtype=np.int32)
+        r = _m2(R)
+        self.L.orc_pf_feature_update(self.h, _d(z), _i(idf), m, _d(r))
+
+    def resampleParticles(self, numEffective, u, resampleStatus=False):
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        keep = np.zeros(self.np_, dtype=np.int32)
+        neff = C.c_double(0)
+        did = self.L.orc_pf_resample(self.h, _d(u), C.c_double(numEffective), int(bool(resampleStatus)), _i(keep),
+                                     C.byref(neff))
+        return keep, neff.value, bool(did)
+
+    def addOneNewFeature(self, Z, R):
+        z, m = _zflat(Z)
+        if m == 0:
+            return
+        r = _m2(R)
+        self.L.orc_pf_add_features(self.h, _d(z), m, _d(r))
+
+    def samplePose(self, xi):
+        xi = np.ascontiguousarray(xi, dtype=np.float64).reshape(-1)
+        self.L.orc_pf_sample_pose(self.h, _d(xi))
+
+    def extractStatesFromParticles(self):
+        X = np.zeros(3)
+        idx = self.L.orc_pf_extract_state(self.h, _d(X))
+        return X, idx
+
+    @property
+    def weights(self):
+        w = np.empty(self.np_)
+        self.L.orc_pf_get_weights(self.h, _d(w))
+        return w
+
+    @weights.setter
+    def weights(self, w):
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        self.L.orc_pf_set_weights(self.h, _d(w))
+
+    @property
+    def poses(self):
+        X = np.empty((self.np_, 3))
+        self.L.orc_pf_get_poses(self.h, _d(X), None)
+        return X
+
+    @property
+    def pose_covs(self):
+        X = np.empty((self.np_, 3))
+        P = np.empty((self.np_, 3, 3))
+        self.L.orc_pf_get_poses(self.h, _d(X), _d(P))
+        return P
+
+    def set_poses(self, X, Pv=None):
+        X = np.ascontiguousarray(X, dtype=np.float64).reshape(-1)
+        if Pv is not None:
+            Pv = np.ascontiguousarray(Pv, dtype=np.float64).reshape(-1)
+        self.L.orc_pf_set_poses(self.h, _d(X), _d(Pv) if Pv is not None else None)
+
+    def features(self, particle):
+        nf = self.num_features
+        XF = np.zeros((nf, 2))
+        PF = np.zeros((nf, 2, 2))
+        self.L.orc_pf_get_features(self.h, int(particle), _d(XF), _d(PF))
+        return XF, PF
+
+
+def stratified_resample(w, u, flags=0):
+    """PF.cpp:546-577 alone: returns (keep, neff, cumW)."""
+    L = lib()
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    n = w.shape[0]
+    keep = np.zeros(n, dtype=np.int32)
+    cum = np.zeros(n)
+    neff = C.c_double(0)
+    L.orc_stratified_resample(_d(w), _d(u), n, C.c_uint(flags), _i(keep), C.byref(neff), _d(cum))
+    return keep, neff.value, cum
+
+
+def sim_tape(max_steps=40000, noise_seed=0, max_obs=400000):
+    """Filter-independent half of test/main.cpp's loop.  Returns dict with controls [S,3]
+    (vn, swan, phi_true), obs_flag [S], obs_ptr [S+1], Z [K,2], tags [K], and constants."""
+    L = lib()
+    controls = np.zeros((max_steps, 3))
+    obs_flag = np.zeros(max_steps, dtype=np.int32)
+    obs_ptr = np.zeros(max_steps + 1, dtype=np.int32)
+    Z = np.zeros((max_obs, 2))
+    tags = np.zeros(max_obs, dtype=np.int32)
+    consts = np.zeros(8)
+    L.orc_sim_tape.restype = C.c_int
+    steps = L.orc_sim_tape(max_steps, C.c_ulonglong(noise_seed), _d(controls), _i(obs_flag), _i(obs_ptr), _d(Z),
+                           _i(tags), max_obs, _d(consts))
+    k = obs_ptr[steps]
+    return dict(steps=steps, controls=controls[:steps], obs_flag=obs_flag[:steps], obs_ptr=obs_ptr[:steps + 1],
+                Z=Z[:k], tags=tags[:k],
+                Q=np.diag([consts[0], consts[1]]), R=np.diag([consts[2], consts[3]]), wb=consts[4], dt=consts[5])
+
+
+def run_tape(filt, tape, first=0, last=None, batch=True, heading=True, table=None, on_step=None, dense_heading=None):
+    """Replays test/main.cpp:132-200 (known associations) on any filter object exposing the
+    reference's method names.  `table` is the feature/observation lookup table (mTABLE)."""
+    QE = 2 * tape["Q"]
+    RE = 8 * tape["R"]
+    if table is None:
+        table = np.zeros(30, dtype=np.int32)
+    last = tape["steps"] if last is None else last
+    for s in range(first, last):
+        vn, swan, phi = tape["controls"][s]
+        filt.predict(vn, swan, QE, tape["wb"], tape["dt"])
+        if dense_heading is None:
+            filt.observeHeading(phi, heading)
+        else:
+            filt.observeHeading(phi, heading, dense=dense_heading)
+        if tape["obs_flag"][s]:
+            a, b = tape["obs_ptr"][s], tape["obs_ptr"][s + 1]
+            if b > a:
+                Z = tape["Z"][a:b].T  # 2 x m
+                idz = tape["tags"][a:b]
+                zf, zn, idf = [], [], []
+                nf = filt.num_landmarks
+                new_ids = []
+                for i, ident in enumerate(idz):  # EKF.cpp:146-233
+                    if table[ident - 1] == 0:
+                        zn.append(i)
+                        new_ids.append(ident)
+                    else:
+                        zf.append(i)
+                        idf.append(table[ident - 1])
+                for k, ident in enumerate(new_ids):
+                    table[ident - 1] = nf + k + 1
+                if zf:
+                    filt.update(Z[:, zf], RE, np.asarray(idf, dtype=np.int32), batch)
+                if zn:
+                    filt.augment(Z[:, zn], RE)
+        if on_step is not None:
+            on_step(s, filt)
+    return table

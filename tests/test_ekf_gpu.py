@@ -1,0 +1,235 @@
+"""GPU parity tests (through the C ABI) of the EKF-SLAM hot path against the CPU oracle.
+
+Bar (BASELINE.json north_star): state / landmark / covariance estimates within 1e-9 relative
+in FP64; association indices exactly equal.  Inputs are seeded; sizes are what the dense oracle
+finishes in seconds; full-size behaviour is covered by size-independent properties
+(test_ekf_properties_gpu.py).
+"""
+import numpy as np
+import pytest
+
+import helpers
+import oracle_py
+from helpers import QE, RE, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9  # north_star tolerance, relative to the largest entry of the compared array
+
+
+def _pair(N, seed, flags, capacity=None):
+    import conan_slam_b200 as cs
+    X, P, lm = helpers.synthetic_map(N, seed)
+    g = cs.EKF(capacity_landmarks=capacity or (N + 8), flags=flags)
+    o = oracle_py.OracleEKF(flags)
+    g.reset(X, P)
+    o.reset(X, P)
+    return g, o, lm
+
+
+def _assert_state(g, o, tol=TOL):
+    assert g.n == o.n
+    assert rel_err(g.X, o.X) < tol
+    Pg, Po = g.P, o.P
+    assert np.array_equal(Pg, Pg.T)  # accessor mirrors the authoritative upper triangle
+    iu = np.triu_indices(o.n)
+    assert rel_err(Pg[iu], Po[iu]) < tol
+
+
+@pytest.mark.parametrize("flags", [0, oracle_py.FLAG_INTENDED])
+@pytest.mark.parametrize("N", [0, 1, 2, 25, 150])
+def test_predict_heading_parity(N, flags):
+    g, o, lm = _pair(N, 10 + N, flags)
+    for k in range(3):
+        for f in (g, o):
+            f.predict(83.33 + k, 0.03 * (k - 1), QE, 73.0, 0.01)
+        _assert_state(g, o)
+        for f in (g, o):
+            f.observeHeading(o.X[2] + 1e-4 * (k + 1), True)
+        _assert_state(g, o)
+    assert g.sync() == 0
+    # useHeading = false is a no-op (EKF.cpp:332-335)
+    before = g.X
+    g.observeHeading(1.0, False)
+    assert np.array_equal(g.X, before)
+
+
+@pytest.mark.parametrize("flags", [0, oracle_py.FLAG_INTENDED])
+@pytest.mark.parametrize("N,m", [(1, 1), (2, 2), (25, 5), (150, 7), (1100, 4)])
+def test_single_update_parity(N, m, flags):
+    g, o, lm = _pair(N, 20 + N, flags)
+    rng = np.random.default_rng(N)
+    ids = (rng.choice(N, size=m, replace=False) + 1).astype(np.int32)
+    Z = helpers.observe(o.X, lm, ids, rng)
+    for f in (g, o):
+        f.update(Z, RE, ids, False)
+    _assert_state(g, o)
+    assert g.sync() == 0
+
+
+@pytest.mark.parametrize("flags", [0, oracle_py.FLAG_INTENDED])
+@pytest.mark.parametrize("N,m", [(1, 1), (7, 7), (25, 5), (150, 16), (150, 32), (1100, 32)])
+def test_batch_update_parity(N, m, flags):
+    """EKF.cpp:93-129 joint update; N=1100 takes the FP64 tensor-core (DMMA) kernel."""
+    g, o, lm = _pair(N, 30 + N, flags)
+    rng = np.random.default_rng(N + m)
+    ids = (rng.choice(N, size=m, replace=False) + 1).astype(np.int32)
+    Z = helpers.observe(o.X, lm, ids, rng)
+    for f in (g, o):
+        f.update(Z, RE, ids, True)
+    _assert_state(g, o)
+    assert g.sync() == 0
+
+
+def test_empty_update_is_noop():
+    """test/main.cpp:188 calls update with an empty ZF whenever every visible landmark is new."""
+    g, o, lm = _pair(5, 3, 0)
+    before_x, before_p = g.X, g.P
+    g.update(np.zeros((2, 0)), RE, np.zeros(0, dtype=np.int32), True)
+    g.update(np.zeros((2, 0)), RE, np.zeros(0, dtype=np.int32), False)
+    assert np.array_equal(g.X, before_x) and np.array_equal(g.P, before_p)
+
+
+@pytest.mark.parametrize("flags", [0, oracle_py.FLAG_INTENDED])
+def test_augment_parity_from_empty_map(flags):
+    """EKF.cpp:9-91: growth from n = 3 (no landmarks) inside the pre-allocated covariance."""
+    import conan_slam_b200 as cs
+    g = cs.EKF(capacity_landmarks=40, flags=flags)
+    o = oracle_py.OracleEKF(flags)
+    X0 = np.array([3.0, -2.0, 0.4])
+    P0 = np.array([[0.5, 0.02, 0.001], [0.02, 0.4, -0.002], [0.001, -0.002, 3e-4]])
+    g.reset(X0, P0)
+    o.reset(X0, P0)
+    rng = np.random.default_rng(0)
+    for round_ in range(4):
+        m = [1, 3, 7, 9][round_]
+        Z = np.stack([rng.uniform(50, 1900, size=m), rng.uniform(-1.5, 1.5, size=m)])
+        for f in (g, o):
+            f.augment(Z, RE)
+            f.predict(83.33, 0.01, QE, 73.0, 0.01)
+        _assert_state(g, o)
+    assert g.num_landmarks == 20
+
+
+def test_augment_capacity_error():
+    import conan_slam_b200 as cs
+    g = cs.EKF(capacity_landmarks=2)
+    g.reset(np.zeros(3), np.eye(3))
+    g.augment(np.array([[10.0, 20.0], [0.1, 0.2]]), RE)
+    with pytest.raises(cs.CslamError) as e:
+        g.augment(np.array([[30.0], [0.3]]), RE)
+    assert e.value.code == 2
+    with pytest.raises(cs.CslamError) as e:
+        g.update(np.array([[30.0], [0.3]]), RE, np.array([3], dtype=np.int32), False)  # idf out of range
+    assert e.value.code == 1
+
+
+@pytest.mark.parametrize("N,m", [(1, 1), (3, 4), (40, 6), (600, 64), (2000, 4)])
+def test_gating_indices_exact(N, m):
+    """EKF.cpp:235-326: association indices must equal the oracle's exactly; the test also
+    checks the decisions are well separated (no accidental near-ties)."""
+    g, o, lm = _pair(N, 50 + N, 0)
+    rng = np.random.default_rng(7 * N + m)
+    k_assoc = min(N, max(1, m // 2))
+    ids = rng.choice(N, size=k_assoc, replace=False) + 1
+    Z = helpers.observe(o.X, lm, ids, rng)
+    # the rest: spurious observations (mostly far from every landmark)
+    extra = m - k_assoc
+    if extra > 0:
+        Zx = np.stack([rng.uniform(30.0, 3000.0, size=extra), rng.uniform(-np.pi, np.pi, size=extra)])
+        Z = np.concatenate([Z, Zx], axis=1)
+    jg, newg, nbg, outg = g.gate(Z, RE, 50.0, 1000.0)
+    jo, newo, nbo, outo, idf_o, _ = o.gate(Z, RE, 50.0, 1000.0, dense=(N <= 40))
+    assert np.array_equal(jg, jo)
+    assert np.array_equal(newg, newo)
+    assert np.array_equal(jg[:k_assoc], ids)
+    hit = jo != 0
+    assert rel_err(nbg[hit], nbo[hit]) < 1e-12 if hit.any() else True
+    miss = ~hit
+    if miss.any():
+        assert np.allclose(outg[miss], outo[miss], rtol=1e-12, atol=0)
+    # dataAssociate wrapper: ZF / idf in observation order; ZN empty in REF_LITERAL (Q5)
+    a = g.dataAssociate(Z, RE, 50.0, 1000.0)
+    assert np.array_equal(a.idf, idf_o)
+    assert np.array_equal(a.ZF, Z[:, hit])
+    assert a.ZN.size == 0
+
+
+def test_gating_tie_lowest_index_wins_and_no_landmarks():
+    import conan_slam_b200 as cs
+    X = np.array([0.0, 0.0, 0.0, 100.0, 50.0, 100.0, 50.0, 100.0, 50.0])
+    P = np.zeros((9, 9))
+    P[0:3, 0:3] = np.diag([0.5, 0.5, 1e-4])
+    blk = np.array([[2.0, 0.3], [0.3, 1.0]])
+    cross = np.array([[0.1, 0.0], [0.0, 0.1], [0.001, -0.002]])
+    for k in range(3):
+        s = 3 + 2 * k
+        P[s:s + 2, s:s + 2] = blk
+        P[0:3, s:s + 2] = cross
+        P[s:s + 2, 0:3] = cross.T
+    g = cs.EKF(capacity_landmarks=4)
+    g.reset(X, P)
+    Z = np.array([[np.hypot(100, 50) + 0.05], [np.arctan2(50, 100) + 0.001]])
+    assert g.gate(Z, RE, 50.0, 1000.0)[0][0] == 1          # three exact ties -> lowest j (Q4)
+    g.reset(np.zeros(3), np.eye(3))                          # nf = 0: everything is "new"
+    j, new, nb, out = g.gate(Z, RE, 50.0, 1000.0)
+    assert j[0] == 0 and new[0] == 1 and np.isinf(out[0]) and np.isinf(nb[0])
+    a = cs.EKF(capacity_landmarks=4, flags=cs.FLAG_INTENDED)
+    a.reset(np.zeros(3), np.eye(3))
+    assert a.dataAssociate(Z, RE, 50.0, 1000.0).ZN.shape == (2, 1)  # Q5 intended: new features returned
+
+
+def test_non_spd_update_is_skipped_and_counted():
+    """slam.h:252-255: a non-finite Cholesky inverse means zero gain — state unchanged."""
+    import conan_slam_b200 as cs
+    X = np.array([0.0, 0.0, 0.0, 50.0, 10.0])
+    P = -np.eye(5)  # negative definite -> S = H P H^T + R not SPD
+    g = cs.EKF(capacity_landmarks=2)
+    o = oracle_py.OracleEKF(0)
+    g.reset(X, P)
+    o.reset(X, P)
+    Z = np.array([[51.0], [0.2]])
+    Rsmall = np.diag([1e-3, 1e-6])
+    g.update(Z, Rsmall, np.array([1], dtype=np.int32), False)
+    assert o.update(Z, Rsmall, np.array([1], dtype=np.int32), False) == 1
+    assert g.sync() == 1
+    assert np.array_equal(g.X, X)
+    assert np.array_equal(g.P, P)
+    g.update(Z, Rsmall, np.array([1], dtype=np.int32), True)
+    assert g.sync() == 2 and np.array_equal(g.X, X)
+
+
+def test_bearing_wrap_at_pi():
+    """Innovation bearing is wrapped through pi2Pi (EKF.cpp:471): observe a landmark almost
+    straight behind the vehicle so z_b - zhat_b crosses +-pi."""
+    import conan_slam_b200 as cs
+    X = np.array([0.0, 0.0, 0.0, -100.0, 0.5])
+    P = np.diag([0.2, 0.2, 1e-4, 1.0, 1.0])
+    g = cs.EKF(capacity_landmarks=2)
+    o = oracle_py.OracleEKF(0)
+    for f in (g, o):
+        f.reset(X, P)
+    zb = np.arctan2(-0.5, -100.0)  # just below -pi side, while zhat is just below +pi
+    Z = np.array([[100.0], [zb]])
+    for f in (g, o):
+        f.update(Z, RE, np.array([1], dtype=np.int32), False)
+    assert rel_err(g.X, o.X) < TOL
+    assert abs(g.X[4] - 0.5) < 1.0  # wrapped innovation: a small correction, not a 2*pi swing
+
+
+def test_main_loop_prefix_parity_literal():
+    """Config 1 (test/main.cpp loop, known associations, batch update, heading known),
+    first 1500 control steps with the LITERAL dense Joseph update in the oracle."""
+    import conan_slam_b200 as cs
+    tape = oracle_py.sim_tape(noise_seed=0)
+    g = cs.EKF(capacity_landmarks=30, flags=0)
+    o = oracle_py.OracleEKF(0)
+    for f in (g, o):
+        f.reset(np.zeros(3), np.zeros((3, 3)))
+    tg = oracle_py.run_tape(g, tape, last=1500)
+    to = oracle_py.run_tape(o, tape, last=1500, dense_heading=True)
+    assert np.array_equal(tg, to)
+    assert g.n == o.n and g.n > 3
+    assert rel_err(g.X, o.X) < TOL
+    iu = np.triu_indices(o.n)
+    assert rel_err(g.P[iu], o.P[iu]) < TOL
