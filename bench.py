@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native conan-slam filter hot path.
+
+Metric (BASELINE.json): EKF updates/sec at N landmarks (+ % of the HBM roofline).
+One EKF update = one full observation cycle for ONE range-bearing observation: Mahalanobis
+gating over all N landmarks + innovation / Kalman gain + in-place covariance update
+(SURVEY.md §8d).  One benchmark "step" = one scan of m = 4 observations: one gating pass shared
+by the scan, then 4 sequential (re-linearised) updates — EKF.cpp:235-326 + :457-479.
+
+Default workload (N = 1 GPU): the north-star headline, a 20,000-landmark map (n = 40,003,
+FP64 P = 12.8 GB, upper triangle streamed in place) — "C3-seq" of BASELINE.md.
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload ...] [--impl reference]
+N > 1 (torchrun, one rank per GPU): see --workload; default is the row-block-sharded covariance
+when available, else independent Monte-Carlo filter replicas (no data-path collective).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+R_BASE = np.diag([0.1 ** 2, (np.pi / 180.0) ** 2])
+RE = 8.0 * R_BASE
+GATE1, GATE2 = 50.0, 1000.0
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ----------------------------------------------------------------------------- clocks ----
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU during the timed region (NVML)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            self.nv = None
+            log(f"[bench] NVML unavailable: {e}")
+
+    def _loop(self):
+        nv = self.nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+            nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        if self._thr is not None:
+            self._stop.set()
+            self._thr.join()
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel, n):
+    """dram bytes per launch from the committed ncu capture, if one exists for this size."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        for e in json.load(open(p)):
+            if e.get("kernel") == kernel and e.get("n") == n:
+                return e.get("dram_bytes_per_launch")
+    return None
+
+
+# ----------------------------------------------------------------------- synthetic map ----
+def synth_landmarks(N, seed):
+    rng = np.random.Generator(np.random.MT19937(seed))
+    side = 10000.0 * np.sqrt(N / 30.0)  # the reference's density: 30 landmarks per ~(10 km)^2
+    return rng.uniform(-side / 2, side / 2, size=(2, N)), rng
+
+
+def range_bearing(pose, lm):
+    dx, dy = lm[0] - pose[0], lm[1] - pose[1]
+    return np.stack([np.hypot(dx, dy), np.arctan2(dy, dx) - pose[2]])
+
+
+def build_ekf(N, device, flags, seed=None, stream=None):
+    """Synthetic N-landmark joint state built ON THE GPU by the filter's own augment kernel from
+    Pvv = diag(1, 1, (1 deg)^2): P_ij = Gv_i Pvv Gv_j^T + blockdiag(Gz R Gz^T)."""
+    import conan_slam_b200 as cs
+    lm, rng = synth_landmarks(N, N if seed is None else seed)
+    ekf = cs.EKF(capacity_landmarks=N, device=device, flags=flags)
+    if stream is not None:
+        ekf.set_stream(stream)
+    pose = np.zeros(3)
+    ekf.reset(pose, np.diag([1.0, 1.0, (np.pi / 180.0) ** 2]))
+    Z = range_bearing(pose, lm)
+    Z[0] += rng.normal(size=N) * 0.1
+    Z[1] += rng.normal(size=N) * (np.pi / 180.0)
+    ekf.augment(Z, RE)
+    ekf.sync()
+    return ekf, lm, rng
+
+
+def make_scans(lm, rng, nscans, m):
+    """Observation scans: m of the landmarks nearest to the (static) true pose, fresh noise."""
+    d = np.hypot(lm[0], lm[1])
+    near = np.argsort(d)[:max(64, m)]
+    scans = []
+    for s in range(nscans):
+        ids = rng.choice(near, size=m, replace=False)
+        Z = range_bearing(np.zeros(3), lm[:, ids])
+        Z[0] += rng.normal(size=m) * 0.1
+        Z[1] += rng.normal(size=m) * (np.pi / 180.0)
+        scans.append((Z, ids + 1))
+    return scans
+
+
+def ekf_scan(ekf, Z):
+    """The user-facing call sequence of one scan (test/main.cpp:193-195): gate, then update."""
+    jbest, is_new, _, _ = ekf.gate(Z, RE, GATE1, GATE2)
+    sel = jbest > 0
+    ekf.update(Z[:, sel], RE, jbest[sel], False)
+    return jbest
+
+
+# --------------------------------------------------------------------------- CPU baseline ----
+def oracle_lib():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_py  # bench.py's cpu_baseline / --impl reference legs may execute oracle/
+    L = oracle_py.lib()
+    L.orc_bench_dense_update_slab.restype = C.c_double
+    L.orc_bench_dense_update_slab.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.orc_bench_dense_gate_pair_slab.restype = C.c_double
+    L.orc_bench_dense_gate_pair_slab.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
+    L.orc_bench_pf_step.restype = C.c_double
+    L.orc_bench_pf_step.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint]
+    return L
+
+
+def cpu_ekf_update_rate(N, threads, slab_cols, reps=2):
+    """Reference algorithm on the host cores, one sequential EKF update on an N-landmark map:
+    dense choleskyUpdate (slam.h:235-266) + dense O(n^2)-per-pair gating (EKF.cpp:131-144) over
+    all N landmarks.  Timed on a slab of `slab_cols` of the n columns and scaled by n/slab."""
+    L = oracle_lib()
+    n = 3 + 2 * N
+    c = min(n, slab_cols)
+    t_upd = L.orc_bench_dense_update_slab(n, c, 2, threads, reps) * n / c
+    t_pair = L.orc_bench_dense_gate_pair_slab(n, c, threads, reps) * n / c
+    t_full = t_upd + N * t_pair
+    return {
+        "value": 1.0 / t_full,
+        "unit": "updates/s",
+        "cores": threads,
+        "kind": "port",
+        "sample": (f"oracle dense choleskyUpdate + dense computeAssociation on a {c}-column slab of the "
+                   f"{n}x{n} FP64 covariance, scaled by n/c; gating = N x per-pair cost (extrapolated)"),
+        "update_only_updates_per_s": 1.0 / t_upd,
+        "seconds_per_update_cov": t_upd,
+        "seconds_per_gate_pair": t_pair,
+    }
+
+
+# --------------------------------------------------------------------------------- main ----
+def run_reference(args):
+    """--impl reference: the reference's own (dense, CPU) algorithm for the same workload, all
+    host threads, each step a bounded slab sample.  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    N = args.landmarks
+    threads = os.cpu_count() or 1
+    n = 3 + 2 * N
+    # size the slab so that warmup + steps finish within ~2 minutes
+    L = oracle_lib()
+    probe_c = 256
+    t_probe = L.orc_bench_dense_update_slab(n, probe_c, 2, threads, 1) + \
+        L.orc_bench_dense_gate_pair_slab(n, probe_c, threads, 1)
+    budget = 100.0 / max(1, args.steps + args.warmup)
+    c = int(max(128, min(n, probe_c * budget / max(t_probe, 1e-6))))
+    c = min(c, int(2e9 // (8 * n)))  # <= 2 GB per slab buffer
+    rates = []
+    for s in range(args.warmup + args.steps):
+        r = cpu_ekf_update_rate(N, threads, c, reps=1)
+        if s >= args.warmup:
+            rates.append(r)
+    t_full = float(np.mean([1.0 / r["value"] for r in rates]))
+    val = 1.0 / t_full
+    base = rates[-1]
+    base["value"] = val
+    base["cores"] = threads
+    out = {
+        "impl": "reference", "metric": "EKF updates/sec", "value": val, "unit": "updates/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 4 * t_full * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"EKF-SLAM {N} landmarks, sequential update (gate+gain+cov), reference dense "
+                               f"algorithm on CPU", "landmarks": N, "state_dim": n, "obs_per_step": 4},
+        "cpu_baseline": base,
+        "e2e": {"value": val, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--landmarks", type=int, default=20000)
+    ap.add_argument("--obs", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--extras", action="store_true", help="also time the other single-GPU configs")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import conan_slam_b200 as cs
+    from conan_slam_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = _lib.load_library()
+
+    N, m = args.landmarks, args.obs
+    n = 3 + 2 * N
+    stream = torch.cuda.Stream(device=local)
+    t0 = time.time()
+    ekf, lm, rng = build_ekf(N, local, cs.FLAG_INTENDED, seed=N + 1000 * rank, stream=stream.cuda_stream)
+    log(f"[bench r{rank}] built {N}-landmark map (n={n}, P={8.0 * n * n / 1e9:.2f} GB) in {time.time() - t0:.1f}s")
+    scans = make_scans(lm, rng, max(8, args.steps + args.warmup), m)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-timed throughput (state resident in HBM) + live kernel timing ----
+    for s in range(args.warmup):
+        ekf_scan(ekf, scans[s % len(scans)][0])
+    ekf.sync()
+    sampler = ClockSampler(local)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    launches0 = lib.cslam_kernel_launches()
+    ekf.profile_begin(args.steps * m + 8)
+    sampler.start()
+    updates = 0
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for s in range(args.steps):
+            jb = ekf_scan(ekf, scans[(args.warmup + s) % len(scans)][0])
+            updates += int((jb > 0).sum())
+        ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    cov_ms, cov_launches, cov_bytes = ekf.profile_end()
+    launches = lib.cslam_kernel_launches() - launches0
+    ms = ev0.elapsed_time(ev1)
+    skipped = ekf.sync()
+
+    # ---- end to end through the public API: host observations in, state + indices out ----
+    X_host = None
+    barrier()
+    t_e0 = torch.cuda.Event(enable_timing=True)
+    t_e1 = torch.cuda.Event(enable_timing=True)
+    e2e_updates = 0
+    with torch.cuda.stream(stream):
+        t_e0.record(stream)
+        for s in range(args.steps):
+            Z = scans[(s + 1) % len(scans)][0]
+            jb = ekf_scan(ekf, Z)
+            X_host = ekf.X  # D2H read of the step's result (n doubles through pinned staging)
+            e2e_updates += int((jb > 0).sum())
+        t_e1.record(stream)
+    barrier()
+    e2e_ms = t_e0.elapsed_time(t_e1)
+
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(t[0]), float(t[1])
+        cnt = torch.tensor([updates, e2e_updates, launches], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        updates, e2e_updates, launches = int(cnt[0]), int(cnt[1]), int(cnt[2])
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        value = updates / (ms * 1e-3)
+        e2e_value = e2e_updates / (e2e_ms * 1e-3)
+        ach = (cov_bytes / cov_launches) / (cov_ms / cov_launches * 1e-3) / 1e9 if cov_launches else 0.0
+        alg_update_bytes = 8.0 * n * (n + 1) + 112.0 * n  # cov R+W + 5 P columns + X + gating/obs share
+        out = {
+            "metric": "EKF updates/sec", "value": value, "unit": "updates/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": (f"EKF-SLAM {N} landmarks (state dim {n}, FP64 P {8.0 * n * n / 1e9:.2f} GB), "
+                             f"range-bearing observations, sequential update: gate + gain + covariance, "
+                             f"{m} observations per scan" + (f", {world} independent filter replicas" if world > 1 else "")),
+                "landmarks": N, "state_dim": n, "obs_per_step": m, "mode": "INTENDED (SURVEY Appendix A)",
+                "l2": "inputs larger than L2 (6.4 GB upper triangle streamed per update)",
+                "parallelism": "replicas only (one independent filter per GPU)" if world > 1 else "single GPU",
+            },
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "updates/s",
+                    "h2d_bytes_per_step": int(2 * m * 8 + 4 * 8 + 2 * 8 + m * 4 + 4 * 8),
+                    "d2h_bytes_per_step": int(n * 8 + m * (4 + 8 + 8))},
+            "gpu_launches": int(launches),
+            "roofline": {
+                "bound": "hbm", "kernel": "k_cov_update<2,128> (slam.h:260, upper-triangle rank-2 update)",
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "peak_source": peak_src, "traffic": ncu_traffic("k_cov_update<2,128>", n),
+                "algorithmic_bytes_per_launch": 8.0 * n * (n + 1),
+                "launches_timed": cov_launches, "avg_launch_ms": cov_ms / max(1, cov_launches),
+                "whole_update_frac": (alg_update_bytes * updates / (ms * 1e-3) / 1e9) / peak,
+            },
+            "skipped_updates": skipped,
+            "state_checksum": float(np.sum(X_host[:3])) if X_host is not None else None,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            t1 = time.time()
+            out["cpu_baseline"] = cpu_ekf_update_rate(N, 1, slab_cols=3000, reps=2)
+            mt = cpu_ekf_update_rate(N, os.cpu_count() or 1, slab_cols=3000, reps=2)
+            out["cpu_baseline"]["all_cores"] = {"cores": mt["cores"], "value": mt["value"],
+                                                "update_only_updates_per_s": mt["update_only_updates_per_s"]}
+            log(f"[bench] cpu baseline took {time.time() - t1:.1f}s")
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -40,6 +40,9 @@ SIGNATURES = {
     "cslam_last_error": (C.c_char_p, []),
     "cslam_version": (C.c_int, []),
     "cslam_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "cslam_kernel_launches": (C.c_ulonglong, []),
+    "cslam_ekf_profile_begin": (C.c_int, [_vp, C.c_int]),
+    "cslam_ekf_profile_end": (C.c_int, [_vp, _dp, C.POINTER(C.c_int), _dp]),
     "cslam_ekf_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_uint]),
     "cslam_ekf_destroy": (C.c_int, [_vp]),
     "cslam_ekf_set_stream": (C.c_int, [_vp, _vp]),

@@ -11,6 +11,7 @@
 namespace cslam {
 
 void set_last_error(const char* fmt, ...);
+void count_launch();  // every kernel launch of the library is counted (bench.py: gpu_launches)
 
 #define CSLAM_CUDA(call)                                                                        \
     do {                                                                                        \

@@ -11,6 +11,7 @@
 //            update rank), r <= 64 — the scaled gain panel of slam.h:257.
 #include <limits>
 #include <new>
+#include <vector>
 
 #include "common.cuh"
 
@@ -63,9 +64,29 @@ struct cslam_ekf {
     size_t pinned_bytes = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    // diagnostics: event pairs around covariance-update launches
+    bool prof = false;
+    std::vector<cudaEvent_t> prof_ev;
+    int prof_used = 0;
+    double prof_bytes = 0.0;
 };
 
 namespace cslam {
+
+struct ProfScope {  // records start/stop events around one covariance-update launch when profiling
+    cslam_ekf* h;
+    bool on;
+    explicit ProfScope(cslam_ekf* h_) : h(h_), on(h_->prof && h_->prof_used + 2 <= (int)h_->prof_ev.size()) {
+        if (on) cudaEventRecord(h->prof_ev[h->prof_used], h->stream);
+    }
+    ~ProfScope() {
+        if (on) {
+            cudaEventRecord(h->prof_ev[h->prof_used + 1], h->stream);
+            h->prof_used += 2;
+            h->prof_bytes += 8.0 * (double)h->n * ((double)h->n + 1.0);
+        }
+    }
+};
 
 // ------------------------------------------------------------------------------------
 // Kernels
@@ -603,12 +624,15 @@ static inline long long tri_tiles(int nt) { return (long long)nt * (nt + 1) / 2;
 template <int R>
 static int launch_cov_update(cslam_ekf* h, double diag_eps) {
     const int n = h->n;
+    ProfScope prof(h);
     if (n >= 2048) {
         const int nt = (n + 127) / 128;
+        count_launch();
         k_cov_update<R, 128><<<(unsigned)tri_tiles(nt), 256, 0, h->stream>>>(h->P, h->ld, n, h->A, h->lda, nt,
                                                                               diag_eps);
     } else {
         const int nt = (n + 63) / 64;
+        count_launch();
         k_cov_update<R, 64><<<(unsigned)tri_tiles(nt), 256, 0, h->stream>>>(h->P, h->ld, n, h->A, h->lda, nt,
                                                                              diag_eps);
     }
@@ -618,10 +642,14 @@ static int launch_cov_update(cslam_ekf* h, double diag_eps) {
 
 static int launch_cov_update_rank(cslam_ekf* h, int r) {
     const int n = h->n;
+    ProfScope prof(h);
     // large maps: FP64 tensor-core kernel; small maps: plain FMA kernel
     if (n >= 1024) return launch_cov_update_dmma(h->P, h->ld, n, h->A, h->lda, r, h->stream);
     const int nt = (n + 63) / 64;
     const size_t smem = (size_t)2 * r * 64 * sizeof(double);
+    CSLAM_CUDA(cudaFuncSetAttribute(k_cov_update_rank<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    2 * kMaxRank * 64 * (int)sizeof(double)));
+    count_launch();
     k_cov_update_rank<64><<<(unsigned)tri_tiles(nt), 256, smem, h->stream>>>(h->P, h->ld, n, h->A, h->lda, r, nt);
     CSLAM_CUDA(cudaGetLastError());
     return CSLAM_OK;
@@ -714,6 +742,7 @@ int cslam_ekf_destroy(cslam_ekf_t* h) {
     cudaFree(h->gate.part_nd); cudaFree(h->gate.part_out); cudaFree(h->gate.part_j);
     cudaFree(h->gate.d_jbest); cudaFree(h->gate.d_nbest); cudaFree(h->gate.d_outer);
     if (h->pinned) cudaFreeHost(h->pinned);
+    for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return CSLAM_OK;
@@ -751,6 +780,7 @@ int cslam_ekf_predict(cslam_ekf_t* h, double v, double swa, const double Q[4], d
     int width = 0;
     if (n > 3) width = (h->flags & CSLAM_FLAG_Q2_FULL_WIDTH) ? n - 3 : n - 4;  // Q2, EKF.cpp:442
     const int blocks = std::max(1, (width + 255) / 256);
+    count_launch();
     k_predict<<<blocks, 256, 0, h->stream>>>(h->X[h->cur], h->P, h->ld, n, v, swa, Q[0], Q[2], Q[1], Q[3], wb, dt,
                                              width, h->ticket);
     CSLAM_CUDA(cudaGetLastError());
@@ -762,6 +792,7 @@ int cslam_ekf_observe_heading(cslam_ekf_t* h, double phi, int use_heading) {
     if (!use_heading) return CSLAM_OK;  // EKF.cpp:332-335
     const int n = h->n;
     const double sigma = 0.01F * kPi / 180.0F;  // EKF.cpp:337
+    count_launch();
     k_heading_gain<<<(n + 255) / 256, 256, 0, h->stream>>>(h->X[h->cur], h->X[h->cur ^ 1], h->P, h->ld, n, phi,
                                                            sigma * sigma, h->A);
     CSLAM_CUDA(cudaGetLastError());
@@ -809,6 +840,7 @@ int cslam_ekf_update(cslam_ekf_t* h, const double* Z, const int32_t* idf, int m,
         CSLAM_REQUIRE(idf[i] >= 1 && idf[i] <= nf, CSLAM_ERR_BAD_ARG, "idf out of range (1-based map slots)");
     if (!batch) {
         for (int i = 0; i < m; i++) {
+            count_launch();
             k_gain_single<<<(n + 255) / 256, 256, 0, h->stream>>>(h->X[h->cur], h->X[h->cur ^ 1], h->P, h->ld, n,
                                                                   Z[2 * i], Z[2 * i + 1], idf[i], R[0], R[1], R[2],
                                                                   R[3], h->flags, h->A, h->lda, h->status);
@@ -826,12 +858,16 @@ int cslam_ekf_update(cslam_ekf_t* h, const double* Z, const int32_t* idf, int m,
     ob.m = m;
     memcpy(ob.R, R, sizeof(double) * 4);
     const int r = 2 * m;
+    count_launch();
     k_batch_prep<<<1, CSLAM_MAX_BATCH_OBS, 0, h->stream>>>(h->X[h->cur], ob, h->small);
+    count_launch();
     k_batch_pht<<<dim3((n + 127) / 128, m), 128, 0, h->stream>>>(h->P, h->ld, n, m, h->small, h->PHT, h->lda);
     const int chol_smem = 2 * kMaxRank * (kMaxRank + 1) * (int)sizeof(double);
     CSLAM_CUDA(cudaFuncSetAttribute(k_batch_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, chol_smem));
+    count_launch();
     k_batch_chol<<<1, 256, chol_smem, h->stream>>>(h->PHT, h->lda, m, R[0], R[1], R[2], R[3], h->flags, h->small,
                                            h->status);
+    count_launch();
     k_batch_w1<<<dim3((n + 127) / 128, (r + 7) / 8), 128, 0, h->stream>>>(h->PHT, h->lda, n, r, h->small,
                                                                            h->X[h->cur], h->X[h->cur ^ 1], h->A);
     CSLAM_CUDA(cudaGetLastError());
@@ -847,6 +883,7 @@ int cslam_ekf_augment(cslam_ekf_t* h, const double* Z, int m, const double R[4])
     CSLAM_REQUIRE(h->n + 2 * m <= h->n_cap, CSLAM_ERR_CAPACITY, "landmark capacity exceeded");
     for (int i = 0; i < m; i++) {
         const int len = h->n;
+        count_launch();
         k_augment<<<(len + 255) / 256, 256, 0, h->stream>>>(h->X[h->cur], h->P, h->ld, len, Z[2 * i], Z[2 * i + 1],
                                                             R[0], R[1], R[2], R[3]);
         CSLAM_CUDA(cudaGetLastError());
@@ -872,10 +909,11 @@ int cslam_ekf_get_cov_block(cslam_ekf_t* h, int r0, int c0, int nr, int nc, doub
     double* tmp = nullptr;
     const size_t cnt = (size_t)nr * nc;
     CSLAM_CUDA(cudaMalloc(&tmp, cnt * sizeof(double)));
+    count_launch();
     k_gather_block<<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(h->P, h->ld, r0, c0, nr, nc, tmp);
     cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, tmp, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    if (e == cudaSuccess) e = cudaMemcpy(out, tmp, cnt * sizeof(double), cudaMemcpyDeviceToHost);
     cudaFree(tmp);
     CSLAM_CUDA(e);
     return CSLAM_OK;
@@ -884,20 +922,22 @@ int cslam_ekf_get_cov_block(cslam_ekf_t* h, int r0, int c0, int nr, int nc, doub
 int cslam_ekf_reset(cslam_ekf_t* h, const double* X, int n, const double* P) {
     if (int rc = check_handle(h)) return rc;
     CSLAM_REQUIRE(X && n >= 3 && n <= h->n_cap && ((n - 3) % 2 == 0), CSLAM_ERR_BAD_ARG, "bad state size");
-    CSLAM_CUDA(cudaStreamSynchronize(h->stream));
-    CSLAM_CUDA(cudaMemset(h->X[0], 0, h->ld * sizeof(double)));
-    CSLAM_CUDA(cudaMemset(h->X[1], 0, h->ld * sizeof(double)));
-    CSLAM_CUDA(cudaMemcpy(h->X[0], X, n * sizeof(double), cudaMemcpyHostToDevice));
+    // everything on the handle's stream: the legacy default stream does not order against it
+    CSLAM_CUDA(cudaMemsetAsync(h->X[0], 0, h->ld * sizeof(double), h->stream));
+    CSLAM_CUDA(cudaMemsetAsync(h->X[1], 0, h->ld * sizeof(double), h->stream));
+    CSLAM_CUDA(cudaMemcpyAsync(h->X[0], X, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     h->cur = 0;
     h->n = n;
-    CSLAM_CUDA(cudaMemset(h->P, 0, (size_t)h->n_cap * h->ld * sizeof(double)));
-    CSLAM_CUDA(cudaMemset(h->status, 0, sizeof(int)));
+    CSLAM_CUDA(cudaMemsetAsync(h->P, 0, (size_t)h->n_cap * h->ld * sizeof(double), h->stream));
+    CSLAM_CUDA(cudaMemsetAsync(h->status, 0, sizeof(int), h->stream));
+    CSLAM_CUDA(cudaStreamSynchronize(h->stream));
     if (P) {
         double* tmp = nullptr;
         const size_t cnt = (size_t)n * n;
         CSLAM_CUDA(cudaMalloc(&tmp, cnt * sizeof(double)));
-        cudaError_t e = cudaMemcpy(tmp, P, cnt * sizeof(double), cudaMemcpyHostToDevice);
+        cudaError_t e = cudaMemcpyAsync(tmp, P, cnt * sizeof(double), cudaMemcpyHostToDevice, h->stream);
         if (e == cudaSuccess) {
+            count_launch();
             k_scatter_upper<<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(h->P, h->ld, n, tmp);
             e = cudaGetLastError();
         }
@@ -905,6 +945,36 @@ int cslam_ekf_reset(cslam_ekf_t* h, const double* X, int n, const double* P) {
         cudaFree(tmp);
         CSLAM_CUDA(e);
     }
+    return CSLAM_OK;
+}
+
+int cslam_ekf_profile_begin(cslam_ekf_t* h, int max_launches) {
+    if (int rc = check_handle(h)) return rc;
+    CSLAM_REQUIRE(max_launches > 0 && max_launches <= (1 << 20), CSLAM_ERR_BAD_ARG, "max_launches out of range");
+    while ((int)h->prof_ev.size() < 2 * max_launches) {
+        cudaEvent_t e;
+        CSLAM_CUDA(cudaEventCreate(&e));
+        h->prof_ev.push_back(e);
+    }
+    h->prof_used = 0;
+    h->prof_bytes = 0.0;
+    h->prof = true;
+    return CSLAM_OK;
+}
+
+int cslam_ekf_profile_end(cslam_ekf_t* h, double* ms, int* launches, double* bytes) {
+    if (int rc = check_handle(h)) return rc;
+    h->prof = false;
+    CSLAM_CUDA(cudaStreamSynchronize(h->stream));
+    double total = 0.0;
+    for (int i = 0; i + 1 < h->prof_used; i += 2) {
+        float t = 0.f;
+        CSLAM_CUDA(cudaEventElapsedTime(&t, h->prof_ev[i], h->prof_ev[i + 1]));
+        total += t;
+    }
+    if (ms) *ms = total;
+    if (launches) *launches = h->prof_used / 2;
+    if (bytes) *bytes = h->prof_bytes;
     return CSLAM_OK;
 }
 

@@ -114,6 +114,7 @@ int launch_cov_update_dmma(double* P, size_t ld, int n, const double* A, size_t 
     const size_t smem = (size_t)rp * (DM_SR + DM_SC) * sizeof(double);
     CSLAM_CUDA(cudaFuncSetAttribute(k_cov_update_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     64 * (DM_SR + DM_SC) * (int)sizeof(double)));
+    count_launch();
     k_cov_update_dmma<<<(unsigned)tiles, 256, smem, stream>>>(P, ld, n, A, lda, r, rp, nbc);
     CSLAM_CUDA(cudaGetLastError());
     return CSLAM_OK;

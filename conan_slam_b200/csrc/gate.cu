@@ -173,6 +173,7 @@ int launch_gate(const double* X, const double* P, size_t ld, int nf, const doubl
     gp.gate1 = gate1;
     gp.gate2 = gate2;
     const int blocks = nf > 0 ? (nf + 255) / 256 : 1;
+    count_launch();
     k_gate<<<blocks, 256, 0, stream>>>(X, P, ld, nf, gp, part_nd, part_out, part_j, ticket, jbest, nbest, outer);
     CSLAM_CUDA(cudaGetLastError());
     return CSLAM_OK;

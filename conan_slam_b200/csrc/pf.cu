@@ -24,8 +24,6 @@
 
 namespace cslam {
 
-constexpr int kScanRadix = 32;
-
 struct PfBuf {
     double* w = nullptr;
     double* xv = nullptr;
@@ -657,6 +655,7 @@ static int run_scan(cslam_pf* h, const double* in, int mode, const double* div) 
     const double* src = in;
     size_t len = h->np;
     for (int l = 0; l < h->levels; l++) {
+        count_launch();
         k_scan_level<<<nblk(len, 256), 256, 0, h->stream>>>(src, len, h->scan[l],
                                                              (l + 1 < h->levels) ? h->scan[l + 1] + 0 : h->d_small + 7,
                                                              l == 0 ? mode : 0, div);
@@ -742,6 +741,7 @@ int cslam_pf_create(cslam_pf_t** out, int num_particles, int capacity_landmarks,
     h->pinned_bytes = 1 << 16;
     TRY(cudaMallocHost(&h->pinned, h->pinned_bytes));
     // PF.cpp:319-341: w = 1/P
+    count_launch();
     k_fill<<<nblk(h->np, 256), 256, 0, h->stream>>>(h->buf[0].w, h->np, 1.0 / (double)h->np);
     // PF.cpp:581-587: DI(0) = k/2 ; DI(i) = DI(i-1) + k  — a sequential chain, built once on the host
     {
@@ -752,7 +752,8 @@ int cslam_pf_create(cslam_pf_t** out, int num_particles, int capacity_landmarks,
             if (i > 0) di = di + k;
             comb[i] = di;
         }
-        TRY(cudaMemcpy(h->comb, comb.data(), (size_t)h->np * sizeof(double), cudaMemcpyHostToDevice));
+        TRY(cudaMemcpyAsync(h->comb, comb.data(), (size_t)h->np * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        TRY(cudaStreamSynchronize(h->stream));
     }
     TRY(cudaStreamSynchronize(h->stream));
 #undef TRY
@@ -805,6 +806,7 @@ int cslam_pf_predict(cslam_pf_t* h, double v, double swa, const double Q[4], dou
     if (int rc = check_pf(h)) return rc;
     CSLAM_REQUIRE(Q != nullptr, CSLAM_ERR_BAD_ARG, "Q is null");
     PfBuf& b = h->buf[h->cur];
+    count_launch();
     k_pf_predict<<<nblk(h->np, 256), 256, 0, h->stream>>>(b.xv, b.pv, h->pp, h->np, v, swa, Q[0], Q[2], Q[1], Q[3],
                                                           wb, dt);
     CSLAM_CUDA(cudaGetLastError());
@@ -816,6 +818,7 @@ int cslam_pf_observe_heading(cslam_pf_t* h, double phi, int use_heading) {
     if (!use_heading) return CSLAM_OK;
     const double sigma = 0.01F * kPi / 180.0F;  // PF.cpp:391
     PfBuf& b = h->buf[h->cur];
+    count_launch();
     k_pf_heading<<<nblk(h->np, 256), 256, 0, h->stream>>>(b.xv, b.pv, h->pp, h->np, phi, sigma * sigma);
     CSLAM_CUDA(cudaGetLastError());
     return CSLAM_OK;
@@ -845,6 +848,7 @@ int cslam_pf_sample_proposal(cslam_pf_t* h, const double* Z, const int32_t* idf,
     const double* dxi = nullptr;
     if (int rc = stage_in(h, xi, (size_t)3 * h->np, xi_on_device, &dxi)) return rc;
     PfBuf& b = h->buf[h->cur];
+    count_launch();
     k_pf_sample_proposal<<<nblk(h->np, 128), 128, 0, h->stream>>>(b.w, b.xv, b.pv, b.xf, b.pf, h->pp, h->np, ob, dxi,
                                                                   h->flags, h->d_ismall + 2);
     CSLAM_CUDA(cudaGetLastError());
@@ -858,6 +862,7 @@ int cslam_pf_feature_update(cslam_pf_t* h, const double* Z, const int32_t* idf, 
     PfObs ob;
     fill_obs(ob, Z, idf, m, R);
     PfBuf& b = h->buf[h->cur];
+    count_launch();
     k_pf_feature_update<<<nblk(h->np, 128), 128, 0, h->stream>>>(b.xv, b.xf, b.pf, h->pp, h->np, ob, h->flags,
                                                                  h->d_ismall + 2);
     CSLAM_CUDA(cudaGetLastError());
@@ -872,6 +877,7 @@ int cslam_pf_add_features(cslam_pf_t* h, const double* Z, int m, const double R[
     PfObs ob;
     fill_obs(ob, Z, nullptr, m, R);
     PfBuf& b = h->buf[h->cur];
+    count_launch();
     k_pf_add_features<<<nblk(h->np, 256), 256, 0, h->stream>>>(b.xv, b.xf, b.pf, h->pp, h->np, h->nf, ob);
     CSLAM_CUDA(cudaGetLastError());
     h->nf += m;
@@ -884,6 +890,7 @@ int cslam_pf_sample_pose(cslam_pf_t* h, const double* xi, int xi_on_device) {
     const double* dxi = nullptr;
     if (int rc = stage_in(h, xi, (size_t)3 * h->np, xi_on_device, &dxi)) return rc;
     PfBuf& b = h->buf[h->cur];
+    count_launch();
     k_pf_sample_pose<<<nblk(h->np, 256), 256, 0, h->stream>>>(b.xv, b.pv, h->pp, h->np, dxi, h->d_ismall + 2);
     CSLAM_CUDA(cudaGetLastError());
     return CSLAM_OK;
@@ -906,25 +913,38 @@ int cslam_pf_resample(cslam_pf_t* h, const double* u, int u_on_device, double nu
     if (intended) {
         // ws = sum w ; particles.w /= ws (PF.cpp:482-487)
         if (int rc = run_scan(h, b.w, 0, nullptr)) return rc;
+        count_launch();
         k_scan_total<<<1, 32, 0, h->stream>>>(h->scan[h->levels - 1], top_len, S + 0);
+        count_launch();
         k_divide<<<nblk(np, 256), 256, 0, h->stream>>>(b.w, np, S + 0);
         // stratifiedResample: W /= W.sum() (PF.cpp:548) ; neff = 1 / sum W^2 (:550-554)
         if (int rc = run_scan(h, b.w, 0, nullptr)) return rc;
+        count_launch();
         k_scan_total<<<1, 32, 0, h->stream>>>(h->scan[h->levels - 1], top_len, S + 1);
         if (int rc = run_scan(h, b.w, 2, S + 1)) return rc;
+        count_launch();
         k_scan_total<<<1, 32, 0, h->stream>>>(h->scan[h->levels - 1], top_len, S + 2);
         // cumulative sum of W (PF.cpp:559-564) in the canonical order
         if (int rc = run_scan(h, b.w, 1, S + 1)) return rc;
+        count_launch();
         k_scan_combine<<<nblk(np, 256), 256, 0, h->stream>>>(sp, np, h->wn);
+        count_launch();
         k_resample_search<<<nblk(np, 256), 256, 0, h->stream>>>(h->wn, h->comb, du, np, h->keep);
     } else {
+        count_launch();
         k_seq_sum<<<1, 32, 0, h->stream>>>(b.w, np, 0, nullptr, S + 0);
+        count_launch();
         k_divide<<<nblk(np, 256), 256, 0, h->stream>>>(b.w, np, S + 0);
+        count_launch();
         k_seq_sum<<<1, 32, 0, h->stream>>>(b.w, np, 0, nullptr, S + 1);
+        count_launch();
         k_seq_sum<<<1, 32, 0, h->stream>>>(b.w, np, 2, S + 1, S + 2);
+        count_launch();
         k_seq_cumsum<<<1, 32, 0, h->stream>>>(b.w, np, S + 1, h->wn);
         CSLAM_CUDA(cudaMemsetAsync(h->d_ismall, 0x7f, sizeof(int), h->stream));  // 0x7f7f7f7f = "no hit"
+        count_launch();
         k_resample_first_hit<<<nblk(np, 256), 256, 0, h->stream>>>(h->wn, h->comb, du, np, h->d_ismall);
+        count_launch();
         k_fill_keep<<<nblk(np, 256), 256, 0, h->stream>>>(h->keep, np, h->d_ismall);
     }
     CSLAM_CUDA(cudaGetLastError());
@@ -933,7 +953,10 @@ int cslam_pf_resample(cslam_pf_t* h, const double* u, int u_on_device, double nu
     CSLAM_CUDA(cudaStreamSynchronize(h->stream));
     const double ne = 1.0 / *static_cast<double*>(h->pinned);
     if (neff) *neff = ne;
-    if (keep) CSLAM_CUDA(cudaMemcpy(keep, h->keep, (size_t)np * sizeof(int), cudaMemcpyDeviceToHost));
+    if (keep) {
+        CSLAM_CUDA(cudaMemcpyAsync(keep, h->keep, (size_t)np * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CSLAM_CUDA(cudaStreamSynchronize(h->stream));
+    }
     const bool doit = (ne < num_effective) && resample_on;
     if (resampled) *resampled = doit ? 1 : 0;
     if (doit) {
@@ -942,12 +965,14 @@ int cslam_pf_resample(cslam_pf_t* h, const double* u, int u_on_device, double nu
         auto gather = [&](const double* s, double* dd, int rows) {
             if (rows <= 0) return;
             const unsigned gy = (unsigned)std::min(rows, 65535);
+            count_launch();
             k_gather_rows<<<dim3(gx, gy), 256, 0, h->stream>>>(s, dd, h->pp, np, rows, h->keep);
         };
         gather(b.xv, d.xv, 3);
         gather(b.pv, d.pv, 9);
         gather(b.xf, d.xf, 2 * h->nf);
         gather(b.pf, d.pf, 3 * h->nf);
+        count_launch();
         k_fill<<<nblk(np, 256), 256, 0, h->stream>>>(d.w, np, 1.0 / (double)np);  // PF.cpp:495
         CSLAM_CUDA(cudaGetLastError());
         h->cur ^= 1;
@@ -958,8 +983,8 @@ int cslam_pf_resample(cslam_pf_t* h, const double* u, int u_on_device, double nu
 int cslam_pf_get_weights(cslam_pf_t* h, double* w) {
     if (int rc = check_pf(h)) return rc;
     CSLAM_REQUIRE(w != nullptr, CSLAM_ERR_BAD_ARG, "null");
+    CSLAM_CUDA(cudaMemcpyAsync(w, h->buf[h->cur].w, (size_t)h->np * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CSLAM_CUDA(cudaStreamSynchronize(h->stream));
-    CSLAM_CUDA(cudaMemcpy(w, h->buf[h->cur].w, (size_t)h->np * sizeof(double), cudaMemcpyDeviceToHost));
     return CSLAM_OK;
 }
 
@@ -967,10 +992,11 @@ static int get_aos(cslam_pf* h, const double* soa, int k, double* out) {
     double* tmp = nullptr;
     const size_t cnt = (size_t)h->np * k;
     CSLAM_CUDA(cudaMalloc(&tmp, cnt * sizeof(double)));
+    count_launch();
     k_soa_to_aos<<<nblk(cnt, 256), 256, 0, h->stream>>>(soa, tmp, h->pp, h->np, k);
     cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, tmp, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    if (e == cudaSuccess) e = cudaMemcpy(out, tmp, cnt * sizeof(double), cudaMemcpyDeviceToHost);
     cudaFree(tmp);
     CSLAM_CUDA(e);
     return CSLAM_OK;
@@ -979,8 +1005,9 @@ static int set_aos(cslam_pf* h, double* soa, int k, const double* in) {
     double* tmp = nullptr;
     const size_t cnt = (size_t)h->np * k;
     CSLAM_CUDA(cudaMalloc(&tmp, cnt * sizeof(double)));
-    cudaError_t e = cudaMemcpy(tmp, in, cnt * sizeof(double), cudaMemcpyHostToDevice);
+    cudaError_t e = cudaMemcpyAsync(tmp, in, cnt * sizeof(double), cudaMemcpyHostToDevice, h->stream);
     if (e == cudaSuccess) {
+        count_launch();
         k_aos_to_soa<<<nblk(cnt, 256), 256, 0, h->stream>>>(tmp, soa, h->pp, h->np, k);
         e = cudaGetLastError();
     }
@@ -1006,12 +1033,14 @@ int cslam_pf_get_features(cslam_pf_t* h, int particle, double* XF, double* PF) {
     if (h->nf == 0) return CSLAM_OK;
     double* tmp = nullptr;
     CSLAM_CUDA(cudaMalloc(&tmp, (size_t)6 * h->nf * sizeof(double)));
+    count_launch();
     k_get_features<<<nblk(h->nf, 128), 128, 0, h->stream>>>(h->buf[h->cur].xf, h->buf[h->cur].pf, h->pp, particle,
                                                             h->nf, tmp, tmp + 2 * h->nf);
     cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(XF, tmp, (size_t)2 * h->nf * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(PF, tmp + 2 * h->nf, (size_t)4 * h->nf * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    if (e == cudaSuccess) e = cudaMemcpy(XF, tmp, (size_t)2 * h->nf * sizeof(double), cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess) e = cudaMemcpy(PF, tmp + 2 * h->nf, (size_t)4 * h->nf * sizeof(double), cudaMemcpyDeviceToHost);
     cudaFree(tmp);
     CSLAM_CUDA(e);
     return CSLAM_OK;
@@ -1019,8 +1048,8 @@ int cslam_pf_get_features(cslam_pf_t* h, int particle, double* XF, double* PF) {
 int cslam_pf_set_weights(cslam_pf_t* h, const double* w) {
     if (int rc = check_pf(h)) return rc;
     CSLAM_REQUIRE(w != nullptr, CSLAM_ERR_BAD_ARG, "null");
+    CSLAM_CUDA(cudaMemcpyAsync(h->buf[h->cur].w, w, (size_t)h->np * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CSLAM_CUDA(cudaStreamSynchronize(h->stream));
-    CSLAM_CUDA(cudaMemcpy(h->buf[h->cur].w, w, (size_t)h->np * sizeof(double), cudaMemcpyHostToDevice));
     return CSLAM_OK;
 }
 int cslam_pf_set_poses(cslam_pf_t* h, const double* X, const double* Pv) {
@@ -1036,7 +1065,9 @@ int cslam_pf_extract_state(cslam_pf_t* h, double X[3], int* index) {
     CSLAM_REQUIRE(X != nullptr, CSLAM_ERR_BAD_ARG, "null");
     const int nw = (h->np + 31) / 32;
     // candidates reuse the resampling scratch (wn: doubles, keep: ints), both idle between calls
+    count_launch();
     k_argmin_w<<<nblk(h->np, 256), 256, 0, h->stream>>>(h->buf[h->cur].w, h->np, h->wn, h->keep);
+    count_launch();
     k_argmin_final<<<1, 1024, 0, h->stream>>>(h->wn, h->keep, nw, h->buf[h->cur].xv, h->pp, h->d_small + 8);
     CSLAM_CUDA(cudaGetLastError());
     CSLAM_CUDA(cudaMemcpyAsync(h->pinned, h->d_small + 8, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));

@@ -1,6 +1,8 @@
 // util.cu — error reporting and library-level entry points of libcslam.so.
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace cslam {
@@ -11,9 +13,12 @@ void set_last_error(const char* fmt, ...) {
     vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
     va_end(ap);
 }
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 }  // namespace cslam
 
 extern "C" {
+unsigned long long cslam_kernel_launches(void) { return cslam::g_launches.load(); }
 const char* cslam_last_error(void) { return cslam::g_last_error; }
 int cslam_version(void) { return CSLAM_VERSION; }
 int cslam_device_count(int* count) {

@@ -94,6 +94,16 @@ class EKF:
         check(self._lib.cslam_ekf_sync(self._h, C.byref(skipped)), "cslam_ekf_sync")
         return skipped.value
 
+    def profile_begin(self, max_launches=4096):
+        check(self._lib.cslam_ekf_profile_begin(self._h, int(max_launches)), "cslam_ekf_profile_begin")
+
+    def profile_end(self):
+        """(summed covariance-kernel ms, launches, summed algorithmic bytes)."""
+        ms, cnt, by = C.c_double(0), C.c_int(0), C.c_double(0)
+        check(self._lib.cslam_ekf_profile_end(self._h, C.byref(ms), C.byref(cnt), C.byref(by)),
+              "cslam_ekf_profile_end")
+        return ms.value, cnt.value, by.value
+
     @property
     def n(self):
         return self._lib.cslam_ekf_n(self._h)

@@ -61,6 +61,8 @@ typedef struct cslam_pf cslam_pf_t;
 const char* cslam_last_error(void);
 int cslam_version(void);
 int cslam_device_count(int* count);
+/* Diagnostics (bench.py): number of CUDA kernels this library has launched since it was loaded. */
+unsigned long long cslam_kernel_launches(void);
 
 /* ------------------------------------------------------------------ EKF-SLAM ---- */
 
@@ -105,6 +107,12 @@ int cslam_ekf_get_cov_block(cslam_ekf_t* h, int r0, int c0, int nr, int nc, doub
 /* Load a state (tests / benchmarks / checkpoint restore): X has n entries, P is a dense
  * row-major n x n matrix (only j >= i is read) or NULL for zeros. */
 int cslam_ekf_reset(cslam_ekf_t* h, const double* X, int n, const double* P);
+/* Diagnostics (bench.py roofline): CUDA-event timing of every covariance-update kernel launch
+ * (slam.h:260 / slam.h:718) on the handle's stream between begin and end.  *ms = summed kernel
+ * time, *launches = how many, *bytes = summed ALGORITHMIC bytes (8*n*(n+1) per launch: one read
+ * and one write of the upper triangle). */
+int cslam_ekf_profile_begin(cslam_ekf_t* h, int max_launches);
+int cslam_ekf_profile_end(cslam_ekf_t* h, double* ms, int* launches, double* bytes);
 /* Device pointers for zero-copy consumers (bench, visualisers): X (n doubles), P (row-major, ld). */
 int cslam_ekf_device_ptrs(cslam_ekf_t* h, void** dX, void** dP, size_t* ld);
 
