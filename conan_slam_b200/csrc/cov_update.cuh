@@ -1,0 +1,110 @@
+// cov_update.cuh — the streaming covariance kernel  P <- P - W1 W1^T  (slam.h:260 and, with
+// r = 1, the Joseph heading update slam.h:718): the north-star kernel, >99 % of an EKF update.
+#pragma once
+#include "common.cuh"
+
+namespace cslam {
+
+// cache-policy variants of the 128-bit accessors (HINT: 0 default, 1 streaming .cs, 2 L1::no_allocate)
+template <int HINT>
+__device__ __forceinline__ double2 cov_ld(const double* p) {
+    if constexpr (HINT == 1) {
+        return __ldcs(reinterpret_cast<const double2*>(p));
+    } else if constexpr (HINT == 2) {
+        double2 v;
+        asm volatile("ld.global.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+        return v;
+    } else {
+        return ld128(p);
+    }
+}
+template <int HINT>
+__device__ __forceinline__ void cov_st(double* p, double2 v) {
+    if constexpr (HINT == 1) {
+        __stcs(reinterpret_cast<double2*>(p), v);
+    } else {
+        st128(p, v);
+    }
+}
+
+// triangular tile index -> (tr, tc), row-major over the upper triangle of an nt x nt tile grid
+__device__ __forceinline__ void tri_tile(long long t, int nt, int& tr, int& tc) {
+    tr = (int)floor(((2.0 * nt + 1.0) - sqrt((2.0 * nt + 1.0) * (2.0 * nt + 1.0) - 8.0 * (double)t)) * 0.5);
+    while ((long long)tr * nt - (long long)tr * (tr - 1) / 2 > t) tr--;
+    while ((long long)(tr + 1) * nt - (long long)(tr + 1) * tr / 2 <= t) tr++;
+    tc = tr + (int)(t - ((long long)tr * nt - (long long)tr * (tr - 1) / 2));
+}
+
+// slam.h:260  P <- P - W1 W1^T over the UPPER TRIANGLE only, in place, FP64.
+// One CTA per T x T tile of the triangle (tiles with tc >= tr); thread = one 16-byte column
+// pair x T/RG rows, all loads of a batch issued before the first use so that every SM keeps
+// tens of KB in flight; the panel rows of the tile are staged in shared memory (broadcast
+// reads), the two panel columns a thread owns stay in registers.  Elements below the
+// diagonal inside diagonal tiles are neither loaded nor stored.  diag_eps implements
+// slam.h:719 (P += I * FLT_MIN) for the heading update.
+// Template knobs: R rank (1 or 2), T tile edge, BATCH loads in flight per thread, MINB minimum
+// resident CTAs per SM (register cap), HINT cache policy of the P accesses.
+template <int R, int T, int BATCH_ = 8, int MINB = 2, int HINT = 0>
+__global__ void __launch_bounds__(256, MINB) k_cov_update(double* __restrict__ P, size_t ld, int n,
+                                                          const double* __restrict__ A, size_t lda, int nt,
+                                                          double diag_eps) {
+    constexpr int CP = T / 2;       // column pairs per tile
+    constexpr int RG = 256 / CP;    // row groups
+    constexpr int RPT = T / RG;     // rows per thread
+    constexpr int BATCH = RPT > BATCH_ ? BATCH_ : RPT;
+    __shared__ double sAr[R][T];
+
+    int tr, tc;
+    tri_tile(blockIdx.x, nt, tr, tc);
+
+    const int i0 = tr * T, j0 = tc * T;
+    for (int idx = threadIdx.x; idx < R * T; idx += 256) {
+        const int k = idx / T, ii = idx % T;
+        sAr[k][ii] = (i0 + ii < n) ? A[(size_t)k * lda + i0 + ii] : 0.0;
+    }
+    const int cp = threadIdx.x % CP, rg = threadIdx.x / CP;
+    const int j = j0 + 2 * cp;
+    double aj0[R], aj1[R];
+#pragma unroll
+    for (int k = 0; k < R; k++) {
+        aj0[k] = (j < n) ? A[(size_t)k * lda + j] : 0.0;
+        aj1[k] = (j + 1 < n) ? A[(size_t)k * lda + j + 1] : 0.0;
+    }
+    __syncthreads();
+    if (j >= n) return;
+    const bool diag_tile = (tr == tc);
+#pragma unroll 1
+    for (int b0 = 0; b0 < RPT; b0 += BATCH) {
+        double2 v[BATCH];
+#pragma unroll
+        for (int b = 0; b < BATCH; b++) {
+            const int ii = rg + (b0 + b) * RG;
+            const int i = i0 + ii;
+            const bool act = (i < n) && (!diag_tile || j + 1 >= i);
+            if (act) v[b] = cov_ld<HINT>(P + (size_t)i * ld + j);
+        }
+#pragma unroll
+        for (int b = 0; b < BATCH; b++) {
+            const int ii = rg + (b0 + b) * RG;
+            const int i = i0 + ii;
+            const bool act = (i < n) && (!diag_tile || j + 1 >= i);
+            if (act) {
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int k = 0; k < R; k++) {
+                    const double ai = sAr[k][ii];
+                    s0 += ai * aj0[k];
+                    s1 += ai * aj1[k];
+                }
+                double2 o = v[b];
+                if (j >= i) o.x = o.x - s0;
+                if (j + 1 < n) o.y = o.y - s1;
+                if (j == i) o.x += diag_eps;
+                if (j + 1 == i) o.y += diag_eps;
+                cov_st<HINT>(P + (size_t)i * ld + j, o);
+            }
+        }
+    }
+}
+
+}  // namespace cslam

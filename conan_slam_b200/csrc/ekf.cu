@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "cov_update.cuh"
 
 namespace cslam {
 
@@ -254,80 +255,6 @@ __global__ void __launch_bounds__(256) k_gain_single(const double* __restrict__ 
     Xout[i] = Xin[i] + (w_0 * g.V[0] + w_1 * g.V[1]);
     A[i] = w1_0;
     A[lda + i] = w1_1;
-}
-
-// slam.h:260  P <- P - W1 W1^T over the UPPER TRIANGLE only, in place, FP64.
-// One CTA per T x T tile of the triangle (tiles with tc >= tr); thread = one 16-byte column
-// pair x T/RG rows, all loads of a batch issued before the first use so that every SM keeps
-// tens of KB in flight; the panel rows of the tile are staged in shared memory (broadcast
-// reads), the two panel columns a thread owns stay in registers.  Elements below the
-// diagonal inside diagonal tiles are neither loaded nor stored.  diag_eps implements
-// slam.h:719 (P += I * FLT_MIN) for the heading update.
-template <int R, int T>
-__global__ void __launch_bounds__(256) k_cov_update(double* __restrict__ P, size_t ld, int n,
-                                                    const double* __restrict__ A, size_t lda, int nt,
-                                                    double diag_eps) {
-    constexpr int CP = T / 2;       // column pairs per tile
-    constexpr int RG = 256 / CP;    // row groups
-    constexpr int RPT = T / RG;     // rows per thread
-    constexpr int BATCH = RPT > 8 ? 8 : RPT;
-    __shared__ double sAr[R][T];
-
-    // triangular tile index -> (tr, tc), row-major over the upper triangle
-    const long long t = blockIdx.x;
-    int tr = (int)floor(((2.0 * nt + 1.0) - sqrt((2.0 * nt + 1.0) * (2.0 * nt + 1.0) - 8.0 * (double)t)) * 0.5);
-    while ((long long)tr * nt - (long long)tr * (tr - 1) / 2 > t) tr--;
-    while ((long long)(tr + 1) * nt - (long long)(tr + 1) * tr / 2 <= t) tr++;
-    const int tc = tr + (int)(t - ((long long)tr * nt - (long long)tr * (tr - 1) / 2));
-
-    const int i0 = tr * T, j0 = tc * T;
-    for (int idx = threadIdx.x; idx < R * T; idx += 256) {
-        const int k = idx / T, ii = idx % T;
-        sAr[k][ii] = (i0 + ii < n) ? A[(size_t)k * lda + i0 + ii] : 0.0;
-    }
-    const int cp = threadIdx.x % CP, rg = threadIdx.x / CP;
-    const int j = j0 + 2 * cp;
-    double aj0[R], aj1[R];
-#pragma unroll
-    for (int k = 0; k < R; k++) {
-        aj0[k] = (j < n) ? A[(size_t)k * lda + j] : 0.0;
-        aj1[k] = (j + 1 < n) ? A[(size_t)k * lda + j + 1] : 0.0;
-    }
-    __syncthreads();
-    if (j >= n) return;
-    const bool diag_tile = (tr == tc);
-#pragma unroll 1
-    for (int b0 = 0; b0 < RPT; b0 += BATCH) {
-        double2 v[BATCH];
-#pragma unroll
-        for (int b = 0; b < BATCH; b++) {
-            const int ii = rg + (b0 + b) * RG;
-            const int i = i0 + ii;
-            const bool act = (i < n) && (!diag_tile || j + 1 >= i);
-            if (act) v[b] = ld128(P + (size_t)i * ld + j);
-        }
-#pragma unroll
-        for (int b = 0; b < BATCH; b++) {
-            const int ii = rg + (b0 + b) * RG;
-            const int i = i0 + ii;
-            const bool act = (i < n) && (!diag_tile || j + 1 >= i);
-            if (act) {
-                double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-                for (int k = 0; k < R; k++) {
-                    const double ai = sAr[k][ii];
-                    s0 += ai * aj0[k];
-                    s1 += ai * aj1[k];
-                }
-                double2 o = v[b];
-                if (j >= i) o.x = o.x - s0;
-                if (j + 1 < n) o.y = o.y - s1;
-                if (j == i) o.x += diag_eps;
-                if (j + 1 == i) o.y += diag_eps;
-                st128(P + (size_t)i * ld + j, o);
-            }
-        }
-    }
 }
 
 // General-rank variant (r <= 64, any r) for the joint update; FP64 FMA, panels in shared
@@ -625,15 +552,17 @@ template <int R>
 static int launch_cov_update(cslam_ekf* h, double diag_eps) {
     const int n = h->n;
     ProfScope prof(h);
+    // tile / batch / occupancy / cache-policy chosen from tools/cov_variants.cu on a B200:
+    // T=128, 4 x 16 B loads in flight per thread, 4 CTAs/SM, streaming (.cs) accesses -> 6.47 TB/s
     if (n >= 2048) {
         const int nt = (n + 127) / 128;
         count_launch();
-        k_cov_update<R, 128><<<(unsigned)tri_tiles(nt), 256, 0, h->stream>>>(h->P, h->ld, n, h->A, h->lda, nt,
+        k_cov_update<R, 128, 4, 4, 1><<<(unsigned)tri_tiles(nt), 256, 0, h->stream>>>(h->P, h->ld, n, h->A, h->lda, nt,
                                                                               diag_eps);
     } else {
         const int nt = (n + 63) / 64;
         count_launch();
-        k_cov_update<R, 64><<<(unsigned)tri_tiles(nt), 256, 0, h->stream>>>(h->P, h->ld, n, h->A, h->lda, nt,
+        k_cov_update<R, 64, 8, 4, 0><<<(unsigned)tri_tiles(nt), 256, 0, h->stream>>>(h->P, h->ld, n, h->A, h->lda, nt,
                                                                              diag_eps);
     }
     CSLAM_CUDA(cudaGetLastError());
