@@ -158,6 +158,74 @@ def ekf_scan(ekf, Z):
     return jbest
 
 
+# ------------------------------------------------------------------------ particle filter ----
+PF_Q = 2.0 * np.diag([0.3 ** 2, (np.pi / 180.0) ** 2])  # test/main.cpp:244
+PF_R = 2.0 * R_BASE                                     # test/main.cpp:245
+PF_CONTROLS_PER_OBS = 6  # mDtObserve / mDtControls = 5.058 -> every 6th control step (test/main.cpp:289-290)
+
+
+class PfScenario:
+    """Synthetic FastSLAM workload: P particles x Nf landmarks, m_obs known associations per
+    observation cycle, resampling forced every cycle.  The vehicle follows the reference's
+    deterministic motion model on the host (nominal pose) so that observations stay consistent
+    with the particle cloud without any device read-back inside the timed loop."""
+
+    def __init__(self, npart, nfeat, m_obs, device, seed, stream=None, rank=0, world=1, nccl_id=None):
+        import conan_slam_b200 as cs
+        self.cs = cs
+        self.npart, self.nfeat, self.m_obs = npart, nfeat, m_obs
+        self.rng = np.random.Generator(np.random.MT19937(seed))
+        kw = {}
+        if world > 1:
+            kw = dict(rank=rank, world=world, nccl_id=nccl_id)
+        self.pf = cs.PF(num_particles=npart, capacity_landmarks=nfeat, device=device, flags=cs.FLAG_INTENDED, **kw)
+        if stream is not None:
+            self.pf.set_stream(stream)
+        self.pose = np.zeros(3)
+        self.v, self.wb, self.dt = 83.33, 73.0, 0.01
+        self.cycle = 0
+        # landmarks ahead of the vehicle, 200 m .. 1900 m
+        rng_l = np.random.Generator(np.random.MT19937(12345))
+        ang = rng_l.uniform(-1.2, 1.2, size=nfeat)
+        rad = rng_l.uniform(200.0, 1900.0, size=nfeat)
+        self.lm = np.stack([rad * np.cos(ang) + 150.0, rad * np.sin(ang)])
+
+    def controls(self):
+        for c in range(PF_CONTROLS_PER_OBS):
+            swa = 0.02 * np.sin(0.3 * (self.cycle * PF_CONTROLS_PER_OBS + c))
+            self.pf.predict(self.v, swa, PF_Q, self.wb, self.dt)
+            # nominal pose: slam.h:952-966 vehicleModel
+            x, y, phi = self.pose
+            self.pose = np.array([x + self.v * self.dt * np.cos(swa + phi), y + self.v * self.dt * np.sin(swa + phi),
+                                  phi + self.v * self.dt * np.sin(swa) / self.wb])
+            self.pf.observeHeading(self.pose[2], True)
+
+    def init_map(self, xi_dev_ptr):
+        """6 control steps, sample the pose (test/main.cpp:319-325), initialise every landmark."""
+        self.controls()
+        self.pf.samplePose(xi_dev_ptr)
+        Z0 = range_bearing(self.pose, self.lm)
+        for b in range(0, self.nfeat, 64):
+            self.pf.addOneNewFeature(Z0[:, b:b + 64], PF_R)
+
+    def observation(self):
+        ids = self.rng.choice(self.nfeat, size=self.m_obs, replace=False)
+        Z = range_bearing(self.pose, self.lm[:, ids])
+        Z[0] += self.rng.normal(size=self.m_obs) * 0.1
+        Z[1] += self.rng.normal(size=self.m_obs) * (np.pi / 180.0)
+        return Z, (ids + 1).astype(np.int32)
+
+    def cycle_step(self, xi_ptr, u_ptr, want_keep=False):
+        """One observation cycle per particle = one 'particle-step' of the metric."""
+        self.controls()
+        Z, ids = self.observation()
+        self.pf.sampleProposal(Z, ids, PF_R, xi_ptr)
+        self.pf.featureUpdate(Z, ids, PF_R)
+        out = self.pf.resampleParticles(float("inf"), u_ptr, True, want_keep=want_keep)
+        self.cycle += 1
+        return out
+
+
 # --------------------------------------------------------------------------- CPU baseline ----
 def oracle_lib():
     sys.path.insert(0, os.path.join(ROOT, "tests"))

@@ -76,6 +76,7 @@ def build_host(force=False):
     deps = [src, os.path.join(HERE, "host", "slam_gpu.hpp"), os.path.join(HERE, "..", "include", "cslam.h")]
     if force or _stale(out, [d for d in deps if os.path.exists(d)]):
         cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-        subprocess.check_call([cxx, "-O2", "-std=c++17", "-I", os.path.join(HERE, "..", "include"), src, "-o", out,
+        subprocess.check_call([cxx, "-O2", "-std=c++17", "-ffp-contract=off", "-I",
+                               os.path.join(HERE, "..", "include"), src, "-o", out,
                                "-L", LIBDIR, "-lcslam", "-Wl,-rpath,$ORIGIN"])
     return out

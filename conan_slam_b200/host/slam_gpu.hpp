@@ -1,0 +1,247 @@
+// slam_gpu.hpp — C++ host adaptor (L1) over the C ABI (include/cslam.h): the reference's `Slam`
+// filter interface (slam/include/slam.h) with the same method names, argument order and
+// index conventions, for drivers written like test/main.cpp.
+//
+// Two layers:
+//   * EkfGpuT<Vec, Mat> / PfGpuT<...> — templates over any dense vector / matrix type with the
+//     Eigen-style surface  rows(), cols(), operator()(i[,j]), resize(...)  (Eigen::VectorXf /
+//     MatrixXf, or the dependency-free cslam_host::DVec / DMat below).  The caller still OWNS
+//     X and P exactly as in the reference (test/main.cpp:107-108): every call takes them by
+//     reference and the adaptor writes the result back — X always, P when n <= p_writeback_max
+//     (copying a 12.8 GB covariance per call is what the GPU path exists to avoid; call
+//     fetchCovariance() explicitly for big maps).
+//   * slam_gpu_eigen.hpp — `class EKFGpu : public Slam` / `class PFGpu : public Slam` overriding
+//     the reference's virtuals, usable when the reference's own headers (and Eigen) are present:
+//     the only edit in test/main.cpp is `new EKF(LM, WP)` -> `new EKFGpu(LM, WP)`.
+//
+// Error convention mirrors the reference (EKF.cpp:22-25 etc.): failures are printed and the call
+// returns; nothing throws across the adaptor.  There is no CPU fallback.
+#pragma once
+#include <cstdint>
+#include <iostream>
+#include <vector>
+
+#include "cslam.h"
+
+namespace cslam_host {
+
+// Minimal dense containers (column-major like Eigen) for drivers built without Eigen.
+struct DVec {
+    std::vector<double> a;
+    DVec() = default;
+    explicit DVec(int n) : a((size_t)n, 0.0) {}
+    int rows() const { return (int)a.size(); }
+    int cols() const { return 1; }
+    int size() const { return (int)a.size(); }
+    void resize(int n) { a.assign((size_t)n, 0.0); }
+    double& operator()(int i) { return a[(size_t)i]; }
+    double operator()(int i) const { return a[(size_t)i]; }
+};
+template <class T>
+struct Mat {
+    int r = 0, c = 0;
+    std::vector<T> a;
+    Mat() = default;
+    Mat(int r_, int c_) : r(r_), c(c_), a((size_t)r_ * c_, T(0)) {}
+    int rows() const { return r; }
+    int cols() const { return c; }
+    int size() const { return r * c; }
+    void resize(int r_, int c_) { r = r_; c = c_; a.assign((size_t)r_ * c_, T(0)); }
+    T& operator()(int i, int j) { return a[(size_t)j * r + i]; }
+    T operator()(int i, int j) const { return a[(size_t)j * r + i]; }
+};
+using DMat = Mat<double>;
+struct IVec {
+    std::vector<int> a;
+    IVec() = default;
+    explicit IVec(int n) : a((size_t)n, 0) {}
+    int rows() const { return (int)a.size(); }
+    int size() const { return (int)a.size(); }
+    void resize(int n) { a.assign((size_t)n, 0); }
+    int& operator()(int i) { return a[(size_t)i]; }
+    int operator()(int i) const { return a[(size_t)i]; }
+};
+
+template <class M>
+struct AssociationT {  // slam.h:438-443
+    M ZF, ZN;
+    std::vector<int> idf;
+};
+
+inline void report(int rc, const char* where) {  // reference style: print and continue
+    if (rc != CSLAM_OK) std::cout << cslam_last_error() << "\t" << where << std::endl;
+}
+
+template <class Vec, class MatT>
+class EkfGpuT {
+  public:
+    // config fields with the reference's defaults (slam.h:65-103)
+    double mVelocity = 83.33F, mMaxSWA = 3.14159265358979323846 / 4.0, mRateSWA = 70.0 * 3.14159265358979323846 / 180.0;
+    double mWheelBase = 73.0F, mDtControls = 0.01;
+    double mSigmaV = 0.3F, mSigmaSWA = 3.14159265358979323846 / 180.0;
+    double mMaxRange = 2000.0F, mDtObserve = 5.058F * 0.01;
+    double mSigmaR = 0.1F, mSigmaB = 3.14159265358979323846 / 180.0;
+    double mGateReject = 50.0F, mGateAugment = 1000.0F;
+    bool mSwitchHeadingKnown = true, mSwitchAssociationKnown = true, mSwitchBatchUpdate = true;
+    std::vector<int> mTABLE;  // slam.h:105
+    int p_writeback_max = 256;
+
+    EkfGpuT(int num_map_landmarks, int capacity_landmarks, int device = 0, unsigned flags = CSLAM_FLAG_REF_LITERAL)
+        : mTABLE((size_t)num_map_landmarks, 0), flags_(flags) {
+        report(cslam_ekf_create(&h_, capacity_landmarks, device, flags), "EKFGpu");
+    }
+    ~EkfGpuT() { cslam_ekf_destroy(h_); }
+    EkfGpuT(const EkfGpuT&) = delete;
+    EkfGpuT& operator=(const EkfGpuT&) = delete;
+    cslam_ekf_t* handle() { return h_; }
+
+    // Slam::predict  slam.h:841-847 / EKF.cpp:406-455
+    void predict(Vec& X, MatT& P, double v, double swa, const MatT& Q, double wb, double dt) {
+        push(X, P);
+        const double q[4] = {Q(0, 0), Q(1, 0), Q(0, 1), Q(1, 1)};
+        report(cslam_ekf_predict(h_, v, swa, q, wb, dt), "predict");
+        pull(X, P);
+    }
+    // Slam::observeHeading  slam.h:788 / EKF.cpp:328-352
+    void observeHeading(Vec& X, MatT& P, double phi, bool useHeading = false) {
+        push(X, P);
+        report(cslam_ekf_observe_heading(h_, phi, useHeading ? 1 : 0), "observeHeading");
+        pull(X, P);
+    }
+    // Slam::update  slam.h:938-943 / EKF.cpp:481-496
+    void update(Vec& X, MatT& P, const MatT& Z, const MatT& R, const std::vector<int>& idf, bool batch = false) {
+        push(X, P);
+        const int m = Z.cols();
+        if (m > 0) {
+            std::vector<double> z((size_t)2 * m);
+            for (int i = 0; i < m; i++) { z[2 * i] = Z(0, i); z[2 * i + 1] = Z(1, i); }
+            std::vector<int32_t> ids(idf.begin(), idf.end());
+            const double r[4] = {R(0, 0), R(1, 0), R(0, 1), R(1, 1)};
+            if (batch) {
+                report(cslam_ekf_update(h_, z.data(), ids.data(), m, r, 1), "batchUpdate");
+            } else {
+                for (int b = 0; b < m; b += CSLAM_MAX_OBS) {
+                    const int mc = (m - b < CSLAM_MAX_OBS) ? m - b : CSLAM_MAX_OBS;
+                    report(cslam_ekf_update(h_, z.data() + 2 * b, ids.data() + b, mc, r, 0), "singleUpdate");
+                }
+            }
+        }
+        pull(X, P);
+    }
+    void singleUpdate(Vec& X, MatT& P, const MatT& Z, const MatT& R, const std::vector<int>& idf) {
+        update(X, P, Z, R, idf, false);
+    }
+    void batchUpdate(Vec& X, MatT& P, const MatT& Z, const MatT& R, const std::vector<int>& idf) {
+        update(X, P, Z, R, idf, true);
+    }
+    // Slam::augment  slam.h:190-191 / EKF.cpp:9-26 — resizes the caller's X and P as the reference does
+    void augment(Vec& X, MatT& P, const MatT& Z, const MatT& R) {
+        push(X, P);
+        const int m = Z.cols();
+        if (m > 0) {
+            std::vector<double> z((size_t)2 * m);
+            for (int i = 0; i < m; i++) { z[2 * i] = Z(0, i); z[2 * i + 1] = Z(1, i); }
+            const double r[4] = {R(0, 0), R(1, 0), R(0, 1), R(1, 1)};
+            for (int b = 0; b < m; b += CSLAM_MAX_OBS) {
+                const int mc = (m - b < CSLAM_MAX_OBS) ? m - b : CSLAM_MAX_OBS;
+                report(cslam_ekf_augment(h_, z.data() + 2 * b, mc, r), "augment");
+            }
+        }
+        pull(X, P);
+    }
+    // Slam::dataAssociate  slam.h:482-487 / EKF.cpp:235-326 (Q5: ZN empty unless CSLAM_FLAG_Q5_RETURN_ZN)
+    AssociationT<MatT> dataAssociate(const Vec& X, const MatT& P, const MatT& Z, const MatT& R, double gate1,
+                                    double gate2) {
+        push(X, P);
+        AssociationT<MatT> out;
+        const int m = Z.cols();
+        std::vector<double> z((size_t)2 * m);
+        for (int i = 0; i < m; i++) { z[2 * i] = Z(0, i); z[2 * i + 1] = Z(1, i); }
+        std::vector<int32_t> jbest((size_t)m, 0);
+        std::vector<uint8_t> is_new((size_t)m, 0);
+        const double r[4] = {R(0, 0), R(1, 0), R(0, 1), R(1, 1)};
+        if (m > 0)
+            report(cslam_ekf_gate(h_, z.data(), m, r, gate1, gate2, jbest.data(), is_new.data(), nullptr, nullptr),
+                   "dataAssociate");
+        int nzf = 0, nzn = 0;
+        for (int i = 0; i < m; i++) { nzf += jbest[i] != 0; nzn += is_new[i] != 0; }
+        out.ZF.resize(2, nzf);
+        int k = 0;
+        for (int i = 0; i < m; i++)
+            if (jbest[i] != 0) { out.ZF(0, k) = Z(0, i); out.ZF(1, k) = Z(1, i); out.idf.push_back(jbest[i]); k++; }
+        if (flags_ & CSLAM_FLAG_Q5_RETURN_ZN) {
+            out.ZN.resize(2, nzn);
+            k = 0;
+            for (int i = 0; i < m; i++)
+                if (is_new[i]) { out.ZN(0, k) = Z(0, i); out.ZN(1, k) = Z(1, i); k++; }
+        } else {
+            out.ZN.resize(0, 0);
+        }
+        return out;
+    }
+    // Slam::dataAssociateTable  slam.h:454-457 / EKF.cpp:146-233 (host bookkeeping)
+    AssociationT<MatT> dataAssociateTable(const Vec& X, const MatT& Z, const std::vector<int>& idz,
+                                         std::vector<int>& table) {
+        AssociationT<MatT> out;
+        std::vector<int> zf, zn, idn;
+        for (size_t i = 0; i < idz.size(); i++) {
+            const int id = idz[i];
+            if (table[(size_t)id - 1] == 0) { zn.push_back((int)i); idn.push_back(id); }
+            else { zf.push_back((int)i); out.idf.push_back(table[(size_t)id - 1]); }
+        }
+        out.ZF.resize(zf.empty() ? 0 : 2, (int)zf.size());
+        for (size_t k = 0; k < zf.size(); k++) { out.ZF(0, (int)k) = Z(0, zf[k]); out.ZF(1, (int)k) = Z(1, zf[k]); }
+        out.ZN.resize(zn.empty() ? 0 : 2, (int)zn.size());
+        for (size_t k = 0; k < zn.size(); k++) { out.ZN(0, (int)k) = Z(0, zn[k]); out.ZN(1, (int)k) = Z(1, zn[k]); }
+        const int nf = (X.rows() - 3) / 2;
+        for (size_t k = 0; k < idn.size(); k++) table[(size_t)idn[k] - 1] = nf + (int)k + 1;
+        return out;
+    }
+    // explicit covariance read-back for maps above p_writeback_max
+    void fetchCovariance(MatT& P) {
+        const int n = cslam_ekf_n(h_);
+        std::vector<double> buf((size_t)n * n);
+        report(cslam_ekf_get_cov_block(h_, 0, 0, n, n, buf.data()), "fetchCovariance");
+        P.resize(n, n);
+        for (int i = 0; i < n; i++)
+            for (int j = 0; j < n; j++) P(i, j) = buf[(size_t)i * n + j];
+    }
+    int skippedUpdates() {
+        int s = 0;
+        report(cslam_ekf_sync(h_, &s), "sync");
+        return s;
+    }
+
+  private:
+    // The caller owns X,P.  On the first call (or if the caller re-seeded them: size differs
+    // from the device state) they are uploaded; afterwards the device copy is authoritative.
+    void push(const Vec& X, const MatT& P) {
+        const int n = X.rows();
+        if (seeded_ && n == cslam_ekf_n(h_)) return;
+        std::vector<double> x((size_t)n), p((size_t)n * n);
+        for (int i = 0; i < n; i++) x[(size_t)i] = X(i);
+        for (int i = 0; i < n; i++)
+            for (int j = 0; j < n; j++) p[(size_t)i * n + j] = P(i, j);
+        report(cslam_ekf_reset(h_, x.data(), n, p.data()), "upload");
+        seeded_ = true;
+    }
+    void pull(Vec& X, MatT& P) {
+        const int n = cslam_ekf_n(h_);
+        std::vector<double> x((size_t)n);
+        report(cslam_ekf_get_state(h_, x.data(), n), "download");
+        if (X.rows() != n) X.resize(n);
+        for (int i = 0; i < n; i++) X(i) = x[(size_t)i];
+        if (n <= p_writeback_max) {
+            fetchCovariance(P);
+        } else if (P.rows() != n) {
+            P.resize(n, n);  // shape follows the reference's resize (EKF.cpp:69); values stay on the GPU
+        }
+    }
+    cslam_ekf_t* h_ = nullptr;
+    unsigned flags_ = 0;
+    bool seeded_ = false;
+};
+
+using EkfGpu = EkfGpuT<DVec, DMat>;
+
+}  // namespace cslam_host

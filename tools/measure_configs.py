@@ -88,48 +88,27 @@ def ekf_configs(which):
 
 def pf_config(npart, nfeat, m_obs=4):
     stream = torch.cuda.Stream()
-    rng = np.random.default_rng(npart + 2)
-    pf = cs.PF(num_particles=npart, capacity_landmarks=nfeat, flags=cs.FLAG_INTENDED)
-    pf.set_stream(stream.cuda_stream)
-    Q = 2 * np.diag([0.3 ** 2, (np.pi / 180) ** 2])
-    R2 = 2 * bench.R_BASE
-    for _ in range(6):
-        pf.predict(83.33, 0.02, Q, 73.0, 0.01)
-        pf.observeHeading(0.001, True)
+    sc = bench.PfScenario(npart, nfeat, m_obs, 0, seed=npart + 2, stream=stream.cuda_stream)
+    pf = sc.pf
     xi = torch.randn(npart, 3, dtype=torch.float64, device="cuda")
     u = torch.randn(npart, dtype=torch.float64, device="cuda") * 0.3
     torch.cuda.synchronize()
-    pf.samplePose(xi.data_ptr())
-    Z0 = np.stack([200 + 1500 * np.arange(nfeat) / nfeat, -1.2 + 2.4 * np.arange(nfeat) / nfeat])
-    for b in range(0, nfeat, 64):
-        pf.addOneNewFeature(Z0[:, b:b + 64], R2)
-    ids = (1 + np.arange(m_obs) * (nfeat // m_obs)).astype(np.int32)
-    Z = Z0[:, ids - 1] + np.array([[0.002], [1e-6]])
-
-    def step():
-        # the reference's cadence: 6 control steps per observation step (mDtObserve / mDtControls = 5.058,
-        # test/main.cpp:289-290); fewer leaves the proposal covariance singular
-        for c in range(6):
-            pf.predict(83.33, 0.02 + 0.001 * c, Q, 73.0, 0.01)
-            pf.observeHeading(0.0012, True)
-        pf.sampleProposal(Z, ids, R2, xi.data_ptr())
-        pf.featureUpdate(Z, ids, R2)
-        pf.resampleParticles(npart + 1, u.data_ptr(), True, want_keep=False)
-
+    sc.init_map(xi.data_ptr())
+    did = []
     for _ in range(2):
-        step()
+        did.append(sc.cycle_step(xi.data_ptr(), u.data_ptr())[2])
     pf.sync()
-    ms = timed(stream, step, 5, None)
-    bytes_per = 6 * 2 * 208 + m_obs * 96 + 2 * (nfeat * 40 + 13 * 8)
+    ms = timed(stream, lambda: did.append(sc.cycle_step(xi.data_ptr(), u.data_ptr())[2]), 5, None)
+    w = pf.weights
+    bytes_per = bench.PF_CONTROLS_PER_OBS * 2 * 208 + m_obs * 96 + 2 * (nfeat * 40 + 13 * 8)
     out = {"config": f"PF {npart} particles x {nfeat} landmarks", "step_ms": ms,
            "particle_steps_per_s": npart / (ms * 1e-3), "bytes_per_particle_step": bytes_per,
-           "hbm_frac": bytes_per * npart / (ms * 1e-3) / 1e9 / PEAK, "bad": pf.sync()}
-    # pieces
-    for name, fn in (("predict", lambda: pf.predict(83.33, 0.02, Q, 73.0, 0.01)),
-                     ("heading", lambda: pf.observeHeading(0.0012, True)),
-                     ("sample_proposal", lambda: pf.sampleProposal(Z, ids, R2, xi.data_ptr())),
-                     ("feature_update", lambda: pf.featureUpdate(Z, ids, R2)),
-                     ("resample", lambda: pf.resampleParticles(npart + 1, u.data_ptr(), True, want_keep=False))):
+           "hbm_frac": bytes_per * npart / (ms * 1e-3) / 1e9 / PEAK, "bad": pf.sync(),
+           "resampled_every_cycle": bool(all(did)), "weights_finite": bool(np.all(np.isfinite(w)))}
+    Z, ids = sc.observation()
+    for name, fn in (("predict", lambda: pf.predict(83.33, 0.02, bench.PF_Q, 73.0, 0.01)),
+                     ("heading", lambda: pf.observeHeading(sc.pose[2], True)),
+                     ("resample", lambda: pf.resampleParticles(float("inf"), u.data_ptr(), True, want_keep=False))):
         out[name + "_ms"] = timed(stream, fn, 3, None)
     print(json.dumps(out), flush=True)
     pf.close()
