@@ -10,7 +10,13 @@
 
 
 using namespace oracle;
-typedef double T;
+// The same file is compiled twice: FP64 (orc_*, the parity oracle) and FP32 (orcf_*, which mimics
+// the reference's own precision and is what tests/test_oracle_vs_ref.py pins against oracle/_ref).
+#ifndef ORC_SCALAR
+#define ORC_SCALAR double
+#define ORC(name) orc_##name
+#endif
+typedef ORC_SCALAR T;
 
 namespace {
 
@@ -25,12 +31,12 @@ struct PfState {
     std::vector<Particle<T>> ps;
 };
 
-Mat<T> mat2(const double* R) {  // 2x2, column-major == Eigen layout
+Mat<T> mat2(const T* R) {  // 2x2, column-major == Eigen layout
     Mat<T> M(2, 2);
     M(0, 0) = R[0]; M(1, 0) = R[1]; M(0, 1) = R[2]; M(1, 1) = R[3];
     return M;
 }
-Mat<T> zmat(const double* Z, int m) {
+Mat<T> zmat(const T* Z, int m) {
     Mat<T> M(m > 0 ? 2 : 0, m);
     for (int i = 0; i < m; i++) {
         M(0, i) = Z[2 * i];
@@ -80,15 +86,15 @@ const float kWp2[5] = {0.0F, -2038.2165605095560749759897589684F, 1707.006369426
 extern "C" {
 
 // ------------------------------------------------------------------ EKF handle ----
-void* orc_ekf_create(unsigned flags) {
+void* ORC(ekf_create)(unsigned flags) {
     EkfState* s = new EkfState();
     s->flags = flags;
     return s;
 }
-void orc_ekf_destroy(void* h) { delete static_cast<EkfState*>(h); }
-int orc_ekf_n(void* h) { return (int)static_cast<EkfState*>(h)->X.size(); }
+void ORC(ekf_destroy)(void* h) { delete static_cast<EkfState*>(h); }
+int ORC(ekf_n)(void* h) { return (int)static_cast<EkfState*>(h)->X.size(); }
 
-void orc_ekf_reset(void* h, const double* X, int n, const double* P) {
+void ORC(ekf_reset)(void* h, const T* X, int n, const T* P) {
     EkfState* s = static_cast<EkfState*>(h);
     s->X.assign(X, X + n);
     s->P = Mat<T>(n, n);
@@ -96,36 +102,36 @@ void orc_ekf_reset(void* h, const double* X, int n, const double* P) {
         for (int i = 0; i < n; i++)
             for (int j = 0; j < n; j++) s->P(i, j) = P[(size_t)i * n + j];
 }
-void orc_ekf_get_state(void* h, double* X) {
+void ORC(ekf_get_state)(void* h, T* X) {
     EkfState* s = static_cast<EkfState*>(h);
     std::copy(s->X.begin(), s->X.end(), X);
 }
-void orc_ekf_get_cov(void* h, double* P) {  // row-major n x n
+void ORC(ekf_get_cov)(void* h, T* P) {  // row-major n x n
     EkfState* s = static_cast<EkfState*>(h);
     const int n = s->P.r;
     for (int i = 0; i < n; i++)
         for (int j = 0; j < n; j++) P[(size_t)i * n + j] = s->P(i, j);
 }
-void orc_ekf_predict(void* h, double v, double swa, const double* Q, double wb, double dt) {
+void ORC(ekf_predict)(void* h, double v, double swa, const T* Q, double wb, double dt) {
     EkfState* s = static_cast<EkfState*>(h);
     ekf_predict<T>(s->X, s->P, v, swa, mat2(Q), wb, dt, s->flags);
 }
-void orc_ekf_observe_heading(void* h, double phi, int use_heading, int dense) {
+void ORC(ekf_observe_heading)(void* h, double phi, int use_heading, int dense) {
     EkfState* s = static_cast<EkfState*>(h);
     ekf_observe_heading<T>(s->X, s->P, phi, use_heading != 0, dense != 0);
 }
-int orc_ekf_update(void* h, const double* Z, const int* idf, int m, const double* R, int batch) {
+int ORC(ekf_update)(void* h, const T* Z, const int* idf, int m, const T* R, int batch) {
     EkfState* s = static_cast<EkfState*>(h);
     std::vector<int> ids(idf, idf + m);
     return ekf_update<T>(s->X, s->P, zmat(Z, m), mat2(R), ids, batch != 0, s->flags);
 }
-void orc_ekf_augment(void* h, const double* Z, int m, const double* R) {
+void ORC(ekf_augment)(void* h, const T* Z, int m, const T* R) {
     EkfState* s = static_cast<EkfState*>(h);
     ekf_augment<T>(s->X, s->P, zmat(Z, m), mat2(R));
 }
 // returns #associated; idf_out (capacity m) = the reference's IDF vector, zn_count = ZN.cols()
-int orc_ekf_gate(void* h, const double* Z, int m, const double* R, double gate1, double gate2, int dense,
-                 int* jbest, uint8_t* is_new, double* nbest, double* outer, int* idf_out, int* zn_count) {
+int ORC(ekf_gate)(void* h, const T* Z, int m, const T* R, double gate1, double gate2, int dense,
+                 int* jbest, uint8_t* is_new, T* nbest, T* outer, int* idf_out, int* zn_count) {
     EkfState* s = static_cast<EkfState*>(h);
     Association<T> a = ekf_data_associate<T>(s->X, s->P, zmat(Z, m), mat2(R), gate1, gate2, s->flags, dense != 0);
     for (int i = 0; i < m; i++) {
@@ -139,7 +145,7 @@ int orc_ekf_gate(void* h, const double* Z, int m, const double* R, double gate1,
     return (int)a.idf.size();
 }
 // EKF.cpp:146-233 on a caller-owned table; outputs split indices (into Z's columns)
-void orc_ekf_table(void* h, const int* idz, int m, int* table, int table_len, int* zf_cols, int* idf, int* n_zf,
+void ORC(ekf_table)(void* h, const int* idz, int m, int* table, int table_len, int* zf_cols, int* idf, int* n_zf,
                    int* zn_cols, int* n_zn) {
     EkfState* s = static_cast<EkfState*>(h);
     std::vector<int> tab(table, table + table_len), ids(idz, idz + m);
@@ -163,8 +169,8 @@ void orc_ekf_table(void* h, const int* idz, int m, int* table, int table_len, in
 // (the reference's clock-seeded draws are not reproducible, so they are inputs).
 // controls[s] = (vn, swan, phi_true); observation steps have obs_ptr[s+1] > obs_ptr[s] or
 // obs_flag[s] = 1 with zero visible landmarks.
-int orc_sim_tape(int max_steps, unsigned long long noise_seed, double* controls, int* obs_flag, int* obs_ptr,
-                 double* Zout, int* tags_out, int max_obs, double* consts /* [8] out */) {
+int ORC(sim_tape)(int max_steps, unsigned long long noise_seed, T* controls, int* obs_flag, int* obs_ptr,
+                 T* Zout, int* tags_out, int max_obs, T* consts /* [8] out */) {
     const T V = 83.33F, maxSWA = (float)(kPi / 4.0F), rateSWA = (float)(70.0F * kPi / 180.0F), wb = 73.0F;
     const double dt = 0.01;
     const T sigmaV = 0.3F, sigmaSWA = (float)(1.0F * kPi / 180.0F);
@@ -228,36 +234,36 @@ int orc_sim_tape(int max_steps, unsigned long long noise_seed, double* controls,
 }
 
 // ------------------------------------------------------------------ PF handle ----
-void* orc_pf_create(int num_particles, unsigned flags) {
+void* ORC(pf_create)(int num_particles, unsigned flags) {
     PfState* s = new PfState();
     s->flags = flags;
     s->ps = pf_initialize_particles<T>(num_particles);
     return s;
 }
-void orc_pf_destroy(void* h) { delete static_cast<PfState*>(h); }
-int orc_pf_num_features(void* h) { return static_cast<PfState*>(h)->ps[0].XF.c; }
-void orc_pf_predict(void* h, double v, double swa, const double* Q, double wb, double dt) {
+void ORC(pf_destroy)(void* h) { delete static_cast<PfState*>(h); }
+int ORC(pf_num_features)(void* h) { return static_cast<PfState*>(h)->ps[0].XF.c; }
+void ORC(pf_predict)(void* h, double v, double swa, const T* Q, double wb, double dt) {
     PfState* s = static_cast<PfState*>(h);
     Mat<T> Qm = mat2(Q);
     for (auto& p : s->ps) pf_predict<T>(p, v, swa, Qm, wb, dt);
 }
-void orc_pf_observe_heading(void* h, double phi, int use_heading) {
+void ORC(pf_observe_heading)(void* h, double phi, int use_heading) {
     PfState* s = static_cast<PfState*>(h);
     for (auto& p : s->ps) pf_observe_heading<T>(p, phi, use_heading != 0);
 }
-void orc_pf_sample_proposal(void* h, const double* Z, const int* idf, int m, const double* R, const double* xi) {
+void ORC(pf_sample_proposal)(void* h, const T* Z, const int* idf, int m, const T* R, const T* xi) {
     PfState* s = static_cast<PfState*>(h);
     Mat<T> Zm = zmat(Z, m), Rm = mat2(R);
     std::vector<int> ids(idf, idf + m);
     for (size_t p = 0; p < s->ps.size(); p++) pf_sample_proposal<T>(s->ps[p], Zm, ids, Rm, xi + 3 * p, s->flags);
 }
-void orc_pf_feature_update(void* h, const double* Z, const int* idf, int m, const double* R) {
+void ORC(pf_feature_update)(void* h, const T* Z, const int* idf, int m, const T* R) {
     PfState* s = static_cast<PfState*>(h);
     Mat<T> Zm = zmat(Z, m), Rm = mat2(R);
     std::vector<int> ids(idf, idf + m);
     for (auto& p : s->ps) pf_feature_update<T>(p, Zm, ids, Rm, s->flags);
 }
-int orc_pf_resample(void* h, const double* u, double num_effective, int resample_on, int* keep, double* neff) {
+int ORC(pf_resample)(void* h, const T* u, double num_effective, int resample_on, int* keep, T* neff) {
     PfState* s = static_cast<PfState*>(h);
     Vec<T> uv(u, u + s->ps.size());
     Stratified<T> st;
@@ -267,20 +273,20 @@ int orc_pf_resample(void* h, const double* u, double num_effective, int resample
     return did ? 1 : 0;
 }
 // stratifiedResample alone (PF.cpp:546-577) on a weight vector
-void orc_stratified_resample(const double* w, const double* u, int len, unsigned flags, int* keep, double* neff,
-                             double* cumw) {
+void ORC(stratified_resample)(const T* w, const T* u, int len, unsigned flags, int* keep, T* neff,
+                             T* cumw) {
     Vec<T> W(w, w + len), U(u, u + len);
     Stratified<T> st = pf_stratified_resample<T>(W, U, flags);
     std::copy(st.keep.begin(), st.keep.end(), keep);
     *neff = st.neff;
     if (cumw) std::copy(W.begin(), W.end(), cumw);
 }
-void orc_pf_add_features(void* h, const double* Z, int m, const double* R) {
+void ORC(pf_add_features)(void* h, const T* Z, int m, const T* R) {
     PfState* s = static_cast<PfState*>(h);
     Mat<T> Zm = zmat(Z, m), Rm = mat2(R);
     for (auto& p : s->ps) pf_add_new_features<T>(p, Zm, Rm);
 }
-void orc_pf_sample_pose(void* h, const double* xi) {  // test/main.cpp:319-325
+void ORC(pf_sample_pose)(void* h, const T* xi) {  // test/main.cpp:319-325
     PfState* s = static_cast<PfState*>(h);
     for (size_t p = 0; p < s->ps.size(); p++) {
         Particle<T>& q = s->ps[p];
@@ -295,11 +301,11 @@ void orc_pf_sample_pose(void* h, const double* xi) {  // test/main.cpp:319-325
         q.P = Mat<T>(3, 3);
     }
 }
-void orc_pf_get_weights(void* h, double* w) {
+void ORC(pf_get_weights)(void* h, T* w) {
     PfState* s = static_cast<PfState*>(h);
     for (size_t p = 0; p < s->ps.size(); p++) w[p] = s->ps[p].w;
 }
-void orc_pf_get_poses(void* h, double* X, double* Pv) {
+void ORC(pf_get_poses)(void* h, T* X, T* Pv) {
     PfState* s = static_cast<PfState*>(h);
     for (size_t p = 0; p < s->ps.size(); p++) {
         for (int i = 0; i < 3; i++) X[3 * p + i] = s->ps[p].X[i];
@@ -308,7 +314,7 @@ void orc_pf_get_poses(void* h, double* X, double* Pv) {
                 for (int j = 0; j < 3; j++) Pv[9 * p + 3 * i + j] = s->ps[p].P(i, j);
     }
 }
-void orc_pf_get_features(void* h, int particle, double* XF, double* PF) {
+void ORC(pf_get_features)(void* h, int particle, T* XF, T* PF) {
     PfState* s = static_cast<PfState*>(h);
     const Particle<T>& q = s->ps[particle];
     for (int f = 0; f < q.XF.c; f++) {
@@ -318,11 +324,11 @@ void orc_pf_get_features(void* h, int particle, double* XF, double* PF) {
             for (int j = 0; j < 2; j++) PF[4 * f + 2 * i + j] = q.PF[f](i, j);
     }
 }
-void orc_pf_set_weights(void* h, const double* w) {
+void ORC(pf_set_weights)(void* h, const T* w) {
     PfState* s = static_cast<PfState*>(h);
     for (size_t p = 0; p < s->ps.size(); p++) s->ps[p].w = w[p];
 }
-void orc_pf_set_poses(void* h, const double* X, const double* Pv) {
+void ORC(pf_set_poses)(void* h, const T* X, const T* Pv) {
     PfState* s = static_cast<PfState*>(h);
     for (size_t p = 0; p < s->ps.size(); p++) {
         for (int i = 0; i < 3; i++) s->ps[p].X[i] = X[3 * p + i];
@@ -331,7 +337,7 @@ void orc_pf_set_poses(void* h, const double* X, const double* Pv) {
                 for (int j = 0; j < 3; j++) s->ps[p].P(i, j) = Pv[9 * p + 3 * i + j];
     }
 }
-int orc_pf_extract_state(void* h, double* X) {  // slam.h:493-511 (Q13: the MINIMUM-weight particle)
+int ORC(pf_extract_state)(void* h, T* X) {  // slam.h:493-511 (Q13: the MINIMUM-weight particle)
     PfState* s = static_cast<PfState*>(h);
     size_t pos = 0;
     for (size_t p = 1; p < s->ps.size(); p++)
@@ -341,9 +347,9 @@ int orc_pf_extract_state(void* h, double* X) {  // slam.h:493-511 (Q13: the MINI
 }
 
 // small standalone pieces for known-answer tests
-double orc_pi2pi(double a) { return pi2pi<T>(a); }
-float orc_pi2pi_f(float a) { return pi2pi<float>(a); }
-int orc_cholesky(const double* M, int n, double* L) {  // column-major in/out; returns used-fallback flag
+double ORC(pi2pi)(double a) { return (double)pi2pi<T>((T)a); }
+float ORC(pi2pi_f)(float a) { return pi2pi<float>(a); }
+int ORC(cholesky)(const T* M, int n, T* L) {  // column-major in/out; returns used-fallback flag
     Mat<T> A(n, n);
     std::copy(M, M + (size_t)n * n, A.a.begin());
     bool fb = false;
@@ -351,7 +357,7 @@ int orc_cholesky(const double* M, int n, double* L) {  // column-major in/out; r
     std::copy(R.a.begin(), R.a.end(), L);
     return fb ? 1 : 0;
 }
-void orc_inverse(const double* M, int n, double* out, double* det) {
+void ORC(inverse)(const T* M, int n, T* out, T* det) {
     Mat<T> A(n, n);
     std::copy(M, M + (size_t)n * n, A.a.begin());
     Mat<T> I = inverse(A);

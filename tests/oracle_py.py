@@ -67,78 +67,112 @@ def _m2(M):
     return np.ascontiguousarray(np.asarray(M, dtype=np.float64).reshape(2, 2).T).reshape(-1)
 
 
+class _Backend:
+    """FP64 (`orc_*`, the parity oracle) or FP32 (`orcf_*`, the reference's own precision)."""
+
+    def __init__(self, f32=False):
+        self.cdll = lib()
+        self.prefix = "orcf_" if f32 else "orc_"
+        self.dtype = np.float32 if f32 else np.float64
+        self.ctype = C.c_float if f32 else C.c_double
+
+    def __getattr__(self, name):
+        fn = getattr(self.cdll, self.prefix + name)
+        if name.endswith("_create"):
+            fn.restype = C.c_void_p
+        return fn
+
+    def arr(self, a):
+        return np.ascontiguousarray(a, dtype=self.dtype)
+
+    def zflat(self, Z):
+        Z = np.asarray(Z, dtype=self.dtype)
+        if Z.size == 0:
+            return np.zeros(0, dtype=self.dtype), 0
+        Z = Z.reshape(2, -1)
+        return np.ascontiguousarray(Z.T).reshape(-1), Z.shape[1]
+
+    def m2(self, M):
+        return np.ascontiguousarray(np.asarray(M, dtype=self.dtype).reshape(2, 2).T).reshape(-1)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
 class OracleEKF:
-    def __init__(self, flags=0):
-        self.L = lib()
-        self.h = C.c_void_p(self.L.orc_ekf_create(flags))
+    def __init__(self, flags=0, f32=False):
+        self.B = _Backend(f32)
+        self.L = self.B
+        self.h = C.c_void_p(self.B.ekf_create(C.c_uint(flags)))
         self.flags = flags
 
     def __del__(self):
         try:
-            self.L.orc_ekf_destroy(self.h)
+            self.B.ekf_destroy(self.h)
         except Exception:
             pass
 
     @property
     def n(self):
-        return self.L.orc_ekf_n(self.h)
+        return self.B.ekf_n(self.h)
 
     @property
     def num_landmarks(self):
         return (self.n - 3) // 2
 
     def reset(self, X, P=None):
-        X = np.ascontiguousarray(X, dtype=np.float64)
+        X = self.B.arr(X)
         if P is not None:
-            P = np.ascontiguousarray(P, dtype=np.float64)
-        self.L.orc_ekf_reset(self.h, _d(X), X.shape[0], _d(P) if P is not None else None)
+            P = self.B.arr(P)
+        self.B.ekf_reset(self.h, _p(X), X.shape[0], _p(P) if P is not None else None)
 
     @property
     def X(self):
-        out = np.empty(self.n)
-        self.L.orc_ekf_get_state(self.h, _d(out))
+        out = np.empty(self.n, dtype=self.B.dtype)
+        self.B.ekf_get_state(self.h, _p(out))
         return out
 
     @property
     def P(self):
         n = self.n
-        out = np.empty((n, n))
-        self.L.orc_ekf_get_cov(self.h, _d(out))
+        out = np.empty((n, n), dtype=self.B.dtype)
+        self.B.ekf_get_cov(self.h, _p(out))
         return out
 
     def predict(self, v, swa, Q, wb, dt):
-        q = _m2(Q)
-        self.L.orc_ekf_predict(self.h, C.c_double(v), C.c_double(swa), _d(q), C.c_double(wb), C.c_double(dt))
+        q = self.B.m2(Q)
+        self.B.ekf_predict(self.h, C.c_double(v), C.c_double(swa), _p(q), C.c_double(wb), C.c_double(dt))
 
     def observeHeading(self, phi, useHeading=False, dense=False):
-        self.L.orc_ekf_observe_heading(self.h, C.c_double(phi), int(bool(useHeading)), int(bool(dense)))
+        self.B.ekf_observe_heading(self.h, C.c_double(phi), int(bool(useHeading)), int(bool(dense)))
 
     def update(self, Z, R, idf, batch=False):
-        z, m = _zflat(Z)
+        z, m = self.B.zflat(Z)
         if m == 0:
             return 0
         idf = np.ascontiguousarray(idf, dtype=np.int32)
-        r = _m2(R)
-        return self.L.orc_ekf_update(self.h, _d(z), _i(idf), m, _d(r), int(bool(batch)))
+        r = self.B.m2(R)
+        return self.B.ekf_update(self.h, _p(z), _p(idf), m, _p(r), int(bool(batch)))
 
     def augment(self, Z, R):
-        z, m = _zflat(Z)
+        z, m = self.B.zflat(Z)
         if m == 0:
             return
-        r = _m2(R)
-        self.L.orc_ekf_augment(self.h, _d(z), m, _d(r))
+        r = self.B.m2(R)
+        self.B.ekf_augment(self.h, _p(z), m, _p(r))
 
     def gate(self, Z, R, gate1, gate2, dense=False):
-        z, m = _zflat(Z)
-        r = _m2(R)
+        z, m = self.B.zflat(Z)
+        r = self.B.m2(R)
         jbest = np.zeros(m, dtype=np.int32)
         is_new = np.zeros(m, dtype=np.uint8)
-        nbest = np.zeros(m)
-        outer = np.zeros(m)
+        nbest = np.zeros(m, dtype=self.B.dtype)
+        outer = np.zeros(m, dtype=self.B.dtype)
         idf = np.zeros(max(m, 1), dtype=np.int32)
         zn = C.c_int(0)
-        na = self.L.orc_ekf_gate(self.h, _d(z), m, _d(r), C.c_double(gate1), C.c_double(gate2), int(bool(dense)),
-                                 _i(jbest), is_new.ctypes.data_as(_u8), _d(nbest), _d(outer), _i(idf), C.byref(zn))
+        na = self.B.ekf_gate(self.h, _p(z), m, _p(r), C.c_double(gate1), C.c_double(gate2), int(bool(dense)),
+                                 _p(jbest), is_new.ctypes.data_as(_u8), _p(nbest), _p(outer), _p(idf), C.byref(zn))
         return jbest, is_new, nbest, outer, idf[:na].copy(), zn.value
 
     def dataAssociateTable(self, idz, table):
@@ -148,20 +182,21 @@ class OracleEKF:
         zn = np.zeros(max(m, 1), dtype=np.int32)
         idf = np.zeros(max(m, 1), dtype=np.int32)
         nzf, nzn = C.c_int(0), C.c_int(0)
-        self.L.orc_ekf_table(self.h, _i(idz), m, _i(table), table.shape[0], _i(zf), _i(idf), C.byref(nzf), _i(zn),
+        self.B.ekf_table(self.h, _p(idz), m, _p(table), table.shape[0], _p(zf), _p(idf), C.byref(nzf), _p(zn),
                              C.byref(nzn))
         return zf[:nzf.value].copy(), idf[:nzf.value].copy(), zn[:nzn.value].copy()
 
 
 class OraclePF:
-    def __init__(self, num_particles, flags=0):
-        self.L = lib()
+    def __init__(self, num_particles, flags=0, f32=False):
+        self.B = _Backend(f32)
+        self.L = self.B
         self.np_ = int(num_particles)
-        self.h = C.c_void_p(self.L.orc_pf_create(self.np_, flags))
+        self.h = C.c_void_p(self.B.pf_create(self.np_, C.c_uint(flags)))
 
     def __del__(self):
         try:
-            self.L.orc_pf_destroy(self.h)
+            self.B.pf_destroy(self.h)
         except Exception:
             pass
 
@@ -171,87 +206,87 @@ class OraclePF:
 
     @property
     def num_features(self):
-        return self.L.orc_pf_num_features(self.h)
+        return self.B.pf_num_features(self.h)
 
     def predict(self, v, swa, Q, wb, dt):
-        q = _m2(Q)
-        self.L.orc_pf_predict(self.h, C.c_double(v), C.c_double(swa), _d(q), C.c_double(wb), C.c_double(dt))
+        q = self.B.m2(Q)
+        self.B.pf_predict(self.h, C.c_double(v), C.c_double(swa), _p(q), C.c_double(wb), C.c_double(dt))
 
     def observeHeading(self, phi, useHeading=False):
-        self.L.orc_pf_observe_heading(self.h, C.c_double(phi), int(bool(useHeading)))
+        self.B.pf_observe_heading(self.h, C.c_double(phi), int(bool(useHeading)))
 
     def sampleProposal(self, Z, idf, R, xi):
-        z, m = _zflat(Z)
+        z, m = self.B.zflat(Z)
         idf = np.ascontiguousarray(idf, dtype=np.int32)
-        xi = np.ascontiguousarray(xi, dtype=np.float64).reshape(-1)
-        r = _m2(R)
-        self.L.orc_pf_sample_proposal(self.h, _d(z), _i(idf), m, _d(r), _d(xi))
+        xi = self.B.arr(xi).reshape(-1)
+        r = self.B.m2(R)
+        self.B.pf_sample_proposal(self.h, _p(z), _p(idf), m, _p(r), _p(xi))
 
     def featureUpdate(self, Z, idf, R):
-        z, m = _zflat(Z)
+        z, m = self.B.zflat(Z)
         idf = np.ascontiguousarray(idf, dtype=np.int32)
-        r = _m2(R)
-        self.L.orc_pf_feature_update(self.h, _d(z), _i(idf), m, _d(r))
+        r = self.B.m2(R)
+        self.B.pf_feature_update(self.h, _p(z), _p(idf), m, _p(r))
 
     def resampleParticles(self, numEffective, u, resampleStatus=False):
-        u = np.ascontiguousarray(u, dtype=np.float64)
+        u = self.B.arr(u)
         keep = np.zeros(self.np_, dtype=np.int32)
-        neff = C.c_double(0)
-        did = self.L.orc_pf_resample(self.h, _d(u), C.c_double(numEffective), int(bool(resampleStatus)), _i(keep),
+        neff = self.B.ctype(0)
+        did = self.B.pf_resample(self.h, _p(u), C.c_double(numEffective), int(bool(resampleStatus)), _p(keep),
                                      C.byref(neff))
         return keep, neff.value, bool(did)
 
     def addOneNewFeature(self, Z, R):
-        z, m = _zflat(Z)
+        z, m = self.B.zflat(Z)
         if m == 0:
             return
-        r = _m2(R)
-        self.L.orc_pf_add_features(self.h, _d(z), m, _d(r))
+        r = self.B.m2(R)
+        self.B.pf_add_features(self.h, _p(z), m, _p(r))
 
     def samplePose(self, xi):
-        xi = np.ascontiguousarray(xi, dtype=np.float64).reshape(-1)
-        self.L.orc_pf_sample_pose(self.h, _d(xi))
+        xi = self.B.arr(xi).reshape(-1)
+        self.B.pf_sample_pose(self.h, _p(xi))
 
     def extractStatesFromParticles(self):
-        X = np.zeros(3)
-        idx = self.L.orc_pf_extract_state(self.h, _d(X))
+        X = np.zeros(3, dtype=self.B.dtype)
+        idx = self.B.pf_extract_state(self.h, _p(X))
         return X, idx
 
     @property
     def weights(self):
-        w = np.empty(self.np_)
-        self.L.orc_pf_get_weights(self.h, _d(w))
+        w = np.empty(self.np_, dtype=self.B.dtype)
+        self.B.pf_get_weights(self.h, _p(w))
         return w
 
     @weights.setter
     def weights(self, w):
-        w = np.ascontiguousarray(w, dtype=np.float64)
-        self.L.orc_pf_set_weights(self.h, _d(w))
+        w = self.B.arr(w)
+        self.B.pf_set_weights(self.h, _p(w))
 
     @property
     def poses(self):
-        X = np.empty((self.np_, 3))
-        self.L.orc_pf_get_poses(self.h, _d(X), None)
+        X = np.empty((self.np_, 3), dtype=self.B.dtype)
+        self.B.pf_get_poses(self.h, _p(X), None)
         return X
 
     @property
     def pose_covs(self):
-        X = np.empty((self.np_, 3))
-        P = np.empty((self.np_, 3, 3))
-        self.L.orc_pf_get_poses(self.h, _d(X), _d(P))
+        X = np.empty((self.np_, 3), dtype=self.B.dtype)
+        P = np.empty((self.np_, 3, 3), dtype=self.B.dtype)
+        self.B.pf_get_poses(self.h, _p(X), _p(P))
         return P
 
     def set_poses(self, X, Pv=None):
-        X = np.ascontiguousarray(X, dtype=np.float64).reshape(-1)
+        X = self.B.arr(X).reshape(-1)
         if Pv is not None:
-            Pv = np.ascontiguousarray(Pv, dtype=np.float64).reshape(-1)
-        self.L.orc_pf_set_poses(self.h, _d(X), _d(Pv) if Pv is not None else None)
+            Pv = self.B.arr(Pv).reshape(-1)
+        self.B.pf_set_poses(self.h, _p(X), _p(Pv) if Pv is not None else None)
 
     def features(self, particle):
         nf = self.num_features
-        XF = np.zeros((nf, 2))
-        PF = np.zeros((nf, 2, 2))
-        self.L.orc_pf_get_features(self.h, int(particle), _d(XF), _d(PF))
+        XF = np.zeros((nf, 2), dtype=self.B.dtype)
+        PF = np.zeros((nf, 2, 2), dtype=self.B.dtype)
+        self.B.pf_get_features(self.h, int(particle), _p(XF), _p(PF))
         return XF, PF
 
 
