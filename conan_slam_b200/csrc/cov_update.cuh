@@ -27,12 +27,27 @@ __device__ __forceinline__ void cov_st(double* p, double2 v) {
     }
 }
 
-// triangular tile index -> (tr, tc), row-major over the upper triangle of an nt x nt tile grid
-__device__ __forceinline__ void tri_tile(long long t, int nt, int& tr, int& tc) {
-    tr = (int)floor(((2.0 * nt + 1.0) - sqrt((2.0 * nt + 1.0) * (2.0 * nt + 1.0) - 8.0 * (double)t)) * 0.5);
-    while ((long long)tr * nt - (long long)tr * (tr - 1) / 2 > t) tr--;
-    while ((long long)(tr + 1) * nt - (long long)(tr + 1) * tr / 2 <= t) tr++;
-    tc = tr + (int)(t - ((long long)tr * nt - (long long)tr * (tr - 1) / 2));
+// Linear tile index -> (tr, tc) over the tiles of the upper triangle that THIS RANK owns, row-major:
+// owned tile rows are tr = l*world + rank (l = 0,1,...), row tr holds the nt - tr tiles tc >= tr, so
+//   first(l) = l*(nt - rank) - world*l*(l-1)/2          (world = 1: the plain triangular index)
+__host__ __device__ __forceinline__ long long shard_first_tile(long long l, int nt, Shard sh) {
+    return l * (long long)(nt - sh.rank) - (long long)sh.world * l * (l - 1) / 2;
+}
+__device__ __forceinline__ void shard_tile(long long t, int nt, Shard sh, int& tr, int& tc) {
+    const double w = (double)sh.world;
+    const double b = (double)(nt - sh.rank) + 0.5 * w;
+    long long l = (long long)floor((b - sqrt(b * b - 2.0 * w * (double)t)) / w);
+    if (l < 0) l = 0;
+    while (shard_first_tile(l, nt, sh) > t) l--;
+    while (shard_first_tile(l + 1, nt, sh) <= t) l++;
+    tr = (int)l * sh.world + sh.rank;
+    tc = tr + (int)(t - shard_first_tile(l, nt, sh));
+}
+// number of owned tiles (host side)
+inline long long shard_tile_count(int nt, Shard sh) {
+    long long cnt = 0;
+    for (int tr = sh.rank; tr < nt; tr += sh.world) cnt += nt - tr;
+    return cnt;
 }
 
 // slam.h:260  P <- P - W1 W1^T over the UPPER TRIANGLE only, in place, FP64.
@@ -47,7 +62,7 @@ __device__ __forceinline__ void tri_tile(long long t, int nt, int& tr, int& tc) 
 template <int R, int T, int BATCH_ = 8, int MINB = 2, int HINT = 0>
 __global__ void __launch_bounds__(256, MINB) k_cov_update(double* __restrict__ P, size_t ld, int n,
                                                           const double* __restrict__ A, size_t lda, int nt,
-                                                          double diag_eps) {
+                                                          double diag_eps, Shard sh) {
     constexpr int CP = T / 2;       // column pairs per tile
     constexpr int RG = 256 / CP;    // row groups
     constexpr int RPT = T / RG;     // rows per thread
@@ -55,7 +70,7 @@ __global__ void __launch_bounds__(256, MINB) k_cov_update(double* __restrict__ P
     __shared__ double sAr[R][T];
 
     int tr, tc;
-    tri_tile(blockIdx.x, nt, tr, tc);
+    shard_tile(blockIdx.x, nt, sh, tr, tc);
 
     const int i0 = tr * T, j0 = tc * T;
     for (int idx = threadIdx.x; idx < R * T; idx += 256) {
@@ -81,7 +96,7 @@ __global__ void __launch_bounds__(256, MINB) k_cov_update(double* __restrict__ P
             const int ii = rg + (b0 + b) * RG;
             const int i = i0 + ii;
             const bool act = (i < n) && (!diag_tile || j + 1 >= i);
-            if (act) v[b] = cov_ld<HINT>(P + (size_t)i * ld + j);
+            if (act) v[b] = cov_ld<HINT>(P + shard_lrow(sh, i) * ld + j);
         }
 #pragma unroll
         for (int b = 0; b < BATCH; b++) {
@@ -101,7 +116,7 @@ __global__ void __launch_bounds__(256, MINB) k_cov_update(double* __restrict__ P
                 if (j + 1 < n) o.y = o.y - s1;
                 if (j == i) o.x += diag_eps;
                 if (j + 1 == i) o.y += diag_eps;
-                cov_st<HINT>(P + (size_t)i * ld + j, o);
+                cov_st<HINT>(P + shard_lrow(sh, i) * ld + j, o);
             }
         }
     }

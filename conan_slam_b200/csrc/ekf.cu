@@ -1,102 +1,37 @@
-// ekf.cu — EKF-SLAM hot path for sm_100a: predict, heading update, Mahalanobis gating,
-// Kalman gain (sparse H), in-place symmetric covariance update over the upper triangle,
-// in-place augmentation, plus the cslam_ekf_* C ABI (include/cslam.h).
+// ekf.cu — EKF-SLAM hot path for sm_100a: predict, heading update, Kalman gain (sparse H),
+// in-place symmetric covariance update over the upper triangle, in-place augmentation, joint
+// (batch) update, plus the cslam_ekf_* C ABI (include/cslam.h).  Gating lives in gate.cu, the
+// streaming covariance kernel in cov_update.cuh, the FP64 tensor-core kernel in ekf_dmma.cu.
 //
 // Data layout in HBM:
 //   X      : 2 x n_cap doubles (ping-pong so gain/heading kernels never read what they write)
-//   P      : n_cap x ld doubles, row-major, ld = n_cap rounded up to 16 doubles (128 B rows);
+//   P      : rows x ld doubles, row-major, ld = n_cap+1 rounded up to 16 doubles (128 B rows);
 //            ONLY the upper triangle (j >= i) is authoritative — the update streams
 //            8*n*(n+1) bytes instead of 16*n^2.
-//   A (W1) : r x lda doubles, column-major over state rows (one contiguous n-vector per
-//            update rank), r <= 64 — the scaled gain panel of slam.h:257.
+//   A (W1) : r x lda doubles, one contiguous n-vector per update rank, r <= 64 (slam.h:257).
+// Multi-GPU (world > 1): P is row-sharded in block-cyclic 128-row tiles (common.cuh Shard); rows
+// 0..2 (R3) and X are replicated and updated redundantly with the same IEEE operations on every
+// rank; per update only the observed landmark's two columns are exchanged (one all-reduce of
+// 2*n doubles), then every rank forms the gain and streams its own rows.
 #include <limits>
 #include <new>
 #include <vector>
 
 #include "common.cuh"
 #include "cov_update.cuh"
+#include "ekf_handle.cuh"
 
 namespace cslam {
-
-// ------------------------------------------------------------------------------------
-// Handle
-// ------------------------------------------------------------------------------------
-constexpr int kMaxRank = 2 * CSLAM_MAX_BATCH_OBS;  // 64
-
-struct BatchSmall {  // device-resident scratch of the joint update (EKF.cpp:93-129)
-    double hu[CSLAM_MAX_BATCH_OBS][2][3];
-    double lu[CSLAM_MAX_BATCH_OBS][2][2];
-    double V[kMaxRank];
-    double G[kMaxRank * kMaxRank];  // row-major r x r: L^-1 (literal) or L^-T (Q1 intended)
-    double u[kMaxRank];             // G * G^T * V
-    int f[CSLAM_MAX_BATCH_OBS];
-};
-
-struct GateScratch {
-    double* part_nd = nullptr;   // [blocks][m]
-    double* part_out = nullptr;  // [blocks][m]
-    int* part_j = nullptr;       // [blocks][m]
-    int* d_jbest = nullptr;      // [CSLAM_MAX_OBS]
-    double* d_nbest = nullptr;
-    double* d_outer = nullptr;
-    int max_blocks = 0;
-};
-
-}  // namespace cslam
-
-struct cslam_ekf {
-    int device = 0;
-    unsigned flags = 0;
-    int cap_landmarks = 0;
-    int n_cap = 0;
-    size_t ld = 0;   // leading dimension of P (doubles)
-    size_t lda = 0;  // leading dimension of A / PHT panels (doubles)
-    int n = 3;
-    int cur = 0;  // which X buffer is current
-    double* X[2] = {nullptr, nullptr};
-    double* P = nullptr;
-    double* A = nullptr;    // [kMaxRank][lda]
-    double* PHT = nullptr;  // [kMaxRank][lda]
-    cslam::BatchSmall* small = nullptr;
-    int* status = nullptr;        // device: #skipped updates
-    unsigned* ticket = nullptr;   // device: last-block tickets (predict, gate)
-    cslam::GateScratch gate;
-    void* pinned = nullptr;  // host staging
-    size_t pinned_bytes = 0;
-    cudaStream_t stream = nullptr;
-    bool own_stream = false;
-    // diagnostics: event pairs around covariance-update launches
-    bool prof = false;
-    std::vector<cudaEvent_t> prof_ev;
-    int prof_used = 0;
-    double prof_bytes = 0.0;
-};
-
-namespace cslam {
-
-struct ProfScope {  // records start/stop events around one covariance-update launch when profiling
-    cslam_ekf* h;
-    bool on;
-    explicit ProfScope(cslam_ekf* h_) : h(h_), on(h_->prof && h_->prof_used + 2 <= (int)h_->prof_ev.size()) {
-        if (on) cudaEventRecord(h->prof_ev[h->prof_used], h->stream);
-    }
-    ~ProfScope() {
-        if (on) {
-            cudaEventRecord(h->prof_ev[h->prof_used + 1], h->stream);
-            h->prof_used += 2;
-            h->prof_bytes += 8.0 * (double)h->n * ((double)h->n + 1.0);
-        }
-    }
-};
 
 // ------------------------------------------------------------------------------------
 // Kernels
 // ------------------------------------------------------------------------------------
 
-// EKF.cpp:406-455 predict.  Rows 0..2 of P for columns [3, 3+width) get Gv * (.) — with
-// Gv = [[1,0,a],[0,1,b],[0,0,1]] that is row0 += a*row2, row1 += b*row2.  The mirrored
-// columns (EKF.cpp:443) live in the lower triangle and are not stored.  The block that
-// draws the last ticket updates Pvv and the pose, after every block has read the old phi.
+// EKF.cpp:406-455 predict on rows 0..2 (`P` here = the row panel R3: P itself on one GPU, the
+// replicated panel when sharded).  Rows 0..1 for columns [3, 3+width) get Gv * (.) — with
+// Gv = [[1,0,a],[0,1,b],[0,0,1]] that is row0 += a*row2, row1 += b*row2.  The mirrored columns
+// (EKF.cpp:443) live in the lower triangle and are not stored.  The block that draws the last
+// ticket updates Pvv and the pose, after every block has read the old phi.
 __global__ void __launch_bounds__(256) k_predict(double* __restrict__ X, double* __restrict__ P, size_t ld, int n,
                                                  double v, double swa, double q00, double q01, double q10,
                                                  double q11, double wb, double dt, int width,
@@ -150,8 +85,8 @@ __global__ void __launch_bounds__(256) k_predict(double* __restrict__ X, double*
 }
 
 // EKF.cpp:328-352 + slam.h:700-725 with H = e_2^T.  Column 2 of P is (P[0][2], P[1][2],
-// row 2 from the diagonal on).  Writes Xout = Xin + W*v and the rank-1 panel a = p/sqrt(S):
-// for symmetric P the Joseph form C P C^T + W R W^T equals P - p p^T / S.
+// row 2 from the diagonal on) — all inside rows 0..2.  Writes Xout = Xin + W*v and the rank-1
+// panel a = p/sqrt(S): for symmetric P the Joseph form C P C^T + W R W^T equals P - p p^T / S.
 __global__ void __launch_bounds__(256) k_heading_gain(const double* __restrict__ Xin, double* __restrict__ Xout,
                                                       const double* __restrict__ P, size_t ld, int n,
                                                       double phi_meas, double R, double* __restrict__ A) {
@@ -166,16 +101,15 @@ __global__ void __launch_bounds__(256) k_heading_gain(const double* __restrict__
 }
 
 // Per-observation prologue of slam.h:235-266 using the sparse H (robot block + one landmark
-// block): only the 5x5 sub-block of P at columns {0,1,2,f,f+1} enters S.
+// block): only the 5x5 sub-block Pc of P at columns {0,1,2,f,f+1} enters S.
 struct GainSmall {
     double H[2][5];
     double G[2][2];
     double V[2];
     int ok;
 };
-__device__ void gain_prologue(const double* __restrict__ X, const double* __restrict__ P, size_t ld, int f,
-                              double zr, double zb, const double R[4], unsigned flags, GainSmall& g) {
-    const int cols[5] = {0, 1, 2, f, f + 1};
+__device__ void gain_prologue(const double* __restrict__ X, const double (&Pc)[5][5], int f, double zr, double zb,
+                              const double R[4], unsigned flags, GainSmall& g) {
     const ObsLin o = observe_lin(X[0], X[1], X[2], X[f], X[f + 1]);
     for (int a = 0; a < 2; a++) {
         for (int c = 0; c < 3; c++) g.H[a][c] = o.hu[a][c];
@@ -184,9 +118,6 @@ __device__ void gain_prologue(const double* __restrict__ X, const double* __rest
     }
     g.V[0] = zr - o.zr;
     g.V[1] = pi2pi(zb - o.zb);
-    double Pc[5][5];
-    for (int a = 0; a < 5; a++)
-        for (int b = a; b < 5; b++) Pc[a][b] = Pc[b][a] = P[(size_t)cols[a] * ld + cols[b]];
     double PHTc[5][2];
     for (int a = 0; a < 5; a++)
         for (int k = 0; k < 2; k++) {
@@ -224,27 +155,48 @@ __device__ void gain_prologue(const double* __restrict__ X, const double* __rest
 
 // slam.h:243,257-259 for one observation: PHT = P H^T (5 columns of P), W1 = PHT G,
 // W = W1 G^T, Xout = Xin + W V; the rank-2 panel A = W1 feeds k_cov_update.
+// SH = false: columns f, f+1 of P are read in place (row part coalesced, column part strided).
+// SH = true : they come from the all-reduced exchange buffer `colbuf`; rows 0..2 from `R3`.
+template <bool SH>
 __global__ void __launch_bounds__(256) k_gain_single(const double* __restrict__ Xin, double* __restrict__ Xout,
-                                                     const double* __restrict__ P, size_t ld, int n, double zr,
+                                                     const double* __restrict__ P, const double* __restrict__ R3,
+                                                     const double* __restrict__ colbuf, size_t ld, int n, double zr,
                                                      double zb, int idf, double r00, double r10, double r01,
                                                      double r11, unsigned flags, double* __restrict__ A, size_t lda,
                                                      int* __restrict__ status) {
     __shared__ GainSmall g;
     const int f = 3 + 2 * (idf - 1);
+    auto pcol = [&](int i, int k) -> double {  // P(i, f + k)
+        if constexpr (SH) {
+            return colbuf[(size_t)k * lda + i];
+        } else {
+            const int c = f + k;
+            return i <= c ? P[(size_t)i * ld + c] : P[(size_t)c * ld + i];
+        }
+    };
     if (threadIdx.x == 0) {
         const double R[4] = {r00, r10, r01, r11};
-        gain_prologue(Xin, P, ld, f, zr, zb, R, flags, g);
+        double Pc[5][5];
+        for (int a = 0; a < 3; a++) {
+            for (int b = a; b < 3; b++) Pc[a][b] = Pc[b][a] = R3[(size_t)a * ld + b];
+            Pc[a][3] = Pc[3][a] = R3[(size_t)a * ld + f];
+            Pc[a][4] = Pc[4][a] = R3[(size_t)a * ld + f + 1];
+        }
+        Pc[3][3] = pcol(f, 0);
+        Pc[3][4] = Pc[4][3] = pcol(f, 1);
+        Pc[4][4] = pcol(f + 1, 1);
+        gain_prologue(Xin, Pc, f, zr, zb, R, flags, g);
         if (!g.ok && blockIdx.x == 0) atomicAdd(status, 1);
     }
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    // P(i, c) for c in {0,1,2,f,f+1}: row i where i <= c (strided in i), row c otherwise (coalesced in i)
-    const double p0 = i <= 0 ? P[(size_t)i * ld + 0] : P[0 * ld + i];
-    const double p1 = i <= 1 ? P[(size_t)i * ld + 1] : P[1 * ld + i];
-    const double p2 = i <= 2 ? P[(size_t)i * ld + 2] : P[2 * ld + i];
-    const double p3 = i <= f ? P[(size_t)i * ld + f] : P[(size_t)f * ld + i];
-    const double p4 = i <= f + 1 ? P[(size_t)i * ld + f + 1] : P[(size_t)(f + 1) * ld + i];
+    // P(i, c) for c in {0,1,2}: rows 0..2 are symmetric-read from R3
+    const double p0 = i <= 0 ? R3[(size_t)i * ld + 0] : R3[0 * ld + i];
+    const double p1 = i <= 1 ? R3[(size_t)i * ld + 1] : R3[1 * ld + i];
+    const double p2 = i <= 2 ? R3[(size_t)i * ld + 2] : R3[2 * ld + i];
+    const double p3 = pcol(i, 0);
+    const double p4 = pcol(i, 1);
     double pht[2];
     for (int k = 0; k < 2; k++)
         pht[k] = (((p0 * g.H[k][0] + p1 * g.H[k][1]) + p2 * g.H[k][2]) + p3 * g.H[k][3]) + p4 * g.H[k][4];
@@ -257,20 +209,74 @@ __global__ void __launch_bounds__(256) k_gain_single(const double* __restrict__ 
     A[lda + i] = w1_1;
 }
 
-// General-rank variant (r <= 64, any r) for the joint update; FP64 FMA, panels in shared
-// memory.  The DMMA kernel in ekf_dmma.cu replaces it for large maps.
+// Sharded column exchange: every rank contributes the entries of columns cols[k] (k < ncols) of
+// the symmetric P that it stores — P[i][c] for owned rows i <= c, and P[c][i] (i > c) if it owns
+// row c — zeros elsewhere; an all-reduce(sum) then yields the complete columns on every rank
+// (x + 0 is exact, so the result is bit-identical to a single-GPU read).
+struct ColList {
+    int c[kMaxRank];
+    int n;
+};
+__global__ void __launch_bounds__(256) k_col_pack(const double* __restrict__ P, size_t ld, int n, ColList cl,
+                                                  double* __restrict__ colbuf, size_t lda, Shard sh) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;
+    if (i >= n) return;
+    const int c = cl.c[k];
+    double v = 0.0;
+    if (i <= c) {
+        if (shard_owns(sh, i)) v = P[shard_lrow(sh, i) * ld + c];
+    } else {
+        if (shard_owns(sh, c)) v = P[shard_lrow(sh, c) * ld + i];
+    }
+    colbuf[(size_t)k * lda + i] = v;
+}
+
+// Replicas of rows 0..2 (ranks != 0) apply the same rank-r update as k_cov_update applies to the
+// authoritative rows on rank 0 — same operations, same order, bit-identical result.
+__global__ void __launch_bounds__(256) k_rows012_update(double* __restrict__ R3, size_t ld, int n,
+                                                        const double* __restrict__ A, size_t lda, int r,
+                                                        double diag_eps) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j >= n || j < i) return;
+    double s = 0.0;
+    for (int k = 0; k < r; k++) s += A[(size_t)k * lda + i] * A[(size_t)k * lda + j];
+    double o = R3[(size_t)i * ld + j] - s;
+    if (j == i) o += diag_eps;
+    R3[(size_t)i * ld + j] = o;
+}
+
+// Replicated cache of the landmarks' 2x2 diagonal blocks for the sharded gate: pack owned entries,
+// zeros elsewhere, all-reduce.  D[0][j] = P_ff, D[1][j] = P_f,f+1, D[2][j] = P_f+1,f+1 (j 0-based).
+__global__ void __launch_bounds__(256) k_diag_pack(const double* __restrict__ P, size_t ld, int nf,
+                                                   double* __restrict__ D, int dcap, Shard sh) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nf) return;
+    const int f = 3 + 2 * j;
+    double a = 0.0, b = 0.0, c = 0.0;
+    if (shard_owns(sh, f)) {
+        a = P[shard_lrow(sh, f) * ld + f];
+        b = P[shard_lrow(sh, f) * ld + f + 1];
+    }
+    if (shard_owns(sh, f + 1)) c = P[shard_lrow(sh, f + 1) * ld + f + 1];
+    D[j] = a;
+    D[(size_t)dcap + j] = b;
+    D[2 * (size_t)dcap + j] = c;
+}
+
+// General-rank variant (r <= 64, any r) for the joint update on small maps; FP64 FMA, panels in
+// shared memory.  The DMMA kernel in ekf_dmma.cu replaces it for large maps.
 template <int T>
 __global__ void __launch_bounds__(256) k_cov_update_rank(double* __restrict__ P, size_t ld, int n,
-                                                         const double* __restrict__ A, size_t lda, int r, int nt) {
+                                                         const double* __restrict__ A, size_t lda, int r, int nt,
+                                                         Shard sh) {
     constexpr int CP = T / 2, RG = 256 / CP, RPT = T / RG;
     extern __shared__ double smem[];
     double* sAr = smem;          // [r][T]
     double* sAc = smem + r * T;  // [r][T]
-    const long long t = blockIdx.x;
-    int tr = (int)floor(((2.0 * nt + 1.0) - sqrt((2.0 * nt + 1.0) * (2.0 * nt + 1.0) - 8.0 * (double)t)) * 0.5);
-    while ((long long)tr * nt - (long long)tr * (tr - 1) / 2 > t) tr--;
-    while ((long long)(tr + 1) * nt - (long long)(tr + 1) * tr / 2 <= t) tr++;
-    const int tc = tr + (int)(t - ((long long)tr * nt - (long long)tr * (tr - 1) / 2));
+    int tr, tc;
+    shard_tile(blockIdx.x, nt, sh, tr, tc);
     const int i0 = tr * T, j0 = tc * T;
     for (int idx = threadIdx.x; idx < r * T; idx += 256) {
         const int k = idx / T, ii = idx % T;
@@ -297,10 +303,11 @@ __global__ void __launch_bounds__(256) k_cov_update_rank(double* __restrict__ P,
     for (int b = 0; b < RPT; b++) {
         const int i = i0 + rg + b * RG;
         if (i < n && j + 1 >= i) {
-            double2 o = ld128(P + (size_t)i * ld + j);
+            double* p = P + shard_lrow(sh, i) * ld + j;
+            double2 o = ld128(p);
             if (j >= i) o.x -= s0[b];
             if (j + 1 < n) o.y -= s1[b];
-            st128(P + (size_t)i * ld + j, o);
+            st128(p, o);
         }
     }
 }
@@ -308,24 +315,32 @@ __global__ void __launch_bounds__(256) k_cov_update_rank(double* __restrict__ P,
 // EKF.cpp:28-91 addOneNewFeature without the copy/resize: the two new columns (rows
 // 0..len-1) and the new 2x2 diagonal block are written inside the pre-allocated P.
 //   P[i][len+k] = (Gv * P[0:3, i])_k ;  P[len:len+2, len:len+2] = Gv Pvv Gv^T + Gz R Gz^T
-__global__ void __launch_bounds__(256) k_augment(double* __restrict__ X, double* __restrict__ P, size_t ld,
-                                                 int len, double r, double b, double r00, double r10, double r01,
-                                                 double r11) {
+// Sharded: every rank writes the rows it owns; rows 0..2 also go to the replicated panel R3.
+__global__ void __launch_bounds__(256) k_augment(double* __restrict__ X, double* __restrict__ P,
+                                                 double* __restrict__ R3, size_t ld, int len, double r, double b,
+                                                 double r00, double r10, double r01, double r11, Shard sh) {
     const double phi = X[2];
     const double s = sin(phi + b), c = cos(phi + b);
     const double g02 = -r * s, g12 = r * c;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < len) {
-        const double p0 = psym(P, ld, 0, i), p1 = psym(P, ld, 1, i), p2 = psym(P, ld, 2, i);
-        P[(size_t)i * ld + len] = p0 + g02 * p2;
-        P[(size_t)i * ld + len + 1] = p1 + g12 * p2;
+        const double p0 = psym(R3, ld, 0, i), p1 = psym(R3, ld, 1, i), p2 = psym(R3, ld, 2, i);
+        const double v0 = p0 + g02 * p2, v1 = p1 + g12 * p2;
+        if (shard_owns(sh, i)) {
+            P[shard_lrow(sh, i) * ld + len] = v0;
+            P[shard_lrow(sh, i) * ld + len + 1] = v1;
+        }
+        if (i < 3 && R3 != P) {
+            R3[(size_t)i * ld + len] = v0;
+            R3[(size_t)i * ld + len + 1] = v1;
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        X[len] = X[0] + r * c;
+        X[len] = X[0] + r * c;  // only X[2], X[0], X[1] are read by other threads: no hazard
         X[len + 1] = X[1] + r * s;
         double Pv[3][3];
         for (int a = 0; a < 3; a++)
-            for (int d = 0; d < 3; d++) Pv[a][d] = psym(P, ld, a, d);
+            for (int d = 0; d < 3; d++) Pv[a][d] = psym(R3, ld, a, d);
         const double Gv[2][3] = {{1, 0, g02}, {0, 1, g12}};
         const double Gz[2][2] = {{c, -r * s}, {s, r * c}};
         const double R[2][2] = {{r00, r01}, {r10, r11}};
@@ -347,11 +362,10 @@ __global__ void __launch_bounds__(256) k_augment(double* __restrict__ X, double*
                 double x = 0, y = 0;
                 for (int k = 0; k < 3; k++) x += GP[a][k] * Gv[d][k];
                 for (int k = 0; k < 2; k++) y += GR[a][k] * Gz[d][k];
-                P[(size_t)(len + a) * ld + len + d] = x + y;
+                if (shard_owns(sh, len + a)) P[shard_lrow(sh, len + a) * ld + len + d] = x + y;
             }
     }
 }
-
 // ---------------------------------------------------------------- joint (batch) update ----
 
 struct ObsPack {  // kernel-parameter transport of one scan (no H2D copy)
@@ -378,15 +392,27 @@ __global__ void k_batch_prep(const double* __restrict__ X, ObsPack ob, BatchSmal
 }
 
 // slam.h:243 PHT = P H^T with the stacked sparse H: 3 + 2m columns of P per state row.
-__global__ void __launch_bounds__(128) k_batch_pht(const double* __restrict__ P, size_t ld, int n, int m,
+// SH: the landmark columns come from the all-reduced exchange buffer (2k, 2k+1), rows 0..2 from R3.
+template <bool SH>
+__global__ void __launch_bounds__(128) k_batch_pht(const double* __restrict__ P, const double* __restrict__ R3,
+                                                   const double* __restrict__ colbuf, size_t ld, int n, int m,
                                                    const BatchSmall* __restrict__ sm, double* __restrict__ PHT,
                                                    size_t lda) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int k = blockIdx.y;
     if (i >= n) return;
     const int f = sm->f[k];
-    const double p0 = psym(P, ld, i, 0), p1 = psym(P, ld, i, 1), p2 = psym(P, ld, i, 2);
-    const double p3 = psym(P, ld, i, f), p4 = psym(P, ld, i, f + 1);
+    const double p0 = psym(R3, ld, i < 3 ? i : 0, i < 3 ? 0 : i);
+    const double p1 = i < 3 ? psym(R3, ld, i, 1) : R3[ld + i];
+    const double p2 = i < 3 ? psym(R3, ld, i, 2) : R3[2 * ld + i];
+    double p3, p4;
+    if constexpr (SH) {
+        p3 = colbuf[(size_t)(2 * k) * lda + i];
+        p4 = colbuf[(size_t)(2 * k + 1) * lda + i];
+    } else {
+        p3 = psym(P, ld, i, f);
+        p4 = psym(P, ld, i, f + 1);
+    }
     for (int a = 0; a < 2; a++)
         PHT[(size_t)(2 * k + a) * lda + i] =
             (((p0 * sm->hu[k][a][0] + p1 * sm->hu[k][a][1]) + p2 * sm->hu[k][a][2]) + p3 * sm->lu[k][a][0]) +
@@ -521,67 +547,116 @@ __global__ void __launch_bounds__(128) k_batch_w1(const double* __restrict__ PHT
 }
 
 // gating kernel lives in gate.cu (separate TU, compiled with -fmad=false)
-int launch_gate(const double* X, const double* P, size_t ld, int nf, const double* Z, int m, const double R[4],
-                double gate1, double gate2, double* part_nd, double* part_out, int* part_j, unsigned* ticket,
-                int* jbest, double* nbest, double* outer, cudaStream_t stream);
+int launch_gate(const double* X, const double* P, const double* R3, const double* D, int dcap, size_t ld, int nf,
+                const double* Z, int m, const double R[4], double gate1, double gate2, double* part_nd,
+                double* part_out, int* part_j, unsigned* ticket, int* jbest, double* nbest, double* outer,
+                cudaStream_t stream);
 
 // ------------------------------------------------------------------------ accessors ----
+// sharded: every rank fills the entries it stores (zeros elsewhere) and the block is all-reduced
 __global__ void k_gather_block(const double* __restrict__ P, size_t ld, int r0, int c0, int nr, int nc,
-                               double* __restrict__ out) {
+                               double* __restrict__ out, Shard sh) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (size_t)nr * nc) return;
     const int i = r0 + (int)(idx / nc), j = c0 + (int)(idx % nc);
-    out[idx] = psym(P, ld, i, j);
+    const int lo = i <= j ? i : j, hi = i <= j ? j : i;
+    out[idx] = shard_owns(sh, lo) ? P[shard_lrow(sh, lo) * ld + hi] : 0.0;
 }
-__global__ void k_scatter_upper(double* __restrict__ P, size_t ld, int n, const double* __restrict__ in) {
+__global__ void k_scatter_upper(double* __restrict__ P, double* __restrict__ R3, size_t ld, int n,
+                                const double* __restrict__ in, Shard sh) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (size_t)n * n) return;
     const int i = (int)(idx / n), j = (int)(idx % n);
-    if (j >= i) P[(size_t)i * ld + j] = in[idx];
+    if (j < i) return;
+    if (shard_owns(sh, i)) P[shard_lrow(sh, i) * ld + j] = in[idx];
+    if (i < 3 && R3 != P) R3[(size_t)i * ld + j] = in[idx];
 }
 
 // defined in ekf_dmma.cu: tensor-core (FP64 DMMA) rank-r update for large maps
-int launch_cov_update_dmma(double* P, size_t ld, int n, const double* A, size_t lda, int r, cudaStream_t stream);
+int launch_cov_update_dmma(double* P, size_t ld, int n, const double* A, size_t lda, int r, Shard sh,
+                           cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------
 // Host-side launch helpers
 // ------------------------------------------------------------------------------------
-static inline long long tri_tiles(int nt) { return (long long)nt * (nt + 1) / 2; }
+static int allreduce_sum(cslam_ekf* h, double* buf, size_t count) {
+    const NcclApi* api = nccl_api();
+    if (!api) return CSLAM_ERR_NCCL;
+    CSLAM_NCCL(api->AllReduce(buf, buf, count, ncclDouble, ncclSum, h->comm, h->stream));
+    return CSLAM_OK;
+}
 
-template <int R>
-static int launch_cov_update(cslam_ekf* h, double diag_eps) {
-    const int n = h->n;
-    ProfScope prof(h);
-    // tile / batch / occupancy / cache-policy chosen from tools/cov_variants.cu on a B200:
-    // T=128, 4 x 16 B loads in flight per thread, 4 CTAs/SM, streaming (.cs) accesses -> 6.47 TB/s
-    if (n >= 2048) {
-        const int nt = (n + 127) / 128;
-        count_launch();
-        k_cov_update<R, 128, 4, 4, 1><<<(unsigned)tri_tiles(nt), 256, 0, h->stream>>>(h->P, h->ld, n, h->A, h->lda, nt,
-                                                                              diag_eps);
-    } else {
-        const int nt = (n + 63) / 64;
-        count_launch();
-        k_cov_update<R, 64, 8, 4, 0><<<(unsigned)tri_tiles(nt), 256, 0, h->stream>>>(h->P, h->ld, n, h->A, h->lda, nt,
-                                                                             diag_eps);
-    }
+// rows 0..2 on the replicas follow the authoritative update (same operations, same order)
+static int replicas_follow(cslam_ekf* h, int r, double diag_eps) {
+    if (h->sh.world == 1 || h->R3 == h->P) return CSLAM_OK;
+    count_launch();
+    k_rows012_update<<<dim3((h->n + 255) / 256, 3), 256, 0, h->stream>>>(h->R3, h->ld, h->n, h->A, h->lda, r,
+                                                                        diag_eps);
     CSLAM_CUDA(cudaGetLastError());
     return CSLAM_OK;
 }
 
+template <int R>
+static int launch_cov_update(cslam_ekf* h, double diag_eps) {
+    const int n = h->n;
+    {
+        ProfScope prof(h);
+        // tile / batch / occupancy / cache-policy chosen from tools/cov_variants.cu on a B200:
+        // T=128, 4 x 16 B loads in flight per thread, 4 CTAs/SM, streaming (.cs) accesses -> 6.47 TB/s
+        if (n >= 2048 || h->sh.world > 1) {
+            const int nt = (n + 127) / 128;
+            const long long tiles = shard_tile_count(nt, h->sh);
+            if (tiles > 0) {
+                count_launch();
+                k_cov_update<R, 128, 4, 4, 1><<<(unsigned)tiles, 256, 0, h->stream>>>(h->P, h->ld, n, h->A, h->lda, nt,
+                                                                                      diag_eps, h->sh);
+            }
+        } else {
+            const int nt = (n + 63) / 64;
+            count_launch();
+            k_cov_update<R, 64, 8, 4, 0><<<(unsigned)shard_tile_count(nt, h->sh), 256, 0, h->stream>>>(
+                h->P, h->ld, n, h->A, h->lda, nt, diag_eps, h->sh);
+        }
+        CSLAM_CUDA(cudaGetLastError());
+    }
+    h->diag_dirty = true;
+    return replicas_follow(h, R, diag_eps);
+}
+
 static int launch_cov_update_rank(cslam_ekf* h, int r) {
     const int n = h->n;
+    h->diag_dirty = true;
+    // large maps (and every sharded map): FP64 tensor-core kernel; small maps: plain FMA kernel
+    if (n >= 1024 || h->sh.world > 1) {
+        {
+            ProfScope prof(h);
+            if (int rc = launch_cov_update_dmma(h->P, h->ld, n, h->A, h->lda, r, h->sh, h->stream)) return rc;
+        }
+        if (h->sh.world > 1) {  // tensor-core rounding differs from the replicas' FMA order: re-broadcast rows 0..2
+            const NcclApi* api = nccl_api();
+            if (!api) return CSLAM_ERR_NCCL;
+            CSLAM_NCCL(api->Broadcast(h->R3, h->R3, 3 * h->ld, ncclDouble, 0, h->comm, h->stream));
+        }
+        return CSLAM_OK;
+    }
     ProfScope prof(h);
-    // large maps: FP64 tensor-core kernel; small maps: plain FMA kernel
-    if (n >= 1024) return launch_cov_update_dmma(h->P, h->ld, n, h->A, h->lda, r, h->stream);
     const int nt = (n + 63) / 64;
     const size_t smem = (size_t)2 * r * 64 * sizeof(double);
     CSLAM_CUDA(cudaFuncSetAttribute(k_cov_update_rank<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     2 * kMaxRank * 64 * (int)sizeof(double)));
     count_launch();
-    k_cov_update_rank<64><<<(unsigned)tri_tiles(nt), 256, smem, h->stream>>>(h->P, h->ld, n, h->A, h->lda, r, nt);
+    k_cov_update_rank<64><<<(unsigned)shard_tile_count(nt, h->sh), 256, smem, h->stream>>>(h->P, h->ld, n, h->A,
+                                                                                          h->lda, r, nt, h->sh);
     CSLAM_CUDA(cudaGetLastError());
     return CSLAM_OK;
+}
+
+// exchange the listed columns of P (sharded only)
+static int exchange_columns(cslam_ekf* h, const ColList& cl) {
+    count_launch();
+    k_col_pack<<<dim3((h->n + 255) / 256, cl.n), 256, 0, h->stream>>>(h->P, h->ld, h->n, cl, h->colbuf, h->lda, h->sh);
+    CSLAM_CUDA(cudaGetLastError());
+    return allreduce_sum(h, h->colbuf, (size_t)cl.n * h->lda);
 }
 
 static int check_handle(const cslam_ekf* h) {
@@ -590,19 +665,13 @@ static int check_handle(const cslam_ekf* h) {
     return CSLAM_OK;
 }
 
-}  // namespace cslam
-
-using namespace cslam;
-
-// ------------------------------------------------------------------------------------
-// C ABI
-// ------------------------------------------------------------------------------------
-extern "C" {
-
-int cslam_ekf_create(cslam_ekf_t** out, int capacity_landmarks, int device, unsigned flags) {
+static int create_common(cslam_ekf_t** out, int capacity_landmarks, int device, unsigned flags, int rank, int world,
+                         const void* nccl_id) {
     CSLAM_REQUIRE(out != nullptr, CSLAM_ERR_BAD_ARG, "out is null");
     CSLAM_REQUIRE(capacity_landmarks >= 0 && capacity_landmarks <= 500000, CSLAM_ERR_BAD_ARG,
                   "capacity_landmarks out of range");
+    CSLAM_REQUIRE(world >= 1 && rank >= 0 && rank < world, CSLAM_ERR_BAD_ARG, "bad rank/world");
+    CSLAM_REQUIRE(world == 1 || nccl_id != nullptr, CSLAM_ERR_BAD_ARG, "sharded handle needs an NCCL unique id");
     *out = nullptr;
     int count = 0;
     CSLAM_CUDA(cudaGetDeviceCount(&count));
@@ -617,11 +686,19 @@ int cslam_ekf_create(cslam_ekf_t** out, int capacity_landmarks, int device, unsi
     h->ld = ((size_t)h->n_cap + 1 + 15) / 16 * 16;  // >= n_cap + 1 so the last column pair stays in-row
     h->lda = h->ld;
     h->n = 3;
+    h->sh = Shard{rank, world};
+    // rows stored here: every owned 128-row tile of the capacity (all rows when world == 1)
+    {
+        const int ntr = (h->n_cap + kShardRows - 1) / kShardRows;
+        int owned = 0;
+        for (int tr = rank; tr < ntr; tr += world) owned++;
+        h->local_rows_cap = world == 1 ? h->n_cap : std::max(owned, 1) * kShardRows;
+    }
     auto fail = [&](int code) {
         cslam_ekf_destroy(h);
         return code;
     };
-    const size_t pbytes = (size_t)h->n_cap * h->ld * sizeof(double);
+    const size_t pbytes = (size_t)h->local_rows_cap * h->ld * sizeof(double);
 #define TRY(call)                                                                            \
     do {                                                                                     \
         cudaError_t e__ = (call);                                                            \
@@ -656,16 +733,59 @@ int cslam_ekf_create(cslam_ekf_t** out, int capacity_landmarks, int device, unsi
     TRY(cudaMemsetAsync(h->PHT, 0, (size_t)kMaxRank * h->lda * sizeof(double), h->stream));
     TRY(cudaMemsetAsync(h->status, 0, sizeof(int), h->stream));
     TRY(cudaMemsetAsync(h->ticket, 0, 4 * sizeof(unsigned), h->stream));
+    h->R3 = h->P;  // one GPU, or rank 0 of a sharded handle: rows 0..2 are the first rows of P
+    if (world > 1) {
+        if (rank != 0) {
+            TRY(cudaMalloc(&h->R3, 3 * h->ld * sizeof(double)));
+            TRY(cudaMemsetAsync(h->R3, 0, 3 * h->ld * sizeof(double), h->stream));
+        }
+        TRY(cudaMalloc(&h->colbuf, (size_t)kMaxRank * h->lda * sizeof(double)));
+        h->dcap = std::max(capacity_landmarks, 1);
+        TRY(cudaMalloc(&h->D, 3 * (size_t)h->dcap * sizeof(double)));
+        const NcclApi* api = nccl_api();
+        if (!api) return fail(CSLAM_ERR_NCCL);
+        ncclUniqueId id;
+        memcpy(&id, nccl_id, sizeof(id));
+        ncclResult_t r = api->CommInitRank(&h->comm, world, id, rank);
+        if (r != ncclSuccess) {
+            set_last_error("ncclCommInitRank -> %s", api->GetErrorString(r));
+            return fail(CSLAM_ERR_NCCL);
+        }
+    }
     TRY(cudaStreamSynchronize(h->stream));
 #undef TRY
     *out = h;
     return CSLAM_OK;
 }
 
+}  // namespace cslam
+
+using namespace cslam;
+
+// ------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------
+extern "C" {
+
+int cslam_ekf_create(cslam_ekf_t** out, int capacity_landmarks, int device, unsigned flags) {
+    return create_common(out, capacity_landmarks, device, flags, 0, 1, nullptr);
+}
+
+int cslam_ekf_create_sharded(cslam_ekf_t** out, int capacity_landmarks, int device, unsigned flags, int rank,
+                             int world, const void* nccl_unique_id) {
+    return create_common(out, capacity_landmarks, device, flags, rank, world, nccl_unique_id);
+}
+
 int cslam_ekf_destroy(cslam_ekf_t* h) {
     if (!h) return CSLAM_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->comm) {
+        const NcclApi* api = nccl_api();
+        if (api) api->CommDestroy(h->comm);
+    }
+    if (h->R3 && h->R3 != h->P) cudaFree(h->R3);
+    cudaFree(h->colbuf); cudaFree(h->D);
     cudaFree(h->X[0]); cudaFree(h->X[1]); cudaFree(h->P); cudaFree(h->A); cudaFree(h->PHT);
     cudaFree(h->small); cudaFree(h->status); cudaFree(h->ticket);
     cudaFree(h->gate.part_nd); cudaFree(h->gate.part_out); cudaFree(h->gate.part_j);
@@ -709,8 +829,9 @@ int cslam_ekf_predict(cslam_ekf_t* h, double v, double swa, const double Q[4], d
     int width = 0;
     if (n > 3) width = (h->flags & CSLAM_FLAG_Q2_FULL_WIDTH) ? n - 3 : n - 4;  // Q2, EKF.cpp:442
     const int blocks = std::max(1, (width + 255) / 256);
+    // rows 0..2 only: on a sharded handle every rank predicts its replica (rank 0: the rows themselves)
     count_launch();
-    k_predict<<<blocks, 256, 0, h->stream>>>(h->X[h->cur], h->P, h->ld, n, v, swa, Q[0], Q[2], Q[1], Q[3], wb, dt,
+    k_predict<<<blocks, 256, 0, h->stream>>>(h->X[h->cur], h->R3, h->ld, n, v, swa, Q[0], Q[2], Q[1], Q[3], wb, dt,
                                              width, h->ticket);
     CSLAM_CUDA(cudaGetLastError());
     return CSLAM_OK;
@@ -722,7 +843,7 @@ int cslam_ekf_observe_heading(cslam_ekf_t* h, double phi, int use_heading) {
     const int n = h->n;
     const double sigma = 0.01F * kPi / 180.0F;  // EKF.cpp:337
     count_launch();
-    k_heading_gain<<<(n + 255) / 256, 256, 0, h->stream>>>(h->X[h->cur], h->X[h->cur ^ 1], h->P, h->ld, n, phi,
+    k_heading_gain<<<(n + 255) / 256, 256, 0, h->stream>>>(h->X[h->cur], h->X[h->cur ^ 1], h->R3, h->ld, n, phi,
                                                            sigma * sigma, h->A);
     CSLAM_CUDA(cudaGetLastError());
     h->cur ^= 1;
@@ -735,11 +856,23 @@ int cslam_ekf_gate(cslam_ekf_t* h, const double* Z, int m, const double R[4], do
     CSLAM_REQUIRE(m >= 0, CSLAM_ERR_BAD_ARG, "m < 0");
     CSLAM_REQUIRE(m == 0 || (Z && R && jbest), CSLAM_ERR_BAD_ARG, "null argument");
     const int nf = (h->n - 3) / 2;
+    if (h->sh.world > 1 && h->diag_dirty && m > 0) {
+        // refresh the replicated diagonal-block cache once per scan: pack owned entries + all-reduce
+        CSLAM_CUDA(cudaMemsetAsync(h->D, 0, 3 * (size_t)h->dcap * sizeof(double), h->stream));
+        if (nf > 0) {
+            count_launch();
+            k_diag_pack<<<(nf + 255) / 256, 256, 0, h->stream>>>(h->P, h->ld, nf, h->D, h->dcap, h->sh);
+            CSLAM_CUDA(cudaGetLastError());
+        }
+        if (int rc = allreduce_sum(h, h->D, 3 * (size_t)h->dcap)) return rc;
+        h->diag_dirty = false;
+    }
     for (int base = 0; base < m; base += CSLAM_MAX_OBS) {
         const int mc = std::min(CSLAM_MAX_OBS, m - base);
-        if (int rc = launch_gate(h->X[h->cur], h->P, h->ld, nf, Z + 2 * base, mc, R, gate1, gate2, h->gate.part_nd,
-                                 h->gate.part_out, h->gate.part_j, h->ticket + 1, h->gate.d_jbest, h->gate.d_nbest,
-                                 h->gate.d_outer, h->stream))
+        if (int rc = launch_gate(h->X[h->cur], h->P, h->R3, h->sh.world > 1 ? h->D : nullptr, h->dcap, h->ld, nf,
+                                 Z + 2 * base, mc, R, gate1, gate2, h->gate.part_nd, h->gate.part_out,
+                                 h->gate.part_j, h->ticket + 1, h->gate.d_jbest, h->gate.d_nbest, h->gate.d_outer,
+                                 h->stream))
             return rc;
         char* pin = static_cast<char*>(h->pinned);
         int* pj = reinterpret_cast<int*>(pin);
@@ -765,14 +898,27 @@ int cslam_ekf_update(cslam_ekf_t* h, const double* Z, const int32_t* idf, int m,
     if (m == 0) return CSLAM_OK;  // test/main.cpp:188 calls update with an empty ZF
     CSLAM_REQUIRE(Z && idf && R, CSLAM_ERR_BAD_ARG, "null argument");
     const int n = h->n, nf = (n - 3) / 2;
+    const bool sharded = h->sh.world > 1;
     for (int i = 0; i < m; i++)
         CSLAM_REQUIRE(idf[i] >= 1 && idf[i] <= nf, CSLAM_ERR_BAD_ARG, "idf out of range (1-based map slots)");
     if (!batch) {
         for (int i = 0; i < m; i++) {
-            count_launch();
-            k_gain_single<<<(n + 255) / 256, 256, 0, h->stream>>>(h->X[h->cur], h->X[h->cur ^ 1], h->P, h->ld, n,
-                                                                  Z[2 * i], Z[2 * i + 1], idf[i], R[0], R[1], R[2],
-                                                                  R[3], h->flags, h->A, h->lda, h->status);
+            if (sharded) {
+                ColList cl;
+                cl.n = 2;
+                cl.c[0] = 3 + 2 * (idf[i] - 1);
+                cl.c[1] = cl.c[0] + 1;
+                if (int rc = exchange_columns(h, cl)) return rc;
+                count_launch();
+                k_gain_single<true><<<(n + 255) / 256, 256, 0, h->stream>>>(
+                    h->X[h->cur], h->X[h->cur ^ 1], h->P, h->R3, h->colbuf, h->ld, n, Z[2 * i], Z[2 * i + 1], idf[i],
+                    R[0], R[1], R[2], R[3], h->flags, h->A, h->lda, h->status);
+            } else {
+                count_launch();
+                k_gain_single<false><<<(n + 255) / 256, 256, 0, h->stream>>>(
+                    h->X[h->cur], h->X[h->cur ^ 1], h->P, h->R3, nullptr, h->ld, n, Z[2 * i], Z[2 * i + 1], idf[i],
+                    R[0], R[1], R[2], R[3], h->flags, h->A, h->lda, h->status);
+            }
             CSLAM_CUDA(cudaGetLastError());
             h->cur ^= 1;
             if (int rc = launch_cov_update<2>(h, 0.0)) return rc;
@@ -789,13 +935,27 @@ int cslam_ekf_update(cslam_ekf_t* h, const double* Z, const int32_t* idf, int m,
     const int r = 2 * m;
     count_launch();
     k_batch_prep<<<1, CSLAM_MAX_BATCH_OBS, 0, h->stream>>>(h->X[h->cur], ob, h->small);
-    count_launch();
-    k_batch_pht<<<dim3((n + 127) / 128, m), 128, 0, h->stream>>>(h->P, h->ld, n, m, h->small, h->PHT, h->lda);
+    if (sharded) {
+        ColList cl;
+        cl.n = r;
+        for (int k = 0; k < m; k++) {
+            cl.c[2 * k] = 3 + 2 * (idf[k] - 1);
+            cl.c[2 * k + 1] = cl.c[2 * k] + 1;
+        }
+        if (int rc = exchange_columns(h, cl)) return rc;
+        count_launch();
+        k_batch_pht<true><<<dim3((n + 127) / 128, m), 128, 0, h->stream>>>(h->P, h->R3, h->colbuf, h->ld, n, m,
+                                                                            h->small, h->PHT, h->lda);
+    } else {
+        count_launch();
+        k_batch_pht<false><<<dim3((n + 127) / 128, m), 128, 0, h->stream>>>(h->P, h->R3, nullptr, h->ld, n, m,
+                                                                             h->small, h->PHT, h->lda);
+    }
     const int chol_smem = 2 * kMaxRank * (kMaxRank + 1) * (int)sizeof(double);
     CSLAM_CUDA(cudaFuncSetAttribute(k_batch_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, chol_smem));
     count_launch();
     k_batch_chol<<<1, 256, chol_smem, h->stream>>>(h->PHT, h->lda, m, R[0], R[1], R[2], R[3], h->flags, h->small,
-                                           h->status);
+                                                   h->status);
     count_launch();
     k_batch_w1<<<dim3((n + 127) / 128, (r + 7) / 8), 128, 0, h->stream>>>(h->PHT, h->lda, n, r, h->small,
                                                                            h->X[h->cur], h->X[h->cur ^ 1], h->A);
@@ -813,11 +973,12 @@ int cslam_ekf_augment(cslam_ekf_t* h, const double* Z, int m, const double R[4])
     for (int i = 0; i < m; i++) {
         const int len = h->n;
         count_launch();
-        k_augment<<<(len + 255) / 256, 256, 0, h->stream>>>(h->X[h->cur], h->P, h->ld, len, Z[2 * i], Z[2 * i + 1],
-                                                            R[0], R[1], R[2], R[3]);
+        k_augment<<<(len + 255) / 256, 256, 0, h->stream>>>(h->X[h->cur], h->P, h->R3, h->ld, len, Z[2 * i],
+                                                            Z[2 * i + 1], R[0], R[1], R[2], R[3], h->sh);
         CSLAM_CUDA(cudaGetLastError());
         h->n += 2;
     }
+    h->diag_dirty = true;
     return CSLAM_OK;
 }
 
@@ -839,11 +1000,15 @@ int cslam_ekf_get_cov_block(cslam_ekf_t* h, int r0, int c0, int nr, int nc, doub
     const size_t cnt = (size_t)nr * nc;
     CSLAM_CUDA(cudaMalloc(&tmp, cnt * sizeof(double)));
     count_launch();
-    k_gather_block<<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(h->P, h->ld, r0, c0, nr, nc, tmp);
+    k_gather_block<<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(h->P, h->ld, r0, c0, nr, nc, tmp, h->sh);
     cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaMemcpyAsync(out, tmp, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    int rc = CSLAM_OK;
+    if (e == cudaSuccess && h->sh.world > 1) rc = allreduce_sum(h, tmp, cnt);  // collective: all ranks call
+    if (e == cudaSuccess && rc == CSLAM_OK)
+        e = cudaMemcpyAsync(out, tmp, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     cudaFree(tmp);
+    if (rc) return rc;
     CSLAM_CUDA(e);
     return CSLAM_OK;
 }
@@ -857,7 +1022,9 @@ int cslam_ekf_reset(cslam_ekf_t* h, const double* X, int n, const double* P) {
     CSLAM_CUDA(cudaMemcpyAsync(h->X[0], X, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     h->cur = 0;
     h->n = n;
-    CSLAM_CUDA(cudaMemsetAsync(h->P, 0, (size_t)h->n_cap * h->ld * sizeof(double), h->stream));
+    h->diag_dirty = true;
+    CSLAM_CUDA(cudaMemsetAsync(h->P, 0, (size_t)h->local_rows_cap * h->ld * sizeof(double), h->stream));
+    if (h->R3 != h->P) CSLAM_CUDA(cudaMemsetAsync(h->R3, 0, 3 * h->ld * sizeof(double), h->stream));
     CSLAM_CUDA(cudaMemsetAsync(h->status, 0, sizeof(int), h->stream));
     CSLAM_CUDA(cudaStreamSynchronize(h->stream));
     if (P) {
@@ -867,7 +1034,7 @@ int cslam_ekf_reset(cslam_ekf_t* h, const double* X, int n, const double* P) {
         cudaError_t e = cudaMemcpyAsync(tmp, P, cnt * sizeof(double), cudaMemcpyHostToDevice, h->stream);
         if (e == cudaSuccess) {
             count_launch();
-            k_scatter_upper<<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(h->P, h->ld, n, tmp);
+            k_scatter_upper<<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(h->P, h->R3, h->ld, n, tmp, h->sh);
             e = cudaGetLastError();
         }
         if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);

@@ -13,6 +13,7 @@
 // once and written once.  Panels are staged in shared memory with a row stride = 4 (mod 16)
 // doubles, which makes the fragment reads bank-conflict free.
 #include "common.cuh"
+#include "cov_update.cuh"
 
 namespace cslam {
 
@@ -28,20 +29,20 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 
 __global__ void __launch_bounds__(256, 2) k_cov_update_dmma(double* __restrict__ P, size_t ld, int n,
                                                             const double* __restrict__ A, size_t lda, int r,
-                                                            int rp, int nbc) {
+                                                            int rp, int nbc, Shard sh) {
     extern __shared__ double smem[];
     double* sR = smem;               // [rp][DM_SR]  negated row panel
     double* sC = smem + rp * DM_SR;  // [rp][DM_SC]  column panel
 
-    // linear tile id -> (br, bc): tile rows come in pairs (2q, 2q+1) that both start at bc = q
+    // linear tile id -> (br, bc): every owned 128-row shard tile `tr` holds two 64-row tile rows
+    // (2tr, 2tr+1) that both start at column tile bc = tr  (nbc - tr tiles each)
     const long long t = blockIdx.x;
-    const double bq = 2.0 * nbc + 1.0;
-    int q = (int)floor((bq - sqrt(bq * bq - 4.0 * (double)t)) * 0.5);
-    while (2LL * q * nbc - (long long)q * (q - 1) > t) q--;
-    while (2LL * (q + 1) * nbc - (long long)(q + 1) * q <= t) q++;
-    const int rem = (int)(t - (2LL * q * nbc - (long long)q * (q - 1)));
-    const int br = rem < (nbc - q) ? 2 * q : 2 * q + 1;
-    const int bc = rem < (nbc - q) ? q + rem : q + rem - (nbc - q);
+    int tr, tcd;
+    shard_tile(t >> 1, nbc, sh, tr, tcd);
+    const long long first = 2 * shard_first_tile((tr - sh.rank) / sh.world, nbc, sh);
+    const int rem = (int)(t - first), cnt = nbc - tr;
+    const int br = rem < cnt ? 2 * tr : 2 * tr + 1;
+    const int bc = rem < cnt ? tr + rem : tr + rem - cnt;
     const int i0 = br * DM_TM, j0 = bc * DM_TN;
 
     for (int idx = threadIdx.x; idx < rp * DM_TM; idx += 256) {
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(256, 2) k_cov_update_dmma(double* __restrict__
             for (int bj = 0; bj < 4; bj++) {
                 const int j = jw + bj * 8 + 2 * lc;
                 double2 v = make_double2(0.0, 0.0);
-                if (i < n && j < n && j + 1 >= i) v = ld128(P + (size_t)i * ld + j);
+                if (i < n && j < n && j + 1 >= i) v = ld128(P + shard_lrow(sh, i) * ld + j);
                 acc[bi][bj][0] = v.x;
                 acc[bi][bj][1] = v.y;
             }
@@ -100,22 +101,22 @@ __global__ void __launch_bounds__(256, 2) k_cov_update_dmma(double* __restrict__
             const int j = jw + bj * 8 + 2 * lc;
             // pairs straddling the diagonal (j + 1 == i) rewrite one unauthoritative lower element
             if (i < n && j < n && j + 1 >= i)
-                st128(P + (size_t)i * ld + j, make_double2(acc[bi][bj][0], acc[bi][bj][1]));
+                st128(P + shard_lrow(sh, i) * ld + j, make_double2(acc[bi][bj][0], acc[bi][bj][1]));
         }
     }
 }
 
-int launch_cov_update_dmma(double* P, size_t ld, int n, const double* A, size_t lda, int r, cudaStream_t stream) {
+int launch_cov_update_dmma(double* P, size_t ld, int n, const double* A, size_t lda, int r, Shard sh,
+                           cudaStream_t stream) {
     const int rp = (r + 3) / 4 * 4;
-    const int nbr = (n + DM_TM - 1) / DM_TM;
     const int nbc = (n + DM_TN - 1) / DM_TN;
-    long long tiles = 0;
-    for (int br = 0; br < nbr; br++) tiles += nbc - br / 2;
+    const long long tiles = 2 * shard_tile_count(nbc, sh);  // a trailing half-empty tile row exits early
+    if (tiles == 0) return CSLAM_OK;
     const size_t smem = (size_t)rp * (DM_SR + DM_SC) * sizeof(double);
     CSLAM_CUDA(cudaFuncSetAttribute(k_cov_update_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     64 * (DM_SR + DM_SC) * (int)sizeof(double)));
     count_launch();
-    k_cov_update_dmma<<<(unsigned)tiles, 256, smem, stream>>>(P, ld, n, A, lda, r, rp, nbc);
+    k_cov_update_dmma<<<(unsigned)tiles, 256, smem, stream>>>(P, ld, n, A, lda, r, rp, nbc, sh);
     CSLAM_CUDA(cudaGetLastError());
     return CSLAM_OK;
 }

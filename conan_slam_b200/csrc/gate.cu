@@ -35,8 +35,11 @@ __device__ __forceinline__ void cand_merge(Cand& a, double nd, int j, double out
     if (out < a.out) a.out = out;
 }
 
-__global__ void __launch_bounds__(256) k_gate(const double* __restrict__ X, const double* __restrict__ P, size_t ld,
-                                              int nf, GatePack gp, double* __restrict__ part_nd,
+// R3 = rows 0..2 of P (P itself on one GPU); D = replicated cache of the diagonal blocks
+// ([3][dcap], sharded handles) or nullptr (read them from P).
+__global__ void __launch_bounds__(256) k_gate(const double* __restrict__ X, const double* __restrict__ P,
+                                              const double* __restrict__ R3, const double* __restrict__ D, int dcap,
+                                              size_t ld, int nf, GatePack gp, double* __restrict__ part_nd,
                                               double* __restrict__ part_out, int* __restrict__ part_j,
                                               unsigned* __restrict__ ticket, int* __restrict__ jbest,
                                               double* __restrict__ nbest, double* __restrict__ outer) {
@@ -62,8 +65,17 @@ __global__ void __launch_bounds__(256) k_gate(const double* __restrict__ X, cons
             H[a][3] = o.lu[a][0]; H[a][4] = o.lu[a][1];
         }
         double Pc[5][5];
-        for (int a = 0; a < 5; a++)
-            for (int b = a; b < 5; b++) Pc[a][b] = Pc[b][a] = P[(size_t)cols[a] * ld + cols[b]];
+        for (int a = 0; a < 3; a++)
+            for (int b = a; b < 5; b++) Pc[a][b] = Pc[b][a] = R3[(size_t)a * ld + cols[b]];
+        if (D) {
+            Pc[3][3] = D[jl - 1];
+            Pc[3][4] = Pc[4][3] = D[(size_t)dcap + jl - 1];
+            Pc[4][4] = D[2 * (size_t)dcap + jl - 1];
+        } else {
+            Pc[3][3] = P[(size_t)f * ld + f];
+            Pc[3][4] = Pc[4][3] = P[(size_t)f * ld + f + 1];
+            Pc[4][4] = P[(size_t)(f + 1) * ld + f + 1];
+        }
         double HP[2][5];
         for (int a = 0; a < 2; a++)
             for (int b = 0; b < 5; b++) {
@@ -162,9 +174,10 @@ __global__ void __launch_bounds__(256) k_gate(const double* __restrict__ X, cons
 }
 
 
-int launch_gate(const double* X, const double* P, size_t ld, int nf, const double* Z, int m, const double R[4],
-                double gate1, double gate2, double* part_nd, double* part_out, int* part_j, unsigned* ticket,
-                int* jbest, double* nbest, double* outer, cudaStream_t stream) {
+int launch_gate(const double* X, const double* P, const double* R3, const double* D, int dcap, size_t ld, int nf,
+                const double* Z, int m, const double R[4], double gate1, double gate2, double* part_nd,
+                double* part_out, int* part_j, unsigned* ticket, int* jbest, double* nbest, double* outer,
+                cudaStream_t stream) {
     GatePack gp;
     memset(&gp, 0, sizeof(gp));
     memcpy(gp.z, Z, sizeof(double) * 2 * m);
@@ -174,7 +187,8 @@ int launch_gate(const double* X, const double* P, size_t ld, int nf, const doubl
     gp.gate2 = gate2;
     const int blocks = nf > 0 ? (nf + 255) / 256 : 1;
     count_launch();
-    k_gate<<<blocks, 256, 0, stream>>>(X, P, ld, nf, gp, part_nd, part_out, part_j, ticket, jbest, nbest, outer);
+    k_gate<<<blocks, 256, 0, stream>>>(X, P, R3, D, dcap, ld, nf, gp, part_nd, part_out, part_j, ticket, jbest, nbest,
+                                       outer);
     CSLAM_CUDA(cudaGetLastError());
     return CSLAM_OK;
 }

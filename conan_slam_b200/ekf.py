@@ -45,7 +45,8 @@ class EKF:
     Config fields carry the reference's defaults (slam.h:65-103).
     """
 
-    def __init__(self, landMarks=None, wayPoints=None, capacity_landmarks=None, device=0, flags=0):
+    def __init__(self, landMarks=None, wayPoints=None, capacity_landmarks=None, device=0, flags=0, rank=0, world=1,
+                 nccl_id=None):
         self._lib = _lib.load_library()
         self.mLM = None if landMarks is None else np.asarray(landMarks, dtype=np.float64)
         self.mWP = None if wayPoints is None else np.asarray(wayPoints, dtype=np.float64)
@@ -70,8 +71,16 @@ class EKF:
         self.mSwitchBatchUpdate = True
         self.flags = flags
         h = C.c_void_p()
-        check(self._lib.cslam_ekf_create(C.byref(h), int(capacity_landmarks), int(device), int(flags)),
-              "cslam_ekf_create")
+        self.rank, self.world = int(rank), int(world)
+        if world > 1:  # row-sharded covariance: one process per GPU, SPMD calls (include/cslam.h)
+            assert nccl_id is not None and len(nccl_id) == 128, "pass the 128-byte id from dist.nccl_unique_id()"
+            buf = C.create_string_buffer(bytes(nccl_id), 128)
+            check(self._lib.cslam_ekf_create_sharded(C.byref(h), int(capacity_landmarks), int(device), int(flags),
+                                                     int(rank), int(world), C.cast(buf, C.c_void_p)),
+                  "cslam_ekf_create_sharded")
+        else:
+            check(self._lib.cslam_ekf_create(C.byref(h), int(capacity_landmarks), int(device), int(flags)),
+                  "cslam_ekf_create")
         self._h = h
 
     def close(self):

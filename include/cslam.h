@@ -71,6 +71,16 @@ unsigned long long cslam_kernel_launches(void);
  * `capacity_landmarks` landmarks (n_cap = 3 + 2*capacity; P is n_cap x ld FP64,
  * row-major, upper triangle authoritative) so augmentation never reallocates. */
 int cslam_ekf_create(cslam_ekf_t** out, int capacity_landmarks, int device, unsigned flags);
+/* Multi-GPU: one process per GPU, the joint covariance ROW-SHARDED over `world` ranks in
+ * block-cyclic 128-row tiles (very large maps: 60,000 landmarks = 115 GB).  X and rows 0..2 of P
+ * are replicated; per update only the observed landmark's two columns of P are exchanged (one
+ * NCCL all-reduce of 2*n doubles), then every rank forms the gain and streams its own rows.
+ * SPMD contract: every rank makes the same calls in the same order (accessors included — 
+ * cslam_ekf_get_cov_block is a collective).  nccl_unique_id: 128 bytes from cslam_nccl_unique_id()
+ * on rank 0, distributed by the host (torch.distributed / MPI / a file).  NCCL is dlopen'ed. */
+int cslam_nccl_unique_id(void* out128);
+int cslam_ekf_create_sharded(cslam_ekf_t** out, int capacity_landmarks, int device, unsigned flags, int rank,
+                             int world, const void* nccl_unique_id);
 int cslam_ekf_destroy(cslam_ekf_t* h);
 /* Run this handle's kernels on a caller-provided cudaStream_t (e.g. a torch stream). */
 int cslam_ekf_set_stream(cslam_ekf_t* h, void* cuda_stream);
