@@ -118,12 +118,12 @@ def range_bearing(pose, lm):
     return np.stack([np.hypot(dx, dy), np.arctan2(dy, dx) - pose[2]])
 
 
-def build_ekf(N, device, flags, seed=None, stream=None):
+def build_ekf(N, device, flags, seed=None, stream=None, rank=0, world=1, nccl_id=None):
     """Synthetic N-landmark joint state built ON THE GPU by the filter's own augment kernel from
     Pvv = diag(1, 1, (1 deg)^2): P_ij = Gv_i Pvv Gv_j^T + blockdiag(Gz R Gz^T)."""
     import conan_slam_b200 as cs
     lm, rng = synth_landmarks(N, N if seed is None else seed)
-    ekf = cs.EKF(capacity_landmarks=N, device=device, flags=flags)
+    ekf = cs.EKF(capacity_landmarks=N, device=device, flags=flags, rank=rank, world=world, nccl_id=nccl_id)
     if stream is not None:
         ekf.set_stream(stream)
     pose = np.zeros(3)
@@ -313,6 +313,8 @@ def main():
     ap.add_argument("--landmarks", type=int, default=20000)
     ap.add_argument("--obs", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--multi", default="sharded", choices=["sharded", "replicas"],
+                    help="N>1: row-sharded covariance of ONE filter (strong scaling) or independent filter replicas")
     ap.add_argument("--extras", action="store_true", help="also time the other single-GPU configs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -340,7 +342,15 @@ def main():
     n = 3 + 2 * N
     stream = torch.cuda.Stream(device=local)
     t0 = time.time()
-    ekf, lm, rng = build_ekf(N, local, cs.FLAG_INTENDED, seed=N + 1000 * rank, stream=stream.cuda_stream)
+    sharded = world > 1 and args.multi == "sharded"
+    if sharded:
+        from conan_slam_b200 import dist as cdist
+        nid = cdist.nccl_unique_id(device=f"cuda:{local}")
+        # one filter, covariance row-sharded over the ranks: identical inputs on every rank (SPMD)
+        ekf, lm, rng = build_ekf(N, local, cs.FLAG_INTENDED, seed=N, stream=stream.cuda_stream, rank=rank,
+                                 world=world, nccl_id=nid)
+    else:
+        ekf, lm, rng = build_ekf(N, local, cs.FLAG_INTENDED, seed=N + 1000 * rank, stream=stream.cuda_stream)
     log(f"[bench r{rank}] built {N}-landmark map (n={n}, P={8.0 * n * n / 1e9:.2f} GB) in {time.time() - t0:.1f}s")
     scans = make_scans(lm, rng, max(8, args.steps + args.warmup), m)
 
@@ -397,7 +407,10 @@ def main():
         ms, e2e_ms = float(t[0]), float(t[1])
         cnt = torch.tensor([updates, e2e_updates, launches], device=f"cuda:{local}", dtype=torch.float64)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-        updates, e2e_updates, launches = int(cnt[0]), int(cnt[1]), int(cnt[2])
+        if sharded:  # every rank took part in the SAME updates: count them once
+            launches = int(cnt[2])
+        else:
+            updates, e2e_updates, launches = int(cnt[0]), int(cnt[1]), int(cnt[2])
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -408,14 +421,19 @@ def main():
         out = {
             "metric": "EKF updates/sec", "value": value, "unit": "updates/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
                 "workload": (f"EKF-SLAM {N} landmarks (state dim {n}, FP64 P {8.0 * n * n / 1e9:.2f} GB), "
                              f"range-bearing observations, sequential update: gate + gain + covariance, "
-                             f"{m} observations per scan" + (f", {world} independent filter replicas" if world > 1 else "")),
+                             f"{m} observations per scan" +
+                             (f", covariance row-sharded over {world} GPUs" if sharded else
+                              (f", {world} independent filter replicas" if world > 1 else ""))),
                 "landmarks": N, "state_dim": n, "obs_per_step": m, "mode": "INTENDED (SURVEY Appendix A)",
-                "l2": "inputs larger than L2 (6.4 GB upper triangle streamed per update)",
-                "parallelism": "replicas only (one independent filter per GPU)" if world > 1 else "single GPU",
+                "l2": f"inputs larger than L2 ({4.0 * n * n / 1e9 / (world if sharded else 1):.1f} GB of upper "
+                      f"triangle streamed per GPU per update)",
+                "parallelism": ("row-sharded covariance (block-cyclic 128-row tiles), NCCL all-reduce of the 2 observed "
+                                "columns per update" if sharded else
+                                ("replicas only (one independent filter per GPU)" if world > 1 else "single GPU")),
             },
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "updates/s",

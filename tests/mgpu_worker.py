@@ -81,10 +81,11 @@ def ekf_checks():
             f.update(Z2, RE, ids2, True)
         check("joint update (DMMA, sharded)")
         Zn = np.array([[700.0, 1200.0, 300.0], [0.4, -0.9, 2.0]])
+        phi_meas = float(o.X[2]) - 2e-4
         for f in (g, o):
             f.augment(Zn, RE)
             f.predict(83.33, -0.01, QE, 73.0, 0.01)
-            f.observeHeading(float(o.X[2]), True)
+            f.observeHeading(phi_meas, True)
         check("augment")
         ids3 = np.array([N + 1, N + 3, 7], dtype=np.int32)
         Z3 = np.stack([np.array([700.0, 300.0, Z[0, 0]]), np.array([0.4, 2.0, Z[1, 0]])])
