@@ -62,6 +62,9 @@ SIGNATURES = {
     "cslam_ekf_reset": (C.c_int, [_vp, _dp, C.c_int, _dp]),
     "cslam_ekf_device_ptrs": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_size_t)]),
     "cslam_pf_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.c_uint]),
+    "cslam_pf_create_sharded": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.c_uint, C.c_int, C.c_int, _vp]),
+    "cslam_pf_ipc_export": (C.c_int, [_vp, _vp]),
+    "cslam_pf_ipc_import": (C.c_int, [_vp, _vp, C.c_int]),
     "cslam_pf_destroy": (C.c_int, [_vp]),
     "cslam_pf_set_stream": (C.c_int, [_vp, _vp]),
     "cslam_pf_sync": (C.c_int, [_vp, C.POINTER(C.c_int)]),

@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "nccl_dl.cuh"
 
 namespace cslam {
 
@@ -56,6 +57,16 @@ struct cslam_pf {
     size_t pinned_bytes = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    // particles split over GPUs (world == 1: single GPU).  np = LOCAL particle count.
+    int rank = 0, world = 1;
+    long long np_global = 0;
+    ncclComm_t comm = nullptr;
+    int gather_level = -1;                 // first scan level computed on all-gathered totals
+    double* gscan[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // global scan levels >= gather_level
+    size_t gscan_len[5] = {0, 0, 0, 0, 0};
+    double* cum_global = nullptr;          // [np_global] all-gathered cumulative weights
+    cslam::PfBuf peer[2][8];               // IPC-mapped buffers of every rank (self = own pointers)
+    bool peers_ready = false;
 };
 
 namespace cslam {
@@ -428,9 +439,9 @@ __device__ __forceinline__ double warp_scan_incl(double x, int lane) {
 // out[i] = inclusive scan within aligned 32-groups of f(in[i]); totals[g] = last of group.
 // mode 0: f(x) = x ; mode 1: f(x) = x / div[0] ; mode 2: f(x) = (x / div[0])^2 — the divisor
 // lives on the device so no host round trip separates the passes.
-__global__ void __launch_bounds__(256) k_scan_level(const double* __restrict__ in, size_t len,
-                                                    double* __restrict__ out, double* __restrict__ totals, int mode,
-                                                    const double* __restrict__ div) {
+// (in may alias out: upper levels are scanned in place)
+__global__ void __launch_bounds__(256) k_scan_level(const double* in, size_t len, double* out, double* totals,
+                                                    int mode, const double* __restrict__ div) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     double x = 0.0;
@@ -481,35 +492,41 @@ __global__ void __launch_bounds__(256) k_divide(double* __restrict__ w, size_t l
     if (i < len) w[i] = w[i] / div[0];
 }
 
-// cum[i] = offsets (top level down) + scan0[i]
+// cum[i] = offsets (top level down) + scan0[i].  Levels below `glevel` are local arrays indexed by the
+// local group index; levels >= glevel are the all-gathered (global) arrays indexed by the global one.
 struct ScanPtrs {
     const double* s[5];
     int levels;
+    int glevel;          // == levels when nothing is gathered (single GPU)
+    long long base;      // global index of local element 0 (rank * np_local)
 };
 __global__ void __launch_bounds__(256) k_scan_combine(ScanPtrs sp, size_t len, double* __restrict__ cum) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= len) return;
     double off = 0.0;
     for (int l = sp.levels - 1; l >= 1; l--) {
-        const size_t gi = i >> (5 * l);  // index of i's group total at level l (an element of level l's array)
+        const size_t gi = (l >= sp.glevel) ? (size_t)((sp.base + (long long)i) >> (5 * l)) : (i >> (5 * l));
         if (gi & 31) off = off + sp.s[l][gi - 1];
     }
     cum[i] = off + sp.s[0][i];
 }
 
 // PF.cpp:566-574.  INTENDED (Q10): keep[c] = min{ i : select[c] < cum[i] } by binary search.
-__global__ void __launch_bounds__(256) k_resample_search(const double* __restrict__ cum, const double* __restrict__ comb,
-                                                         const double* __restrict__ u, int np, int* __restrict__ keep) {
+// `cum` holds ncum cumulative weights (all particles of all ranks); this rank resolves its nslots slots.
+__global__ void __launch_bounds__(256) k_resample_search(const double* __restrict__ cum, int ncum,
+                                                         const double* __restrict__ comb,
+                                                         const double* __restrict__ u, int nslots,
+                                                         int* __restrict__ keep) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= np) return;
-    const double k = 1.0 / (double)np;
+    if (c >= nslots) return;
+    const double k = 1.0 / (double)ncum;
     const double sel = comb[c] + u[c] * (k - k / 2.0);
-    int lo = 0, hi = np;
+    int lo = 0, hi = ncum;
     while (lo < hi) {
         const int mid = (lo + hi) / 2;
         if (sel < cum[mid]) hi = mid; else lo = mid + 1;
     }
-    keep[c] = lo < np ? lo : np - 1;
+    keep[c] = lo < ncum ? lo : ncum - 1;
 }
 // REF_LITERAL: the first i with select[i] < cum[i] takes every slot (all zeros if none).
 __global__ void __launch_bounds__(256) k_resample_first_hit(const double* __restrict__ cum,
@@ -544,6 +561,27 @@ __global__ void __launch_bounds__(256) k_gather_rows(const double* __restrict__ 
         double2 v;
         v.x = s[k0];
         v.y = s[k1];
+        st128(dst + (size_t)r * pp + c, v);
+    }
+}
+// Multi-GPU variant: keep[] holds GLOBAL source indices; the survivor's rows are read straight from
+// the owning rank's buffer over NVLink (IPC-mapped peer pointers) — the all-to-all of the
+// resampling step is fused into the gather kernel, no staging copy.
+struct PeerRows {
+    const double* base[8];
+};
+__global__ void __launch_bounds__(256) k_gather_rows_peer(PeerRows src, double* __restrict__ dst, size_t pp,
+                                                          int np, int rows, const int* __restrict__ keep) {
+    const int c = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    if (c >= np) return;
+    const int g0 = keep[c];
+    const int g1 = (c + 1 < np) ? keep[c + 1] : g0;
+    const double* s0 = src.base[g0 / np] + (g0 % np);
+    const double* s1 = src.base[g1 / np] + (g1 % np);
+    for (int r = blockIdx.y; r < rows; r += gridDim.y) {
+        double2 v;
+        v.x = s0[(size_t)r * pp];
+        v.y = s1[(size_t)r * pp];
         st128(dst + (size_t)r * pp + c, v);
     }
 }
@@ -650,21 +688,50 @@ static int stage_in(cslam_pf* h, const double* src, size_t count, int on_device,
     return CSLAM_OK;
 }
 
-// canonical hierarchical scan of f(in) into h->scan[*]; returns the top level index
+// Canonical hierarchical scan of f(in).  Local levels (whole 32-groups inside this rank) go to
+// h->scan[l]; from h->gather_level on, the group totals of ALL ranks are all-gathered in rank order
+// and the remaining levels are computed redundantly on every rank in h->gscan[l] — exactly the
+// arrays a single GPU would compute, so every sum is bit-identical for any rank count.
 static int run_scan(cslam_pf* h, const double* in, int mode, const double* div) {
     const double* src = in;
     size_t len = h->np;
-    for (int l = 0; l < h->levels; l++) {
+    const int L = h->gather_level < 0 ? h->levels : h->gather_level;
+    for (int l = 0; l < L; l++) {
+        double* totals = (l + 1 < h->levels) ? h->scan[l + 1] : h->d_small + 7;
         count_launch();
-        k_scan_level<<<nblk(len, 256), 256, 0, h->stream>>>(src, len, h->scan[l],
-                                                             (l + 1 < h->levels) ? h->scan[l + 1] + 0 : h->d_small + 7,
-                                                             l == 0 ? mode : 0, div);
-        // level l+1's INPUT is the totals array; it is scanned in place into scan[l+1]
-        src = h->scan[l + 1];
+        k_scan_level<<<nblk(len, 256), 256, 0, h->stream>>>(src, len, h->scan[l], totals, l == 0 ? mode : 0, div);
+        src = h->scan[l + 1];  // level l+1's INPUT is the totals array; it is scanned in place
         len = (len + 31) / 32;
+    }
+    if (L < h->levels) {
+        const NcclApi* api = nccl_api();
+        if (!api) return CSLAM_ERR_NCCL;
+        CSLAM_NCCL(api->AllGather(h->scan[L], h->gscan[L], len, ncclDouble, h->comm, h->stream));
+        size_t glen = len * (size_t)h->world;
+        for (int l = L; l < h->levels; l++) {
+            double* totals = (l + 1 < h->levels) ? h->gscan[l + 1] : h->d_small + 7;
+            count_launch();
+            k_scan_level<<<nblk(glen, 256), 256, 0, h->stream>>>(h->gscan[l], glen, h->gscan[l], totals, 0, div);
+            glen = (glen + 31) / 32;
+        }
     }
     CSLAM_CUDA(cudaGetLastError());
     return CSLAM_OK;
+}
+static ScanPtrs scan_ptrs(const cslam_pf* h) {
+    ScanPtrs sp;
+    const int L = h->gather_level < 0 ? h->levels : h->gather_level;
+    for (int l = 0; l < 5; l++) sp.s[l] = (l >= L) ? h->gscan[l] : h->scan[l];
+    sp.levels = h->levels;
+    sp.glevel = L;
+    sp.base = (long long)h->rank * h->np;
+    return sp;
+}
+static const double* scan_top(const cslam_pf* h, size_t* len) {
+    const int t = h->levels - 1;
+    const bool g = h->gather_level >= 0 && t >= h->gather_level;
+    *len = g ? h->gscan_len[t] : h->scan_len[t];
+    return g ? h->gscan[t] : h->scan[t];
 }
 
 }  // namespace cslam
@@ -673,9 +740,14 @@ using namespace cslam;
 
 extern "C" {
 
-int cslam_pf_create(cslam_pf_t** out, int num_particles, int capacity_landmarks, int device, unsigned flags) {
+static int pf_create_common(cslam_pf_t** out, int num_particles, int capacity_landmarks, int device, unsigned flags,
+                            int rank, int world, const void* nccl_id) {
     CSLAM_REQUIRE(out != nullptr, CSLAM_ERR_BAD_ARG, "out is null");
     CSLAM_REQUIRE(num_particles >= 1 && capacity_landmarks >= 0, CSLAM_ERR_BAD_ARG, "bad sizes");
+    CSLAM_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world, CSLAM_ERR_BAD_ARG, "bad rank/world");
+    CSLAM_REQUIRE(world == 1 || (nccl_id != nullptr && num_particles % 32 == 0), CSLAM_ERR_BAD_ARG,
+                  "sharded PF needs an NCCL id and a local particle count that is a multiple of 32");
+    CSLAM_REQUIRE((long long)num_particles * world < (1LL << 31), CSLAM_ERR_UNSUPPORTED, "too many particles");
     *out = nullptr;
     int count = 0;
     CSLAM_CUDA(cudaGetDeviceCount(&count));
@@ -688,6 +760,9 @@ int cslam_pf_create(cslam_pf_t** out, int num_particles, int capacity_landmarks,
     h->np = num_particles;
     h->pp = ((size_t)num_particles + 31) / 32 * 32;
     h->nf_cap = capacity_landmarks;
+    h->rank = rank;
+    h->world = world;
+    h->np_global = (long long)num_particles * world;
     auto fail = [&](int code) {
         cslam_pf_destroy(h);
         return code;
@@ -712,23 +787,42 @@ int cslam_pf_create(cslam_pf_t** out, int num_particles, int capacity_landmarks,
         TRY(cudaMemsetAsync(h->buf[b].w, 0, pp * sizeof(double), h->stream));
         TRY(cudaMemsetAsync(h->buf[b].xv, 0, 3 * pp * sizeof(double), h->stream));
         TRY(cudaMemsetAsync(h->buf[b].pv, 0, 9 * pp * sizeof(double), h->stream));
+        h->peer[b][rank] = h->buf[b];
     }
-    // scan hierarchy
+    // scan hierarchy: the level structure is that of the GLOBAL particle count (identical for any
+    // world size); a level is local while this rank's share of its input is whole 32-groups.
     {
-        size_t len = h->np;
-        int l = 0;
+        size_t glen[6];
+        int levels = 0;
+        size_t len = (size_t)h->np_global;
         while (true) {
-            h->scan_len[l] = len;
-            TRY(cudaMalloc(&h->scan[l], (len + 32) * sizeof(double)));
-            l++;
+            glen[levels++] = len;
             if (len <= 32) break;
             len = (len + 31) / 32;
-            if (l >= 5) break;
+            if (levels >= 5) break;
         }
-        h->levels = l;
-        if (l >= 5 && h->scan_len[4] > 32) {
+        if (glen[levels - 1] > 32) {
             set_last_error("cslam_pf_create: too many particles for a 5-level radix-32 scan");
             return fail(CSLAM_ERR_UNSUPPORTED);
+        }
+        h->levels = levels;
+        size_t llen = h->np;
+        int L = 0;
+        if (world == 1) {
+            L = levels;
+        } else {
+            while (L < levels && llen % 32 == 0) { L++; llen /= 32; }
+            h->gather_level = L;
+        }
+        llen = h->np;
+        for (int l = 0; l <= L && l < levels; l++) {  // scan[L] holds the local totals that get all-gathered
+            h->scan_len[l] = (world == 1) ? glen[l] : llen;
+            TRY(cudaMalloc(&h->scan[l], (h->scan_len[l] + 32) * sizeof(double)));
+            llen = (llen + 31) / 32;
+        }
+        for (int l = L; l < levels; l++) {
+            h->gscan_len[l] = glen[l];
+            TRY(cudaMalloc(&h->gscan[l], (glen[l] + 32) * sizeof(double)));
         }
     }
     TRY(cudaMalloc(&h->comb, pp * sizeof(double)));
@@ -742,18 +836,32 @@ int cslam_pf_create(cslam_pf_t** out, int num_particles, int capacity_landmarks,
     TRY(cudaMallocHost(&h->pinned, h->pinned_bytes));
     // PF.cpp:319-341: w = 1/P
     count_launch();
-    k_fill<<<nblk(h->np, 256), 256, 0, h->stream>>>(h->buf[0].w, h->np, 1.0 / (double)h->np);
-    // PF.cpp:581-587: DI(0) = k/2 ; DI(i) = DI(i-1) + k  — a sequential chain, built once on the host
+    k_fill<<<nblk(h->np, 256), 256, 0, h->stream>>>(h->buf[0].w, h->np, 1.0 / (double)h->np_global);
+    // PF.cpp:581-587: DI(0) = k/2 ; DI(i) = DI(i-1) + k  — a sequential chain over ALL slots, built once
+    // on the host; every rank keeps the slice of its own slots
     {
         std::vector<double> comb(h->np);
-        const double k = 1.0 / (double)h->np;
+        const double k = 1.0 / (double)h->np_global;
         double di = k / 2.0;
-        for (int i = 0; i < h->np; i++) {
+        const long long first = (long long)rank * h->np;
+        for (long long i = 0; i < first + h->np; i++) {
             if (i > 0) di = di + k;
-            comb[i] = di;
+            if (i >= first) comb[(size_t)(i - first)] = di;
         }
         TRY(cudaMemcpyAsync(h->comb, comb.data(), (size_t)h->np * sizeof(double), cudaMemcpyHostToDevice, h->stream));
         TRY(cudaStreamSynchronize(h->stream));
+    }
+    if (world > 1) {
+        TRY(cudaMalloc(&h->cum_global, (size_t)h->np_global * sizeof(double)));
+        const NcclApi* api = nccl_api();
+        if (!api) return fail(CSLAM_ERR_NCCL);
+        ncclUniqueId id;
+        memcpy(&id, nccl_id, sizeof(id));
+        ncclResult_t r = api->CommInitRank(&h->comm, world, id, rank);
+        if (r != ncclSuccess) {
+            set_last_error("ncclCommInitRank -> %s", api->GetErrorString(r));
+            return fail(CSLAM_ERR_NCCL);
+        }
     }
     TRY(cudaStreamSynchronize(h->stream));
 #undef TRY
@@ -761,15 +869,75 @@ int cslam_pf_create(cslam_pf_t** out, int num_particles, int capacity_landmarks,
     return CSLAM_OK;
 }
 
+int cslam_pf_create(cslam_pf_t** out, int num_particles, int capacity_landmarks, int device, unsigned flags) {
+    return pf_create_common(out, num_particles, capacity_landmarks, device, flags, 0, 1, nullptr);
+}
+
+int cslam_pf_create_sharded(cslam_pf_t** out, int num_particles_local, int capacity_landmarks, int device,
+                            unsigned flags, int rank, int world, const void* nccl_unique_id) {
+    return pf_create_common(out, num_particles_local, capacity_landmarks, device, flags, rank, world, nccl_unique_id);
+}
+
+// 10 cudaIpcMemHandle_t (64 bytes each): {w, xv, pv, xf, pf} of both ping-pong buffers
+int cslam_pf_ipc_export(cslam_pf_t* h, void* out640) {
+    if (int rc = check_pf(h)) return rc;
+    CSLAM_REQUIRE(out640 != nullptr, CSLAM_ERR_BAD_ARG, "null");
+    cudaIpcMemHandle_t* hs = static_cast<cudaIpcMemHandle_t*>(out640);
+    for (int b = 0; b < 2; b++) {
+        CSLAM_CUDA(cudaIpcGetMemHandle(&hs[5 * b + 0], h->buf[b].w));
+        CSLAM_CUDA(cudaIpcGetMemHandle(&hs[5 * b + 1], h->buf[b].xv));
+        CSLAM_CUDA(cudaIpcGetMemHandle(&hs[5 * b + 2], h->buf[b].pv));
+        CSLAM_CUDA(cudaIpcGetMemHandle(&hs[5 * b + 3], h->buf[b].xf));
+        CSLAM_CUDA(cudaIpcGetMemHandle(&hs[5 * b + 4], h->buf[b].pf));
+    }
+    return CSLAM_OK;
+}
+// all: world x 640 bytes in rank order (every rank's export).  Maps the peers' buffers (NVLink P2P).
+int cslam_pf_ipc_import(cslam_pf_t* h, const void* all, int world) {
+    if (int rc = check_pf(h)) return rc;
+    CSLAM_REQUIRE(all != nullptr && world == h->world, CSLAM_ERR_BAD_ARG, "bad argument");
+    const cudaIpcMemHandle_t* hs = static_cast<const cudaIpcMemHandle_t*>(all);
+    for (int r = 0; r < world; r++) {
+        if (r == h->rank) continue;
+        for (int b = 0; b < 2; b++) {
+            void* p[5];
+            for (int k = 0; k < 5; k++)
+                CSLAM_CUDA(cudaIpcOpenMemHandle(&p[k], hs[10 * r + 5 * b + k], cudaIpcMemLazyEnablePeerAccess));
+            h->peer[b][r].w = static_cast<double*>(p[0]);
+            h->peer[b][r].xv = static_cast<double*>(p[1]);
+            h->peer[b][r].pv = static_cast<double*>(p[2]);
+            h->peer[b][r].xf = static_cast<double*>(p[3]);
+            h->peer[b][r].pf = static_cast<double*>(p[4]);
+        }
+    }
+    h->peers_ready = true;
+    return CSLAM_OK;
+}
+
 int cslam_pf_destroy(cslam_pf_t* h) {
     if (!h) return CSLAM_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->peers_ready) {
+        for (int r = 0; r < h->world; r++) {
+            if (r == h->rank) continue;
+            for (int b = 0; b < 2; b++) {
+                cudaIpcCloseMemHandle(h->peer[b][r].w); cudaIpcCloseMemHandle(h->peer[b][r].xv);
+                cudaIpcCloseMemHandle(h->peer[b][r].pv); cudaIpcCloseMemHandle(h->peer[b][r].xf);
+                cudaIpcCloseMemHandle(h->peer[b][r].pf);
+            }
+        }
+    }
+    if (h->comm) {
+        const NcclApi* api = nccl_api();
+        if (api) api->CommDestroy(h->comm);
+    }
     for (int b = 0; b < 2; b++) {
         cudaFree(h->buf[b].w); cudaFree(h->buf[b].xv); cudaFree(h->buf[b].pv);
         cudaFree(h->buf[b].xf); cudaFree(h->buf[b].pf);
     }
-    for (int l = 0; l < 5; l++) cudaFree(h->scan[l]);
+    for (int l = 0; l < 5; l++) { cudaFree(h->scan[l]); cudaFree(h->gscan[l]); }
+    cudaFree(h->cum_global);
     cudaFree(h->comb); cudaFree(h->wn); cudaFree(h->keep); cudaFree(h->d_in);
     cudaFree(h->d_small); cudaFree(h->d_ismall);
     if (h->pinned) cudaFreeHost(h->pinned);
@@ -906,30 +1074,38 @@ int cslam_pf_resample(cslam_pf_t* h, const double* u, int u_on_device, double nu
     if (int rc = stage_in(h, u, (size_t)np, u_on_device, &du)) return rc;
     double* S = h->d_small;  // S[0] = sum w, S[1] = sum W, S[2] = sum W^2
     const bool intended = (h->flags & CSLAM_FLAG_Q10_SEARCH) != 0;
-    ScanPtrs sp;
-    for (int l = 0; l < 5; l++) sp.s[l] = h->scan[l];
-    sp.levels = h->levels;
-    const size_t top_len = h->scan_len[h->levels - 1];
+    CSLAM_REQUIRE(h->world == 1 || (intended && h->peers_ready), CSLAM_ERR_UNSUPPORTED,
+                  "multi-GPU resampling needs CSLAM_FLAG_Q10_SEARCH and cslam_pf_ipc_import");
+    const ScanPtrs sp = scan_ptrs(h);
+    size_t top_len = 0;
+    const double* top = scan_top(h, &top_len);
     if (intended) {
         // ws = sum w ; particles.w /= ws (PF.cpp:482-487)
         if (int rc = run_scan(h, b.w, 0, nullptr)) return rc;
         count_launch();
-        k_scan_total<<<1, 32, 0, h->stream>>>(h->scan[h->levels - 1], top_len, S + 0);
+        k_scan_total<<<1, 32, 0, h->stream>>>(top, top_len, S + 0);
         count_launch();
         k_divide<<<nblk(np, 256), 256, 0, h->stream>>>(b.w, np, S + 0);
         // stratifiedResample: W /= W.sum() (PF.cpp:548) ; neff = 1 / sum W^2 (:550-554)
         if (int rc = run_scan(h, b.w, 0, nullptr)) return rc;
         count_launch();
-        k_scan_total<<<1, 32, 0, h->stream>>>(h->scan[h->levels - 1], top_len, S + 1);
+        k_scan_total<<<1, 32, 0, h->stream>>>(top, top_len, S + 1);
         if (int rc = run_scan(h, b.w, 2, S + 1)) return rc;
         count_launch();
-        k_scan_total<<<1, 32, 0, h->stream>>>(h->scan[h->levels - 1], top_len, S + 2);
+        k_scan_total<<<1, 32, 0, h->stream>>>(top, top_len, S + 2);
         // cumulative sum of W (PF.cpp:559-564) in the canonical order
         if (int rc = run_scan(h, b.w, 1, S + 1)) return rc;
         count_launch();
         k_scan_combine<<<nblk(np, 256), 256, 0, h->stream>>>(sp, np, h->wn);
+        const double* cum = h->wn;
+        if (h->world > 1) {  // every rank searches the cumulative weights of ALL particles
+            const NcclApi* api = nccl_api();
+            if (!api) return CSLAM_ERR_NCCL;
+            CSLAM_NCCL(api->AllGather(h->wn, h->cum_global, (size_t)np, ncclDouble, h->comm, h->stream));
+            cum = h->cum_global;
+        }
         count_launch();
-        k_resample_search<<<nblk(np, 256), 256, 0, h->stream>>>(h->wn, h->comb, du, np, h->keep);
+        k_resample_search<<<nblk(np, 256), 256, 0, h->stream>>>(cum, (int)h->np_global, h->comb, du, np, h->keep);
     } else {
         count_launch();
         k_seq_sum<<<1, 32, 0, h->stream>>>(b.w, np, 0, nullptr, S + 0);
@@ -962,18 +1138,24 @@ int cslam_pf_resample(cslam_pf_t* h, const double* u, int u_on_device, double nu
     if (doit) {
         PfBuf& d = h->buf[h->cur ^ 1];
         const unsigned gx = nblk(((size_t)np + 1) / 2, 256);
-        auto gather = [&](const double* s, double* dd, int rows) {
+        auto gather = [&](double* PfBuf::*field, int rows) {
             if (rows <= 0) return;
             const unsigned gy = (unsigned)std::min(rows, 65535);
             count_launch();
-            k_gather_rows<<<dim3(gx, gy), 256, 0, h->stream>>>(s, dd, h->pp, np, rows, h->keep);
+            if (h->world == 1) {
+                k_gather_rows<<<dim3(gx, gy), 256, 0, h->stream>>>(b.*field, d.*field, h->pp, np, rows, h->keep);
+            } else {
+                PeerRows pr;
+                for (int r = 0; r < 8; r++) pr.base[r] = r < h->world ? h->peer[h->cur][r].*field : nullptr;
+                k_gather_rows_peer<<<dim3(gx, gy), 256, 0, h->stream>>>(pr, d.*field, h->pp, np, rows, h->keep);
+            }
         };
-        gather(b.xv, d.xv, 3);
-        gather(b.pv, d.pv, 9);
-        gather(b.xf, d.xf, 2 * h->nf);
-        gather(b.pf, d.pf, 3 * h->nf);
+        gather(&PfBuf::xv, 3);
+        gather(&PfBuf::pv, 9);
+        gather(&PfBuf::xf, 2 * h->nf);
+        gather(&PfBuf::pf, 3 * h->nf);
         count_launch();
-        k_fill<<<nblk(np, 256), 256, 0, h->stream>>>(d.w, np, 1.0 / (double)np);  // PF.cpp:495
+        k_fill<<<nblk(np, 256), 256, 0, h->stream>>>(d.w, np, 1.0 / (double)h->np_global);  // PF.cpp:495
         CSLAM_CUDA(cudaGetLastError());
         h->cur ^= 1;
     }

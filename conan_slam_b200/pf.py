@@ -26,7 +26,8 @@ class PF:
     """Drop-in for `std::shared_ptr<Slam> pfSlam(new PF(LM, WP))` + initializeParticles(n)
     (test/main.cpp:204-208; slam.h:688 -> PF.cpp:319-341)."""
 
-    def __init__(self, num_particles=100, capacity_landmarks=30, landMarks=None, wayPoints=None, device=0, flags=0):
+    def __init__(self, num_particles=100, capacity_landmarks=30, landMarks=None, wayPoints=None, device=0, flags=0,
+                 rank=0, world=1, nccl_id=None):
         self._lib = _lib.load_library()
         self.mLM = None if landMarks is None else np.asarray(landMarks, dtype=np.float64)
         self.mWP = None if wayPoints is None else np.asarray(wayPoints, dtype=np.float64)
@@ -37,9 +38,34 @@ class PF:
         self.mTABLE = np.zeros(capacity_landmarks if self.mLM is None else self.mLM.shape[1], dtype=np.int32)
         self.flags = flags
         h = C.c_void_p()
-        check(self._lib.cslam_pf_create(C.byref(h), int(num_particles), int(capacity_landmarks), int(device),
-                                        int(flags)), "cslam_pf_create")
-        self._h = h
+        self.rank, self.world = int(rank), int(world)
+        if world > 1:
+            # num_particles = LOCAL count; particles are block-partitioned over the ranks (include/cslam.h)
+            assert nccl_id is not None and len(nccl_id) == 128
+            buf = C.create_string_buffer(bytes(nccl_id), 128)
+            check(self._lib.cslam_pf_create_sharded(C.byref(h), int(num_particles), int(capacity_landmarks),
+                                                    int(device), int(flags), int(rank), int(world),
+                                                    C.cast(buf, C.c_void_p)), "cslam_pf_create_sharded")
+            self._h = h
+            self._exchange_ipc(device)
+        else:
+            check(self._lib.cslam_pf_create(C.byref(h), int(num_particles), int(capacity_landmarks), int(device),
+                                            int(flags)), "cslam_pf_create")
+            self._h = h
+
+    def _exchange_ipc(self, device):
+        """Every rank exports its buffers' CUDA-IPC handles; torch.distributed carries them around."""
+        import torch
+        import torch.distributed as dist
+        mine = C.create_string_buffer(640)
+        check(self._lib.cslam_pf_ipc_export(self._h, C.cast(mine, C.c_void_p)), "cslam_pf_ipc_export")
+        dev = f"cuda:{device}" if dist.get_backend() == "nccl" else "cpu"
+        t = torch.frombuffer(bytearray(mine.raw), dtype=torch.uint8).to(dev)
+        parts = [torch.zeros(640, dtype=torch.uint8, device=dev) for _ in range(self.world)]
+        dist.all_gather(parts, t)
+        blob = b"".join(bytes(p.cpu().numpy().tobytes()) for p in parts)
+        allb = C.create_string_buffer(blob, 640 * self.world)
+        check(self._lib.cslam_pf_ipc_import(self._h, C.cast(allb, C.c_void_p), self.world), "cslam_pf_ipc_import")
 
     def close(self):
         if getattr(self, "_h", None):

@@ -131,6 +131,17 @@ int cslam_ekf_device_ptrs(cslam_ekf_t* h, void** dX, void** dP, size_t* ld);
 /* Replaces `new PF(LM, WP)` + Slam::initializeParticles(n) (slam.h:688 -> PF.cpp:319-341):
  * w = 1/P, X = 0, P = 0, no features.  SoA over particles on the device. */
 int cslam_pf_create(cslam_pf_t** out, int num_particles, int capacity_landmarks, int device, unsigned flags);
+/* Multi-GPU: particles block-partitioned over `world` ranks (one process per GPU); num_particles_local
+ * must be a multiple of 32 and equal on every rank.  Per-particle kernels are local.  Resampling:
+ * the upper levels of the canonical scan are all-gathered (a few KB), the cumulative weights are
+ * all-gathered (8 B per particle), every rank resolves its own output slots, and survivors that live
+ * on other ranks are read straight from the owner's HBM over NVLink inside the gather kernel
+ * (peer buffers mapped with CUDA IPC: export on every rank, exchange on the host, import).
+ * Requires CSLAM_FLAG_Q10_SEARCH.  keep[] then holds GLOBAL particle indices.  SPMD call contract. */
+int cslam_pf_create_sharded(cslam_pf_t** out, int num_particles_local, int capacity_landmarks, int device,
+                            unsigned flags, int rank, int world, const void* nccl_unique_id);
+int cslam_pf_ipc_export(cslam_pf_t* h, void* out640);
+int cslam_pf_ipc_import(cslam_pf_t* h, const void* all_ranks_640_each, int world);
 int cslam_pf_destroy(cslam_pf_t* h);
 int cslam_pf_set_stream(cslam_pf_t* h, void* cuda_stream);
 int cslam_pf_sync(cslam_pf_t* h, int* skipped_updates);

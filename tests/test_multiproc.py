@@ -45,3 +45,13 @@ def test_sharded_ekf_parity(world):
     out = _torchrun(world, ["--what", "ekf"])
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-6000:]
     assert out.stdout.count("sharded EKF parity ok") == world
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_pf_parity(world):
+    if _gpu_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    out = _torchrun(world, ["--what", "pf"])
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-6000:]
+    assert out.stdout.count("sharded PF parity ok") == world
