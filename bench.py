@@ -263,6 +263,138 @@ def cpu_ekf_update_rate(N, threads, slab_cols, reps=2):
     }
 
 
+def cpu_pf_rate(nfeat, m_obs, threads, particles=2000):
+    L = oracle_lib()
+    t = L.orc_bench_pf_step(particles, nfeat, m_obs, threads, 0x1F)
+    return {"value": 1.0 / t, "unit": "particle-steps/s", "cores": threads, "kind": "port",
+            "sample": f"oracle AoS particle step (6 predict+heading, sampleProposal, featureUpdate, resample with deep "
+                      f"copy) on {particles} particles x {nfeat} landmarks, per-particle cost"}
+
+
+def run_pf(args):
+    """--workload pf: C4 of BASELINE.json — FastSLAM, 1M particles x 500 landmarks, m_obs = 4 known
+    associations per observation cycle, resampling every cycle; particles split over the GPUs."""
+    import torch
+    import torch.distributed as dist
+
+    import conan_slam_b200 as cs
+    from conan_slam_b200 import _lib
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = _lib.load_library()
+    P, nfeat, m_obs = args.particles, args.pf_landmarks, args.obs
+    assert P % (32 * world) == 0
+    Pl = P // world
+    stream = torch.cuda.Stream(device=local)
+    nid = None
+    if world > 1:
+        from conan_slam_b200 import dist as cdist
+        nid = cdist.nccl_unique_id(device=f"cuda:{local}")
+    sc = PfScenario(Pl, nfeat, m_obs, local, seed=P + 2, stream=stream.cuda_stream, rank=rank, world=world, nccl_id=nid)
+    pf = sc.pf
+    gen = torch.Generator(device=f"cuda:{local}")
+    gen.manual_seed(1234 + rank)
+    xi = torch.randn(Pl, 3, dtype=torch.float64, device=f"cuda:{local}", generator=gen)
+    u = torch.randn(Pl, dtype=torch.float64, device=f"cuda:{local}", generator=gen) * 0.3
+    xi_h = torch.empty(Pl, 3, dtype=torch.float64).pin_memory()
+    u_h = torch.empty(Pl, dtype=torch.float64).pin_memory()
+    xi_h.copy_(xi)
+    u_h.copy_(u)
+    torch.cuda.synchronize()
+    sc.init_map(xi.data_ptr())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        sc.cycle_step(xi.data_ptr(), u.data_ptr())
+    pf.sync()
+    sampler = ClockSampler(local)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    launches0 = lib.cslam_kernel_launches()
+    pf.profile_begin(args.steps + 4)
+    sampler.start()
+    did = []
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(args.steps):
+            did.append(sc.cycle_step(xi.data_ptr(), u.data_ptr())[2])
+        ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    g_ms, g_cnt, g_bytes = pf.profile_end()
+    launches = lib.cslam_kernel_launches() - launches0
+    ms = ev0.elapsed_time(ev1)
+    # end to end: the step's random draws come from pinned HOST memory, the weights go back to the host
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    xi_np, u_np = xi_h.numpy(), u_h.numpy()
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(args.steps):
+            sc.controls()
+            Z, ids = sc.observation()
+            pf.sampleProposal(Z, ids, PF_R, xi_np)
+            pf.featureUpdate(Z, ids, PF_R)
+            pf.resampleParticles(float("inf"), u_np, True, want_keep=False)
+            sc.cycle += 1
+            Xe, _ = pf.extractStatesFromParticles()  # D2H of the step's result
+        e1.record(stream)
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    w = pf.weights
+    ok = bool(all(did)) and bool(np.all(np.isfinite(w))) and pf.sync() == 0
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(t[0]), float(t[1])
+        c = torch.tensor([launches], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        launches = int(c[0])
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        value = P * args.steps / (ms * 1e-3)
+        bytes_step = PF_CONTROLS_PER_OBS * 2 * 208 + m_obs * 96 + 2 * (nfeat * 40 + 13 * 8)
+        ach = (g_bytes / g_cnt) / (g_ms / g_cnt * 1e-3) / 1e9 if g_cnt else 0.0
+        out = {
+            "metric": "PF particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"particle filter (FastSLAM) {P} particles x {nfeat} landmarks, {m_obs} known "
+                                   f"associations per observation cycle (6 predict+heading, sampleProposal, "
+                                   f"featureUpdate), resampling every cycle, particles split over {world} GPU(s)",
+                       "particles": P, "landmarks": nfeat, "obs_per_step": m_obs, "mode": "INTENDED",
+                       "l2": f"inputs larger than L2 ({Pl * nfeat * 40 / 1e9:.1f} GB of particle state per GPU)",
+                       "parallelism": "particles block-partitioned; NCCL all-gather of scan tops + cumulative weights; "
+                                      "survivors read from peers over NVLink inside the gather kernel"
+                       if world > 1 else "single GPU"},
+            "clocks": clocks,
+            "e2e": {"value": P * args.steps / (e2e_ms * 1e-3), "unit": "particle-steps/s",
+                    "h2d_bytes_per_step": int(Pl * 4 * 8 + m_obs * 28 + 6 * 40), "d2h_bytes_per_step": 48},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_gather_rows (PF.cpp:494-498 survivor copy)", "achieved": ach,
+                         "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src, "traffic": None,
+                         "algorithmic_bytes_per_launch": g_bytes / max(1, g_cnt), "launches_timed": g_cnt,
+                         "avg_launch_ms": g_ms / max(1, g_cnt),
+                         "whole_step_frac": bytes_step * Pl / (ms / args.steps * 1e-3) / 1e9 / peak},
+            "valid": ok,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            out["cpu_baseline"] = cpu_pf_rate(nfeat, m_obs, 1)
+            out["cpu_baseline"]["all_cores"] = cpu_pf_rate(nfeat, m_obs, os.cpu_count() or 1, particles=8000)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # --------------------------------------------------------------------------------- main ----
 def run_reference(args):
     """--impl reference: the reference's own (dense, CPU) algorithm for the same workload, all
@@ -315,11 +447,17 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--multi", default="sharded", choices=["sharded", "replicas"],
                     help="N>1: row-sharded covariance of ONE filter (strong scaling) or independent filter replicas")
-    ap.add_argument("--extras", action="store_true", help="also time the other single-GPU configs")
+    ap.add_argument("--workload", default="ekf", choices=["ekf", "pf"],
+                    help="ekf: the headline (BASELINE.json metric, first half); pf: particle-steps/sec (C4)")
+    ap.add_argument("--particles", type=int, default=1 << 20)
+    ap.add_argument("--pf-landmarks", type=int, default=500)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.workload == "pf":
+        run_pf(args)
         return
 
     import torch
@@ -417,7 +555,8 @@ def main():
         value = updates / (ms * 1e-3)
         e2e_value = e2e_updates / (e2e_ms * 1e-3)
         ach = (cov_bytes / cov_launches) / (cov_ms / cov_launches * 1e-3) / 1e9 if cov_launches else 0.0
-        alg_update_bytes = 8.0 * n * (n + 1) + 112.0 * n  # cov R+W + 5 P columns + X + gating/obs share
+        shards = world if sharded else 1   # per-GPU figures: each rank streams 1/world of the triangle
+        alg_update_bytes = (8.0 * n * (n + 1)) / shards + 112.0 * n  # cov R+W + 5 P columns + X + gating
         out = {
             "metric": "EKF updates/sec", "value": value, "unit": "updates/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -443,10 +582,11 @@ def main():
             "roofline": {
                 "bound": "hbm", "kernel": "k_cov_update<2,128> (slam.h:260, upper-triangle rank-2 update)",
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "peak_source": peak_src, "traffic": ncu_traffic("k_cov_update<2,128>", n),
-                "algorithmic_bytes_per_launch": 8.0 * n * (n + 1),
+                "peak_source": peak_src, "traffic": ncu_traffic("k_cov_update<2,128>", n) if world == 1 else None,
+                "algorithmic_bytes_per_launch": 8.0 * n * (n + 1) / shards, "per": "GPU",
                 "launches_timed": cov_launches, "avg_launch_ms": cov_ms / max(1, cov_launches),
-                "whole_update_frac": (alg_update_bytes * updates / (ms * 1e-3) / 1e9) / peak,
+                "whole_update_frac": (alg_update_bytes * (updates if (sharded or world == 1) else updates / world)
+                                      / (ms * 1e-3) / 1e9) / peak,
             },
             "skipped_updates": skipped,
             "state_checksum": float(np.sum(X_host[:3])) if X_host is not None else None,

@@ -77,6 +77,8 @@ SIGNATURES = {
     "cslam_pf_resample": (C.c_int, [_vp, _vp, C.c_int, C.c_double, C.c_int, _ip, _dp, C.POINTER(C.c_int)]),
     "cslam_pf_add_features": (C.c_int, [_vp, _dp, C.c_int, _dp]),
     "cslam_pf_sample_pose": (C.c_int, [_vp, _vp, C.c_int]),
+    "cslam_pf_profile_begin": (C.c_int, [_vp, C.c_int]),
+    "cslam_pf_profile_end": (C.c_int, [_vp, _dp, C.POINTER(C.c_int), _dp]),
     "cslam_pf_get_weights": (C.c_int, [_vp, _dp]),
     "cslam_pf_get_poses": (C.c_int, [_vp, _dp]),
     "cslam_pf_get_pose_covs": (C.c_int, [_vp, _dp]),

@@ -67,6 +67,10 @@ struct cslam_pf {
     double* cum_global = nullptr;          // [np_global] all-gathered cumulative weights
     cslam::PfBuf peer[2][8];               // IPC-mapped buffers of every rank (self = own pointers)
     bool peers_ready = false;
+    // diagnostics: CUDA events around the gather-copy launches of each resample
+    bool prof = false;
+    std::vector<cudaEvent_t> prof_ev;
+    int prof_used = 0;
 };
 
 namespace cslam {
@@ -941,6 +945,7 @@ int cslam_pf_destroy(cslam_pf_t* h) {
     cudaFree(h->comb); cudaFree(h->wn); cudaFree(h->keep); cudaFree(h->d_in);
     cudaFree(h->d_small); cudaFree(h->d_ismall);
     if (h->pinned) cudaFreeHost(h->pinned);
+    for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return CSLAM_OK;
@@ -1150,15 +1155,50 @@ int cslam_pf_resample(cslam_pf_t* h, const double* u, int u_on_device, double nu
                 k_gather_rows_peer<<<dim3(gx, gy), 256, 0, h->stream>>>(pr, d.*field, h->pp, np, rows, h->keep);
             }
         };
+        const bool prof = h->prof && h->prof_used + 2 <= (int)h->prof_ev.size();
+        if (prof) cudaEventRecord(h->prof_ev[h->prof_used], h->stream);
         gather(&PfBuf::xv, 3);
         gather(&PfBuf::pv, 9);
         gather(&PfBuf::xf, 2 * h->nf);
         gather(&PfBuf::pf, 3 * h->nf);
+        if (prof) {
+            cudaEventRecord(h->prof_ev[h->prof_used + 1], h->stream);
+            h->prof_used += 2;
+        }
         count_launch();
         k_fill<<<nblk(np, 256), 256, 0, h->stream>>>(d.w, np, 1.0 / (double)h->np_global);  // PF.cpp:495
         CSLAM_CUDA(cudaGetLastError());
         h->cur ^= 1;
     }
+    return CSLAM_OK;
+}
+
+int cslam_pf_profile_begin(cslam_pf_t* h, int max_resamples) {
+    if (int rc = check_pf(h)) return rc;
+    CSLAM_REQUIRE(max_resamples > 0 && max_resamples <= (1 << 16), CSLAM_ERR_BAD_ARG, "out of range");
+    while ((int)h->prof_ev.size() < 2 * max_resamples) {
+        cudaEvent_t e;
+        CSLAM_CUDA(cudaEventCreate(&e));
+        h->prof_ev.push_back(e);
+    }
+    h->prof_used = 0;
+    h->prof = true;
+    return CSLAM_OK;
+}
+int cslam_pf_profile_end(cslam_pf_t* h, double* ms, int* resamples, double* bytes) {
+    if (int rc = check_pf(h)) return rc;
+    h->prof = false;
+    CSLAM_CUDA(cudaStreamSynchronize(h->stream));
+    double total = 0.0;
+    for (int i = 0; i + 1 < h->prof_used; i += 2) {
+        float t = 0.f;
+        CSLAM_CUDA(cudaEventElapsedTime(&t, h->prof_ev[i], h->prof_ev[i + 1]));
+        total += t;
+    }
+    if (ms) *ms = total;
+    if (resamples) *resamples = h->prof_used / 2;
+    // algorithmic bytes of one gather-copy: every SoA row of every local particle read once, written once
+    if (bytes) *bytes = (double)(h->prof_used / 2) * 2.0 * 8.0 * (12.0 + 5.0 * h->nf) * (double)h->np;
     return CSLAM_OK;
 }
 

@@ -86,6 +86,15 @@ class PF:
         check(self._lib.cslam_pf_sync(self._h, C.byref(bad)), "cslam_pf_sync")
         return bad.value
 
+    def profile_begin(self, max_resamples=1024):
+        check(self._lib.cslam_pf_profile_begin(self._h, int(max_resamples)), "cslam_pf_profile_begin")
+
+    def profile_end(self):
+        """(summed gather-copy ms, resamples, summed algorithmic bytes)."""
+        ms, cnt, by = C.c_double(0), C.c_int(0), C.c_double(0)
+        check(self._lib.cslam_pf_profile_end(self._h, C.byref(ms), C.byref(cnt), C.byref(by)), "cslam_pf_profile_end")
+        return ms.value, cnt.value, by.value
+
     @property
     def num_particles(self):
         return self._lib.cslam_pf_num_particles(self._h)

@@ -171,6 +171,11 @@ int cslam_pf_add_features(cslam_pf_t* h, const double* Z, int m, const double R[
 /* particles[i].X = multivariateNormalGaussianDistribution(X,P,1); P = 0   test/main.cpp:319-325 */
 int cslam_pf_sample_pose(cslam_pf_t* h, const double* xi, int xi_on_device);
 
+/* Diagnostics (bench.py roofline): CUDA-event timing of the gather-copy of every resample between
+ * begin and end; *bytes = summed algorithmic bytes (2 x 8 x (12 + 5*Nf) per local particle). */
+int cslam_pf_profile_begin(cslam_pf_t* h, int max_resamples);
+int cslam_pf_profile_end(cslam_pf_t* h, double* ms, int* resamples, double* bytes);
+
 /* Accessors: weights (P), poses ([p][3]), pose covariances ([p][9] row-major),
  * features of one particle (XF [f][2], PF [f][4] row-major 2x2). */
 int cslam_pf_get_weights(cslam_pf_t* h, double* w);
