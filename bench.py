@@ -352,6 +352,12 @@ def run_pf(args):
     e2e_ms = e0.elapsed_time(e1)
     w = pf.weights
     ok = bool(all(did)) and bool(np.all(np.isfinite(w))) and pf.sync() == 0
+    # one extra untimed cycle with the indices read back: how many survivors cross rank boundaries
+    keep, neff_last, _ = sc.cycle_step(xi.data_ptr(), u.data_ptr(), want_keep=True)
+    remote_frac = float(np.mean((keep // Pl) != rank))
+    distinct = int(np.unique(keep).shape[0])
+    log(f"[bench r{rank}] neff={neff_last:.1f} of {P}, remote survivors {100 * remote_frac:.1f} %, "
+        f"{distinct} distinct sources for {Pl} slots")
     if world > 1:
         t = torch.tensor([ms, e2e_ms], device=f"cuda:{local}", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -385,7 +391,8 @@ def run_pf(args):
                          "algorithmic_bytes_per_launch": g_bytes / max(1, g_cnt), "launches_timed": g_cnt,
                          "avg_launch_ms": g_ms / max(1, g_cnt),
                          "whole_step_frac": bytes_step * Pl / (ms / args.steps * 1e-3) / 1e9 / peak},
-            "valid": ok,
+            "valid": ok, "neff": neff_last, "remote_survivor_frac_rank0": remote_frac,
+            "distinct_sources_rank0": distinct,
         }
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_pf_rate(nfeat, m_obs, 1)

@@ -17,6 +17,7 @@
 // Built with -fmad=false and written in the oracle's operation order (matmul = ascending-k
 // accumulation from zero, PartialPivLU inverse, LLT) so weights and poses track
 // oracle/slam_oracle.hpp to rounding of libm calls only.
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -67,6 +68,7 @@ struct cslam_pf {
     double* cum_global = nullptr;          // [np_global] all-gathered cumulative weights
     cslam::PfBuf peer[2][8];               // IPC-mapped buffers of every rank (self = own pointers)
     bool peers_ready = false;
+    const double** d_peer_tab = nullptr;   // device copy of the peers' base pointers
     // diagnostics: CUDA events around the gather-copy launches of each resample
     bool prof = false;
     std::vector<cudaEvent_t> prof_ev;
@@ -571,17 +573,17 @@ __global__ void __launch_bounds__(256) k_gather_rows(const double* __restrict__ 
 // Multi-GPU variant: keep[] holds GLOBAL source indices; the survivor's rows are read straight from
 // the owning rank's buffer over NVLink (IPC-mapped peer pointers) — the all-to-all of the
 // resampling step is fused into the gather kernel, no staging copy.
-struct PeerRows {
-    const double* base[8];
-};
-__global__ void __launch_bounds__(256) k_gather_rows_peer(PeerRows src, double* __restrict__ dst, size_t pp,
-                                                          int np, int rows, const int* __restrict__ keep) {
+// (the per-rank base pointers live in a small device table: indexing a by-value kernel parameter
+//  dynamically would spill it to local memory in every thread)
+__global__ void __launch_bounds__(256) k_gather_rows_peer(const double* const* __restrict__ base,
+                                                          double* __restrict__ dst, size_t pp, int np, int rows,
+                                                          const int* __restrict__ keep) {
     const int c = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
     if (c >= np) return;
     const int g0 = keep[c];
     const int g1 = (c + 1 < np) ? keep[c + 1] : g0;
-    const double* s0 = src.base[g0 / np] + (g0 % np);
-    const double* s1 = src.base[g1 / np] + (g1 % np);
+    const double* __restrict__ s0 = base[g0 / np] + (g0 % np);
+    const double* __restrict__ s1 = base[g1 / np] + (g1 % np);
     for (int r = blockIdx.y; r < rows; r += gridDim.y) {
         double2 v;
         v.x = s0[(size_t)r * pp];
@@ -942,6 +944,7 @@ int cslam_pf_destroy(cslam_pf_t* h) {
     }
     for (int l = 0; l < 5; l++) { cudaFree(h->scan[l]); cudaFree(h->gscan[l]); }
     cudaFree(h->cum_global);
+    cudaFree(h->d_peer_tab);
     cudaFree(h->comb); cudaFree(h->wn); cudaFree(h->keep); cudaFree(h->d_in);
     cudaFree(h->d_small); cudaFree(h->d_ismall);
     if (h->pinned) cudaFreeHost(h->pinned);
@@ -1143,24 +1146,35 @@ int cslam_pf_resample(cslam_pf_t* h, const double* u, int u_on_device, double nu
     if (doit) {
         PfBuf& d = h->buf[h->cur ^ 1];
         const unsigned gx = nblk(((size_t)np + 1) / 2, 256);
-        auto gather = [&](double* PfBuf::*field, int rows) {
+        if (!h->d_peer_tab) {  // device table of every rank's base pointers: [buffer][xv,pv,xf,pf][rank]
+            CSLAM_CUDA(cudaMalloc(&h->d_peer_tab, 2 * 4 * 8 * sizeof(double*)));
+            const double* tab[2][4][8] = {};
+            for (int bb = 0; bb < 2; bb++)
+                for (int r = 0; r < h->world; r++) {
+                    tab[bb][0][r] = h->peer[bb][r].xv; tab[bb][1][r] = h->peer[bb][r].pv;
+                    tab[bb][2][r] = h->peer[bb][r].xf; tab[bb][3][r] = h->peer[bb][r].pf;
+                }
+            CSLAM_CUDA(cudaMemcpyAsync(h->d_peer_tab, tab, sizeof(tab), cudaMemcpyHostToDevice, h->stream));
+            CSLAM_CUDA(cudaStreamSynchronize(h->stream));
+        }
+        auto gather = [&](double* PfBuf::*field, int slot, int rows) {
             if (rows <= 0) return;
             const unsigned gy = (unsigned)std::min(rows, 65535);
             count_launch();
-            if (h->world == 1) {
+            static const bool force_peer = getenv("CSLAM_PF_FORCE_PEER_KERNEL") != nullptr;  // development switch
+            if (h->world == 1 && !force_peer) {
                 k_gather_rows<<<dim3(gx, gy), 256, 0, h->stream>>>(b.*field, d.*field, h->pp, np, rows, h->keep);
             } else {
-                PeerRows pr;
-                for (int r = 0; r < 8; r++) pr.base[r] = r < h->world ? h->peer[h->cur][r].*field : nullptr;
-                k_gather_rows_peer<<<dim3(gx, gy), 256, 0, h->stream>>>(pr, d.*field, h->pp, np, rows, h->keep);
+                k_gather_rows_peer<<<dim3(gx, gy), 256, 0, h->stream>>>(h->d_peer_tab + (h->cur * 4 + slot) * 8,
+                                                                        d.*field, h->pp, np, rows, h->keep);
             }
         };
         const bool prof = h->prof && h->prof_used + 2 <= (int)h->prof_ev.size();
         if (prof) cudaEventRecord(h->prof_ev[h->prof_used], h->stream);
-        gather(&PfBuf::xv, 3);
-        gather(&PfBuf::pv, 9);
-        gather(&PfBuf::xf, 2 * h->nf);
-        gather(&PfBuf::pf, 3 * h->nf);
+        gather(&PfBuf::xv, 0, 3);
+        gather(&PfBuf::pv, 1, 9);
+        gather(&PfBuf::xf, 2, 2 * h->nf);
+        gather(&PfBuf::pf, 3, 3 * h->nf);
         if (prof) {
             cudaEventRecord(h->prof_ev[h->prof_used + 1], h->stream);
             h->prof_used += 2;
