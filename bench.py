@@ -35,6 +35,25 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# Only the ONE JSON result line may reach stdout: libraries (e.g. NCCL's version banner) write to
+# fd 1 directly, so fd 1 is pointed at stderr and the result goes out through a saved duplicate.
+_RESULT_OUT = None
+
+
+def _capture_stdout():
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    out = _RESULT_OUT or sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
+
+
 # ----------------------------------------------------------------------------- clocks ----
 class ClockSampler:
     """Samples SM clock / throttle reasons of one GPU during the timed region (NVML)."""
@@ -397,7 +416,7 @@ def run_pf(args):
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_pf_rate(nfeat, m_obs, 1)
             out["cpu_baseline"]["all_cores"] = cpu_pf_rate(nfeat, m_obs, os.cpu_count() or 1, particles=8000)
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -440,7 +459,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def main():
@@ -459,6 +478,7 @@ def main():
     ap.add_argument("--particles", type=int, default=1 << 20)
     ap.add_argument("--pf-landmarks", type=int, default=500)
     args = ap.parse_args()
+    _capture_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
@@ -605,7 +625,7 @@ def main():
             out["cpu_baseline"]["all_cores"] = {"cores": mt["cores"], "value": mt["value"],
                                                 "update_only_updates_per_s": mt["update_only_updates_per_s"]}
             log(f"[bench] cpu baseline took {time.time() - t1:.1f}s")
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
