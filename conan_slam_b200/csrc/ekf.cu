@@ -573,8 +573,9 @@ __global__ void k_scatter_upper(double* __restrict__ P, double* __restrict__ R3,
 }
 
 // defined in ekf_dmma.cu: tensor-core (FP64 DMMA) rank-r update for large maps
+size_t dmma_panel_doubles(int n_cap);
 int launch_cov_update_dmma(double* P, size_t ld, int n, const double* A, size_t lda, int r, Shard sh,
-                           cudaStream_t stream);
+                           double* panels, int n_cap, int chunk, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------
 // Host-side launch helpers
@@ -628,9 +629,16 @@ static int launch_cov_update_rank(cslam_ekf* h, int r) {
     h->diag_dirty = true;
     // large maps (and every sharded map): FP64 tensor-core kernel; small maps: plain FMA kernel
     if (n >= 1024 || h->sh.world > 1) {
+        if (!h->dmma_panels) {
+            const size_t bytes = dmma_panel_doubles(h->n_cap) * sizeof(double);
+            CSLAM_CUDA(cudaMalloc(&h->dmma_panels, bytes));
+            CSLAM_CUDA(cudaMemsetAsync(h->dmma_panels, 0, bytes, h->stream));
+        }
         {
             ProfScope prof(h);
-            if (int rc = launch_cov_update_dmma(h->P, h->ld, n, h->A, h->lda, r, h->sh, h->stream)) return rc;
+            if (int rc = launch_cov_update_dmma(h->P, h->ld, n, h->A, h->lda, r, h->sh, h->dmma_panels, h->n_cap, 0,
+                                                h->stream))
+                return rc;
         }
         if (h->sh.world > 1) {  // tensor-core rounding differs from the replicas' FMA order: re-broadcast rows 0..2
             const NcclApi* api = nccl_api();
@@ -787,6 +795,7 @@ int cslam_ekf_destroy(cslam_ekf_t* h) {
     if (h->R3 && h->R3 != h->P) cudaFree(h->R3);
     cudaFree(h->colbuf); cudaFree(h->D);
     cudaFree(h->X[0]); cudaFree(h->X[1]); cudaFree(h->P); cudaFree(h->A); cudaFree(h->PHT);
+    cudaFree(h->dmma_panels);
     cudaFree(h->small); cudaFree(h->status); cudaFree(h->ticket);
     cudaFree(h->gate.part_nd); cudaFree(h->gate.part_out); cudaFree(h->gate.part_j);
     cudaFree(h->gate.d_jbest); cudaFree(h->gate.d_nbest); cudaFree(h->gate.d_outer);

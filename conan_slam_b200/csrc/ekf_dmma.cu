@@ -2,121 +2,297 @@
 // rank-r panel (r = 2m <= 64) on the FP64 tensor cores of sm_100a.
 //
 // FP64 is not a tcgen05.mma kind: Blackwell's FP64 tensor path is the warp-level
-// mma.sync.aligned.m8n8k4.f64 (SASS: DMMA).  The update is a real rank-r contraction
-// (8 flop/B at r = 64, above the FP64 ridge) only in this batched case; the sequential
-// rank-1/2 updates stay on the streaming kernel in ekf.cu.
+// mma.sync.aligned.m8n8k4.f64 (SASS: DMMA.8x8x4; the wider PTX shapes m16n8k{4,8,16} lower to
+// the same instruction).  The update is a real rank-r contraction (8 flop/B at r = 64, above
+// the FP64 ridge) only in this batched case; the sequential rank-1/2 updates stay on the
+// streaming kernel in cov_update.cuh.
 //
-// Tiling: one CTA = 64 x 128 tile of the upper triangle (tiles with any j >= i), 8 warps,
-// each warp a 32 x 32 sub-tile = 4 x 4 DMMA blocks.  The accumulator fragments ARE the
-// covariance: they are loaded straight from P (C operand), the negated row panel is the A
-// operand, the column panel the B operand, and the fragments are stored back — P is read
-// once and written once.  Panels are staged in shared memory with a row stride = 4 (mod 16)
-// doubles, which makes the fragment reads bank-conflict free.
+// Structure (one CTA per SM, 8 warps, each a 32 x 32 sub-tile = 4 x 4 DMMA blocks):
+//   * a CTA owns a CHUNK of consecutive 128 x 64 tiles of ONE 128-row strip of the upper
+//     triangle; the strip's (negated) row panel is brought into shared memory once per chunk;
+//   * the column panel of every tile arrives by a single TMA bulk copy (cp.async.bulk +
+//     mbarrier complete_tx) from a pre-tiled, pre-padded copy of the panel into a 4-deep ring;
+//     full/empty mbarriers hand the buffers between the producer lane and the 8 warps, so
+//     there is no CTA-wide barrier in the loop and the warps drift apart (one warp's load/store
+//     phase overlaps another's DMMA phase);
+//   * the accumulator fragments ARE the covariance: the fragments of tile t+1 are loaded
+//     straight from P into a second register set BEFORE the DMMAs of tile t issue, so the HBM
+//     stream (read next / write previous) overlaps the tensor pipe; P is read once, written once;
+//   * panels sit in shared memory with a row stride = 4 (mod 16) doubles: conflict-free
+//     fragment reads (the 16 lanes of a half-warp cover 16 distinct 8-byte banks).
 #include "common.cuh"
 #include "cov_update.cuh"
 
 namespace cslam {
 
-constexpr int DM_TM = 64, DM_TN = 128;
-constexpr int DM_SR = DM_TM + 4;  // 68
-constexpr int DM_SC = DM_TN + 4;  // 132
+constexpr int DM_TM = 128, DM_TN = 64, DM_K = 64;
+constexpr int DM_SR = DM_TM + 4;  // 132: row-panel stride  (doubles)
+constexpr int DM_SC = DM_TN + 4;  // 68 : column-panel stride
+constexpr int DM_NBUF = 4;               // column-panel ring depth
+constexpr int DM_THREADS = 8 * 32;       // 8 warps, one 32 x 32 sub-tile each
+constexpr int DM_SMEM = (DM_K * DM_SR + DM_NBUF * DM_K * DM_SC) * (int)sizeof(double) + 128;
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
 }
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
 
-__global__ void __launch_bounds__(256, 2) k_cov_update_dmma(double* __restrict__ P, size_t ld, int n,
-                                                            const double* __restrict__ A, size_t lda, int r,
-                                                            int rp, int nbc, Shard sh) {
-    extern __shared__ double smem[];
-    double* sR = smem;               // [rp][DM_SR]  negated row panel
-    double* sC = smem + rp * DM_SR;  // [rp][DM_SC]  column panel
+// Pre-tiled panels: Ac[tc][k][DM_SC] = A[k][tc*64 + jj], Ar[tr][k][DM_SR] = -A[k][tr*128 + ii]
+// (zero beyond n / beyond rank r), each tile a contiguous block one bulk copy brings in.
+__global__ void __launch_bounds__(256) k_dmma_panels(const double* __restrict__ A, size_t lda, int n, int r,
+                                                     int ncols, double* __restrict__ Ar, double* __restrict__ Ac) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;
+    if (i >= ncols) return;
+    const double v = (k < r && i < n) ? A[(size_t)k * lda + i] : 0.0;
+    Ac[(size_t)(i / DM_TN) * (DM_K * DM_SC) + k * DM_SC + (i % DM_TN)] = v;
+    Ar[(size_t)(i / DM_TM) * (DM_K * DM_SR) + k * DM_SR + (i % DM_TM)] = -v;
+}
 
-    // linear tile id -> (br, bc): every owned 128-row shard tile `tr` holds two 64-row tile rows
-    // (2tr, 2tr+1) that both start at column tile bc = tr  (nbc - tr tiles each)
-    const long long t = blockIdx.x;
-    int tr, tcd;
-    shard_tile(t >> 1, nbc, sh, tr, tcd);
-    const long long first = 2 * shard_first_tile((tr - sh.rank) / sh.world, nbc, sh);
-    const int rem = (int)(t - first), cnt = nbc - tr;
-    const int br = rem < cnt ? 2 * tr : 2 * tr + 1;
-    const int bc = rem < cnt ? tr + rem : tr + rem - cnt;
-    const int i0 = br * DM_TM, j0 = bc * DM_TN;
-
-    for (int idx = threadIdx.x; idx < rp * DM_TM; idx += 256) {
-        const int k = idx / DM_TM, ii = idx % DM_TM;
-        sR[k * DM_SR + ii] = (k < r && i0 + ii < n) ? -A[(size_t)k * lda + i0 + ii] : 0.0;
-    }
-    for (int idx = threadIdx.x; idx < rp * DM_TN; idx += 256) {
-        const int k = idx / DM_TN, jj = idx % DM_TN;
-        sC[k * DM_SC + jj] = (k < r && j0 + jj < n) ? A[(size_t)k * lda + j0 + jj] : 0.0;
-    }
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wr = warp >> 2, wc = warp & 3;
-    const int lr = lane >> 2, lc = lane & 3;
-    const int iw = i0 + wr * 32, jw = j0 + wc * 32;
-    // a warp sub-tile entirely below the diagonal has nothing to do
-    const bool warp_active = (jw + 31 >= iw) && (iw < n) && (jw < n);
-
-    double acc[4][4][2];
-    if (warp_active) {
+// One 32 x 32 warp sub-tile: f += (-row panel) x (column panel) over k = 0..rp-1, the a/b fragments
+// of k-step s+1 fetched from shared memory while the 16 DMMAs of k-step s issue.
+template <bool FULL>
+__device__ __forceinline__ void dmma_tile(double (&f)[4][4][2], const double* __restrict__ pr,
+                                          const double* __restrict__ pc, int rp) {
+    double a0[4], b0[4], a1[4], b1[4];
+    const int nks = FULL ? DM_K / 4 : rp / 4;
 #pragma unroll
-        for (int bi = 0; bi < 4; bi++) {
-            const int i = iw + bi * 8 + lr;
+    for (int x = 0; x < 4; x++) {
+        a0[x] = pr[x * 8];
+        b0[x] = pc[x * 8];
+    }
 #pragma unroll
-            for (int bj = 0; bj < 4; bj++) {
-                const int j = jw + bj * 8 + 2 * lc;
-                double2 v = make_double2(0.0, 0.0);
-                if (i < n && j < n && j + 1 >= i) v = ld128(P + shard_lrow(sh, i) * ld + j);
-                acc[bi][bj][0] = v.x;
-                acc[bi][bj][1] = v.y;
+    for (int ks = 0; ks < (FULL ? DM_K / 4 : 16); ks += 2) {
+        if (!FULL && ks >= nks) break;
+        if (FULL || ks + 1 < nks) {
+#pragma unroll
+            for (int x = 0; x < 4; x++) {
+                a1[x] = pr[(ks + 1) * 4 * DM_SR + x * 8];
+                b1[x] = pc[(ks + 1) * 4 * DM_SC + x * 8];
             }
-        }
-    }
-    __syncthreads();
-    if (!warp_active) return;
-
-    const double* pr = sR + lc * DM_SR + wr * 32 + lr;
-    const double* pc = sC + lc * DM_SC + wc * 32 + lr;
-    for (int k0 = 0; k0 < rp; k0 += 4) {
-        double a[4], b[4];
-#pragma unroll
-        for (int x = 0; x < 4; x++) {
-            a[x] = pr[k0 * DM_SR + x * 8];
-            b[x] = pc[k0 * DM_SC + x * 8];
         }
 #pragma unroll
         for (int bi = 0; bi < 4; bi++)
 #pragma unroll
-            for (int bj = 0; bj < 4; bj++) dmma884(acc[bi][bj][0], acc[bi][bj][1], a[bi], b[bj]);
-    }
+            for (int bj = 0; bj < 4; bj++) dmma884(f[bi][bj][0], f[bi][bj][1], a0[bi], b0[bj]);
+        if (FULL || ks + 1 < nks) {
+            if ((FULL && ks + 2 < DM_K / 4) || (!FULL && ks + 2 < nks)) {
 #pragma unroll
-    for (int bi = 0; bi < 4; bi++) {
-        const int i = iw + bi * 8 + lr;
+                for (int x = 0; x < 4; x++) {
+                    a0[x] = pr[(ks + 2) * 4 * DM_SR + x * 8];
+                    b0[x] = pc[(ks + 2) * 4 * DM_SC + x * 8];
+                }
+            }
 #pragma unroll
-        for (int bj = 0; bj < 4; bj++) {
-            const int j = jw + bj * 8 + 2 * lc;
-            // pairs straddling the diagonal (j + 1 == i) rewrite one unauthoritative lower element
-            if (i < n && j < n && j + 1 >= i)
-                st128(P + shard_lrow(sh, i) * ld + j, make_double2(acc[bi][bj][0], acc[bi][bj][1]));
+            for (int bi = 0; bi < 4; bi++)
+#pragma unroll
+                for (int bj = 0; bj < 4; bj++) dmma884(f[bi][bj][0], f[bi][bj][1], a1[bi], b1[bj]);
         }
     }
 }
 
+template <bool FULL>
+__global__ void __launch_bounds__(DM_THREADS, 1) k_cov_update_dmma(double* __restrict__ P, size_t ld, int n,
+                                                                   const double* __restrict__ Ar,
+                                                                   const double* __restrict__ Ac, int rp, int nbc,
+                                                                   int chunk, Shard sh) {
+    extern __shared__ __align__(128) double smem[];
+    double* sR = smem;                 // [rp][DM_SR]  negated row panel of the strip
+    double* sC = smem + DM_K * DM_SR;  // [DM_NBUF][rp][DM_SC] column panels (ring)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sC + DM_NBUF * DM_K * DM_SC);
+
+    const int tr = blockIdx.y * sh.world + sh.rank;  // 128-row strip (global tile row)
+    const int c0 = 2 * tr + blockIdx.x * chunk;      // first 64-column tile of this chunk
+    if (c0 >= nbc) return;
+    const int c1 = min(c0 + chunk, nbc);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * DM_NBUF, bar_row = bar_empty + 8 * DM_NBUF;
+    const uint32_t row_bytes = (uint32_t)rp * DM_SR * sizeof(double);
+    const uint32_t col_bytes = (uint32_t)rp * DM_SC * sizeof(double);
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < DM_NBUF; s++) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 8);  // one arrival per consumer warp
+        }
+        mbar_init(bar_row, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // Producer role (lane 0 of warp 0, inside its own consumer loop): at step q it refills the ring
+    // slot that tile q-2 used with the panel of tile q+2, so it only ever waits for warps that lag
+    // two whole tiles behind.
+    auto produce = [&](int q) {  // q = tile index within the chunk
+        if (c0 + q >= c1) return;
+        const int s = q % DM_NBUF;
+        if (q >= DM_NBUF) mbar_wait(bar_empty + 8 * s, ((q / DM_NBUF) - 1) & 1);
+        mbar_expect_tx(bar_full + 8 * s, col_bytes);
+        bulk_g2s(smem_u32(sC + s * (DM_K * DM_SC)), Ac + (size_t)(c0 + q) * (DM_K * DM_SC), col_bytes,
+                 bar_full + 8 * s);
+    };
+    if (tid == 0) {
+        mbar_expect_tx(bar_row, row_bytes);
+        bulk_g2s(smem_u32(sR), Ar + (size_t)tr * (DM_K * DM_SR), row_bytes, bar_row);
+        produce(0);
+        produce(1);
+    }
+
+    // ---------------- consumers
+    const int wr = warp >> 1, wc = warp & 1;
+    const int lr = lane >> 2, lc = lane & 3;
+    const int iw = tr * DM_TM + wr * 32;
+    // row bases of the 4 fragment rows this lane owns (rows >= n are never dereferenced)
+    double* prow[4];
+#pragma unroll
+    for (int bi = 0; bi < 4; bi++) prow[bi] = P + shard_lrow(sh, iw + bi * 8 + lr) * ld + 2 * lc;
+
+    // sub-tile state: 0 = nothing to do (below the diagonal / outside), 1 = interior (no masks), 2 = masked
+    auto tile_kind = [&](int tc) -> int {
+        const int jw = tc * DM_TN + wc * 32;
+        if (!((jw + 31 >= iw) && (iw < n) && (jw < n))) return 0;
+        return (jw >= iw + 32 && jw + 32 <= n && iw + 32 <= n) ? 1 : 2;
+    };
+    auto load_tile = [&](int tc, int kind, double(&f)[4][4][2]) {
+        const int jw = tc * DM_TN + wc * 32;
+        if (kind == 1) {
+#pragma unroll
+            for (int bi = 0; bi < 4; bi++)
+#pragma unroll
+                for (int bj = 0; bj < 4; bj++) {
+                    const double2 v = __ldcs(reinterpret_cast<const double2*>(prow[bi] + jw + bj * 8));
+                    f[bi][bj][0] = v.x;
+                    f[bi][bj][1] = v.y;
+                }
+        } else if (kind == 2) {
+#pragma unroll
+            for (int bi = 0; bi < 4; bi++) {
+                const int i = iw + bi * 8 + lr;
+#pragma unroll
+                for (int bj = 0; bj < 4; bj++) {
+                    const int j = jw + bj * 8 + 2 * lc;
+                    double2 v = make_double2(0.0, 0.0);
+                    if (i < n && j < n && j + 1 >= i) v = __ldcs(reinterpret_cast<const double2*>(prow[bi] + jw + bj * 8));
+                    f[bi][bj][0] = v.x;
+                    f[bi][bj][1] = v.y;
+                }
+            }
+        }
+    };
+    auto store_tile = [&](int tc, int kind, double(&f)[4][4][2]) {
+        const int jw = tc * DM_TN + wc * 32;
+        if (kind == 1) {
+#pragma unroll
+            for (int bi = 0; bi < 4; bi++)
+#pragma unroll
+                for (int bj = 0; bj < 4; bj++)
+                    __stcs(reinterpret_cast<double2*>(prow[bi] + jw + bj * 8),
+                           make_double2(f[bi][bj][0], f[bi][bj][1]));
+        } else {
+#pragma unroll
+            for (int bi = 0; bi < 4; bi++) {
+                const int i = iw + bi * 8 + lr;
+#pragma unroll
+                for (int bj = 0; bj < 4; bj++) {
+                    const int j = jw + bj * 8 + 2 * lc;
+                    // pairs straddling the diagonal (j + 1 == i) rewrite one unauthoritative lower element
+                    if (i < n && j < n && j + 1 >= i)
+                        __stcs(reinterpret_cast<double2*>(prow[bi] + jw + bj * 8),
+                               make_double2(f[bi][bj][0], f[bi][bj][1]));
+                }
+            }
+        }
+    };
+    const double* pr = sR + lc * DM_SR + wr * 32 + lr;
+    // one pipeline step: prefetch tile t+1 into `nxt`, finish tile t from `cur`, hand its panel buffer back
+    auto step = [&](int t, double(&cur)[4][4][2], int cur_kind, double(&nxt)[4][4][2]) -> int {
+        const int q = t - c0, s = q % DM_NBUF;
+        int nxt_kind = 0;
+        if (tid == 0) produce(q + 2);
+        if (t + 1 < c1) {
+            nxt_kind = tile_kind(t + 1);
+            load_tile(t + 1, nxt_kind, nxt);
+        }
+        // every warp waits (also one with nothing to do): a warp may not run ahead of the panel ring
+        mbar_wait(bar_full + 8 * s, (q / DM_NBUF) & 1);
+        if (cur_kind) {
+            dmma_tile<FULL>(cur, pr, sC + s * (DM_K * DM_SC) + lc * DM_SC + wc * 32 + lr, rp);
+            store_tile(t, cur_kind, cur);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + 8 * s);  // this warp is done reading panel buffer s
+        return nxt_kind;
+    };
+
+    double fa[4][4][2], fb[4][4][2];
+    int kind_a = tile_kind(c0), kind_b = 0;
+    load_tile(c0, kind_a, fa);
+    mbar_wait(bar_row, 0);
+    for (int t = c0; t < c1; t += 2) {
+        kind_b = step(t, fa, kind_a, fb);
+        if (t + 1 < c1) kind_a = step(t + 1, fb, kind_b, fa);
+    }
+}
+
+// Ar / Ac: pre-tiled panel buffers owned by the handle (dmma_panel_doubles() each).
+size_t dmma_panel_doubles(int n_cap) {
+    const size_t ntr = ((size_t)n_cap + DM_TM - 1) / DM_TM;
+    return ntr * DM_K * DM_SR + 2 * ntr * DM_K * DM_SC;  // Ar then Ac (2 column tiles per strip)
+}
+
 int launch_cov_update_dmma(double* P, size_t ld, int n, const double* A, size_t lda, int r, Shard sh,
-                           cudaStream_t stream) {
+                           double* panels, int n_cap, int chunk, cudaStream_t stream) {
     const int rp = (r + 3) / 4 * 4;
+    const int ntr = (n + DM_TM - 1) / DM_TM;
     const int nbc = (n + DM_TN - 1) / DM_TN;
-    const long long tiles = 2 * shard_tile_count(nbc, sh);  // a trailing half-empty tile row exits early
-    if (tiles == 0) return CSLAM_OK;
-    const size_t smem = (size_t)rp * (DM_SR + DM_SC) * sizeof(double);
-    CSLAM_CUDA(cudaFuncSetAttribute(k_cov_update_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    64 * (DM_SR + DM_SC) * (int)sizeof(double)));
+    const size_t ntr_cap = ((size_t)n_cap + DM_TM - 1) / DM_TM;
+    double* Ar = panels;
+    double* Ac = panels + ntr_cap * DM_K * DM_SR;
+    if (chunk <= 0) chunk = 16;
     count_launch();
-    k_cov_update_dmma<<<(unsigned)tiles, 256, smem, stream>>>(P, ld, n, A, lda, r, rp, nbc, sh);
+    k_dmma_panels<<<dim3((ntr * DM_TM + 255) / 256, rp), 256, 0, stream>>>(A, lda, n, r, ntr * DM_TM, Ar, Ac);
+    CSLAM_CUDA(cudaGetLastError());
+    int strips = 0;
+    for (int tr = sh.rank; tr < ntr; tr += sh.world) strips++;
+    if (strips == 0) return CSLAM_OK;
+    const dim3 grid((nbc + chunk - 1) / chunk, strips);
+    count_launch();
+    if (rp == DM_K) {
+        CSLAM_CUDA(cudaFuncSetAttribute(k_cov_update_dmma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DM_SMEM));
+        k_cov_update_dmma<true><<<grid, DM_THREADS, DM_SMEM, stream>>>(P, ld, n, Ar, Ac, rp, nbc, chunk, sh);
+    } else {
+        CSLAM_CUDA(cudaFuncSetAttribute(k_cov_update_dmma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DM_SMEM));
+        k_cov_update_dmma<false><<<grid, DM_THREADS, DM_SMEM, stream>>>(P, ld, n, Ar, Ac, rp, nbc, chunk, sh);
+    }
     CSLAM_CUDA(cudaGetLastError());
     return CSLAM_OK;
 }

@@ -46,6 +46,7 @@ struct cslam_ekf {
     double* P = nullptr;
     double* A = nullptr;    // [kMaxRank][lda]
     double* PHT = nullptr;  // [kMaxRank][lda]
+    double* dmma_panels = nullptr;  // pre-tiled panel copies of the tensor-core joint update (lazy)
     cslam::BatchSmall* small = nullptr;
     int* status = nullptr;        // device: #skipped updates
     unsigned* ticket = nullptr;   // device: last-block tickets (predict, gate)

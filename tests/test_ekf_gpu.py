@@ -68,7 +68,7 @@ def test_single_update_parity(N, m, flags):
 
 
 @pytest.mark.parametrize("flags", [0, oracle_py.FLAG_INTENDED])
-@pytest.mark.parametrize("N,m", [(1, 1), (7, 7), (25, 5), (150, 16), (150, 32), (1100, 32)])
+@pytest.mark.parametrize("N,m", [(1, 1), (7, 7), (25, 5), (150, 16), (150, 32), (1100, 32), (1100, 5), (700, 17)])
 def test_batch_update_parity(N, m, flags):
     """EKF.cpp:93-129 joint update; N=1100 takes the FP64 tensor-core (DMMA) kernel."""
     g, o, lm = _pair(N, 30 + N, flags)
