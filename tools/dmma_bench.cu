@@ -11,6 +11,7 @@
 #include "../conan_slam_b200/csrc/ekf_dmma.cu"
 
 using namespace cslam;
+namespace cslam { extern int g_dmma_dbg; }
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1);} } while (0)
 
@@ -196,7 +197,7 @@ int main(int argc, char** argv) {
     };
     // correctness: one application of each kernel on identical inputs must agree bit for bit
     run_v1(P1);
-    if (launch_cov_update_dmma(P2, ld, n, A, ld, r, sh, panels, n, 16, 0)) { printf("launch failed: %s\n", cslam_last_error()); return 1; }
+    if (launch_cov_update_dmma(P2, ld, n, A, ld, r, sh, panels, n, 32, 0)) { printf("launch failed: %s\n", cslam_last_error()); return 1; }
     CK(cudaDeviceSynchronize());
     CK(cudaMemset(bad, 0, 8));
     k_cmp<<<148 * 8, 256>>>(P1, P2, ld, n, bad);
@@ -210,7 +211,11 @@ int main(int argc, char** argv) {
     CK(cudaDeviceSynchronize());
     CK(cudaEventElapsedTime(&ms, e0, e1));
     printf("v1  (round-1 kernel)         : %8.3f ms  %6.2f TFLOP/s  %7.1f GB/s\n", ms / reps, flop / (ms / reps * 1e-3) / 1e12, gb / (ms / reps * 1e-3));
-    for (int chunk : {4, 8, 16, 32, 64}) {
+    for (int dbg : {0, 1, 2, 3})
+    for (int chunk : {16, 32, 64}) {
+        const int grp = 0;
+        g_dmma_dbg = dbg;
+        printf("dbg=%d (1: no P loads, 2: no P stores) ", dbg);
         launch_cov_update_dmma(P2, ld, n, A, ld, r, sh, panels, n, chunk, 0);
         CK(cudaDeviceSynchronize());
         CK(cudaEventRecord(e0));
@@ -218,7 +223,7 @@ int main(int argc, char** argv) {
         CK(cudaEventRecord(e1));
         CK(cudaDeviceSynchronize());
         CK(cudaEventElapsedTime(&ms, e0, e1));
-        printf("production kernel, chunk=%2d   : %8.3f ms  %6.2f TFLOP/s  %7.1f GB/s (incl. panel tiling kernel)\n", chunk, ms / reps, flop / (ms / reps * 1e-3) / 1e12, gb / (ms / reps * 1e-3));
+        printf("production kernel, G=%d chunk=%2d   : %8.3f ms  %6.2f TFLOP/s  %7.1f GB/s (incl. panel tiling kernel)\n", grp, chunk, ms / reps, flop / (ms / reps * 1e-3) / 1e12, gb / (ms / reps * 1e-3));
     }
     return 0;
 }
