@@ -169,12 +169,30 @@ def make_scans(lm, rng, nscans, m):
     return scans
 
 
-def ekf_scan(ekf, Z):
-    """The user-facing call sequence of one scan (test/main.cpp:193-195): gate, then update."""
+def ekf_scan(ekf, Z, batch=False):
+    """The user-facing call sequence of one scan (test/main.cpp:193-195): gate, then update
+    (batch=False: singleUpdate EKF.cpp:457-479; batch=True: one joint batchUpdate EKF.cpp:93-129)."""
+    if not batch and ekf.world == 1:
+        # one asynchronous submission, association indices stay on the device (cslam_ekf_scan);
+        # the indices are read back behind the gate kernel while the updates run
+        return ekf.scan(Z, RE, GATE1, GATE2)[0]
     jbest, is_new, _, _ = ekf.gate(Z, RE, GATE1, GATE2)
     sel = jbest > 0
-    ekf.update(Z[:, sel], RE, jbest[sel], False)
+    ekf.update(Z[:, sel], RE, jbest[sel], batch)
     return jbest
+
+
+def dmma_peak():
+    """FP64 tensor-core peak measured on this pool's B200 by tools/dmma_bench.cu (MEASURED_PEAKS.json
+    carries only the bf16 figure); the best line of profiles/dmma_bench_r01.txt."""
+    p = os.path.join(ROOT, "profiles", "dmma_bench_r01.txt")
+    best = 0.0
+    if os.path.exists(p):
+        for line in open(p):
+            if line.startswith("DMMA.8x8x4 peak"):
+                best = max(best, float(line.split(":")[-1].split()[0]))
+    return (best, "measured (tools/dmma_bench.cu -> profiles/dmma_bench_r01.txt)") if best else \
+        (40.0, "nominal B200 FP64 tensor")
 
 
 # ------------------------------------------------------------------------ particle filter ----
@@ -469,7 +487,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--landmarks", type=int, default=20000)
-    ap.add_argument("--obs", type=int, default=4)
+    ap.add_argument("--obs", type=int, default=None, help="observations per scan (default 4; 32 with --batch)")
+    ap.add_argument("--batch", action="store_true",
+                    help="C3 of BASELINE.json: one JOINT update of all observations of a scan (rank 2m, FP64 tensor cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--multi", default="sharded", choices=["sharded", "replicas"],
                     help="N>1: row-sharded covariance of ONE filter (strong scaling) or independent filter replicas")
@@ -479,6 +499,8 @@ def main():
     ap.add_argument("--pf-landmarks", type=int, default=500)
     args = ap.parse_args()
     _capture_stdout()
+    if args.obs is None:
+        args.obs = 32 if args.batch else 4
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
@@ -526,8 +548,9 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-timed throughput (state resident in HBM) + live kernel timing ----
+    batch = bool(args.batch)
     for s in range(args.warmup):
-        ekf_scan(ekf, scans[s % len(scans)][0])
+        ekf_scan(ekf, scans[s % len(scans)][0], batch)
     ekf.sync()
     sampler = ClockSampler(local)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -539,8 +562,8 @@ def main():
     with torch.cuda.stream(stream):
         ev0.record(stream)
         for s in range(args.steps):
-            jb = ekf_scan(ekf, scans[(args.warmup + s) % len(scans)][0])
-            updates += int((jb > 0).sum())
+            jb = ekf_scan(ekf, scans[(args.warmup + s) % len(scans)][0], batch)
+            updates += (1 if batch else int((jb > 0).sum()))
         ev1.record(stream)
     barrier()
     clocks = sampler.stop()
@@ -559,9 +582,9 @@ def main():
         t_e0.record(stream)
         for s in range(args.steps):
             Z = scans[(s + 1) % len(scans)][0]
-            jb = ekf_scan(ekf, Z)
+            jb = ekf_scan(ekf, Z, batch)
             X_host = ekf.X  # D2H read of the step's result (n doubles through pinned staging)
-            e2e_updates += int((jb > 0).sum())
+            e2e_updates += (1 if batch else int((jb > 0).sum()))
         t_e1.record(stream)
     barrier()
     e2e_ms = t_e0.elapsed_time(t_e1)
@@ -584,20 +607,50 @@ def main():
         ach = (cov_bytes / cov_launches) / (cov_ms / cov_launches * 1e-3) / 1e9 if cov_launches else 0.0
         shards = world if sharded else 1   # per-GPU figures: each rank streams 1/world of the triangle
         alg_update_bytes = (8.0 * n * (n + 1)) / shards + 112.0 * n  # cov R+W + 5 P columns + X + gating
+        r_rank = 2 * m
+        if batch:
+            # joint update: bytes 8n(n+1) + (3+2m)*8n + 88N, flops 2*r*n(n+1)/2
+            alg_update_bytes = (8.0 * n * (n + 1)) / shards + (3 + r_rank) * 8.0 * n + 88.0 * N
+            flops = float(r_rank) * n * (n + 1) / shards
+            tpeak, tsrc = dmma_peak()
+            t_launch = cov_ms / max(1, cov_launches) * 1e-3
+            roof = {
+                "bound": "tensor", "kernel": "k_cov_update_dmma (slam.h:260, rank-2m update on FP64 tensor cores, "
+                                             "DMMA.8x8x4) incl. its panel-tiling kernel",
+                "achieved": flops / t_launch / 1e12 if cov_launches else 0.0, "peak": tpeak, "unit": "TFLOP/s",
+                "frac": (flops / t_launch / 1e12) / tpeak if cov_launches else 0.0, "peak_source": tsrc,
+                "traffic": ncu_traffic("k_cov_update_dmma", n) if world == 1 else None,
+                "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": 8.0 * n * (n + 1) / shards,
+                "hbm_gbs_same_launch": (cov_bytes / cov_launches) / t_launch / 1e9 if cov_launches else 0.0,
+                "hbm_frac_same_launch": ((cov_bytes / cov_launches) / t_launch / 1e9) / peak if cov_launches else 0.0,
+                "per": "GPU", "launches_timed": cov_launches, "avg_launch_ms": cov_ms / max(1, cov_launches),
+            }
+        else:
+            roof = {
+                "bound": "hbm", "kernel": "k_cov_update<2,128> (slam.h:260, upper-triangle rank-2 update)",
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "peak_source": peak_src, "traffic": ncu_traffic("k_cov_update<2,128>", n) if world == 1 else None,
+                "algorithmic_bytes_per_launch": 8.0 * n * (n + 1) / shards, "per": "GPU",
+                "launches_timed": cov_launches, "avg_launch_ms": cov_ms / max(1, cov_launches),
+                "whole_update_frac": (alg_update_bytes * (updates if (sharded or world == 1) else updates / world)
+                                      / (ms * 1e-3) / 1e9) / peak,
+            }
+        upd_kind = (f"batched JOINT update of {m} observations per scan (rank {r_rank}): gate + stacked gain + "
+                    f"tensor-core covariance update" if batch else
+                    f"sequential update: gate + gain + covariance, {m} observations per scan")
         out = {
             "metric": "EKF updates/sec", "value": value, "unit": "updates/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
                 "workload": (f"EKF-SLAM {N} landmarks (state dim {n}, FP64 P {8.0 * n * n / 1e9:.2f} GB), "
-                             f"range-bearing observations, sequential update: gate + gain + covariance, "
-                             f"{m} observations per scan" +
+                             f"range-bearing observations, {upd_kind}" +
                              (f", covariance row-sharded over {world} GPUs" if sharded else
                               (f", {world} independent filter replicas" if world > 1 else ""))),
                 "landmarks": N, "state_dim": n, "obs_per_step": m, "mode": "INTENDED (SURVEY Appendix A)",
                 "l2": f"inputs larger than L2 ({4.0 * n * n / 1e9 / (world if sharded else 1):.1f} GB of upper "
                       f"triangle streamed per GPU per update)",
-                "parallelism": ("row-sharded covariance (block-cyclic 128-row tiles), NCCL all-reduce of the 2 observed "
+                "parallelism": ("row-sharded covariance (block-cyclic 128-row tiles), NCCL all-reduce of the observed "
                                 "columns per update" if sharded else
                                 ("replicas only (one independent filter per GPU)" if world > 1 else "single GPU")),
             },
@@ -606,18 +659,12 @@ def main():
                     "h2d_bytes_per_step": int(2 * m * 8 + 4 * 8 + 2 * 8 + m * 4 + 4 * 8),
                     "d2h_bytes_per_step": int(n * 8 + m * (4 + 8 + 8))},
             "gpu_launches": int(launches),
-            "roofline": {
-                "bound": "hbm", "kernel": "k_cov_update<2,128> (slam.h:260, upper-triangle rank-2 update)",
-                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "peak_source": peak_src, "traffic": ncu_traffic("k_cov_update<2,128>", n) if world == 1 else None,
-                "algorithmic_bytes_per_launch": 8.0 * n * (n + 1) / shards, "per": "GPU",
-                "launches_timed": cov_launches, "avg_launch_ms": cov_ms / max(1, cov_launches),
-                "whole_update_frac": (alg_update_bytes * (updates if (sharded or world == 1) else updates / world)
-                                      / (ms * 1e-3) / 1e9) / peak,
-            },
+            "roofline": roof,
             "skipped_updates": skipped,
             "state_checksum": float(np.sum(X_host[:3])) if X_host is not None else None,
         }
+        if batch:
+            out["observations_per_s"] = value * m
         if not args.no_cpu_baseline and world == 1:
             t1 = time.time()
             out["cpu_baseline"] = cpu_ekf_update_rate(N, 1, slab_cols=3000, reps=2)

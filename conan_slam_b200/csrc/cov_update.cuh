@@ -57,17 +57,23 @@ inline long long shard_tile_count(int nt, Shard sh) {
 // reads), the two panel columns a thread owns stay in registers.  Elements below the
 // diagonal inside diagonal tiles are neither loaded nor stored.  diag_eps implements
 // slam.h:719 (P += I * FLT_MIN) for the heading update.
+// live (nullable): device flag of a fused scan, 0 = skip this update (EKF.cpp:287-295 found no match).
 // Template knobs: R rank (1 or 2), T tile edge, BATCH loads in flight per thread, MINB minimum
 // resident CTAs per SM (register cap), HINT cache policy of the P accesses.
 template <int R, int T, int BATCH_ = 8, int MINB = 2, int HINT = 0>
 __global__ void __launch_bounds__(256, MINB) k_cov_update(double* __restrict__ P, size_t ld, int n,
                                                           const double* __restrict__ A, size_t lda, int nt,
-                                                          double diag_eps, Shard sh) {
+                                                          double diag_eps, Shard sh,
+                                                          const int* __restrict__ live = nullptr) {
     constexpr int CP = T / 2;       // column pairs per tile
     constexpr int RG = 256 / CP;    // row groups
     constexpr int RPT = T / RG;     // rows per thread
     constexpr int BATCH = RPT > BATCH_ ? BATCH_ : RPT;
     __shared__ double sAr[R][T];
+    // device-side association (cslam_ekf_scan): *live == 0 means "no landmark passed the gate for
+    // this observation" and the whole update is a no-op; the flag is fetched together with the
+    // panels so that its latency is not a serial prefix of every CTA
+    const int live_v = live != nullptr ? *live : 1;
 
     int tr, tc;
     shard_tile(blockIdx.x, nt, sh, tr, tc);
@@ -86,7 +92,7 @@ __global__ void __launch_bounds__(256, MINB) k_cov_update(double* __restrict__ P
         aj1[k] = (j + 1 < n) ? A[(size_t)k * lda + j + 1] : 0.0;
     }
     __syncthreads();
-    if (j >= n) return;
+    if (j >= n || live_v == 0) return;
     const bool diag_tile = (tr == tc);
 #pragma unroll 1
     for (int b0 = 0; b0 < RPT; b0 += BATCH) {
@@ -104,9 +110,11 @@ __global__ void __launch_bounds__(256, MINB) k_cov_update(double* __restrict__ P
             const int i = i0 + ii;
             const bool act = (i < n) && (!diag_tile || j + 1 >= i);
             if (act) {
-                double s0 = 0.0, s1 = 0.0;
+                // dot product over the panel rows, first product taken as is (no 0 + x: one DADD
+                // less per element; differs from a zero-initialised sum only in the sign of a zero)
+                double s0 = sAr[0][ii] * aj0[0], s1 = sAr[0][ii] * aj1[0];
 #pragma unroll
-                for (int k = 0; k < R; k++) {
+                for (int k = 1; k < R; k++) {
                     const double ai = sAr[k][ii];
                     s0 += ai * aj0[k];
                     s1 += ai * aj1[k];
@@ -116,6 +124,85 @@ __global__ void __launch_bounds__(256, MINB) k_cov_update(double* __restrict__ P
                 if (j + 1 < n) o.y = o.y - s1;
                 if (j == i) o.x += diag_eps;
                 if (j + 1 == i) o.y += diag_eps;
+                cov_st<HINT>(P + shard_lrow(sh, i) * ld + j, o);
+            }
+        }
+    }
+}
+
+// The rank-2 term one sequential update subtracts from P(i, j):  a0_i a0_j + a1_i a1_j  — the
+// operation order of k_cov_update<2> above (no FMA contraction in this translation unit), shared
+// with the gain kernel's view of "P after the pending updates".
+__device__ __forceinline__ double rank2_term(double a0i, double a1i, double a0j, double a1j) {
+    double s = a0i * a0j;
+    s += a1i * a1j;
+    return s;
+}
+
+// M consecutive SEQUENTIAL rank-2 updates (EKF.cpp:457-479: one per observation, each gain
+// re-linearised after the previous one) applied in ONE pass over the upper triangle:
+//   P(i,j) <- ((P(i,j) - t_0) - t_1) ... - t_{M-1},   t_q = rank2_term of panel rows 2q, 2q+1
+// which is, operation for operation, what M launches of k_cov_update<2> compute — the result is
+// bit-identical, the covariance is read and written once instead of M times.  The gain kernel of
+// observation q sees P "after updates 0..q-1" by applying the same terms to the few entries it reads
+// (k_gain_single, kprev).  live: M device flags (nullable); a skipped observation has a zero panel.
+template <int M, int T, int BATCH_ = 4, int MINB = 2, int HINT = 1>
+__global__ void __launch_bounds__(256, MINB) k_cov_update_multi(double* __restrict__ P, size_t ld, int n,
+                                                                const double* __restrict__ A, size_t lda, int nt,
+                                                                Shard sh, const int* __restrict__ live) {
+    constexpr int R = 2 * M;
+    constexpr int CP = T / 2, RG = 256 / CP, RPT = T / RG;
+    constexpr int BATCH = RPT > BATCH_ ? BATCH_ : RPT;
+    __shared__ double sAr[R][T];
+    int any_live = 1;
+    if (live != nullptr) {
+        any_live = 0;
+#pragma unroll
+        for (int q = 0; q < M; q++) any_live |= live[q];
+    }
+    int tr, tc;
+    shard_tile(blockIdx.x, nt, sh, tr, tc);
+    const int i0 = tr * T, j0 = tc * T;
+    for (int idx = threadIdx.x; idx < R * T; idx += 256) {
+        const int k = idx / T, ii = idx % T;
+        sAr[k][ii] = (i0 + ii < n) ? A[(size_t)k * lda + i0 + ii] : 0.0;
+    }
+    const int cp = threadIdx.x % CP, rg = threadIdx.x / CP;
+    const int j = j0 + 2 * cp;
+    double aj0[R], aj1[R];
+#pragma unroll
+    for (int k = 0; k < R; k++) {
+        aj0[k] = (j < n) ? A[(size_t)k * lda + j] : 0.0;
+        aj1[k] = (j + 1 < n) ? A[(size_t)k * lda + j + 1] : 0.0;
+    }
+    __syncthreads();
+    if (j >= n || any_live == 0) return;
+    const bool diag_tile = (tr == tc);
+#pragma unroll 1
+    for (int b0 = 0; b0 < RPT; b0 += BATCH) {
+        double2 v[BATCH];
+#pragma unroll
+        for (int b = 0; b < BATCH; b++) {
+            const int ii = rg + (b0 + b) * RG;
+            const int i = i0 + ii;
+            const bool act = (i < n) && (!diag_tile || j + 1 >= i);
+            if (act) v[b] = cov_ld<HINT>(P + shard_lrow(sh, i) * ld + j);
+        }
+#pragma unroll
+        for (int b = 0; b < BATCH; b++) {
+            const int ii = rg + (b0 + b) * RG;
+            const int i = i0 + ii;
+            const bool act = (i < n) && (!diag_tile || j + 1 >= i);
+            if (act) {
+                double2 o = v[b];
+#pragma unroll
+                for (int q = 0; q < M; q++) {
+                    const double a0i = sAr[2 * q][ii], a1i = sAr[2 * q + 1][ii];
+                    const double s0 = rank2_term(a0i, a1i, aj0[2 * q], aj0[2 * q + 1]);
+                    const double s1 = rank2_term(a0i, a1i, aj1[2 * q], aj1[2 * q + 1]);
+                    if (j >= i) o.x = o.x - s0;
+                    if (j + 1 < n) o.y = o.y - s1;
+                }
                 cov_st<HINT>(P + shard_lrow(sh, i) * ld + j, o);
             }
         }

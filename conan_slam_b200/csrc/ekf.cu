@@ -154,59 +154,108 @@ __device__ void gain_prologue(const double* __restrict__ X, const double (&Pc)[5
 }
 
 // slam.h:243,257-259 for one observation: PHT = P H^T (5 columns of P), W1 = PHT G,
-// W = W1 G^T, Xout = Xin + W V; the rank-2 panel A = W1 feeds k_cov_update.
+// W = W1 G^T, Xout = Xin + W V; the rank-2 panel W1 (rows 2*kprev, 2*kprev+1 of A) feeds the
+// covariance kernel.
 // SH = false: columns f, f+1 of P are read in place (row part coalesced, column part strided).
 // SH = true : they come from the all-reduced exchange buffer `colbuf`; rows 0..2 from `R3`.
+// kprev > 0: the covariance passes of the kprev previous observations of this scan have NOT run yet
+// (k_cov_update_multi applies them all in one pass afterwards); every entry of P read here is brought
+// to its "after those updates" value by subtracting the pending rank-2 terms in update order — the
+// same operations the covariance kernel will perform, so the values are bit-identical.
+// idf_dev != nullptr: the association index is read from device memory (fused scan); 0 = skipped.
 template <bool SH>
 __global__ void __launch_bounds__(256) k_gain_single(const double* __restrict__ Xin, double* __restrict__ Xout,
                                                      const double* __restrict__ P, const double* __restrict__ R3,
                                                      const double* __restrict__ colbuf, size_t ld, int n, double zr,
                                                      double zb, int idf, double r00, double r10, double r01,
                                                      double r11, unsigned flags, double* __restrict__ A, size_t lda,
-                                                     int* __restrict__ status) {
+                                                     int* __restrict__ status, const int* __restrict__ idf_dev,
+                                                     int kprev) {
     __shared__ GainSmall g;
+    __shared__ double sPc[5][5];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double* __restrict__ Aout = A + (size_t)2 * kprev * lda;
+    if (idf_dev != nullptr) {  // fused scan: the association index stays on the device
+        idf = *idf_dev;
+        if (idf == 0) {  // no landmark passed the gate: X is carried over, a zero panel is a no-op update
+            if (i < n) {
+                Xout[i] = Xin[i];
+                Aout[i] = 0.0;
+                Aout[lda + i] = 0.0;
+            }
+            return;
+        }
+    }
     const int f = 3 + 2 * (idf - 1);
-    auto pcol = [&](int i, int k) -> double {  // P(i, f + k)
+    // stored value of P(r, c), r <= c, c in {0, 1, 2, f, f+1}
+    auto praw = [&](int r, int c) -> double {
+        if (r < 3) return R3[(size_t)r * ld + c];
         if constexpr (SH) {
-            return colbuf[(size_t)k * lda + i];
+            return colbuf[(size_t)(c - f) * lda + r];
         } else {
-            const int c = f + k;
-            return i <= c ? P[(size_t)i * ld + c] : P[(size_t)c * ld + i];
+            return P[(size_t)r * ld + c];
         }
     };
+    // P(r, c) after the kprev pending updates
+    auto pfix = [&](double v, int r, int c) -> double {
+        for (int q = 0; q < kprev; q++) {
+            const double* a0 = A + (size_t)2 * q * lda;
+            const double* a1 = a0 + lda;
+            v = v - rank2_term(a0[r], a1[r], a0[c], a1[c]);
+        }
+        return v;
+    };
+    if (threadIdx.x < 25) {
+        const int a = threadIdx.x / 5, b = threadIdx.x % 5;
+        const int ca = a < 3 ? a : f + (a - 3), cb = b < 3 ? b : f + (b - 3);
+        const int r = min(ca, cb), c = max(ca, cb);
+        sPc[a][b] = pfix(praw(r, c), r, c);
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
         const double R[4] = {r00, r10, r01, r11};
         double Pc[5][5];
-        for (int a = 0; a < 3; a++) {
-            for (int b = a; b < 3; b++) Pc[a][b] = Pc[b][a] = R3[(size_t)a * ld + b];
-            Pc[a][3] = Pc[3][a] = R3[(size_t)a * ld + f];
-            Pc[a][4] = Pc[4][a] = R3[(size_t)a * ld + f + 1];
-        }
-        Pc[3][3] = pcol(f, 0);
-        Pc[3][4] = Pc[4][3] = pcol(f, 1);
-        Pc[4][4] = pcol(f + 1, 1);
+        for (int a = 0; a < 5; a++)
+            for (int b = 0; b < 5; b++) Pc[a][b] = sPc[a][b];
         gain_prologue(Xin, Pc, f, zr, zb, R, flags, g);
         if (!g.ok && blockIdx.x == 0) atomicAdd(status, 1);
     }
     __syncthreads();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    // P(i, c) for c in {0,1,2}: rows 0..2 are symmetric-read from R3
-    const double p0 = i <= 0 ? R3[(size_t)i * ld + 0] : R3[0 * ld + i];
-    const double p1 = i <= 1 ? R3[(size_t)i * ld + 1] : R3[1 * ld + i];
-    const double p2 = i <= 2 ? R3[(size_t)i * ld + 2] : R3[2 * ld + i];
-    const double p3 = pcol(i, 0);
-    const double p4 = pcol(i, 1);
+    double pc[5];  // P(i, c) for c in {0, 1, 2, f, f+1}
+#pragma unroll
+    for (int b = 0; b < 5; b++) {
+        const int c = b < 3 ? b : f + (b - 3);
+        double v;
+        if (b < 3) {
+            v = i <= c ? R3[(size_t)i * ld + c] : R3[(size_t)c * ld + i];
+        } else if constexpr (SH) {
+            v = colbuf[(size_t)(b - 3) * lda + i];
+        } else {
+            v = i <= c ? P[(size_t)i * ld + c] : P[(size_t)c * ld + i];
+        }
+        pc[b] = v;
+    }
+    for (int q = 0; q < kprev; q++) {
+        const double* a0 = A + (size_t)2 * q * lda;
+        const double* a1 = a0 + lda;
+        const double a0i = a0[i], a1i = a1[i];
+#pragma unroll
+        for (int b = 0; b < 5; b++) {
+            const int c = b < 3 ? b : f + (b - 3);
+            pc[b] = pc[b] - rank2_term(a0i, a1i, a0[c], a1[c]);
+        }
+    }
     double pht[2];
     for (int k = 0; k < 2; k++)
-        pht[k] = (((p0 * g.H[k][0] + p1 * g.H[k][1]) + p2 * g.H[k][2]) + p3 * g.H[k][3]) + p4 * g.H[k][4];
+        pht[k] = (((pc[0] * g.H[k][0] + pc[1] * g.H[k][1]) + pc[2] * g.H[k][2]) + pc[3] * g.H[k][3]) + pc[4] * g.H[k][4];
     const double w1_0 = pht[0] * g.G[0][0] + pht[1] * g.G[1][0];
     const double w1_1 = pht[0] * g.G[0][1] + pht[1] * g.G[1][1];
     const double w_0 = w1_0 * g.G[0][0] + w1_1 * g.G[0][1];
     const double w_1 = w1_0 * g.G[1][0] + w1_1 * g.G[1][1];
     Xout[i] = Xin[i] + (w_0 * g.V[0] + w_1 * g.V[1]);
-    A[i] = w1_0;
-    A[lda + i] = w1_1;
+    Aout[i] = w1_0;
+    Aout[lda + i] = w1_1;
 }
 
 // Sharded column exchange: every rank contributes the entries of columns cols[k] (k < ncols) of
@@ -240,8 +289,8 @@ __global__ void __launch_bounds__(256) k_rows012_update(double* __restrict__ R3,
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = blockIdx.y;
     if (j >= n || j < i) return;
-    double s = 0.0;
-    for (int k = 0; k < r; k++) s += A[(size_t)k * lda + i] * A[(size_t)k * lda + j];
+    double s = A[i] * A[j];  // the operations of k_cov_update / k_cov_update_multi, in their order
+    for (int k = 1; k < r; k++) s += A[(size_t)k * lda + i] * A[(size_t)k * lda + j];
     double o = R3[(size_t)i * ld + j] - s;
     if (j == i) o += diag_eps;
     R3[(size_t)i * ld + j] = o;
@@ -597,8 +646,23 @@ static int replicas_follow(cslam_ekf* h, int r, double diag_eps) {
     return CSLAM_OK;
 }
 
+// ... and the grouped form: g sequential rank-2 terms subtracted one after the other (k_cov_update_multi)
+__global__ void __launch_bounds__(256) k_rows012_update_multi(double* __restrict__ R3, size_t ld, int n,
+                                                              const double* __restrict__ A, size_t lda, int g) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j >= n || j < i) return;
+    double o = R3[(size_t)i * ld + j];
+    for (int q = 0; q < g; q++) {
+        const double* a0 = A + (size_t)2 * q * lda;
+        const double* a1 = a0 + lda;
+        o = o - rank2_term(a0[i], a1[i], a0[j], a1[j]);
+    }
+    R3[(size_t)i * ld + j] = o;
+}
+
 template <int R>
-static int launch_cov_update(cslam_ekf* h, double diag_eps) {
+static int launch_cov_update(cslam_ekf* h, double diag_eps, const int* live = nullptr) {
     const int n = h->n;
     {
         ProfScope prof(h);
@@ -610,13 +674,13 @@ static int launch_cov_update(cslam_ekf* h, double diag_eps) {
             if (tiles > 0) {
                 count_launch();
                 k_cov_update<R, 128, 4, 4, 1><<<(unsigned)tiles, 256, 0, h->stream>>>(h->P, h->ld, n, h->A, h->lda, nt,
-                                                                                      diag_eps, h->sh);
+                                                                                      diag_eps, h->sh, live);
             }
         } else {
             const int nt = (n + 63) / 64;
             count_launch();
             k_cov_update<R, 64, 8, 4, 0><<<(unsigned)shard_tile_count(nt, h->sh), 256, 0, h->stream>>>(
-                h->P, h->ld, n, h->A, h->lda, nt, diag_eps, h->sh);
+                h->P, h->ld, n, h->A, h->lda, nt, diag_eps, h->sh, live);
         }
         CSLAM_CUDA(cudaGetLastError());
     }
@@ -659,12 +723,95 @@ static int launch_cov_update_rank(cslam_ekf* h, int r) {
     return CSLAM_OK;
 }
 
+// Covariance pass of a group of g sequential updates whose panels sit in rows 0..2g-1 of A.
+static int launch_cov_update_multi(cslam_ekf* h, int g, const int* live) {
+    if (g == 1) return launch_cov_update<2>(h, 0.0, live);
+    const int n = h->n;
+    h->diag_dirty = true;
+    {
+    ProfScope prof(h);
+    count_launch();
+#define CSLAM_MULTI(M, MINB)                                                                                     \
+    case M:                                                                                                      \
+        if (n >= 2048 || h->sh.world > 1) {                                                                      \
+            const int nt = (n + 127) / 128;                                                                      \
+            if (shard_tile_count(nt, h->sh) == 0) break;                                                         \
+            k_cov_update_multi<M, 128, 4, MINB, 1><<<(unsigned)shard_tile_count(nt, h->sh), 256, 0, h->stream>>>( \
+                h->P, h->ld, n, h->A, h->lda, nt, h->sh, live);                                                  \
+        } else {                                                                                                 \
+            const int nt = (n + 63) / 64;                                                                        \
+            k_cov_update_multi<M, 64, 4, MINB, 0><<<(unsigned)shard_tile_count(nt, h->sh), 256, 0, h->stream>>>(  \
+                h->P, h->ld, n, h->A, h->lda, nt, h->sh, live);                                                  \
+        }                                                                                                        \
+        break;
+    switch (g) {
+        CSLAM_MULTI(2, 4)  // MINB (resident CTAs / SM) per group size from tools/cov_variants.cu on a B200
+        CSLAM_MULTI(3, 3)
+        CSLAM_MULTI(4, 3)
+        CSLAM_MULTI(5, 2)
+        CSLAM_MULTI(6, 2)
+        CSLAM_MULTI(7, 2)
+        CSLAM_MULTI(8, 2)
+        default:
+            set_last_error("launch_cov_update_multi: bad group size %d", g);
+            return CSLAM_ERR_BAD_ARG;
+    }
+#undef CSLAM_MULTI
+    }
+    CSLAM_CUDA(cudaGetLastError());
+    if (h->sh.world > 1 && h->R3 != h->P) {  // replicas of rows 0..2 follow, same operations
+        count_launch();
+        k_rows012_update_multi<<<dim3((n + 255) / 256, 3), 256, 0, h->stream>>>(h->R3, h->ld, n, h->A, h->lda, g);
+        CSLAM_CUDA(cudaGetLastError());
+    }
+    return CSLAM_OK;
+}
+
+constexpr int kSeqGroup = 8;  // sequential updates whose covariance passes are merged into one
+
 // exchange the listed columns of P (sharded only)
 static int exchange_columns(cslam_ekf* h, const ColList& cl) {
     count_launch();
     k_col_pack<<<dim3((h->n + 255) / 256, cl.n), 256, 0, h->stream>>>(h->P, h->ld, h->n, cl, h->colbuf, h->lda, h->sh);
     CSLAM_CUDA(cudaGetLastError());
     return allreduce_sum(h, h->colbuf, (size_t)cl.n * h->lda);
+}
+
+// singleUpdate (EKF.cpp:457-479): per observation a gain kernel (re-linearised at the X the previous
+// observation produced, P seen through the pending rank-2 terms), per group of up to kSeqGroup
+// observations ONE pass over the covariance.  idf_host / idf_dev: exactly one is non-null (idf_dev:
+// single-GPU fused scan).  Sharded handles exchange the observation's two columns of P first.
+static int sequential_updates(cslam_ekf* h, const double* Z, const int32_t* idf_host, const int* idf_dev, int m,
+                              const double R[4]) {
+    const int n = h->n;
+    const bool sharded = h->sh.world > 1;
+    for (int base = 0; base < m; base += kSeqGroup) {
+        const int g = std::min(kSeqGroup, m - base);
+        for (int k = 0; k < g; k++) {
+            const int i = base + k;
+            if (sharded) {
+                ColList cl;
+                cl.n = 2;
+                cl.c[0] = 3 + 2 * (idf_host[i] - 1);
+                cl.c[1] = cl.c[0] + 1;
+                if (int rc = exchange_columns(h, cl)) return rc;
+                count_launch();
+                k_gain_single<true><<<(n + 255) / 256, 256, 0, h->stream>>>(
+                    h->X[h->cur], h->X[h->cur ^ 1], h->P, h->R3, h->colbuf, h->ld, n, Z[2 * i], Z[2 * i + 1],
+                    idf_host[i], R[0], R[1], R[2], R[3], h->flags, h->A, h->lda, h->status, nullptr, k);
+            } else {
+                count_launch();
+                k_gain_single<false><<<(n + 255) / 256, 256, 0, h->stream>>>(
+                    h->X[h->cur], h->X[h->cur ^ 1], h->P, h->R3, nullptr, h->ld, n, Z[2 * i], Z[2 * i + 1],
+                    idf_host ? idf_host[i] : 0, R[0], R[1], R[2], R[3], h->flags, h->A, h->lda, h->status,
+                    idf_dev ? idf_dev + i : nullptr, k);
+            }
+            CSLAM_CUDA(cudaGetLastError());
+            h->cur ^= 1;
+        }
+        if (int rc = launch_cov_update_multi(h, g, idf_dev ? idf_dev + base : nullptr)) return rc;
+    }
+    return CSLAM_OK;
 }
 
 static int check_handle(const cslam_ekf* h) {
@@ -716,6 +863,7 @@ static int create_common(cslam_ekf_t** out, int capacity_landmarks, int device, 
         }                                                                                    \
     } while (0)
     TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    TRY(cudaEventCreateWithFlags(&h->scan_ev, cudaEventDisableTiming));
     h->own_stream = true;
     TRY(cudaMalloc(&h->X[0], h->ld * sizeof(double)));
     TRY(cudaMalloc(&h->X[1], h->ld * sizeof(double)));
@@ -801,6 +949,7 @@ int cslam_ekf_destroy(cslam_ekf_t* h) {
     cudaFree(h->gate.d_jbest); cudaFree(h->gate.d_nbest); cudaFree(h->gate.d_outer);
     if (h->pinned) cudaFreeHost(h->pinned);
     for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
+    if (h->scan_ev) cudaEventDestroy(h->scan_ev);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return CSLAM_OK;
@@ -910,30 +1059,7 @@ int cslam_ekf_update(cslam_ekf_t* h, const double* Z, const int32_t* idf, int m,
     const bool sharded = h->sh.world > 1;
     for (int i = 0; i < m; i++)
         CSLAM_REQUIRE(idf[i] >= 1 && idf[i] <= nf, CSLAM_ERR_BAD_ARG, "idf out of range (1-based map slots)");
-    if (!batch) {
-        for (int i = 0; i < m; i++) {
-            if (sharded) {
-                ColList cl;
-                cl.n = 2;
-                cl.c[0] = 3 + 2 * (idf[i] - 1);
-                cl.c[1] = cl.c[0] + 1;
-                if (int rc = exchange_columns(h, cl)) return rc;
-                count_launch();
-                k_gain_single<true><<<(n + 255) / 256, 256, 0, h->stream>>>(
-                    h->X[h->cur], h->X[h->cur ^ 1], h->P, h->R3, h->colbuf, h->ld, n, Z[2 * i], Z[2 * i + 1], idf[i],
-                    R[0], R[1], R[2], R[3], h->flags, h->A, h->lda, h->status);
-            } else {
-                count_launch();
-                k_gain_single<false><<<(n + 255) / 256, 256, 0, h->stream>>>(
-                    h->X[h->cur], h->X[h->cur ^ 1], h->P, h->R3, nullptr, h->ld, n, Z[2 * i], Z[2 * i + 1], idf[i],
-                    R[0], R[1], R[2], R[3], h->flags, h->A, h->lda, h->status);
-            }
-            CSLAM_CUDA(cudaGetLastError());
-            h->cur ^= 1;
-            if (int rc = launch_cov_update<2>(h, 0.0)) return rc;
-        }
-        return CSLAM_OK;
-    }
+    if (!batch) return sequential_updates(h, Z, idf, nullptr, m, R);
     CSLAM_REQUIRE(m <= CSLAM_MAX_BATCH_OBS, CSLAM_ERR_UNSUPPORTED, "joint update supports at most 32 observations");
     ObsPack ob;
     memset(&ob, 0, sizeof(ob));
@@ -971,6 +1097,41 @@ int cslam_ekf_update(cslam_ekf_t* h, const double* Z, const int32_t* idf, int m,
     CSLAM_CUDA(cudaGetLastError());
     h->cur ^= 1;
     return launch_cov_update_rank(h, r);
+}
+
+int cslam_ekf_scan(cslam_ekf_t* h, const double* Z, int m, const double R[4], double gate1, double gate2,
+                   int32_t* jbest, uint8_t* is_new) {
+    if (int rc = check_handle(h)) return rc;
+    CSLAM_REQUIRE(m >= 0 && m <= CSLAM_MAX_OBS, CSLAM_ERR_BAD_ARG, "m out of range (0..CSLAM_MAX_OBS)");
+    CSLAM_REQUIRE(h->sh.world == 1, CSLAM_ERR_UNSUPPORTED, "fused scan is single-GPU (sharded: gate + update)");
+    if (m == 0) return CSLAM_OK;
+    CSLAM_REQUIRE(Z && R, CSLAM_ERR_BAD_ARG, "null argument");
+    const int n = h->n, nf = (n - 3) / 2;
+    // dataAssociate at the pre-update state for the whole scan (test/main.cpp:193), indices stay in d_jbest
+    if (int rc = launch_gate(h->X[h->cur], h->P, h->R3, nullptr, h->dcap, h->ld, nf, Z, m, R, gate1, gate2,
+                             h->gate.part_nd, h->gate.part_out, h->gate.part_j, h->ticket + 1, h->gate.d_jbest,
+                             h->gate.d_nbest, h->gate.d_outer, h->stream))
+        return rc;
+    if (jbest || is_new) {  // optional read-back, queued behind the gate only: overlaps the updates
+        char* pin = static_cast<char*>(h->pinned);
+        CSLAM_CUDA(cudaMemcpyAsync(pin, h->gate.d_jbest, m * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CSLAM_CUDA(cudaMemcpyAsync(pin + 2048, h->gate.d_outer, m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CSLAM_CUDA(cudaEventRecord(h->scan_ev, h->stream));
+    }
+    // singleUpdate (EKF.cpp:457-479): re-linearised per observation, in observation order
+    if (nf > 0) {
+        if (int rc = sequential_updates(h, Z, nullptr, h->gate.d_jbest, m, R)) return rc;
+    }
+    if (jbest || is_new) {
+        CSLAM_CUDA(cudaEventSynchronize(h->scan_ev));
+        const int* pj = reinterpret_cast<const int*>(h->pinned);
+        const double* po = reinterpret_cast<const double*>(static_cast<char*>(h->pinned) + 2048);
+        for (int i = 0; i < m; i++) {
+            if (jbest) jbest[i] = pj[i];
+            if (is_new) is_new[i] = (pj[i] == 0 && po[i] > gate2) ? 1 : 0;  // EKF.cpp:287-295
+        }
+    }
+    return CSLAM_OK;
 }
 
 int cslam_ekf_augment(cslam_ekf_t* h, const double* Z, int m, const double R[4]) {

@@ -54,6 +54,7 @@ struct cslam_ekf {
     void* pinned = nullptr;  // host staging
     size_t pinned_bytes = 0;
     cudaStream_t stream = nullptr;
+    cudaEvent_t scan_ev = nullptr;  // marks "association indices of the last fused scan are in pinned memory"
     bool own_stream = false;
     // row sharding over GPUs (world == 1: single GPU, R3 aliases P, no NCCL)
     cslam::Shard sh = {0, 1};

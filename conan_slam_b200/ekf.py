@@ -211,6 +211,25 @@ class EKF:
                                            dptr(outer)), "cslam_ekf_gate")
         return jbest, is_new, nbest, outer
 
+    def scan(self, Z, R, gate1, gate2, want_indices=True):
+        """dataAssociate + update(batch=False) of the associated observations as ONE asynchronous
+        submission (test/main.cpp:193-195): the association indices stay on the device.  Returns
+        (jbest, is_new) when want_indices (read back while the updates run), else None."""
+        Zm, zflat = _z(Z)
+        m = Zm.shape[1]
+        if m == 0:
+            return (np.zeros(0, np.int32), np.zeros(0, np.uint8)) if want_indices else None
+        r = _m2(R)
+        if want_indices:
+            jbest = np.zeros(m, dtype=np.int32)
+            is_new = np.zeros(m, dtype=np.uint8)
+            check(self._lib.cslam_ekf_scan(self._h, dptr(zflat), m, dptr(r), float(gate1), float(gate2),
+                                           iptr(jbest), is_new.ctypes.data_as(_lib._u8p)), "cslam_ekf_scan")
+            return jbest, is_new
+        check(self._lib.cslam_ekf_scan(self._h, dptr(zflat), m, dptr(r), float(gate1), float(gate2), None, None),
+              "cslam_ekf_scan")
+        return None
+
     def dataAssociate(self, Z, R, gate1, gate2):
         """slam.h:482-487 / EKF.cpp:235-326.  ZN follows Q5: empty unless FLAG Q5_RETURN_ZN."""
         Zm, _ = _z(Z)

@@ -106,6 +106,15 @@ int cslam_ekf_gate(cslam_ekf_t* h, const double* Z, int m, const double R[4], do
  *   batch=1: batchUpdate  EKF.cpp:93-129  (one joint rank-2m update; m <= CSLAM_MAX_BATCH_OBS)
  * both through Slam::choleskyUpdate slam.h:235-266.  Asynchronous. m == 0 is a no-op. */
 int cslam_ekf_update(cslam_ekf_t* h, const double* Z, const int32_t* idf, int m, const double R[4], int batch);
+/* One observation cycle with NO host round trip between association and update — the call pair
+ * test/main.cpp:193-195 (dataAssociate EKF.cpp:235-326, then update with batch=false -> singleUpdate
+ * EKF.cpp:457-479) as one asynchronous submission: the gate kernel leaves the association indices in
+ * device memory, every gain / covariance kernel reads its own index there and exits when no landmark
+ * passed the gate.  jbest / is_new (nullable) are read back behind the gate kernel, overlapping the
+ * updates; pass NULL for a fully asynchronous scan.  Results are identical to cslam_ekf_gate followed by
+ * cslam_ekf_update(batch = 0) on the associated observations.  Single-GPU handles only. */
+int cslam_ekf_scan(cslam_ekf_t* h, const double* Z, int m, const double R[4], double gate1, double gate2,
+                   int32_t* jbest, uint8_t* is_new);
 /* Slam::augment(X,P,Z,R)                                slam.h:190-191 -> EKF.cpp:9-26 -> :28-91 */
 int cslam_ekf_augment(cslam_ekf_t* h, const double* Z, int m, const double R[4]);
 

@@ -155,6 +155,33 @@ def test_gating_indices_exact(N, m):
     assert a.ZN.size == 0
 
 
+@pytest.mark.parametrize("flags", [0, oracle_py.FLAG_INTENDED])
+@pytest.mark.parametrize("N,m", [(0, 2), (3, 4), (40, 6), (600, 9), (1100, 5)])
+def test_fused_scan_equals_gate_then_update(N, m, flags):
+    """cslam_ekf_scan (association indices stay on the device) == dataAssociate + singleUpdate
+    (test/main.cpp:193-195) of the oracle: same indices, same state; spurious observations that
+    pass no gate must leave the filter untouched."""
+    g, o, lm = _pair(N, 70 + N, flags)
+    rng = np.random.default_rng(11 * N + m)
+    k_assoc = min(N, max(1, m // 2)) if N else 0
+    ids = rng.choice(N, size=k_assoc, replace=False) + 1 if N else np.zeros(0, dtype=np.int64)
+    Z = helpers.observe(o.X, lm, ids, rng) if k_assoc else np.zeros((2, 0))
+    extra = m - k_assoc
+    Zx = np.stack([rng.uniform(3000.0, 9000.0, size=extra), rng.uniform(-np.pi, np.pi, size=extra)])
+    Z = np.concatenate([Z, Zx], axis=1)
+    Z = Z[:, rng.permutation(m)]  # associated and spurious observations interleaved
+    for rep in range(2):  # second scan: asynchronous form, indices fetched by a separate gate
+        jo, newo, _, _, idf_o, _ = o.gate(Z, RE, 50.0, 1000.0, dense=(N <= 40))
+        o.update(Z[:, jo != 0], RE, idf_o, False)
+        if rep == 0:
+            jg, newg = g.scan(Z, RE, 50.0, 1000.0)
+            assert np.array_equal(jg, jo) and np.array_equal(newg, newo)
+        else:
+            assert g.scan(Z, RE, 50.0, 1000.0, want_indices=False) is None
+        _assert_state(g, o)
+    assert g.sync() == 0
+
+
 def test_gating_tie_lowest_index_wins_and_no_landmarks():
     import conan_slam_b200 as cs
     X = np.array([0.0, 0.0, 0.0, 100.0, 50.0, 100.0, 50.0, 100.0, 50.0])

@@ -18,10 +18,27 @@ float run(double* P, size_t ld, int n, const double* A, size_t lda, int reps) {
     const long long tiles = (long long)nt * (nt + 1) / 2;
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    k_cov_update<R, T, B, MINB, HINT><<<(unsigned)tiles, 256>>>(P, ld, n, A, lda, nt, 0.0);
+    k_cov_update<R, T, B, MINB, HINT><<<(unsigned)tiles, 256>>>(P, ld, n, A, lda, nt, 0.0, Shard{0, 1});
     CK(cudaDeviceSynchronize());
     CK(cudaEventRecord(e0));
-    for (int i = 0; i < reps; i++) k_cov_update<R, T, B, MINB, HINT><<<(unsigned)tiles, 256>>>(P, ld, n, A, lda, nt, 0.0);
+    for (int i = 0; i < reps; i++) k_cov_update<R, T, B, MINB, HINT><<<(unsigned)tiles, 256>>>(P, ld, n, A, lda, nt, 0.0, Shard{0, 1});
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    return ms / reps;
+}
+
+template <int M, int T, int B, int MINB, int HINT>
+float run_multi(double* P, size_t ld, int n, const double* A, size_t lda, int reps) {
+    const int nt = (n + T - 1) / T;
+    const long long tiles = (long long)nt * (nt + 1) / 2;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    k_cov_update_multi<M, T, B, MINB, HINT><<<(unsigned)tiles, 256>>>(P, ld, n, A, lda, nt, Shard{0, 1}, nullptr);
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < reps; i++)
+        k_cov_update_multi<M, T, B, MINB, HINT><<<(unsigned)tiles, 256>>>(P, ld, n, A, lda, nt, Shard{0, 1}, nullptr);
     CK(cudaEventRecord(e1));
     CK(cudaDeviceSynchronize());
     float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
@@ -34,9 +51,9 @@ int main(int argc, char** argv) {
     const size_t ld = ((size_t)n + 1 + 15) / 16 * 16;
     double *P, *A;
     CK(cudaMalloc(&P, ld * n * sizeof(double)));
-    CK(cudaMalloc(&A, 2 * ld * sizeof(double)));
+    CK(cudaMalloc(&A, 16 * ld * sizeof(double)));
     CK(cudaMemset(P, 0, ld * n * sizeof(double)));
-    CK(cudaMemset(A, 0, 2 * ld * sizeof(double)));
+    CK(cudaMemset(A, 0, 16 * ld * sizeof(double)));
     const double gb = 8.0 * n * ((double)n + 1.0) / 1e9;
 #define RUN(R, T, B, MINB, HINT) { float ms = run<R, T, B, MINB, HINT>(P, ld, n, A, ld, reps); \
     printf("n=%d R=%d T=%3d BATCH=%2d MINB=%d HINT=%d : %8.4f ms  %8.1f GB/s\n", n, R, T, B, MINB, HINT, ms, gb / (ms * 1e-3)); }
@@ -54,5 +71,21 @@ int main(int argc, char** argv) {
     RUN(2, 64, 8, 6, 0)
     RUN(1, 128, 8, 2, 0)
     RUN(1, 128, 8, 4, 1)
+#define RUNM(M, T, B, MINB, HINT) { float ms = run_multi<M, T, B, MINB, HINT>(P, ld, n, A, ld, reps); \
+    printf("n=%d multi M=%d T=%3d BATCH=%2d MINB=%d HINT=%d : %8.4f ms  %8.1f GB/s  (%.1f updates/ms)\n", n, M, T, B, MINB, HINT, ms, gb / (ms * 1e-3), M / ms); }
+    RUNM(2, 128, 4, 4, 1)
+    RUNM(2, 128, 4, 3, 1)
+    RUNM(3, 128, 4, 3, 1)
+    RUNM(4, 128, 4, 3, 1)
+    RUNM(4, 128, 4, 2, 1)
+    RUNM(4, 128, 8, 2, 1)
+    RUNM(4, 128, 2, 3, 1)
+    RUNM(4, 128, 2, 4, 1)
+    RUNM(4, 128, 4, 4, 1)
+    RUNM(4, 64, 4, 3, 1)
+    RUNM(4, 64, 4, 4, 1)
+    RUNM(8, 128, 4, 2, 1)
+    RUNM(8, 128, 2, 2, 1)
+    RUNM(8, 64, 4, 2, 1)
     return 0;
 }
