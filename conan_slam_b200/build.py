@@ -80,4 +80,12 @@ def build_host(force=False):
         subprocess.check_call([cxx, "-O2", "-std=c++17", "-ffp-contract=off", "-I",
                                os.path.join(HERE, "..", "include"), src, "-o", out,
                                "-L", LIBDIR, "-lcslam", "-Wl,-rpath,$ORIGIN"])
+    # the particle-filter driver (population-level adaptor PfGpuT)
+    src2 = os.path.join(HERE, "host", "pf_main.cpp")
+    out2 = os.path.join(LIBDIR, "pf_main")
+    if os.path.exists(src2) and (force or _stale(out2, [d for d in deps[1:] + [src2] if os.path.exists(d)])):
+        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        subprocess.check_call([cxx, "-O2", "-std=c++17", "-ffp-contract=off", "-I",
+                               os.path.join(HERE, "..", "include"), src2, "-o", out2,
+                               "-L", LIBDIR, "-lcslam", "-Wl,-rpath,$ORIGIN"])
     return out

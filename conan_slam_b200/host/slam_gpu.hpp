@@ -10,9 +10,11 @@
 //     reference and the adaptor writes the result back — X always, P when n <= p_writeback_max
 //     (copying a 12.8 GB covariance per call is what the GPU path exists to avoid; call
 //     fetchCovariance() explicitly for big maps).
-//   * slam_gpu_eigen.hpp — `class EKFGpu : public Slam` / `class PFGpu : public Slam` overriding
-//     the reference's virtuals, usable when the reference's own headers (and Eigen) are present:
-//     the only edit in test/main.cpp is `new EKF(LM, WP)` -> `new EKFGpu(LM, WP)`.
+//   * slam_gpu_eigen.hpp — `class EKFGpu : public Slam` overriding the reference's virtuals, usable
+//     when the reference's own headers (and Eigen) are present: the only edit in test/main.cpp is
+//     `new EKF(LM, WP)` -> `new EKFGpu(LM, WP)`.  The particle filter is exposed at
+//     population level (PfGpuT below): the reference's per-particle virtuals are called in driver
+//     loops over a host std::vector<Particle_t>, one PfGpuT call replaces one such loop.
 //
 // Error convention mirrors the reference (EKF.cpp:22-25 etc.): failures are printed and the call
 // returns; nothing throws across the adaptor.  There is no CPU fallback.
@@ -179,6 +181,39 @@ class EkfGpuT {
         }
         return out;
     }
+    // dataAssociate + update(batch = false) of the associated observations as ONE asynchronous
+    // submission (test/main.cpp:193-195 without the host round trip; cslam_ekf_scan): the association
+    // indices stay on the device.  Returns the same Association_t as dataAssociate (ZF, ZN, idf).
+    AssociationT<MatT> scan(Vec& X, MatT& P, const MatT& Z, const MatT& R, double gate1, double gate2) {
+        push(X, P);
+        AssociationT<MatT> out;
+        const int m = Z.cols();
+        std::vector<double> z((size_t)2 * m);
+        for (int i = 0; i < m; i++) { z[2 * i] = Z(0, i); z[2 * i + 1] = Z(1, i); }
+        std::vector<int32_t> jbest((size_t)m, 0);
+        std::vector<uint8_t> is_new((size_t)m, 0);
+        const double r[4] = {R(0, 0), R(1, 0), R(0, 1), R(1, 1)};
+        for (int b = 0; b < m; b += CSLAM_MAX_OBS) {
+            const int mc = (m - b < CSLAM_MAX_OBS) ? m - b : CSLAM_MAX_OBS;
+            report(cslam_ekf_scan(h_, z.data() + 2 * b, mc, r, gate1, gate2, jbest.data() + b, is_new.data() + b), "scan");
+        }
+        int nzf = 0, nzn = 0;
+        for (int i = 0; i < m; i++) { nzf += jbest[i] != 0; nzn += is_new[i] != 0; }
+        out.ZF.resize(2, nzf);
+        int k = 0;
+        for (int i = 0; i < m; i++)
+            if (jbest[i] != 0) { out.ZF(0, k) = Z(0, i); out.ZF(1, k) = Z(1, i); out.idf.push_back(jbest[i]); k++; }
+        if (flags_ & CSLAM_FLAG_Q5_RETURN_ZN) {
+            out.ZN.resize(2, nzn);
+            k = 0;
+            for (int i = 0; i < m; i++)
+                if (is_new[i]) { out.ZN(0, k) = Z(0, i); out.ZN(1, k) = Z(1, i); k++; }
+        } else {
+            out.ZN.resize(0, 0);
+        }
+        pull(X, P);
+        return out;
+    }
     // Slam::dataAssociateTable  slam.h:454-457 / EKF.cpp:146-233 (host bookkeeping)
     AssociationT<MatT> dataAssociateTable(const Vec& X, const MatT& Z, const std::vector<int>& idz,
                                          std::vector<int>& table) {
@@ -243,5 +278,148 @@ class EkfGpuT {
 };
 
 using EkfGpu = EkfGpuT<DVec, DMat>;
+
+// Particle filter (FastSLAM 2.0 style) — the PF half of the `Slam` interface at POPULATION level.
+// The reference exposes per-particle virtuals and lets the driver loop over a host
+// std::vector<Particle_t> (test/main.cpp:279-286, 305-309, 316-327); here the particles live on the
+// GPU as a struct of arrays and each method below is one driver loop:
+//
+//     for (pl...) predict(particles[pl], vn, swan, QE, wb, dt);      ->  pf.predict(vn, swan, QE, wb, dt);
+//     for (pl...) observeHeading(particles[pl], phi, known);         ->  pf.observeHeading(phi, known);
+//     for (i...) { sampleProposal(particles[i], ZF, IDF, RE);        ->  pf.sampleProposal(ZF, IDF, RE, xi);
+//                  featureUpdate(particles[i], ZF, IDF, RE); }       ->  pf.featureUpdate(ZF, IDF, RE);
+//     resampleParticles(particles, mNumEffective, mSwitchResample);  ->  pf.resampleParticles(neff_min, u, on);
+//     for (i...) { [X = multivariateNormal...(X, P, 1); P = 0;]      ->  pf.samplePose(xi);
+//                  addOneNewFeature(particles[i], ZN, RE); }         ->  pf.addOneNewFeature(ZN, RE);
+//     extractStatesFromParticles(particles)                          ->  pf.extractStatesFromParticles();
+//
+// Random draws are INPUTS: xi = 3 standard normals per particle ([p][3]),
+// u = one deviate per resampling slot; the reference draws them inside slam.h:753-764 / PF.cpp:579-596.
+template <class Vec, class MatT>
+class PfGpuT {
+  public:
+    int mNumParticles = 100;
+    double mNumEffective = 75.0;  // slam.h:92-93 (0.75 * 100, fixed at construction in the reference)
+    std::vector<int> mTABLE;
+
+    PfGpuT(int num_map_landmarks, int num_particles, int capacity_landmarks, int device = 0,
+           unsigned flags = CSLAM_FLAG_REF_LITERAL)
+        : mNumParticles(num_particles), mTABLE((size_t)num_map_landmarks, 0) {
+        // Slam::initializeParticles(n)  slam.h:688 / PF.cpp:319-341
+        report(cslam_pf_create(&h_, num_particles, capacity_landmarks, device, flags), "PFGpu");
+    }
+    ~PfGpuT() { cslam_pf_destroy(h_); }
+    PfGpuT(const PfGpuT&) = delete;
+    PfGpuT& operator=(const PfGpuT&) = delete;
+    cslam_pf_t* handle() { return h_; }
+    int numFeatures() const { return cslam_pf_num_features(h_); }  // particles[0].XF.cols(), main.cpp:299
+
+    // Slam::predict(Particle_t&, ...) for every particle   slam.h:858-863 / PF.cpp:419-471
+    void predict(double v, double swa, const MatT& Q, double wb, double dt) {
+        const double q[4] = {Q(0, 0), Q(1, 0), Q(0, 1), Q(1, 1)};
+        report(cslam_pf_predict(h_, v, swa, q, wb, dt), "predict");
+    }
+    // Slam::observeHeading(Particle_t&, phi, use)          slam.h:796 / PF.cpp:382-417
+    void observeHeading(double phi, bool useHeading = false) {
+        report(cslam_pf_observe_heading(h_, phi, useHeading ? 1 : 0), "observeHeading");
+    }
+    // Slam::sampleProposal(Particle_t&, Z, idf, R)         slam.h:881-884 / PF.cpp:502-544
+    void sampleProposal(const MatT& Z, const std::vector<int>& idf, const MatT& R, const std::vector<double>& xi) {
+        const int m = Z.cols();
+        if (m == 0) return;
+        std::vector<double> z = flat(Z);
+        std::vector<int32_t> ids(idf.begin(), idf.end());
+        const double r[4] = {R(0, 0), R(1, 0), R(0, 1), R(1, 1)};
+        report(cslam_pf_sample_proposal(h_, z.data(), ids.data(), m, r, xi.data(), 0), "sampleProposal");
+    }
+    // Slam::featureUpdate(Particle_t&, Z, idf, R)          slam.h:549-552 / PF.cpp:222-277
+    void featureUpdate(const MatT& Z, const std::vector<int>& idf, const MatT& R) {
+        const int m = Z.cols();
+        if (m == 0) return;
+        std::vector<double> z = flat(Z);
+        std::vector<int32_t> ids(idf.begin(), idf.end());
+        const double r[4] = {R(0, 0), R(1, 0), R(0, 1), R(1, 1)};
+        report(cslam_pf_feature_update(h_, z.data(), ids.data(), m, r), "featureUpdate");
+    }
+    // Slam::resampleParticles(particles, numEffective, on)  slam.h:871-872 / PF.cpp:473-500; returns Keep
+    // (0-based source index per slot, Q11), neff through the out-parameter.
+    std::vector<int32_t> resampleParticles(double numEffective, const std::vector<double>& u, bool resampleStatus,
+                                           double* neff = nullptr, bool* resampled = nullptr) {
+        std::vector<int32_t> keep((size_t)mNumParticles, 0);
+        double ne = 0.0;
+        int did = 0;
+        report(cslam_pf_resample(h_, u.data(), 0, numEffective, resampleStatus ? 1 : 0, keep.data(), &ne, &did),
+               "resampleParticles");
+        if (neff) *neff = ne;
+        if (resampled) *resampled = did != 0;
+        return keep;
+    }
+    // Slam::addOneNewFeature(Particle_t&, Z, R)            slam.h:134 / PF.cpp:9-60
+    void addOneNewFeature(const MatT& Z, const MatT& R) {
+        const int m = Z.cols();
+        if (m == 0) return;
+        std::vector<double> z = flat(Z);
+        const double r[4] = {R(0, 0), R(1, 0), R(0, 1), R(1, 1)};
+        for (int b = 0; b < m; b += CSLAM_MAX_OBS) {
+            const int mc = (m - b < CSLAM_MAX_OBS) ? m - b : CSLAM_MAX_OBS;
+            report(cslam_pf_add_features(h_, z.data() + 2 * b, mc, r), "addOneNewFeature");
+        }
+    }
+    // particles[i].X = multivariateNormalGaussianDistribution(X, P, 1); P = 0     test/main.cpp:319-325
+    void samplePose(const std::vector<double>& xi) { report(cslam_pf_sample_pose(h_, xi.data(), 0), "samplePose"); }
+    // Slam::dataAssociateTable(Z, idz, table, nf)          slam.h:468-471 — EKF-style bookkeeping (Q8)
+    AssociationT<MatT> dataAssociateTable(const MatT& Z, const std::vector<int>& idz, std::vector<int>& table, int nf) {
+        AssociationT<MatT> out;
+        std::vector<int> zf, zn, idn;
+        for (size_t i = 0; i < idz.size(); i++) {
+            const int id = idz[i];
+            if (table[(size_t)id - 1] == 0) { zn.push_back((int)i); idn.push_back(id); }
+            else { zf.push_back((int)i); out.idf.push_back(table[(size_t)id - 1]); }
+        }
+        out.ZF.resize(zf.empty() ? 0 : 2, (int)zf.size());
+        for (size_t k = 0; k < zf.size(); k++) { out.ZF(0, (int)k) = Z(0, zf[k]); out.ZF(1, (int)k) = Z(1, zf[k]); }
+        out.ZN.resize(zn.empty() ? 0 : 2, (int)zn.size());
+        for (size_t k = 0; k < zn.size(); k++) { out.ZN(0, (int)k) = Z(0, zn[k]); out.ZN(1, (int)k) = Z(1, zn[k]); }
+        for (size_t k = 0; k < idn.size(); k++) table[(size_t)idn[k] - 1] = nf + (int)k + 1;
+        return out;
+    }
+    // Slam::extractStatesFromParticles  slam.h:493-511: pose of the MINIMUM-weight particle (Q13)
+    Vec extractStatesFromParticles(int* index = nullptr) {
+        double x[3] = {0, 0, 0};
+        int idx = 0;
+        report(cslam_pf_extract_state(h_, x, &idx), "extractStatesFromParticles");
+        Vec out;
+        out.resize(3);
+        for (int i = 0; i < 3; i++) out(i) = x[i];
+        if (index) *index = idx;
+        return out;
+    }
+    std::vector<double> weights() {
+        std::vector<double> w((size_t)mNumParticles);
+        report(cslam_pf_get_weights(h_, w.data()), "weights");
+        return w;
+    }
+    std::vector<double> poses() {  // [p][3]
+        std::vector<double> x((size_t)3 * mNumParticles);
+        report(cslam_pf_get_poses(h_, x.data()), "poses");
+        return x;
+    }
+    int skippedUpdates() {
+        int s = 0;
+        report(cslam_pf_sync(h_, &s), "sync");
+        return s;
+    }
+
+  private:
+    static std::vector<double> flat(const MatT& Z) {
+        const int m = Z.cols();
+        std::vector<double> z((size_t)2 * m);
+        for (int i = 0; i < m; i++) { z[2 * i] = Z(0, i); z[2 * i + 1] = Z(1, i); }
+        return z;
+    }
+    cslam_pf_t* h_ = nullptr;
+};
+
+using PfGpu = PfGpuT<DVec, DMat>;
 
 }  // namespace cslam_host
