@@ -646,6 +646,49 @@ static int replicas_follow(cslam_ekf* h, int r, double diag_eps) {
     return CSLAM_OK;
 }
 
+// The replicated diagonal-block cache D of a sharded handle follows every FMA-path covariance pass the
+// same way (same operations on its 3 entries per landmark), so the gate needs no pack + all-reduce
+// per scan: terms = number of sequential updates in the pass, rows = panel rows per update (1: heading
+// update slam.h:718 with its diagonal FLT_MIN, 2: landmark update).
+__global__ void __launch_bounds__(256) k_diag_follow(double* __restrict__ D, int dcap, int nf,
+                                                     const double* __restrict__ A, size_t lda, int terms, int rows,
+                                                     double diag_eps, bool add_eps) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nf) return;
+    const int f = 3 + 2 * j;
+    double d00 = D[j], d01 = D[(size_t)dcap + j], d11 = D[2 * (size_t)dcap + j];
+    for (int q = 0; q < terms; q++) {
+        const double* a0 = A + (size_t)rows * q * lda;
+        if (rows == 2) {
+            const double* a1 = a0 + lda;
+            d00 = d00 - rank2_term(a0[f], a1[f], a0[f], a1[f]);
+            d01 = d01 - rank2_term(a0[f], a1[f], a0[f + 1], a1[f + 1]);
+            d11 = d11 - rank2_term(a0[f + 1], a1[f + 1], a0[f + 1], a1[f + 1]);
+        } else {
+            d00 = d00 - a0[f] * a0[f];
+            d01 = d01 - a0[f] * a0[f + 1];
+            d11 = d11 - a0[f + 1] * a0[f + 1];
+        }
+    }
+    if (add_eps) {  // k_cov_update adds diag_eps on the diagonal (also when it is 0.0); k_cov_update_multi does not
+        d00 += diag_eps;
+        d11 += diag_eps;
+    }
+    D[j] = d00;
+    D[(size_t)dcap + j] = d01;
+    D[2 * (size_t)dcap + j] = d11;
+}
+static int diag_follow(cslam_ekf* h, int terms, int rows, double diag_eps, bool add_eps) {
+    if (h->sh.world == 1 || h->diag_dirty) return CSLAM_OK;  // no cache / cache stale anyway (next gate re-packs)
+    const int nf = (h->n - 3) / 2;
+    if (nf == 0) return CSLAM_OK;
+    count_launch();
+    k_diag_follow<<<(nf + 255) / 256, 256, 0, h->stream>>>(h->D, h->dcap, nf, h->A, h->lda, terms, rows, diag_eps,
+                                                           add_eps);
+    CSLAM_CUDA(cudaGetLastError());
+    return CSLAM_OK;
+}
+
 // ... and the grouped form: g sequential rank-2 terms subtracted one after the other (k_cov_update_multi)
 __global__ void __launch_bounds__(256) k_rows012_update_multi(double* __restrict__ R3, size_t ld, int n,
                                                               const double* __restrict__ A, size_t lda, int g) {
@@ -684,7 +727,7 @@ static int launch_cov_update(cslam_ekf* h, double diag_eps, const int* live = nu
         }
         CSLAM_CUDA(cudaGetLastError());
     }
-    h->diag_dirty = true;
+    if (int rc = diag_follow(h, 1, R, diag_eps, true)) return rc;
     return replicas_follow(h, R, diag_eps);
 }
 
@@ -727,7 +770,6 @@ static int launch_cov_update_rank(cslam_ekf* h, int r) {
 static int launch_cov_update_multi(cslam_ekf* h, int g, const int* live) {
     if (g == 1) return launch_cov_update<2>(h, 0.0, live);
     const int n = h->n;
-    h->diag_dirty = true;
     {
     ProfScope prof(h);
     count_launch();
@@ -759,6 +801,7 @@ static int launch_cov_update_multi(cslam_ekf* h, int g, const int* live) {
 #undef CSLAM_MULTI
     }
     CSLAM_CUDA(cudaGetLastError());
+    if (int rc = diag_follow(h, g, 2, 0.0, false)) return rc;
     if (h->sh.world > 1 && h->R3 != h->P) {  // replicas of rows 0..2 follow, same operations
         count_launch();
         k_rows012_update_multi<<<dim3((n + 255) / 256, 3), 256, 0, h->stream>>>(h->R3, h->ld, n, h->A, h->lda, g);
@@ -787,18 +830,22 @@ static int sequential_updates(cslam_ekf* h, const double* Z, const int32_t* idf_
     const bool sharded = h->sh.world > 1;
     for (int base = 0; base < m; base += kSeqGroup) {
         const int g = std::min(kSeqGroup, m - base);
+        if (sharded) {  // ONE exchange per group: the 2g observed columns of the not-yet-updated P
+            ColList cl;
+            cl.n = 2 * g;
+            for (int k = 0; k < g; k++) {
+                cl.c[2 * k] = 3 + 2 * (idf_host[base + k] - 1);
+                cl.c[2 * k + 1] = cl.c[2 * k] + 1;
+            }
+            if (int rc = exchange_columns(h, cl)) return rc;
+        }
         for (int k = 0; k < g; k++) {
             const int i = base + k;
             if (sharded) {
-                ColList cl;
-                cl.n = 2;
-                cl.c[0] = 3 + 2 * (idf_host[i] - 1);
-                cl.c[1] = cl.c[0] + 1;
-                if (int rc = exchange_columns(h, cl)) return rc;
                 count_launch();
                 k_gain_single<true><<<(n + 255) / 256, 256, 0, h->stream>>>(
-                    h->X[h->cur], h->X[h->cur ^ 1], h->P, h->R3, h->colbuf, h->ld, n, Z[2 * i], Z[2 * i + 1],
-                    idf_host[i], R[0], R[1], R[2], R[3], h->flags, h->A, h->lda, h->status, nullptr, k);
+                    h->X[h->cur], h->X[h->cur ^ 1], h->P, h->R3, h->colbuf + (size_t)2 * k * h->lda, h->ld, n, Z[2 * i],
+                    Z[2 * i + 1], idf_host[i], R[0], R[1], R[2], R[3], h->flags, h->A, h->lda, h->status, nullptr, k);
             } else {
                 count_launch();
                 k_gain_single<false><<<(n + 255) / 256, 256, 0, h->stream>>>(
@@ -873,7 +920,7 @@ static int create_common(cslam_ekf_t** out, int capacity_landmarks, int device, 
     TRY(cudaMalloc(&h->small, sizeof(BatchSmall)));
     TRY(cudaMalloc(&h->status, sizeof(int)));
     TRY(cudaMalloc(&h->ticket, 4 * sizeof(unsigned)));
-    h->gate.max_blocks = (capacity_landmarks + 255) / 256 + 1;
+    h->gate.max_blocks = (capacity_landmarks + 127) / 128 + 1;  // k_gate runs 128-thread blocks
     TRY(cudaMalloc(&h->gate.part_nd, (size_t)h->gate.max_blocks * CSLAM_MAX_OBS * sizeof(double)));
     TRY(cudaMalloc(&h->gate.part_out, (size_t)h->gate.max_blocks * CSLAM_MAX_OBS * sizeof(double)));
     TRY(cudaMalloc(&h->gate.part_j, (size_t)h->gate.max_blocks * CSLAM_MAX_OBS * sizeof(int)));

@@ -37,15 +37,17 @@ __device__ __forceinline__ void cand_merge(Cand& a, double nd, int j, double out
 
 // R3 = rows 0..2 of P (P itself on one GPU); D = replicated cache of the diagonal blocks
 // ([3][dcap], sharded handles) or nullptr (read them from P).
-__global__ void __launch_bounds__(256) k_gate(const double* __restrict__ X, const double* __restrict__ P,
+constexpr int kGateThreads = 128;  // 4 warps: twice the CTAs of a 256-thread block (20k landmarks -> 157 CTAs >= 148 SMs)
+__global__ void __launch_bounds__(kGateThreads) k_gate(const double* __restrict__ X, const double* __restrict__ P,
                                               const double* __restrict__ R3, const double* __restrict__ D, int dcap,
                                               size_t ld, int nf, GatePack gp, double* __restrict__ part_nd,
                                               double* __restrict__ part_out, int* __restrict__ part_j,
                                               unsigned* __restrict__ ticket, int* __restrict__ jbest,
                                               double* __restrict__ nbest, double* __restrict__ outer) {
-    __shared__ double s_nd[8][CSLAM_MAX_OBS];
-    __shared__ double s_out[8][CSLAM_MAX_OBS];
-    __shared__ int s_j[8][CSLAM_MAX_OBS];
+    constexpr int NW = kGateThreads / 32;
+    __shared__ double s_nd[NW][CSLAM_MAX_OBS];
+    __shared__ double s_out[NW][CSLAM_MAX_OBS];
+    __shared__ int s_j[NW][CSLAM_MAX_OBS];
     __shared__ bool is_last;
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
     const int jl = blockIdx.x * blockDim.x + threadIdx.x + 1;  // 1-based landmark id
@@ -149,7 +151,7 @@ __global__ void __launch_bounds__(256) k_gate(const double* __restrict__ X, cons
     __syncthreads();
     for (int i = threadIdx.x; i < gp.m; i += blockDim.x) {
         Cand c{s_nd[0][i], s_out[0][i], s_j[0][i]};
-        for (int w = 1; w < 8; w++) cand_merge(c, s_nd[w][i], s_j[w][i], s_out[w][i]);
+        for (int w = 1; w < NW; w++) cand_merge(c, s_nd[w][i], s_j[w][i], s_out[w][i]);
         part_nd[(size_t)blockIdx.x * CSLAM_MAX_OBS + i] = c.nd;
         part_out[(size_t)blockIdx.x * CSLAM_MAX_OBS + i] = c.out;
         part_j[(size_t)blockIdx.x * CSLAM_MAX_OBS + i] = c.j;
@@ -160,15 +162,26 @@ __global__ void __launch_bounds__(256) k_gate(const double* __restrict__ X, cons
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    for (int i = threadIdx.x; i < gp.m; i += blockDim.x) {
+    // final stage: one warp per observation, lanes stride over the per-block candidates, then the same
+    // lexicographic (nd, j) merge across the warp — the order of merges does not change the result
+    for (int i = warp; i < gp.m; i += NW) {
         Cand c{inf, inf, 0x7fffffff};
-        for (unsigned b = 0; b < gridDim.x; b++)
+        for (unsigned b = lane; b < gridDim.x; b += 32)
             cand_merge(c, ((volatile double*)part_nd)[(size_t)b * CSLAM_MAX_OBS + i],
                        ((volatile int*)part_j)[(size_t)b * CSLAM_MAX_OBS + i],
                        ((volatile double*)part_out)[(size_t)b * CSLAM_MAX_OBS + i]);
-        jbest[i] = (c.j == 0x7fffffff) ? 0 : c.j;
-        nbest[i] = c.nd;
-        outer[i] = c.out;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double ond = __shfl_xor_sync(0xffffffffu, c.nd, off);
+            const double oout = __shfl_xor_sync(0xffffffffu, c.out, off);
+            const int oj = __shfl_xor_sync(0xffffffffu, c.j, off);
+            cand_merge(c, ond, oj, oout);
+        }
+        if (lane == 0) {
+            jbest[i] = (c.j == 0x7fffffff) ? 0 : c.j;
+            nbest[i] = c.nd;
+            outer[i] = c.out;
+        }
     }
     if (threadIdx.x == 0) *ticket = 0;
 }
@@ -185,9 +198,9 @@ int launch_gate(const double* X, const double* P, const double* R3, const double
     memcpy(gp.R, R, sizeof(double) * 4);
     gp.gate1 = gate1;
     gp.gate2 = gate2;
-    const int blocks = nf > 0 ? (nf + 255) / 256 : 1;
+    const int blocks = nf > 0 ? (nf + kGateThreads - 1) / kGateThreads : 1;
     count_launch();
-    k_gate<<<blocks, 256, 0, stream>>>(X, P, R3, D, dcap, ld, nf, gp, part_nd, part_out, part_j, ticket, jbest, nbest,
+    k_gate<<<blocks, kGateThreads, 0, stream>>>(X, P, R3, D, dcap, ld, nf, gp, part_nd, part_out, part_j, ticket, jbest, nbest,
                                        outer);
     CSLAM_CUDA(cudaGetLastError());
     return CSLAM_OK;

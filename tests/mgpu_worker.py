@@ -73,8 +73,15 @@ def ekf_checks():
         for f in (g, o):
             f.update(Z, RE, ids, False)
         check("sequential update")
-        jg = g.gate(Z, RE, 50.0, 1000.0)[0]
-        assert np.array_equal(jg, o.gate(Z, RE, 50.0, 1000.0)[0])
+        # the replicated diagonal-block cache FOLLOWED the grouped update (no re-pack): same decisions, same nd
+        gg, go = g.gate(Z, RE, 50.0, 1000.0), o.gate(Z, RE, 50.0, 1000.0)
+        assert np.array_equal(gg[0], go[0]) and rel_err(gg[2], go[2]) < 1e-9, (gg[2], go[2])
+        for f in (g, o):
+            f.observeHeading(float(o.X[2]) + 5e-5, True)
+            f.update(Z[:, :1], RE, ids[:1], False)
+        check("heading + single update (cache follows rank-1 and rank-2 passes)")
+        gg, go = g.gate(Z, RE, 50.0, 1000.0), o.gate(Z, RE, 50.0, 1000.0)
+        assert np.array_equal(gg[0], go[0]) and rel_err(gg[2], go[2]) < 1e-9, (gg[2], go[2])
         ids2 = (rng.choice(N, size=16, replace=False) + 1).astype(np.int32)
         Z2 = helpers.observe(o.X, lm, ids2, rng)
         for f in (g, o):
