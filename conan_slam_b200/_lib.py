@@ -61,6 +61,9 @@ SIGNATURES = {
     "cslam_ekf_get_state": (C.c_int, [_vp, _dp, C.c_int]),
     "cslam_ekf_get_cov_block": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _dp]),
     "cslam_ekf_reset": (C.c_int, [_vp, _dp, C.c_int, _dp]),
+    "cslam_ekf_get_landmark_covs": (C.c_int, [_vp, C.c_int, C.c_int, _dp]),
+    "cslam_ekf_save": (C.c_int, [_vp, C.c_char_p]),
+    "cslam_ekf_load": (C.c_int, [_vp, C.c_char_p]),
     "cslam_ekf_device_ptrs": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_size_t)]),
     "cslam_pf_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.c_uint]),
     "cslam_pf_create_sharded": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.c_uint, C.c_int, C.c_int, _vp]),

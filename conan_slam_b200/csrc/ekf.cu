@@ -1230,6 +1230,146 @@ int cslam_ekf_get_cov_block(cslam_ekf_t* h, int r0, int c0, int nr, int nc, doub
     return CSLAM_OK;
 }
 
+// Landmark marginals for visualisation (the README's uncertainty ellipses) without pulling P:
+// per landmark j0 <= j < j0 + count the 2x2 diagonal block packed as (P_ff, P_f,f+1, P_f+1,f+1).
+__global__ void __launch_bounds__(256) k_landmark_covs(const double* __restrict__ P, size_t ld, int j0, int count,
+                                                       double* __restrict__ out, Shard sh) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const int f = 3 + 2 * (j0 + t);
+    double a = 0.0, b = 0.0, c = 0.0;
+    if (shard_owns(sh, f)) {
+        a = P[shard_lrow(sh, f) * ld + f];
+        b = P[shard_lrow(sh, f) * ld + f + 1];
+    }
+    if (shard_owns(sh, f + 1)) c = P[shard_lrow(sh, f + 1) * ld + f + 1];
+    out[3 * (size_t)t] = a;
+    out[3 * (size_t)t + 1] = b;
+    out[3 * (size_t)t + 2] = c;
+}
+
+int cslam_ekf_get_landmark_covs(cslam_ekf_t* h, int first_landmark, int count, double* out) {
+    if (int rc = check_handle(h)) return rc;
+    const int nf = (h->n - 3) / 2;
+    CSLAM_REQUIRE(first_landmark >= 1 && count >= 0 && first_landmark - 1 + count <= nf, CSLAM_ERR_BAD_ARG,
+                  "landmark range out of bounds (1-based ids)");
+    if (count == 0) return CSLAM_OK;
+    CSLAM_REQUIRE(out != nullptr, CSLAM_ERR_BAD_ARG, "out is null");
+    double* tmp = nullptr;
+    const size_t cnt = 3 * (size_t)count;
+    CSLAM_CUDA(cudaMalloc(&tmp, cnt * sizeof(double)));
+    count_launch();
+    k_landmark_covs<<<(count + 255) / 256, 256, 0, h->stream>>>(h->P, h->ld, first_landmark - 1, count, tmp, h->sh);
+    cudaError_t e = cudaGetLastError();
+    int rc = CSLAM_OK;
+    if (e == cudaSuccess && h->sh.world > 1) rc = allreduce_sum(h, tmp, cnt);  // collective: all ranks call
+    if (e == cudaSuccess && rc == CSLAM_OK)
+        e = cudaMemcpyAsync(out, tmp, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(tmp);
+    if (rc) return rc;
+    CSLAM_CUDA(e);
+    return CSLAM_OK;
+}
+
+// Checkpoint (the reference has none: X, P and mTABLE live in the driver).  File = header
+// {magic, version, n, flags} + X[n] + the upper triangle of P row by row (row i: n - i doubles),
+// i.e. the device layout minus padding; 8*n*(n+1)/2 bytes instead of 8*n*n.  Single-GPU handles.
+namespace {
+struct CkptHeader {
+    char magic[8];
+    uint32_t version;
+    uint32_t flags;
+    int32_t n;
+    int32_t reserved;
+};
+const char kCkptMagic[8] = {'C', 'S', 'L', 'A', 'M', 'E', 'K', 'F'};
+}  // namespace
+
+int cslam_ekf_save(cslam_ekf_t* h, const char* path) {
+    if (int rc = check_handle(h)) return rc;
+    CSLAM_REQUIRE(path != nullptr, CSLAM_ERR_BAD_ARG, "path is null");
+    CSLAM_REQUIRE(h->sh.world == 1, CSLAM_ERR_UNSUPPORTED, "checkpoints are single-GPU (sharded: save per block)");
+    CSLAM_CUDA(cudaStreamSynchronize(h->stream));
+    FILE* f = fopen(path, "wb");
+    CSLAM_REQUIRE(f != nullptr, CSLAM_ERR_BAD_ARG, "cannot open checkpoint file for writing");
+    const int n = h->n;
+    CkptHeader hd;
+    memcpy(hd.magic, kCkptMagic, 8);
+    hd.version = 1;
+    hd.flags = h->flags;
+    hd.n = n;
+    hd.reserved = 0;
+    bool ok = fwrite(&hd, sizeof(hd), 1, f) == 1;
+    std::vector<double> host((size_t)std::max<size_t>(n, 1 << 20));
+    cudaError_t e = cudaMemcpy(host.data(), h->X[h->cur], n * sizeof(double), cudaMemcpyDeviceToHost);
+    ok = ok && e == cudaSuccess && fwrite(host.data(), sizeof(double), n, f) == (size_t)n;
+    // rows in slabs of ~8 MB through a 2D copy (pitch = ld), upper part written per row
+    const int slab = std::max(1, (int)((size_t)(1 << 20) / std::max(n, 1)));
+    std::vector<double> rows((size_t)slab * n);
+    for (int i0 = 0; ok && i0 < n; i0 += slab) {
+        const int nr = std::min(slab, n - i0);
+        e = cudaMemcpy2D(rows.data(), (size_t)n * sizeof(double), h->P + (size_t)i0 * h->ld, h->ld * sizeof(double),
+                         (size_t)n * sizeof(double), nr, cudaMemcpyDeviceToHost);
+        ok = e == cudaSuccess;
+        for (int r = 0; ok && r < nr; r++) {
+            const int i = i0 + r;
+            ok = fwrite(rows.data() + (size_t)r * n + i, sizeof(double), n - i, f) == (size_t)(n - i);
+        }
+    }
+    ok = (fclose(f) == 0) && ok;
+    if (e != cudaSuccess) {
+        set_last_error("cslam_ekf_save: %s", cudaGetErrorString(e));
+        return CSLAM_ERR_CUDA;
+    }
+    CSLAM_REQUIRE(ok, CSLAM_ERR_BAD_ARG, "short write to the checkpoint file");
+    return CSLAM_OK;
+}
+
+int cslam_ekf_load(cslam_ekf_t* h, const char* path) {
+    if (int rc = check_handle(h)) return rc;
+    CSLAM_REQUIRE(path != nullptr, CSLAM_ERR_BAD_ARG, "path is null");
+    CSLAM_REQUIRE(h->sh.world == 1, CSLAM_ERR_UNSUPPORTED, "checkpoints are single-GPU (sharded: load per block)");
+    FILE* f = fopen(path, "rb");
+    CSLAM_REQUIRE(f != nullptr, CSLAM_ERR_BAD_ARG, "cannot open checkpoint file");
+    CkptHeader hd;
+    bool ok = fread(&hd, sizeof(hd), 1, f) == 1 && memcmp(hd.magic, kCkptMagic, 8) == 0 && hd.version == 1;
+    if (!ok || hd.n < 3 || hd.n > h->n_cap || (hd.n - 3) % 2 != 0) {
+        fclose(f);
+        set_last_error("cslam_ekf_load: not a checkpoint of this library, or it exceeds the handle's capacity");
+        return CSLAM_ERR_BAD_ARG;
+    }
+    const int n = hd.n;
+    CSLAM_CUDA(cudaStreamSynchronize(h->stream));
+    std::vector<double> x((size_t)n);
+    ok = fread(x.data(), sizeof(double), n, f) == (size_t)n;
+    cudaError_t e = cudaSuccess;
+    if (ok) e = cudaMemcpy(h->X[h->cur], x.data(), n * sizeof(double), cudaMemcpyHostToDevice);
+    const int slab = std::max(1, (int)((size_t)(1 << 20) / std::max(n, 1)));
+    std::vector<double> rows((size_t)slab * n, 0.0);
+    for (int i0 = 0; ok && e == cudaSuccess && i0 < n; i0 += slab) {
+        const int nr = std::min(slab, n - i0);
+        for (int r = 0; ok && r < nr; r++) {
+            const int i = i0 + r;
+            for (int j = 0; j < i; j++) rows[(size_t)r * n + j] = 0.0;  // below the diagonal: unauthoritative
+            ok = fread(rows.data() + (size_t)r * n + i, sizeof(double), n - i, f) == (size_t)(n - i);
+        }
+        if (ok)
+            e = cudaMemcpy2D(h->P + (size_t)i0 * h->ld, h->ld * sizeof(double), rows.data(), (size_t)n * sizeof(double),
+                             (size_t)n * sizeof(double), nr, cudaMemcpyHostToDevice);
+    }
+    fclose(f);
+    if (e != cudaSuccess) {
+        set_last_error("cslam_ekf_load: %s", cudaGetErrorString(e));
+        return CSLAM_ERR_CUDA;
+    }
+    CSLAM_REQUIRE(ok, CSLAM_ERR_BAD_ARG, "truncated checkpoint file");
+    h->n = n;
+    h->diag_dirty = true;
+    CSLAM_CUDA(cudaMemsetAsync(h->status, 0, sizeof(int), h->stream));
+    return CSLAM_OK;
+}
+
 int cslam_ekf_reset(cslam_ekf_t* h, const double* X, int n, const double* P) {
     if (int rc = check_handle(h)) return rc;
     CSLAM_REQUIRE(X && n >= 3 && n <= h->n_cap && ((n - 3) % 2 == 0), CSLAM_ERR_BAD_ARG, "bad state size");

@@ -131,6 +131,23 @@ class EKF:
             pp = dptr(P)
         check(self._lib.cslam_ekf_reset(self._h, dptr(X), n, pp), "cslam_ekf_reset")
 
+    def save(self, path):
+        """Checkpoint X and the upper triangle of P (the reference has no persistence)."""
+        check(self._lib.cslam_ekf_save(self._h, str(path).encode()), "cslam_ekf_save")
+
+    def load(self, path):
+        check(self._lib.cslam_ekf_load(self._h, str(path).encode()), "cslam_ekf_load")
+
+    def landmark_covs(self, first=1, count=None):
+        """2x2 marginal covariances of landmarks first .. first+count-1 (1-based) as (count, 2, 2)."""
+        if count is None:
+            count = self.num_landmarks - first + 1
+        out = np.zeros((count, 3), dtype=np.float64)
+        if count:
+            check(self._lib.cslam_ekf_get_landmark_covs(self._h, int(first), int(count), dptr(out)),
+                  "cslam_ekf_get_landmark_covs")
+        return np.stack([np.stack([out[:, 0], out[:, 1]], -1), np.stack([out[:, 1], out[:, 2]], -1)], -2)
+
     # -- accessors (the driver owns X,P in the reference) -------------------------
     @property
     def X(self):

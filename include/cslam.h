@@ -123,6 +123,15 @@ int cslam_ekf_augment(cslam_ekf_t* h, const double* Z, int m, const double R[4])
  * lower triangle mirrored from the authoritative upper one. */
 int cslam_ekf_get_state(cslam_ekf_t* h, double* X, int max_n);
 int cslam_ekf_get_cov_block(cslam_ekf_t* h, int r0, int c0, int nr, int nc, double* out);
+/* Landmark marginals without reading P back (visualisation of the uncertainty ellipses, README.md:15-22;
+ * "next" row of SURVEY.md §8f): for the 1-based landmarks first .. first+count-1 the 2x2 diagonal block
+ * packed as out[3*k + {0,1,2}] = (P_ff, P_f,f+1, P_f+1,f+1).  Collective on sharded handles. */
+int cslam_ekf_get_landmark_covs(cslam_ekf_t* h, int first_landmark, int count, double* out);
+/* Checkpoint / restore of X and the upper triangle of P (the reference keeps X, P in the driver and has
+ * no persistence): header + X[n] + row i of P from the diagonal on, 4*n*(n+1) bytes of
+ * covariance.  load() requires n <= the handle's capacity.  Single-GPU handles. */
+int cslam_ekf_save(cslam_ekf_t* h, const char* path);
+int cslam_ekf_load(cslam_ekf_t* h, const char* path);
 /* Load a state (tests / benchmarks / checkpoint restore): X has n entries, P is a dense
  * row-major n x n matrix (only j >= i is read) or NULL for zeros. */
 int cslam_ekf_reset(cslam_ekf_t* h, const double* X, int n, const double* P);

@@ -260,3 +260,35 @@ def test_main_loop_prefix_parity_literal():
     assert rel_err(g.X, o.X) < TOL
     iu = np.triu_indices(o.n)
     assert rel_err(g.P[iu], o.P[iu]) < TOL
+
+
+def test_checkpoint_roundtrip_and_landmark_marginals(tmp_path):
+    """SURVEY §8f "next" rows: checkpoint of X + upper triangle of P restores a bit-identical filter
+    (same subsequent updates); landmark 2x2 marginals come back without reading P."""
+    import conan_slam_b200 as cs
+    g, o, lm = _pair(60, 321, oracle_py.FLAG_INTENDED)
+    rng = np.random.default_rng(5)
+    ids = (rng.choice(60, size=4, replace=False) + 1).astype(np.int32)
+    Z = helpers.observe(o.X, lm, ids, rng)
+    g.update(Z, RE, ids, False)
+    Pg = g.P
+    covs = g.landmark_covs()
+    assert covs.shape == (60, 2, 2)
+    for j in (0, 17, 59):
+        f = 3 + 2 * j
+        assert np.array_equal(covs[j], Pg[f:f + 2, f:f + 2])
+    assert np.array_equal(g.landmark_covs(first=10, count=3), covs[9:12])
+    path = tmp_path / "ekf.ckpt"
+    g.save(path)
+    assert path.stat().st_size == 24 + 8 * g.n + 4 * g.n * (g.n + 1)
+    g2 = cs.EKF(capacity_landmarks=64, flags=oracle_py.FLAG_INTENDED)
+    g2.load(path)
+    assert g2.n == g.n and np.array_equal(g2.X, g.X) and np.array_equal(g2.P, Pg)
+    for f in (g, g2):
+        f.predict(83.33, 0.01, helpers.QE, 73.0, 0.01)
+        f.observeHeading(float(o.X[2]) + 1e-4, True)
+        f.update(Z[:, :2], RE, ids[:2], True)
+    assert np.array_equal(g2.X, g.X) and np.array_equal(g2.P, g.P)
+    small = cs.EKF(capacity_landmarks=8)
+    with pytest.raises(Exception):
+        small.load(path)  # exceeds capacity
