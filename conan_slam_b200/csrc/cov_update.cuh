@@ -150,10 +150,14 @@ template <int M, int T, int BATCH_ = 4, int MINB = 2, int HINT = 1>
 __global__ void __launch_bounds__(256, MINB) k_cov_update_multi(double* __restrict__ P, size_t ld, int n,
                                                                 const double* __restrict__ A, size_t lda, int nt,
                                                                 Shard sh, const int* __restrict__ live) {
-    constexpr int R = 2 * M;
     constexpr int CP = T / 2, RG = 256 / CP, RPT = T / RG;
     constexpr int BATCH = RPT > BATCH_ ? BATCH_ : RPT;
-    __shared__ double sAr[R][T];
+    // Both panels of the tile live in shared memory, so a thread keeps only ONE update's four column
+    // values in registers at a time (the register budget decides how many CTAs stream concurrently):
+    //   sRow[i][q]  = (a0_i, a1_i) of update q   — read as one broadcast 16-byte load per (row, q)
+    //   sCol0/1[q][cp] = (a0_j, a0_j+1) / (a1_j, a1_j+1) — one conflict-free 16-byte load each per (batch, q)
+    __shared__ double2 sRow[T][M];
+    __shared__ double2 sCol0[M][CP], sCol1[M][CP];
     int any_live = 1;
     if (live != nullptr) {
         any_live = 0;
@@ -163,48 +167,54 @@ __global__ void __launch_bounds__(256, MINB) k_cov_update_multi(double* __restri
     int tr, tc;
     shard_tile(blockIdx.x, nt, sh, tr, tc);
     const int i0 = tr * T, j0 = tc * T;
-    for (int idx = threadIdx.x; idx < R * T; idx += 256) {
-        const int k = idx / T, ii = idx % T;
-        sAr[k][ii] = (i0 + ii < n) ? A[(size_t)k * lda + i0 + ii] : 0.0;
+    for (int idx = threadIdx.x; idx < M * T; idx += 256) {
+        const int q = idx / T, ii = idx % T;
+        const bool in = i0 + ii < n;
+        sRow[ii][q] = make_double2(in ? A[(size_t)(2 * q) * lda + i0 + ii] : 0.0,
+                                   in ? A[(size_t)(2 * q + 1) * lda + i0 + ii] : 0.0);
+    }
+    for (int idx = threadIdx.x; idx < M * CP; idx += 256) {
+        const int q = idx / CP, c = idx % CP;
+        const int jj = j0 + 2 * c;
+        const double* a0 = A + (size_t)(2 * q) * lda;
+        const double* a1 = a0 + lda;
+        sCol0[q][c] = make_double2(jj < n ? a0[jj] : 0.0, jj + 1 < n ? a0[jj + 1] : 0.0);
+        sCol1[q][c] = make_double2(jj < n ? a1[jj] : 0.0, jj + 1 < n ? a1[jj + 1] : 0.0);
     }
     const int cp = threadIdx.x % CP, rg = threadIdx.x / CP;
     const int j = j0 + 2 * cp;
-    double aj0[R], aj1[R];
-#pragma unroll
-    for (int k = 0; k < R; k++) {
-        aj0[k] = (j < n) ? A[(size_t)k * lda + j] : 0.0;
-        aj1[k] = (j + 1 < n) ? A[(size_t)k * lda + j + 1] : 0.0;
-    }
     __syncthreads();
     if (j >= n || any_live == 0) return;
     const bool diag_tile = (tr == tc);
+    const bool y_in = j + 1 < n;
 #pragma unroll 1
     for (int b0 = 0; b0 < RPT; b0 += BATCH) {
         double2 v[BATCH];
 #pragma unroll
         for (int b = 0; b < BATCH; b++) {
-            const int ii = rg + (b0 + b) * RG;
-            const int i = i0 + ii;
+            const int i = i0 + rg + (b0 + b) * RG;
             const bool act = (i < n) && (!diag_tile || j + 1 >= i);
             if (act) v[b] = cov_ld<HINT>(P + shard_lrow(sh, i) * ld + j);
         }
 #pragma unroll
-        for (int b = 0; b < BATCH; b++) {
-            const int ii = rg + (b0 + b) * RG;
-            const int i = i0 + ii;
-            const bool act = (i < n) && (!diag_tile || j + 1 >= i);
-            if (act) {
-                double2 o = v[b];
+        for (int q = 0; q < M; q++) {
+            const double2 c0 = sCol0[q][cp], c1 = sCol1[q][cp];
 #pragma unroll
-                for (int q = 0; q < M; q++) {
-                    const double a0i = sAr[2 * q][ii], a1i = sAr[2 * q + 1][ii];
-                    const double s0 = rank2_term(a0i, a1i, aj0[2 * q], aj0[2 * q + 1]);
-                    const double s1 = rank2_term(a0i, a1i, aj1[2 * q], aj1[2 * q + 1]);
-                    if (j >= i) o.x = o.x - s0;
-                    if (j + 1 < n) o.y = o.y - s1;
-                }
-                cov_st<HINT>(P + shard_lrow(sh, i) * ld + j, o);
+            for (int b = 0; b < BATCH; b++) {
+                const int ii = rg + (b0 + b) * RG;
+                const int i = i0 + ii;
+                const double2 r = sRow[ii][q];
+                const double s0 = rank2_term(r.x, r.y, c0.x, c1.x);
+                const double s1 = rank2_term(r.x, r.y, c0.y, c1.y);
+                if (j >= i) v[b].x = v[b].x - s0;
+                if (y_in) v[b].y = v[b].y - s1;
             }
+        }
+#pragma unroll
+        for (int b = 0; b < BATCH; b++) {
+            const int i = i0 + rg + (b0 + b) * RG;
+            const bool act = (i < n) && (!diag_tile || j + 1 >= i);
+            if (act) cov_st<HINT>(P + shard_lrow(sh, i) * ld + j, v[b]);
         }
     }
 }

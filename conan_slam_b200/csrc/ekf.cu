@@ -782,18 +782,20 @@ static int launch_cov_update_multi(cslam_ekf* h, int g, const int* live) {
                 h->P, h->ld, n, h->A, h->lda, nt, h->sh, live);                                                  \
         } else {                                                                                                 \
             const int nt = (n + 63) / 64;                                                                        \
-            k_cov_update_multi<M, 64, 4, MINB, 0><<<(unsigned)shard_tile_count(nt, h->sh), 256, 0, h->stream>>>(  \
+            k_cov_update_multi<M, 64, 4, 2, 0><<<(unsigned)shard_tile_count(nt, h->sh), 256, 0, h->stream>>>(  \
                 h->P, h->ld, n, h->A, h->lda, nt, h->sh, live);                                                  \
         }                                                                                                        \
         break;
     switch (g) {
-        CSLAM_MULTI(2, 4)  // MINB (resident CTAs / SM) per group size from tools/cov_variants.cu on a B200
-        CSLAM_MULTI(3, 3)
-        CSLAM_MULTI(4, 3)
-        CSLAM_MULTI(5, 2)
-        CSLAM_MULTI(6, 2)
-        CSLAM_MULTI(7, 2)
-        CSLAM_MULTI(8, 2)
+        // 4 resident CTAs / SM for every group size (64 registers: one update's column values at a
+        // time); tools/cov_variants.cu on a B200, N=20k: M=2 2.27 ms, M=4 2.47 ms, M=8 3.14 ms
+        CSLAM_MULTI(2, 4)
+        CSLAM_MULTI(3, 4)
+        CSLAM_MULTI(4, 4)
+        CSLAM_MULTI(5, 4)
+        CSLAM_MULTI(6, 4)
+        CSLAM_MULTI(7, 4)
+        CSLAM_MULTI(8, 4)
         default:
             set_last_error("launch_cov_update_multi: bad group size %d", g);
             return CSLAM_ERR_BAD_ARG;

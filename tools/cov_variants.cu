@@ -74,18 +74,18 @@ int main(int argc, char** argv) {
 #define RUNM(M, T, B, MINB, HINT) { float ms = run_multi<M, T, B, MINB, HINT>(P, ld, n, A, ld, reps); \
     printf("n=%d multi M=%d T=%3d BATCH=%2d MINB=%d HINT=%d : %8.4f ms  %8.1f GB/s  (%.1f updates/ms)\n", n, M, T, B, MINB, HINT, ms, gb / (ms * 1e-3), M / ms); }
     RUNM(2, 128, 4, 4, 1)
-    RUNM(2, 128, 4, 3, 1)
-    RUNM(3, 128, 4, 3, 1)
+    RUNM(2, 128, 8, 4, 1)
+    RUNM(3, 128, 4, 4, 1)
     RUNM(4, 128, 4, 3, 1)
-    RUNM(4, 128, 4, 2, 1)
-    RUNM(4, 128, 8, 2, 1)
-    RUNM(4, 128, 2, 3, 1)
-    RUNM(4, 128, 2, 4, 1)
     RUNM(4, 128, 4, 4, 1)
-    RUNM(4, 64, 4, 3, 1)
+    RUNM(4, 128, 4, 5, 1)
+    RUNM(4, 128, 8, 3, 1)
+    RUNM(4, 128, 8, 4, 1)
+    RUNM(4, 128, 2, 5, 1)
     RUNM(4, 64, 4, 4, 1)
-    RUNM(8, 128, 4, 2, 1)
-    RUNM(8, 128, 2, 2, 1)
-    RUNM(8, 64, 4, 2, 1)
+    RUNM(4, 64, 8, 4, 1)
+    RUNM(8, 128, 4, 4, 1)
+    RUNM(8, 128, 8, 4, 1)
+    RUNM(8, 128, 4, 3, 1)
     return 0;
 }
