@@ -308,6 +308,68 @@ def cpu_pf_rate(nfeat, m_obs, threads, particles=2000):
                       f"copy) on {particles} particles x {nfeat} landmarks, per-particle cost"}
 
 
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libconanslam_ref.so")
+
+
+def ref_ekf_update_rate(N, budget_s=20.0):
+    """The reference's OWN code (slam/src/EKF.cpp + slam.h compiled unmodified by oracle/Makefile `_ref`,
+    FP32, single-threaded as the reference is) timed on a bounded sample: one EKF::update (singleUpdate ->
+    Slam::choleskyUpdate, dense P*H^T and the n x n temporary) and a few EKF::computeAssociation pairs
+    on an N_s-landmark map, scaled to N landmarks by the dense algorithm's own complexity — (n/n_s)^2
+    per update and per gate pair, N pairs per observation (EKF.cpp:257-284).  None if oracle/_ref is
+    not built (the GPU box only has what the snapshot carried)."""
+    if not os.path.exists(REF_SO):
+        return None
+    L = C.CDLL(REF_SO)
+    L.ref_ekf_create.restype = C.c_void_p
+    fp, ip, vp = C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_void_p
+    L.ref_ekf_reset.argtypes = [vp, fp, C.c_int, fp]
+    L.ref_ekf_update.argtypes = [vp, fp, ip, C.c_int, fp, C.c_int]
+    L.ref_ekf_compute_association.argtypes = [vp, fp, fp, C.c_int, fp, fp]
+    L.ref_ekf_destroy.argtypes = [vp]
+    n = 3 + 2 * N
+    Rf = np.ascontiguousarray(RE, dtype=np.float32)
+
+    def sample(Ns, pairs):
+        ns = 3 + 2 * Ns
+        lm, rng = synth_landmarks(Ns, Ns)
+        X = np.concatenate([np.zeros(3), lm.T.reshape(-1)]).astype(np.float32)
+        P = np.full((ns, ns), 1e-3, dtype=np.float32)
+        P[np.arange(ns), np.arange(ns)] = 1.0
+        h = C.c_void_p(L.ref_ekf_create())
+        L.ref_ekf_reset(h, X.ctypes.data_as(fp), ns, P.ctypes.data_as(fp))
+        del P
+        j = int(np.argmin(np.hypot(lm[0], lm[1]))) + 1
+        z = range_bearing(np.zeros(3), lm[:, j - 1:j]).T.reshape(-1).astype(np.float32)
+        idf = np.array([j], dtype=np.int32)
+        t0 = time.perf_counter()
+        L.ref_ekf_update(h, z.ctypes.data_as(fp), idf.ctypes.data_as(ip), 1, Rf.ctypes.data_as(fp), 0)
+        t_upd = time.perf_counter() - t0
+        nis, nd = C.c_float(), C.c_float()
+        t0 = time.perf_counter()
+        for k in range(pairs):
+            L.ref_ekf_compute_association(h, z.ctypes.data_as(fp), Rf.ctypes.data_as(fp), 1 + (j + k) % Ns,
+                                          C.byref(nis), C.byref(nd))
+        t_pair = (time.perf_counter() - t0) / pairs
+        L.ref_ekf_destroy(h)
+        return ns, t_upd, t_pair
+
+    ns, t_upd, t_pair = sample(500, 2)                      # probe
+    per_n2 = (t_upd + 3 * t_pair) / (ns * ns)
+    Ns = int(min(N, max(500, (np.sqrt(budget_s / max(per_n2, 1e-12)) - 3) / 2), 8000))
+    ns, t_upd, t_pair = sample(Ns, 3)
+    scale = (n / ns) ** 2
+    t_full = scale * t_upd + N * scale * t_pair
+    return {
+        "value": 1.0 / t_full, "unit": "updates/s", "cores": 1, "kind": "reference",
+        "sample": (f"the reference's own EKF::update + EKF::computeAssociation (oracle/_ref: slam/src/EKF.cpp, slam.h "
+                   f"compiled unmodified, FP32, single-threaded) on a {Ns}-landmark map (n_s={ns}), scaled by "
+                   f"(n/n_s)^2 = {scale:.1f} per dense update and per gate pair, {N} pairs per observation (extrapolated)"),
+        "update_only_updates_per_s": 1.0 / (scale * t_upd),
+        "seconds_per_update_cov": scale * t_upd, "seconds_per_gate_pair": scale * t_pair,
+    }
+
+
 def run_pf(args):
     """--workload pf: C4 of BASELINE.json — FastSLAM, 1M particles x 500 landmarks, m_obs = 4 known
     associations per observation cycle, resampling every cycle; particles split over the GPUs."""
@@ -458,21 +520,30 @@ def run_reference(args):
     c = int(max(128, min(n, probe_c * budget / max(t_probe, 1e-6))))
     c = min(c, int(2e9 // (8 * n)))  # <= 2 GB per slab buffer
     rates = []
+    use_ref = os.path.exists(REF_SO)
     for s in range(args.warmup + args.steps):
-        r = cpu_ekf_update_rate(N, threads, c, reps=1)
+        # the reference's own compiled sources when oracle/_ref travelled with the snapshot, else the port
+        r = ref_ekf_update_rate(N, budget_s=60.0 / max(1, args.steps + args.warmup)) if use_ref else \
+            cpu_ekf_update_rate(N, threads, c, reps=1)
         if s >= args.warmup:
             rates.append(r)
     t_full = float(np.mean([1.0 / r["value"] for r in rates]))
     val = 1.0 / t_full
     base = rates[-1]
     base["value"] = val
-    base["cores"] = threads
+    if use_ref:
+        port = cpu_ekf_update_rate(N, threads, c, reps=1)
+        base["oracle_port_all_cores"] = {"cores": threads, "value": port["value"], "kind": "port",
+                                         "update_only_updates_per_s": port["update_only_updates_per_s"]}
+    else:
+        base["cores"] = threads
     out = {
         "impl": "reference", "metric": "EKF updates/sec", "value": val, "unit": "updates/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 4 * t_full * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"EKF-SLAM {N} landmarks, sequential update (gate+gain+cov), reference dense "
-                               f"algorithm on CPU", "landmarks": N, "state_dim": n, "obs_per_step": 4},
+        "config": {"workload": f"EKF-SLAM {N} landmarks (state dim {n}), range-bearing observations, sequential "
+                               f"update: gate + gain + covariance, 4 observations per scan - the reference's dense "
+                               f"CPU algorithm", "landmarks": N, "state_dim": n, "obs_per_step": 4},
         "cpu_baseline": base,
         "e2e": {"value": val, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -667,10 +738,14 @@ def main():
             out["observations_per_s"] = value * m
         if not args.no_cpu_baseline and world == 1:
             t1 = time.time()
-            out["cpu_baseline"] = cpu_ekf_update_rate(N, 1, slab_cols=3000, reps=2)
+            # the reference's own compiled sources (oracle/_ref) when they travelled with the snapshot,
+            # else the oracle port; the multi-threaded port beside it as a generous baseline
+            out["cpu_baseline"] = ref_ekf_update_rate(N, budget_s=12.0) or \
+                cpu_ekf_update_rate(N, 1, slab_cols=3000, reps=2)
             mt = cpu_ekf_update_rate(N, os.cpu_count() or 1, slab_cols=3000, reps=2)
-            out["cpu_baseline"]["all_cores"] = {"cores": mt["cores"], "value": mt["value"],
-                                                "update_only_updates_per_s": mt["update_only_updates_per_s"]}
+            out["cpu_baseline"]["oracle_port_all_cores"] = {
+                "cores": mt["cores"], "value": mt["value"], "kind": "port",
+                "update_only_updates_per_s": mt["update_only_updates_per_s"]}
             log(f"[bench] cpu baseline took {time.time() - t1:.1f}s")
         emit(out)
     if world > 1:
