@@ -172,7 +172,7 @@ def make_scans(lm, rng, nscans, m):
 def ekf_scan(ekf, Z, batch=False):
     """The user-facing call sequence of one scan (test/main.cpp:193-195): gate, then update
     (batch=False: singleUpdate EKF.cpp:457-479; batch=True: one joint batchUpdate EKF.cpp:93-129)."""
-    if not batch and ekf.world == 1:
+    if not batch:
         # one asynchronous submission, association indices stay on the device (cslam_ekf_scan);
         # the indices are read back behind the gate kernel while the updates run
         return ekf.scan(Z, RE, GATE1, GATE2)[0]

@@ -266,14 +266,22 @@ struct ColList {
     int c[kMaxRank];
     int n;
 };
+// idf_dev (nullable): fused scan — column k belongs to observation k/2 whose 1-based landmark index is
+// read from device memory (0 = no landmark passed the gate: the column is not needed, zeros are sent).
 __global__ void __launch_bounds__(256) k_col_pack(const double* __restrict__ P, size_t ld, int n, ColList cl,
-                                                  double* __restrict__ colbuf, size_t lda, Shard sh) {
+                                                  double* __restrict__ colbuf, size_t lda, Shard sh,
+                                                  const int* __restrict__ idf_dev) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int k = blockIdx.y;
     if (i >= n) return;
-    const int c = cl.c[k];
+    int c = cl.c[k];
+    if (idf_dev != nullptr) {
+        const int j = idf_dev[k >> 1];
+        c = j > 0 ? 3 + 2 * (j - 1) + (k & 1) : -1;
+    }
     double v = 0.0;
-    if (i <= c) {
+    if (c < 0) {
+    } else if (i <= c) {
         if (shard_owns(sh, i)) v = P[shard_lrow(sh, i) * ld + c];
     } else {
         if (shard_owns(sh, c)) v = P[shard_lrow(sh, c) * ld + i];
@@ -815,9 +823,10 @@ static int launch_cov_update_multi(cslam_ekf* h, int g, const int* live) {
 constexpr int kSeqGroup = 8;  // sequential updates whose covariance passes are merged into one
 
 // exchange the listed columns of P (sharded only)
-static int exchange_columns(cslam_ekf* h, const ColList& cl) {
+static int exchange_columns(cslam_ekf* h, const ColList& cl, const int* idf_dev = nullptr) {
     count_launch();
-    k_col_pack<<<dim3((h->n + 255) / 256, cl.n), 256, 0, h->stream>>>(h->P, h->ld, h->n, cl, h->colbuf, h->lda, h->sh);
+    k_col_pack<<<dim3((h->n + 255) / 256, cl.n), 256, 0, h->stream>>>(h->P, h->ld, h->n, cl, h->colbuf, h->lda, h->sh,
+                                                                      idf_dev);
     CSLAM_CUDA(cudaGetLastError());
     return allreduce_sum(h, h->colbuf, (size_t)cl.n * h->lda);
 }
@@ -825,7 +834,7 @@ static int exchange_columns(cslam_ekf* h, const ColList& cl) {
 // singleUpdate (EKF.cpp:457-479): per observation a gain kernel (re-linearised at the X the previous
 // observation produced, P seen through the pending rank-2 terms), per group of up to kSeqGroup
 // observations ONE pass over the covariance.  idf_host / idf_dev: exactly one is non-null (idf_dev:
-// single-GPU fused scan).  Sharded handles exchange the observation's two columns of P first.
+// fused scan, indices in device memory).  Sharded handles exchange the group's 2g columns of P first.
 static int sequential_updates(cslam_ekf* h, const double* Z, const int32_t* idf_host, const int* idf_dev, int m,
                               const double R[4]) {
     const int n = h->n;
@@ -836,10 +845,10 @@ static int sequential_updates(cslam_ekf* h, const double* Z, const int32_t* idf_
             ColList cl;
             cl.n = 2 * g;
             for (int k = 0; k < g; k++) {
-                cl.c[2 * k] = 3 + 2 * (idf_host[base + k] - 1);
+                cl.c[2 * k] = idf_host ? 3 + 2 * (idf_host[base + k] - 1) : 0;
                 cl.c[2 * k + 1] = cl.c[2 * k] + 1;
             }
-            if (int rc = exchange_columns(h, cl)) return rc;
+            if (int rc = exchange_columns(h, cl, idf_dev ? idf_dev + base : nullptr)) return rc;
         }
         for (int k = 0; k < g; k++) {
             const int i = base + k;
@@ -847,7 +856,8 @@ static int sequential_updates(cslam_ekf* h, const double* Z, const int32_t* idf_
                 count_launch();
                 k_gain_single<true><<<(n + 255) / 256, 256, 0, h->stream>>>(
                     h->X[h->cur], h->X[h->cur ^ 1], h->P, h->R3, h->colbuf + (size_t)2 * k * h->lda, h->ld, n, Z[2 * i],
-                    Z[2 * i + 1], idf_host[i], R[0], R[1], R[2], R[3], h->flags, h->A, h->lda, h->status, nullptr, k);
+                    Z[2 * i + 1], idf_host ? idf_host[i] : 0, R[0], R[1], R[2], R[3], h->flags, h->A, h->lda, h->status,
+                    idf_dev ? idf_dev + i : nullptr, k);
             } else {
                 count_launch();
                 k_gain_single<false><<<(n + 255) / 256, 256, 0, h->stream>>>(
@@ -1057,23 +1067,31 @@ int cslam_ekf_observe_heading(cslam_ekf_t* h, double phi, int use_heading) {
     return launch_cov_update<1>(h, kFltMin);
 }
 
+// Sharded handles: (re)build the replicated diagonal-block cache the gate reads — pack owned entries +
+// all-reduce.  Needed only after reset / augment / a tensor-core joint update; the FMA-path updates
+// keep it current themselves (k_diag_follow).
+static int refresh_diag_cache(cslam_ekf* h) {
+    if (h->sh.world == 1 || !h->diag_dirty) return CSLAM_OK;
+    const int nf = (h->n - 3) / 2;
+    CSLAM_CUDA(cudaMemsetAsync(h->D, 0, 3 * (size_t)h->dcap * sizeof(double), h->stream));
+    if (nf > 0) {
+        count_launch();
+        k_diag_pack<<<(nf + 255) / 256, 256, 0, h->stream>>>(h->P, h->ld, nf, h->D, h->dcap, h->sh);
+        CSLAM_CUDA(cudaGetLastError());
+    }
+    if (int rc = allreduce_sum(h, h->D, 3 * (size_t)h->dcap)) return rc;
+    h->diag_dirty = false;
+    return CSLAM_OK;
+}
+
 int cslam_ekf_gate(cslam_ekf_t* h, const double* Z, int m, const double R[4], double gate1, double gate2,
                    int32_t* jbest, uint8_t* is_new, double* nbest, double* outer) {
     if (int rc = check_handle(h)) return rc;
     CSLAM_REQUIRE(m >= 0, CSLAM_ERR_BAD_ARG, "m < 0");
     CSLAM_REQUIRE(m == 0 || (Z && R && jbest), CSLAM_ERR_BAD_ARG, "null argument");
     const int nf = (h->n - 3) / 2;
-    if (h->sh.world > 1 && h->diag_dirty && m > 0) {
-        // refresh the replicated diagonal-block cache once per scan: pack owned entries + all-reduce
-        CSLAM_CUDA(cudaMemsetAsync(h->D, 0, 3 * (size_t)h->dcap * sizeof(double), h->stream));
-        if (nf > 0) {
-            count_launch();
-            k_diag_pack<<<(nf + 255) / 256, 256, 0, h->stream>>>(h->P, h->ld, nf, h->D, h->dcap, h->sh);
-            CSLAM_CUDA(cudaGetLastError());
-        }
-        if (int rc = allreduce_sum(h, h->D, 3 * (size_t)h->dcap)) return rc;
-        h->diag_dirty = false;
-    }
+    if (m > 0)
+        if (int rc = refresh_diag_cache(h)) return rc;
     for (int base = 0; base < m; base += CSLAM_MAX_OBS) {
         const int mc = std::min(CSLAM_MAX_OBS, m - base);
         if (int rc = launch_gate(h->X[h->cur], h->P, h->R3, h->sh.world > 1 ? h->D : nullptr, h->dcap, h->ld, nf,
@@ -1152,12 +1170,13 @@ int cslam_ekf_scan(cslam_ekf_t* h, const double* Z, int m, const double R[4], do
                    int32_t* jbest, uint8_t* is_new) {
     if (int rc = check_handle(h)) return rc;
     CSLAM_REQUIRE(m >= 0 && m <= CSLAM_MAX_OBS, CSLAM_ERR_BAD_ARG, "m out of range (0..CSLAM_MAX_OBS)");
-    CSLAM_REQUIRE(h->sh.world == 1, CSLAM_ERR_UNSUPPORTED, "fused scan is single-GPU (sharded: gate + update)");
     if (m == 0) return CSLAM_OK;
     CSLAM_REQUIRE(Z && R, CSLAM_ERR_BAD_ARG, "null argument");
     const int n = h->n, nf = (n - 3) / 2;
+    if (int rc = refresh_diag_cache(h)) return rc;
     // dataAssociate at the pre-update state for the whole scan (test/main.cpp:193), indices stay in d_jbest
-    if (int rc = launch_gate(h->X[h->cur], h->P, h->R3, nullptr, h->dcap, h->ld, nf, Z, m, R, gate1, gate2,
+    if (int rc = launch_gate(h->X[h->cur], h->P, h->R3, h->sh.world > 1 ? h->D : nullptr, h->dcap, h->ld, nf, Z, m, R,
+                             gate1, gate2,
                              h->gate.part_nd, h->gate.part_out, h->gate.part_j, h->ticket + 1, h->gate.d_jbest,
                              h->gate.d_nbest, h->gate.d_outer, h->stream))
         return rc;

@@ -112,7 +112,8 @@ int cslam_ekf_update(cslam_ekf_t* h, const double* Z, const int32_t* idf, int m,
  * device memory, every gain / covariance kernel reads its own index there and exits when no landmark
  * passed the gate.  jbest / is_new (nullable) are read back behind the gate kernel, overlapping the
  * updates; pass NULL for a fully asynchronous scan.  Results are identical to cslam_ekf_gate followed by
- * cslam_ekf_update(batch = 0) on the associated observations.  Single-GPU handles only. */
+ * cslam_ekf_update(batch = 0) on the associated observations.  Works on sharded handles too (every rank
+ * computes the same indices from its replicated gate inputs; SPMD call contract). */
 int cslam_ekf_scan(cslam_ekf_t* h, const double* Z, int m, const double R[4], double gate1, double gate2,
                    int32_t* jbest, uint8_t* is_new);
 /* Slam::augment(X,P,Z,R)                                slam.h:190-191 -> EKF.cpp:9-26 -> :28-91 */

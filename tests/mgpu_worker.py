@@ -87,6 +87,16 @@ def ekf_checks():
             f.update(Z[:, :1], RE, ids[:1], False)
         check("heading + single update (cache follows rank-1 and rank-2 passes)")
         same_gate()
+        # fused scan on the sharded handle: 10 observations (two groups), one of them passing no gate
+        ids_s = (rng.choice(N, size=9, replace=False) + 1).astype(np.int32)
+        Zs = np.concatenate([helpers.observe(o.X, lm, ids_s, rng)[:, :5], np.array([[9000.0], [1.0]]),
+                             helpers.observe(o.X, lm, ids_s, rng)[:, 5:]], axis=1)
+        jo = o.gate(Zs, RE, 50.0, 1000.0)[0]
+        o.update(Zs[:, jo != 0], RE, jo[jo != 0], False)
+        jg, _ = g.scan(Zs, RE, 50.0, 1000.0)
+        assert np.array_equal(jg, jo) and jo[5] == 0, (jg, jo)
+        check("fused scan (sharded)")
+        same_gate()
         ids2 = (rng.choice(N, size=16, replace=False) + 1).astype(np.int32)
         Z2 = helpers.observe(o.X, lm, ids2, rng)
         for f in (g, o):

@@ -55,7 +55,7 @@ def test_predict_heading_parity(N, flags):
 
 
 @pytest.mark.parametrize("flags", [0, oracle_py.FLAG_INTENDED])
-@pytest.mark.parametrize("N,m", [(1, 1), (2, 2), (25, 5), (150, 7), (1100, 4)])
+@pytest.mark.parametrize("N,m", [(1, 1), (2, 2), (25, 5), (150, 7), (150, 20), (1100, 4), (1100, 9)])
 def test_single_update_parity(N, m, flags):
     g, o, lm = _pair(N, 20 + N, flags)
     rng = np.random.default_rng(N)
@@ -156,7 +156,7 @@ def test_gating_indices_exact(N, m):
 
 
 @pytest.mark.parametrize("flags", [0, oracle_py.FLAG_INTENDED])
-@pytest.mark.parametrize("N,m", [(0, 2), (3, 4), (40, 6), (600, 9), (1100, 5)])
+@pytest.mark.parametrize("N,m", [(0, 2), (3, 4), (40, 6), (600, 9), (600, 21), (1100, 5)])
 def test_fused_scan_equals_gate_then_update(N, m, flags):
     """cslam_ekf_scan (association indices stay on the device) == dataAssociate + singleUpdate
     (test/main.cpp:193-195) of the oracle: same indices, same state; spurious observations that
