@@ -74,8 +74,9 @@ def ekf_checks():
             f.update(Z, RE, ids, False)
         check("sequential update")
         # the replicated diagonal-block cache FOLLOWED the grouped update (no re-pack): same decisions, same nd
-        def same_gate():
-            gg, go = g.gate(Z, RE, 50.0, 1000.0), o.gate(Z, RE, 50.0, 1000.0)
+        def same_gate(Zq=None):
+            Zq = Z if Zq is None else Zq
+            gg, go = g.gate(Zq, RE, 50.0, 1000.0), o.gate(Zq, RE, 50.0, 1000.0)
             hit = go[0] != 0
             assert np.array_equal(gg[0], go[0]) and np.array_equal(np.isinf(gg[2]), np.isinf(go[2])), (gg, go)
             assert not hit.any() or rel_err(gg[2][hit], go[2][hit]) < 1e-9, (gg[2], go[2])
@@ -96,7 +97,7 @@ def ekf_checks():
         jg, _ = g.scan(Zs, RE, 50.0, 1000.0)
         assert np.array_equal(jg, jo) and jo[5] == 0, (jg, jo)
         check("fused scan (sharded)")
-        same_gate()
+        same_gate(helpers.observe(o.X, lm, (rng.choice(N, size=6, replace=False) + 1).astype(np.int32), rng))
         ids2 = (rng.choice(N, size=16, replace=False) + 1).astype(np.int32)
         Z2 = helpers.observe(o.X, lm, ids2, rng)
         for f in (g, o):
