@@ -27,32 +27,10 @@ namespace cslam {
 // Kernels
 // ------------------------------------------------------------------------------------
 
-// EKF.cpp:406-455 predict on rows 0..2 (`P` here = the row panel R3: P itself on one GPU, the
-// replicated panel when sharded).  Rows 0..1 for columns [3, 3+width) get Gv * (.) — with
-// Gv = [[1,0,a],[0,1,b],[0,0,1]] that is row0 += a*row2, row1 += b*row2.  The mirrored columns
-// (EKF.cpp:443) live in the lower triangle and are not stored.  The block that draws the last
-// ticket updates Pvv and the pose, after every block has read the old phi.
-__global__ void __launch_bounds__(256) k_predict(double* __restrict__ X, double* __restrict__ P, size_t ld, int n,
-                                                 double v, double swa, double q00, double q01, double q10,
-                                                 double q11, double wb, double dt, int width,
-                                                 unsigned* __restrict__ ticket) {
-    const double phi = X[2];
-    const double s = sin(swa + phi), c = cos(swa + phi);
-    const double g02 = -v * dt * s, g12 = v * dt * c;
-    const int col = 3 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (col < 3 + width) {
-        const double p0 = P[col], p1 = P[ld + col], p2 = P[2 * ld + col];
-        P[col] = p0 + g02 * p2;
-        P[ld + col] = p1 + g12 * p2;
-    }
-    __shared__ bool is_last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (!is_last || threadIdx.x != 0) return;
-    *ticket = 0;
-    // Pvv <- Gv Pvv Gv^T + Gu Q Gu^T   (EKF.cpp:439)
+// Pvv <- Gv Pvv Gv^T + Gu Q Gu^T (EKF.cpp:439) and the pose advance (EKF.cpp:446-450), one thread.
+__device__ void predict_pvv_pose(double* __restrict__ X, double* __restrict__ P, size_t ld, double v, double swa,
+                                 double q00, double q01, double q10, double q11, double wb, double dt, double phi,
+                                 double s, double c, double g02, double g12) {
     double Pv[3][3];
     for (int i = 0; i < 3; i++)
         for (int j = 0; j < 3; j++) Pv[i][j] = psym(P, ld, i, j);
@@ -84,6 +62,34 @@ __global__ void __launch_bounds__(256) k_predict(double* __restrict__ X, double*
     X[2] = pi2pi(phi + v * dt * sin(swa) / wb);
 }
 
+// EKF.cpp:406-455 predict on rows 0..2 (`P` here = the row panel R3: P itself on one GPU, the
+// replicated panel when sharded).  Rows 0..1 for columns [3, 3+width) get Gv * (.) — with
+// Gv = [[1,0,a],[0,1,b],[0,0,1]] that is row0 += a*row2, row1 += b*row2.  The mirrored columns
+// (EKF.cpp:443) live in the lower triangle and are not stored.  The block that draws the last
+// ticket updates Pvv and the pose, after every block has read the old phi.
+__global__ void __launch_bounds__(256) k_predict(double* __restrict__ X, double* __restrict__ P, size_t ld, int n,
+                                                 double v, double swa, double q00, double q01, double q10,
+                                                 double q11, double wb, double dt, int width,
+                                                 unsigned* __restrict__ ticket) {
+    const double phi = X[2];
+    const double s = sin(swa + phi), c = cos(swa + phi);
+    const double g02 = -v * dt * s, g12 = v * dt * c;
+    const int col = 3 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (col < 3 + width) {
+        const double p0 = P[col], p1 = P[ld + col], p2 = P[2 * ld + col];
+        P[col] = p0 + g02 * p2;
+        P[ld + col] = p1 + g12 * p2;
+    }
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!is_last || threadIdx.x != 0) return;
+    *ticket = 0;
+    predict_pvv_pose(X, P, ld, v, swa, q00, q01, q10, q11, wb, dt, phi, s, c, g02, g12);
+}
+
 // EKF.cpp:328-352 + slam.h:700-725 with H = e_2^T.  Column 2 of P is (P[0][2], P[1][2],
 // row 2 from the diagonal on) — all inside rows 0..2.  Writes Xout = Xin + W*v and the rank-1
 // panel a = p/sqrt(S): for symmetric P the Joseph form C P C^T + W R W^T equals P - p p^T / S.
@@ -98,6 +104,68 @@ __global__ void __launch_bounds__(256) k_heading_gain(const double* __restrict__
     const double p = i < 2 ? P[(size_t)i * ld + 2] : P[2 * ld + i];
     Xout[i] = Xin[i] + (p * SI) * v;
     A[i] = p / sqrt(S);
+}
+
+// Small maps (test/main.cpp's own 30-landmark world, n <= kSmallN): k consecutive control steps —
+// predict (EKF.cpp:406-455) then observeHeading (EKF.cpp:328-352 -> slam.h:700-725) per step, the body
+// of test/main.cpp:140-168 — in ONE launch of ONE CTA.  At n = 63 every per-step kernel is pure launch
+// latency (first "next" row); here the phases of a step are separated by __syncthreads and
+// the 32 KB covariance stays in L1/L2.  Same operations per element as k_predict / k_heading_gain /
+// k_cov_update<1>, hence bit-identical results.
+constexpr int kSmallN = 1024;
+constexpr int kMaxControlSteps = 16;
+struct ControlPack {
+    double v[kMaxControlSteps], swa[kMaxControlSteps], phi[kMaxControlSteps];
+    int k, use_heading, width;
+    double q00, q01, q10, q11, wb, dt, r_heading;
+};
+__global__ void __launch_bounds__(1024) k_control_steps(double* __restrict__ X, double* __restrict__ P, size_t ld,
+                                                        int n, ControlPack cp, double* __restrict__ pose_trace) {
+    __shared__ double sA[kSmallN];
+    const int tid = threadIdx.x;
+    for (int st = 0; st < cp.k; st++) {
+        // ---- predict
+        const double v = cp.v[st], swa = cp.swa[st];
+        const double phi = X[2];
+        const double s = sin(swa + phi), c = cos(swa + phi);
+        const double g02 = -v * cp.dt * s, g12 = v * cp.dt * c;
+        for (int col = 3 + tid; col < 3 + cp.width; col += blockDim.x) {
+            const double p0 = P[col], p1 = P[ld + col], p2 = P[2 * ld + col];
+            P[col] = p0 + g02 * p2;
+            P[ld + col] = p1 + g12 * p2;
+        }
+        __syncthreads();  // every thread has read the old phi
+        if (tid == 0) predict_pvv_pose(X, P, ld, v, swa, cp.q00, cp.q01, cp.q10, cp.q11, cp.wb, cp.dt, phi, s, c, g02, g12);
+        __syncthreads();
+        // ---- observeHeading: gain (k_heading_gain) ...
+        if (cp.use_heading) {
+            const double vinn = pi2pi(cp.phi[st] - X[2]);
+            const double S = P[2 * ld + 2] + cp.r_heading;
+            const double SI = 1.0 / S;
+            double p = 0.0, x = 0.0;
+            if (tid < n) {  // n <= kSmallN = blockDim.x
+                p = tid < 2 ? P[(size_t)tid * ld + 2] : P[2 * ld + tid];
+                x = X[tid];
+            }
+            __syncthreads();  // X[2] and column 2 are read before anyone overwrites them
+            if (tid < n) {
+                X[tid] = x + (p * SI) * vinn;
+                sA[tid] = p / sqrt(S);
+            }
+            __syncthreads();
+            // ... and the rank-1 pass over the upper triangle (k_cov_update<1>, diag_eps = FLT_MIN, slam.h:719)
+            for (int idx = tid; idx < n * n; idx += blockDim.x) {
+                const int i = idx / n, j = idx % n;
+                if (j < i) continue;
+                double o = P[(size_t)i * ld + j] - sA[i] * sA[j];
+                if (j == i) o += kFltMin;
+                P[(size_t)i * ld + j] = o;
+            }
+            __syncthreads();
+        }
+        if (pose_trace != nullptr && tid < 3) pose_trace[3 * st + tid] = X[tid];
+        __syncthreads();
+    }
 }
 
 // Per-observation prologue of slam.h:235-266 using the sparse H (robot block + one landmark
@@ -1082,6 +1150,68 @@ static int refresh_diag_cache(cslam_ekf* h) {
     if (int rc = allreduce_sum(h, h->D, 3 * (size_t)h->dcap)) return rc;
     h->diag_dirty = false;
     return CSLAM_OK;
+}
+
+int cslam_ekf_control_steps(cslam_ekf_t* h, int k, const double* v, const double* swa, const double* phi,
+                            int use_heading, const double Q[4], double wb, double dt, double* pose_trace) {
+    if (int rc = check_handle(h)) return rc;
+    CSLAM_REQUIRE(k >= 0, CSLAM_ERR_BAD_ARG, "k < 0");
+    if (k == 0) return CSLAM_OK;
+    CSLAM_REQUIRE(v && swa && Q && (phi || !use_heading), CSLAM_ERR_BAD_ARG, "null argument");
+    const double sigma = 0.01F * kPi / 180.0F;  // EKF.cpp:337
+    double* trace_dev = nullptr;
+    if (pose_trace) CSLAM_CUDA(cudaMalloc(&trace_dev, (size_t)3 * k * sizeof(double)));
+    int rc = CSLAM_OK;
+    for (int base = 0; base < k && rc == CSLAM_OK; base += kMaxControlSteps) {
+        const int kc = std::min(kMaxControlSteps, k - base);
+        const int n = h->n;
+        int width = 0;
+        if (n > 3) width = (h->flags & CSLAM_FLAG_Q2_FULL_WIDTH) ? n - 3 : n - 4;  // Q2, EKF.cpp:442
+        if (n <= kSmallN && h->sh.world == 1) {
+            ControlPack cp;
+            memset(&cp, 0, sizeof(cp));
+            for (int i = 0; i < kc; i++) {
+                cp.v[i] = v[base + i];
+                cp.swa[i] = swa[base + i];
+                cp.phi[i] = phi ? phi[base + i] : 0.0;
+            }
+            cp.k = kc; cp.use_heading = use_heading ? 1 : 0; cp.width = width;
+            cp.q00 = Q[0]; cp.q01 = Q[2]; cp.q10 = Q[1]; cp.q11 = Q[3];
+            cp.wb = wb; cp.dt = dt; cp.r_heading = sigma * sigma;
+            count_launch();
+            k_control_steps<<<1, 1024, 0, h->stream>>>(h->X[h->cur], h->P, h->ld, n, cp,
+                                                       trace_dev ? trace_dev + 3 * base : nullptr);
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) {
+                set_last_error("k_control_steps -> %s", cudaGetErrorString(e));
+                rc = CSLAM_ERR_CUDA;
+            }
+        } else {  // big or sharded maps: the per-step kernels, still one call and no host round trip
+            for (int i = 0; i < kc && rc == CSLAM_OK; i++) {
+                rc = cslam_ekf_predict(h, v[base + i], swa[base + i], Q, wb, dt);
+                if (rc == CSLAM_OK) rc = cslam_ekf_observe_heading(h, phi ? phi[base + i] : 0.0, use_heading);
+                if (rc == CSLAM_OK && trace_dev) {
+                    cudaError_t e = cudaMemcpyAsync(trace_dev + 3 * (base + i), h->X[h->cur], 3 * sizeof(double),
+                                                    cudaMemcpyDeviceToDevice, h->stream);
+                    if (e != cudaSuccess) rc = CSLAM_ERR_CUDA;
+                }
+            }
+        }
+    }
+    if (rc == CSLAM_OK && pose_trace) {
+        cudaError_t e = cudaMemcpyAsync(pose_trace, trace_dev, (size_t)3 * k * sizeof(double), cudaMemcpyDeviceToHost,
+                                        h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) {
+            set_last_error("cslam_ekf_control_steps: %s", cudaGetErrorString(e));
+            rc = CSLAM_ERR_CUDA;
+        }
+    }
+    if (trace_dev) {
+        cudaStreamSynchronize(h->stream);
+        cudaFree(trace_dev);
+    }
+    return rc;
 }
 
 int cslam_ekf_gate(cslam_ekf_t* h, const double* Z, int m, const double R[4], double gate1, double gate2,

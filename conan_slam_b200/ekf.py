@@ -228,6 +228,21 @@ class EKF:
                                            dptr(outer)), "cslam_ekf_gate")
         return jbest, is_new, nbest, outer
 
+    def controlSteps(self, v, swa, phi, useHeading, Q, wb, dt, want_trace=True):
+        """k control steps (predict + observeHeading each, test/main.cpp:140-168) in one call; on small
+        maps one single-CTA launch.  Returns the (k, 3) pose trace when want_trace."""
+        v = np.ascontiguousarray(v, dtype=np.float64).reshape(-1)
+        swa = np.ascontiguousarray(swa, dtype=np.float64).reshape(-1)
+        phi = np.ascontiguousarray(phi, dtype=np.float64).reshape(-1)
+        k = v.shape[0]
+        assert swa.shape[0] == k and phi.shape[0] == k
+        q = _m2(Q)
+        trace = np.zeros((k, 3), dtype=np.float64) if want_trace else None
+        check(self._lib.cslam_ekf_control_steps(self._h, k, dptr(v), dptr(swa), dptr(phi), int(bool(useHeading)),
+                                                dptr(q), float(wb), float(dt), dptr(trace) if want_trace else None),
+              "cslam_ekf_control_steps")
+        return trace
+
     def scan(self, Z, R, gate1, gate2, want_indices=True):
         """dataAssociate + update(batch=False) of the associated observations as ONE asynchronous
         submission (test/main.cpp:193-195): the association indices stay on the device.  Returns

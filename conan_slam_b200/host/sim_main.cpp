@@ -113,7 +113,7 @@ void getObservations(const DVec& X, const DMat& LM, double rmax, DMat& Z, std::v
 int main(int argc, char** argv) {
     unsigned flags = CSLAM_FLAG_REF_LITERAL;
     int max_steps = 1 << 30, print_every = 2000;
-    bool gated = false;
+    bool gated = false, fused = false;
     std::string trace;
     for (int i = 1; i < argc; i++) {
         if (!strcmp(argv[i], "--flags") && i + 1 < argc) flags = (unsigned)atoi(argv[++i]);
@@ -121,6 +121,7 @@ int main(int argc, char** argv) {
         else if (!strcmp(argv[i], "--trace") && i + 1 < argc) trace = argv[++i];
         else if (!strcmp(argv[i], "--print-every") && i + 1 < argc) print_every = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--gated")) gated = true;
+        else if (!strcmp(argv[i], "--fused")) fused = true;  // control steps between observations in one call
     }
     DMat LM(2, 30), WP(2, 5);
     for (int i = 0; i < 30; i++) { LM(0, i) = kLm1[i]; LM(1, i) = kLm2[i]; }
@@ -149,6 +150,7 @@ int main(int argc, char** argv) {
     for (auto& v : RE.a) v *= 8;
 
     FILE* tf = trace.empty() ? nullptr : fopen(trace.c_str(), "wb");
+    std::vector<double> pend_v, pend_s, pend_p;
     int indexlooper = 0;
     while (iwp <= WP.cols() && iwp > 0 && indexlooper < max_steps) {
         ++indexlooper;
@@ -157,10 +159,31 @@ int main(int argc, char** argv) {
         computeSWA(XTrue, WP, iwp, atWaypoint, swa, rateSWA, maxSWA, dt);          // test/main.cpp:140
         vehicleModel(XTrue, velocity, swa, wheelBase, dt);                         // :156
         const double vn = velocity, swan = swa;                                    // :162 (control noise off)
-        ekfSlam.predict(X, P, vn, swan, QE, wheelBase, dt);                        // :165
-        ekfSlam.observeHeading(X, P, XTrue(2), ekfSlam.mSwitchHeadingKnown);       // :168
         dtsum = dtsum + dt;
-        if (dtsum >= dtObserve) {                                                  // :172
+        const bool observe = dtsum >= dtObserve;                                   // :172
+        if (fused) {
+            // the controls do not depend on the filter: buffer them and hand all steps up to the next
+            // observation to ONE call (cslam_ekf_control_steps; a single launch on this 30-landmark map)
+            pend_v.push_back(vn); pend_s.push_back(swan); pend_p.push_back(XTrue(2));
+            const bool last = !(iwp <= WP.cols() && iwp > 0 && indexlooper < max_steps);
+            if (observe || last || pend_v.size() >= 64) {
+                std::vector<double> tr;
+                ekfSlam.controlSteps(X, P, pend_v, pend_s, pend_p, ekfSlam.mSwitchHeadingKnown, QE, wheelBase, dt, &tr);
+                if (tf) {
+                    for (size_t k = 0; k + 1 < pend_v.size(); k++) {  // the last step is recorded below
+                        const double rec[4] = {tr[3 * k], tr[3 * k + 1], tr[3 * k + 2], (double)X.rows()};
+                        fwrite(rec, sizeof(double), 4, tf);
+                    }
+                }
+                pend_v.clear(); pend_s.clear(); pend_p.clear();
+            } else {
+                continue;  // nothing to record yet: this step's pose comes back with the batch
+            }
+        } else {
+            ekfSlam.predict(X, P, vn, swan, QE, wheelBase, dt);                    // :165
+            ekfSlam.observeHeading(X, P, XTrue(2), ekfSlam.mSwitchHeadingKnown);   // :168
+        }
+        if (observe) {
             dtsum = 0.0;
             DMat Z;
             std::vector<int> visible;

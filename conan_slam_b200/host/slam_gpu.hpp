@@ -110,6 +110,21 @@ class EkfGpuT {
         report(cslam_ekf_observe_heading(h_, phi, useHeading ? 1 : 0), "observeHeading");
         pull(X, P);
     }
+    // k control steps in one call: per step predict + observeHeading (test/main.cpp:140-168); the controls
+    // and the measured heading come from the simulator / odometry and do not depend on the filter.
+    // trace (nullable): 3*k doubles, X[0..2] after each step.
+    void controlSteps(Vec& X, MatT& P, const std::vector<double>& v, const std::vector<double>& swa,
+                      const std::vector<double>& phi, bool useHeading, const MatT& Q, double wb, double dt,
+                      std::vector<double>* trace = nullptr) {
+        push(X, P);
+        const int k = (int)v.size();
+        const double q[4] = {Q(0, 0), Q(1, 0), Q(0, 1), Q(1, 1)};
+        if (trace) trace->assign((size_t)3 * k, 0.0);
+        report(cslam_ekf_control_steps(h_, k, v.data(), swa.data(), phi.data(), useHeading ? 1 : 0, q, wb, dt,
+                                       trace ? trace->data() : nullptr),
+               "controlSteps");
+        pull(X, P);
+    }
     // Slam::update  slam.h:938-943 / EKF.cpp:481-496
     void update(Vec& X, MatT& P, const MatT& Z, const MatT& R, const std::vector<int>& idf, bool batch = false) {
         push(X, P);

@@ -94,6 +94,16 @@ int cslam_ekf_capacity(const cslam_ekf_t* h);
 int cslam_ekf_predict(cslam_ekf_t* h, double v, double swa, const double Q[4], double wb, double dt);
 /* Slam::observeHeading(X,P,phi,useHeading)              slam.h:788 -> EKF.cpp:328-352 -> slam.h:700-725 */
 int cslam_ekf_observe_heading(cslam_ekf_t* h, double phi, int use_heading);
+/* k consecutive control steps — per step Slam::predict then Slam::observeHeading, i.e. the body of
+ * test/main.cpp:140-168 for k iterations (the controls v[i], swa[i] and the measured heading phi[i] do not
+ * depend on the filter, so a driver can hand over all steps up to the next observation at once).  On
+ * small maps (n <= 1024: the reference's own 30-landmark world) all k steps run in ONE single-CTA
+ * launch — the first "next" row of SURVEY.md §8f; larger / sharded maps run the per-step kernels.
+ * Results are bit-identical to k calls of cslam_ekf_predict + cslam_ekf_observe_heading.
+ * pose_trace (nullable, host, 3*k doubles): X[0..2] after each step (the reference prints X every
+ * iteration, test/main.cpp:134-137); passing it makes the call synchronous. */
+int cslam_ekf_control_steps(cslam_ekf_t* h, int k, const double* v, const double* swa, const double* phi,
+                            int use_heading, const double Q[4], double wb, double dt, double* pose_trace);
 /* Slam::dataAssociate(X,P,Z,R,gate1,gate2)              slam.h:482-487 -> EKF.cpp:235-326 (+131-144)
  * Per observation i: jbest[i] = 1-based nearest in-gate landmark (0 = none, lowest j wins ties),
  * is_new[i] = (jbest==0 && min_j nis > gate2).  nbest/outer are optional (nullable):

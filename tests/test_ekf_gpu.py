@@ -292,3 +292,37 @@ def test_checkpoint_roundtrip_and_landmark_marginals(tmp_path):
     small = cs.EKF(capacity_landmarks=8)
     with pytest.raises(Exception):
         small.load(path)  # exceeds capacity
+
+
+@pytest.mark.parametrize("flags", [0, oracle_py.FLAG_INTENDED])
+@pytest.mark.parametrize("N", [0, 30, 400, 700])
+def test_control_steps_equal_stepwise_calls(N, flags):
+    """cslam_ekf_control_steps (single-CTA launch for n <= 1024, per-step kernels above) is bit-identical
+    to k x (predict, observeHeading) and matches the oracle."""
+    import conan_slam_b200 as cs
+    X, P, lm = helpers.synthetic_map(N, 40 + N)
+    a = cs.EKF(capacity_landmarks=N + 2, flags=flags)
+    b = cs.EKF(capacity_landmarks=N + 2, flags=flags)
+    o = oracle_py.OracleEKF(flags)
+    for f in (a, b, o):
+        f.reset(X, P)
+    k = 19  # > kMaxControlSteps: two launches
+    rng = np.random.default_rng(N)
+    v = 83.33 + rng.normal(size=k)
+    swa = 0.05 * rng.normal(size=k)
+    phi = X[2] + np.cumsum(v * 0.01 * np.sin(swa) / 73.0) + 1e-4 * rng.normal(size=k)
+    trace = a.controlSteps(v, swa, phi, True, QE, 73.0, 0.01)
+    want = []
+    for i in range(k):
+        for f in (b, o):
+            f.predict(v[i], swa[i], QE, 73.0, 0.01)
+            f.observeHeading(phi[i], True)
+        want.append(b.X[:3].copy())
+    assert np.array_equal(trace, np.asarray(want))
+    assert np.array_equal(a.X, b.X) and np.array_equal(a.P, b.P)
+    _assert_state(a, o)
+    # heading unknown: predict only
+    a.controlSteps(v[:3], swa[:3], phi[:3], False, QE, 73.0, 0.01, want_trace=False)
+    for i in range(3):
+        b.predict(v[i], swa[i], QE, 73.0, 0.01)
+    assert np.array_equal(a.X, b.X) and np.array_equal(a.P, b.P)

@@ -38,13 +38,16 @@ def test_c1_oracle_matches_golden_fixture():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("flags", [0, 31])
-def test_c1_cpp_driver_full_trace_parity(flags, tmp_path):
+def test_c1_cpp_driver_full_trace_parity(flags, fused, tmp_path):
+    """fused: the control steps between two observations go through cslam_ekf_control_steps (one
+    single-CTA launch per batch) instead of one predict + one observeHeading call per step."""
     from conan_slam_b200 import build
     exe = build.build_host()
     trace = str(tmp_path / "trace.bin")
-    out = subprocess.run([exe, "--flags", str(flags), "--trace", trace, "--print-every", "0"], capture_output=True,
-                         text=True, timeout=600)
+    out = subprocess.run([exe, "--flags", str(flags), "--trace", trace, "--print-every", "0"] +
+                         (["--fused"] if fused else []), capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr
     assert "skipped updates=0" in out.stdout
     tape, rows, Xf = _oracle_trace(flags)
