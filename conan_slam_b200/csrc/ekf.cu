@@ -119,8 +119,10 @@ struct ControlPack {
     int k, use_heading, width;
     double q00, q01, q10, q11, wb, dt, r_heading;
 };
-__global__ void __launch_bounds__(1024) k_control_steps(double* __restrict__ X, double* __restrict__ P, size_t ld,
-                                                        int n, ControlPack cp, double* __restrict__ pose_trace) {
+// X and P are deliberately NOT __restrict__: threads of the CTA communicate through them across
+// __syncthreads (with __restrict__ the compiler forwards a thread's own earlier load of X[2] past the barrier).
+__global__ void __launch_bounds__(1024) k_control_steps(double* X, double* P, size_t ld, int n, ControlPack cp,
+                                                        double* __restrict__ pose_trace) {
     __shared__ double sA[kSmallN];
     const int tid = threadIdx.x;
     for (int st = 0; st < cp.k; st++) {
