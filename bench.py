@@ -697,10 +697,15 @@ def main():
                 "per": "GPU", "launches_timed": cov_launches, "avg_launch_ms": cov_ms / max(1, cov_launches),
             }
         else:
+            mg = min(m, 8)  # sequential updates of a scan share one pass in groups of up to 8
+            kname = f"k_cov_update_multi<{mg},128>" if mg > 1 else "k_cov_update<2,128>"
             roof = {
-                "bound": "hbm", "kernel": "k_cov_update<2,128> (slam.h:260, upper-triangle rank-2 update)",
+                "bound": "hbm",
+                "kernel": (f"{kname} (slam.h:260 for the {mg} sequential updates of a scan, ONE read + write of the "
+                           f"upper triangle)" if mg > 1 else f"{kname} (slam.h:260, upper-triangle rank-2 update)"),
+                "updates_per_launch": mg,
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "peak_source": peak_src, "traffic": ncu_traffic("k_cov_update<2,128>", n) if world == 1 else None,
+                "peak_source": peak_src, "traffic": ncu_traffic(kname, n) if world == 1 else None,
                 "algorithmic_bytes_per_launch": 8.0 * n * (n + 1) / shards, "per": "GPU",
                 "launches_timed": cov_launches, "avg_launch_ms": cov_ms / max(1, cov_launches),
                 "whole_update_frac": (alg_update_bytes * (updates if (sharded or world == 1) else updates / world)

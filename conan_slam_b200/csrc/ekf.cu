@@ -178,7 +178,7 @@ struct GainSmall {
     double V[2];
     int ok;
 };
-__device__ void gain_prologue(const double* __restrict__ X, const double (&Pc)[5][5], int f, double zr, double zb,
+__device__ void gain_prologue(const double* X, const double (&Pc)[5][5], int f, double zr, double zb,
                               const double R[4], unsigned flags, GainSmall& g) {
     const ObsLin o = observe_lin(X[0], X[1], X[2], X[f], X[f + 1]);
     for (int a = 0; a < 2; a++) {
@@ -233,28 +233,24 @@ __device__ void gain_prologue(const double* __restrict__ X, const double (&Pc)[5
 // to its "after those updates" value by subtracting the pending rank-2 terms in update order — the
 // same operations the covariance kernel will perform, so the values are bit-identical.
 // idf_dev != nullptr: the association index is read from device memory (fused scan); 0 = skipped.
+// Body shared by the two launch shapes below: the thread block computes the observation's small
+// prologue (25 threads bring the 5x5 block of P up to date, one thread factorises), then every thread
+// handles the state entries i = i0, i0 + stride, ...  Pointers that other threads of the block write
+// before a __syncthreads (X buffers, panel A) are not __restrict__.
 template <bool SH>
-__global__ void __launch_bounds__(256) k_gain_single(const double* __restrict__ Xin, double* __restrict__ Xout,
-                                                     const double* __restrict__ P, const double* __restrict__ R3,
-                                                     const double* __restrict__ colbuf, size_t ld, int n, double zr,
-                                                     double zb, int idf, double r00, double r10, double r01,
-                                                     double r11, unsigned flags, double* __restrict__ A, size_t lda,
-                                                     int* __restrict__ status, const int* __restrict__ idf_dev,
-                                                     int kprev) {
-    __shared__ GainSmall g;
-    __shared__ double sPc[5][5];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    double* __restrict__ Aout = A + (size_t)2 * kprev * lda;
-    if (idf_dev != nullptr) {  // fused scan: the association index stays on the device
-        idf = *idf_dev;
-        if (idf == 0) {  // no landmark passed the gate: X is carried over, a zero panel is a no-op update
-            if (i < n) {
-                Xout[i] = Xin[i];
-                Aout[i] = 0.0;
-                Aout[lda + i] = 0.0;
-            }
-            return;
+__device__ __forceinline__ void gain_body(const double* Xin, double* Xout, const double* __restrict__ P,
+                                          const double* __restrict__ R3, const double* __restrict__ colbuf,
+                                          size_t ld, int n, double zr, double zb, int idf, const double (&R)[4],
+                                          unsigned flags, double* A, size_t lda, int* __restrict__ status, int kprev,
+                                          int i0, int stride, bool count_status, GainSmall& g, double (&sPc)[5][5]) {
+    double* Aout = A + (size_t)2 * kprev * lda;
+    if (idf == 0) {  // no landmark passed the gate: X is carried over, a zero panel is a no-op update
+        for (int i = i0; i < n; i += stride) {
+            Xout[i] = Xin[i];
+            Aout[i] = 0.0;
+            Aout[lda + i] = 0.0;
         }
+        return;
     }
     const int f = 3 + 2 * (idf - 1);
     // stored value of P(r, c), r <= c, c in {0, 1, 2, f, f+1}
@@ -283,49 +279,95 @@ __global__ void __launch_bounds__(256) k_gain_single(const double* __restrict__ 
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        const double R[4] = {r00, r10, r01, r11};
         double Pc[5][5];
         for (int a = 0; a < 5; a++)
             for (int b = 0; b < 5; b++) Pc[a][b] = sPc[a][b];
         gain_prologue(Xin, Pc, f, zr, zb, R, flags, g);
-        if (!g.ok && blockIdx.x == 0) atomicAdd(status, 1);
+        if (!g.ok && count_status) atomicAdd(status, 1);
     }
     __syncthreads();
-    if (i >= n) return;
-    double pc[5];  // P(i, c) for c in {0, 1, 2, f, f+1}
-#pragma unroll
-    for (int b = 0; b < 5; b++) {
-        const int c = b < 3 ? b : f + (b - 3);
-        double v;
-        if (b < 3) {
-            v = i <= c ? R3[(size_t)i * ld + c] : R3[(size_t)c * ld + i];
-        } else if constexpr (SH) {
-            v = colbuf[(size_t)(b - 3) * lda + i];
-        } else {
-            v = i <= c ? P[(size_t)i * ld + c] : P[(size_t)c * ld + i];
-        }
-        pc[b] = v;
-    }
-    for (int q = 0; q < kprev; q++) {
-        const double* a0 = A + (size_t)2 * q * lda;
-        const double* a1 = a0 + lda;
-        const double a0i = a0[i], a1i = a1[i];
+    for (int i = i0; i < n; i += stride) {
+        double pc[5];  // P(i, c) for c in {0, 1, 2, f, f+1}
 #pragma unroll
         for (int b = 0; b < 5; b++) {
             const int c = b < 3 ? b : f + (b - 3);
-            pc[b] = pc[b] - rank2_term(a0i, a1i, a0[c], a1[c]);
+            double v;
+            if (b < 3) {
+                v = i <= c ? R3[(size_t)i * ld + c] : R3[(size_t)c * ld + i];
+            } else if constexpr (SH) {
+                v = colbuf[(size_t)(b - 3) * lda + i];
+            } else {
+                v = i <= c ? P[(size_t)i * ld + c] : P[(size_t)c * ld + i];
+            }
+            pc[b] = v;
         }
+        for (int q = 0; q < kprev; q++) {
+            const double* a0 = A + (size_t)2 * q * lda;
+            const double* a1 = a0 + lda;
+            const double a0i = a0[i], a1i = a1[i];
+#pragma unroll
+            for (int b = 0; b < 5; b++) {
+                const int c = b < 3 ? b : f + (b - 3);
+                pc[b] = pc[b] - rank2_term(a0i, a1i, a0[c], a1[c]);
+            }
+        }
+        double pht[2];
+        for (int k = 0; k < 2; k++)
+            pht[k] = (((pc[0] * g.H[k][0] + pc[1] * g.H[k][1]) + pc[2] * g.H[k][2]) + pc[3] * g.H[k][3]) + pc[4] * g.H[k][4];
+        const double w1_0 = pht[0] * g.G[0][0] + pht[1] * g.G[1][0];
+        const double w1_1 = pht[0] * g.G[0][1] + pht[1] * g.G[1][1];
+        const double w_0 = w1_0 * g.G[0][0] + w1_1 * g.G[0][1];
+        const double w_1 = w1_0 * g.G[1][0] + w1_1 * g.G[1][1];
+        Xout[i] = Xin[i] + (w_0 * g.V[0] + w_1 * g.V[1]);
+        Aout[i] = w1_0;
+        Aout[lda + i] = w1_1;
     }
-    double pht[2];
-    for (int k = 0; k < 2; k++)
-        pht[k] = (((pc[0] * g.H[k][0] + pc[1] * g.H[k][1]) + pc[2] * g.H[k][2]) + pc[3] * g.H[k][3]) + pc[4] * g.H[k][4];
-    const double w1_0 = pht[0] * g.G[0][0] + pht[1] * g.G[1][0];
-    const double w1_1 = pht[0] * g.G[0][1] + pht[1] * g.G[1][1];
-    const double w_0 = w1_0 * g.G[0][0] + w1_1 * g.G[0][1];
-    const double w_1 = w1_0 * g.G[1][0] + w1_1 * g.G[1][1];
-    Xout[i] = Xin[i] + (w_0 * g.V[0] + w_1 * g.V[1]);
-    Aout[i] = w1_0;
-    Aout[lda + i] = w1_1;
+}
+
+// One observation, one thread per state entry (any n).
+template <bool SH>
+__global__ void __launch_bounds__(256) k_gain_single(const double* Xin, double* Xout, const double* __restrict__ P,
+                                                     const double* __restrict__ R3,
+                                                     const double* __restrict__ colbuf, size_t ld, int n, double zr,
+                                                     double zb, int idf, double r00, double r10, double r01,
+                                                     double r11, unsigned flags, double* A, size_t lda,
+                                                     int* __restrict__ status, const int* __restrict__ idf_dev,
+                                                     int kprev) {
+    __shared__ GainSmall g;
+    __shared__ double sPc[5][5];
+    if (idf_dev != nullptr) idf = *idf_dev;  // fused scan: the association index stays on the device
+    const double R[4] = {r00, r10, r01, r11};
+    gain_body<SH>(Xin, Xout, P, R3, colbuf, ld, n, zr, zb, idf, R, flags, A, lda, status, kprev,
+                  blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, blockIdx.x == 0, g, sPc);
+}
+
+// Moderate maps (n <= kGainGroupMaxN): all g <= 8 observations of a group in ONE single-CTA launch —
+// observation k+1 is re-linearised at the X observation k produced (ping-pong Xa -> Xb -> Xa ...), the
+// panels accumulate in rows 0..2g-1 of A exactly as g launches of k_gain_single would leave them.
+// At n = 4 003 (C2) a gain launch is ~9 us of mostly launch + dependency latency; here the g gains cost
+// one launch.
+constexpr int kGainGroupMaxN = 8192;
+struct GainGroupPack {
+    double z[2 * 8];
+    int idf[8];
+    int g;
+    double R[4];
+};
+__global__ void __launch_bounds__(1024) k_gain_group(double* Xa, double* Xb, const double* __restrict__ P,
+                                                     const double* __restrict__ R3, size_t ld, int n,
+                                                     GainGroupPack gp, unsigned flags, double* A, size_t lda,
+                                                     int* __restrict__ status, const int* __restrict__ idf_dev) {
+    __shared__ GainSmall g;
+    __shared__ double sPc[5][5];
+    const double R[4] = {gp.R[0], gp.R[1], gp.R[2], gp.R[3]};
+    for (int k = 0; k < gp.g; k++) {
+        const int idf = idf_dev != nullptr ? idf_dev[k] : gp.idf[k];
+        const double* Xin = (k & 1) ? Xb : Xa;
+        double* Xout = (k & 1) ? Xa : Xb;
+        gain_body<false>(Xin, Xout, P, R3, nullptr, ld, n, gp.z[2 * k], gp.z[2 * k + 1], idf, R, flags, A, lda, status,
+                         k, threadIdx.x, blockDim.x, true, g, sPc);
+        __syncthreads();  // X and the new panel rows are complete before the next observation reads them
+    }
 }
 
 // Sharded column exchange: every rank contributes the entries of columns cols[k] (k < ncols) of
@@ -919,6 +961,24 @@ static int sequential_updates(cslam_ekf* h, const double* Z, const int32_t* idf_
                 cl.c[2 * k + 1] = cl.c[2 * k] + 1;
             }
             if (int rc = exchange_columns(h, cl, idf_dev ? idf_dev + base : nullptr)) return rc;
+        }
+        if (!sharded && g > 1 && n <= kGainGroupMaxN) {  // all gains of the group in one single-CTA launch
+            GainGroupPack gp;
+            memset(&gp, 0, sizeof(gp));
+            for (int k = 0; k < g; k++) {
+                gp.z[2 * k] = Z[2 * (base + k)];
+                gp.z[2 * k + 1] = Z[2 * (base + k) + 1];
+                gp.idf[k] = idf_host ? idf_host[base + k] : 0;
+            }
+            gp.g = g;
+            memcpy(gp.R, R, sizeof(double) * 4);
+            count_launch();
+            k_gain_group<<<1, 1024, 0, h->stream>>>(h->X[h->cur], h->X[h->cur ^ 1], h->P, h->R3, h->ld, n, gp, h->flags,
+                                                    h->A, h->lda, h->status, idf_dev ? idf_dev + base : nullptr);
+            CSLAM_CUDA(cudaGetLastError());
+            h->cur ^= (g & 1);
+            if (int rc = launch_cov_update_multi(h, g, idf_dev ? idf_dev + base : nullptr)) return rc;
+            continue;
         }
         for (int k = 0; k < g; k++) {
             const int i = base + k;

@@ -76,7 +76,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  : "memory");
 }
 
-// Pre-tiled panels: Ac[tc][k][DM_SC] = A[k][tc*64 + jj], Ar[tr][k][DM_SR] = -A[k][tr*128 + ii]
+// Pre-tiled panels: Ac[tc][k][DM_SC] = A[k][tc*DM_TN + jj], Ar[tr][k][DM_SR] = -A[k][tr*DM_TM + ii]
 // (zero beyond n / beyond rank r), each tile a contiguous block one bulk copy brings in.
 __global__ void __launch_bounds__(256) k_dmma_panels(const double* __restrict__ A, size_t lda, int n, int r,
                                                      int ncols, double* __restrict__ Ar, double* __restrict__ Ac) {
@@ -132,6 +132,9 @@ __global__ void __launch_bounds__(DM_THREADS, 1) k_cov_update_dmma(double* __res
                                                                    const double* __restrict__ Ar,
                                                                    const double* __restrict__ Ac, int rp, int nbc,
                                                                    int chunk, Shard sh, int dbg) {
+#ifndef CSLAM_DMMA_ABLATION
+    dbg = 0;  // the load/store ablation of tools/dmma_bench.cu is compiled out of the library
+#endif
     extern __shared__ __align__(128) double smem[];
     double* sR = smem;                 // [rp][DM_SR]  negated row panel of the strip
     double* sC = smem + DM_K * DM_SR;  // [DM_NBUF][rp][DM_SC] column panels (ring)

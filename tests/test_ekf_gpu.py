@@ -67,6 +67,26 @@ def test_single_update_parity(N, m, flags):
     assert g.sync() == 0
 
 
+def test_sequential_update_large_map():
+    """n = 8 203 > 8 192: the per-observation gain kernels (k_gain_single seeing P through the pending
+    rank-2 terms) + one multi pass — the path the 20 000-landmark bench takes; smaller maps take the
+    single-CTA grouped gain kernel."""
+    g, o, lm = _pair(4100, 4120, oracle_py.FLAG_INTENDED)
+    rng = np.random.default_rng(4100)
+    ids = (rng.choice(4100, size=3, replace=False) + 1).astype(np.int32)
+    Z = helpers.observe(o.X, lm, ids, rng)
+    jg, _ = g.scan(Z, RE, 50.0, 1000.0)
+    o.update(Z, RE, ids, False)
+    assert np.array_equal(jg, ids)
+    assert rel_err(g.X, o.X) < TOL
+    # covariance: rows 0..2, the observed landmarks' rows and a random sample of the rest
+    rows = np.unique(np.concatenate([[0, 1, 2], 3 + 2 * (ids - 1), 4 + 2 * (ids - 1), rng.choice(o.n, size=40)]))
+    Pg = g.P
+    for i in rows:
+        assert rel_err(Pg[i, i:], o.P[i, i:]) < TOL
+    assert g.sync() == 0
+
+
 @pytest.mark.parametrize("flags", [0, oracle_py.FLAG_INTENDED])
 @pytest.mark.parametrize("N,m", [(1, 1), (7, 7), (25, 5), (150, 16), (150, 32), (1100, 32), (1100, 5), (700, 17)])
 def test_batch_update_parity(N, m, flags):

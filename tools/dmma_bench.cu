@@ -2,8 +2,10 @@
 //   (1) DMMA.8x8x4 peak of the GPU (register-resident chains),
 //   (2) the production kernel (ekf_dmma.cu) against the first-round kernel (kept here only as a
 //       bit-exact cross-check and speed reference), several chunk lengths.
+//   (3) ablation of the production kernel: dbg & 1 skips the covariance loads, dbg & 2 the stores.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -I conan_slam_b200/csrc \
 //        tools/dmma_bench.cu conan_slam_b200/lib/util.o -ldl -o tools/bin/dmma_bench
+#define CSLAM_DMMA_ABLATION 1
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
