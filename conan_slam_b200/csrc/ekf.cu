@@ -233,10 +233,11 @@ __device__ void gain_prologue(const double* X, const double (&Pc)[5][5], int f, 
 // to its "after those updates" value by subtracting the pending rank-2 terms in update order — the
 // same operations the covariance kernel will perform, so the values are bit-identical.
 // idf_dev != nullptr: the association index is read from device memory (fused scan); 0 = skipped.
-// Body shared by the two launch shapes below: the thread block computes the observation's small
-// prologue (25 threads bring the 5x5 block of P up to date, one thread factorises), then every thread
-// handles the state entries i = i0, i0 + stride, ...  Pointers that other threads of the block write
-// before a __syncthreads (X buffers, panel A) are not __restrict__.
+// The thread block computes the observation's small prologue (25 threads bring the 5x5 block of P up
+// to date, one thread factorises), then every thread handles the state entries i = i0, i0 + stride, ...
+// (A single-CTA variant looping over all observations of a scan was measured and dropped: at n = 4 003
+// one CTA cannot keep enough loads in flight — 124 us per 4-observation scan against 91 us for four
+// 16-CTA launches.)
 template <bool SH>
 __device__ __forceinline__ void gain_body(const double* Xin, double* Xout, const double* __restrict__ P,
                                           const double* __restrict__ R3, const double* __restrict__ colbuf,
@@ -324,7 +325,6 @@ __device__ __forceinline__ void gain_body(const double* Xin, double* Xout, const
     }
 }
 
-// One observation, one thread per state entry (any n).
 template <bool SH>
 __global__ void __launch_bounds__(256) k_gain_single(const double* Xin, double* Xout, const double* __restrict__ P,
                                                      const double* __restrict__ R3,
@@ -339,35 +339,6 @@ __global__ void __launch_bounds__(256) k_gain_single(const double* Xin, double* 
     const double R[4] = {r00, r10, r01, r11};
     gain_body<SH>(Xin, Xout, P, R3, colbuf, ld, n, zr, zb, idf, R, flags, A, lda, status, kprev,
                   blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, blockIdx.x == 0, g, sPc);
-}
-
-// Moderate maps (n <= kGainGroupMaxN): all g <= 8 observations of a group in ONE single-CTA launch —
-// observation k+1 is re-linearised at the X observation k produced (ping-pong Xa -> Xb -> Xa ...), the
-// panels accumulate in rows 0..2g-1 of A exactly as g launches of k_gain_single would leave them.
-// At n = 4 003 (C2) a gain launch is ~9 us of mostly launch + dependency latency; here the g gains cost
-// one launch.
-constexpr int kGainGroupMaxN = 8192;
-struct GainGroupPack {
-    double z[2 * 8];
-    int idf[8];
-    int g;
-    double R[4];
-};
-__global__ void __launch_bounds__(1024) k_gain_group(double* Xa, double* Xb, const double* __restrict__ P,
-                                                     const double* __restrict__ R3, size_t ld, int n,
-                                                     GainGroupPack gp, unsigned flags, double* A, size_t lda,
-                                                     int* __restrict__ status, const int* __restrict__ idf_dev) {
-    __shared__ GainSmall g;
-    __shared__ double sPc[5][5];
-    const double R[4] = {gp.R[0], gp.R[1], gp.R[2], gp.R[3]};
-    for (int k = 0; k < gp.g; k++) {
-        const int idf = idf_dev != nullptr ? idf_dev[k] : gp.idf[k];
-        const double* Xin = (k & 1) ? Xb : Xa;
-        double* Xout = (k & 1) ? Xa : Xb;
-        gain_body<false>(Xin, Xout, P, R3, nullptr, ld, n, gp.z[2 * k], gp.z[2 * k + 1], idf, R, flags, A, lda, status,
-                         k, threadIdx.x, blockDim.x, true, g, sPc);
-        __syncthreads();  // X and the new panel rows are complete before the next observation reads them
-    }
 }
 
 // Sharded column exchange: every rank contributes the entries of columns cols[k] (k < ncols) of
@@ -961,24 +932,6 @@ static int sequential_updates(cslam_ekf* h, const double* Z, const int32_t* idf_
                 cl.c[2 * k + 1] = cl.c[2 * k] + 1;
             }
             if (int rc = exchange_columns(h, cl, idf_dev ? idf_dev + base : nullptr)) return rc;
-        }
-        if (!sharded && g > 1 && n <= kGainGroupMaxN) {  // all gains of the group in one single-CTA launch
-            GainGroupPack gp;
-            memset(&gp, 0, sizeof(gp));
-            for (int k = 0; k < g; k++) {
-                gp.z[2 * k] = Z[2 * (base + k)];
-                gp.z[2 * k + 1] = Z[2 * (base + k) + 1];
-                gp.idf[k] = idf_host ? idf_host[base + k] : 0;
-            }
-            gp.g = g;
-            memcpy(gp.R, R, sizeof(double) * 4);
-            count_launch();
-            k_gain_group<<<1, 1024, 0, h->stream>>>(h->X[h->cur], h->X[h->cur ^ 1], h->P, h->R3, h->ld, n, gp, h->flags,
-                                                    h->A, h->lda, h->status, idf_dev ? idf_dev + base : nullptr);
-            CSLAM_CUDA(cudaGetLastError());
-            h->cur ^= (g & 1);
-            if (int rc = launch_cov_update_multi(h, g, idf_dev ? idf_dev + base : nullptr)) return rc;
-            continue;
         }
         for (int k = 0; k < g; k++) {
             const int i = base + k;

@@ -68,9 +68,8 @@ def test_single_update_parity(N, m, flags):
 
 
 def test_sequential_update_large_map():
-    """n = 8 203 > 8 192: the per-observation gain kernels (k_gain_single seeing P through the pending
-    rank-2 terms) + one multi pass — the path the 20 000-landmark bench takes; smaller maps take the
-    single-CTA grouped gain kernel."""
+    """A larger map (n = 8 203, 128-wide tiles, several tile rows): fused scan = gate + gain kernels
+    seeing P through the pending rank-2 terms + one multi pass, the path the 20 000-landmark bench takes."""
     g, o, lm = _pair(4100, 4120, oracle_py.FLAG_INTENDED)
     rng = np.random.default_rng(4100)
     ids = (rng.choice(4100, size=3, replace=False) + 1).astype(np.int32)
