@@ -345,3 +345,35 @@ def test_control_steps_equal_stepwise_calls(N, flags):
     for i in range(3):
         b.predict(v[i], swa[i], QE, 73.0, 0.01)
     assert np.array_equal(a.X, b.X) and np.array_equal(a.P, b.P)
+
+
+@pytest.mark.parametrize("N", [62, 63, 126, 127, 510, 1022, 1023, 1086, 1087])
+def test_tile_boundary_sizes(N):
+    """State sizes straddling the tile edges of every covariance kernel (n = 3 + 2N around 128, 256,
+    1024 = DMMA threshold, 2048 = switch from 64- to 128-wide tiles, 17 x 128): heading update (rank 1),
+    fused scan (grouped rank-2 pass), joint update (FMA kernel below n = 1024, tensor cores above),
+    augmentation into the last tile — full covariance against the oracle."""
+    g, o, lm = _pair(N, 7000 + N, oracle_py.FLAG_INTENDED, capacity=N + 3)
+    rng = np.random.default_rng(N)
+    phi1 = float(o.X[2]) + 1e-4
+    for f in (g, o):
+        f.predict(83.33, 0.01, QE, 73.0, 0.01)
+        f.observeHeading(phi1, True)
+    _assert_state(g, o)
+    ids = (rng.choice(N, size=5, replace=False) + 1).astype(np.int32)
+    Z = helpers.observe(o.X, lm, ids, rng)
+    jg, _ = g.scan(Z, RE, 50.0, 1000.0)
+    assert np.array_equal(jg, ids)
+    o.update(Z, RE, ids, False)
+    _assert_state(g, o)
+    ids2 = (rng.choice(N, size=3, replace=False) + 1).astype(np.int32)
+    Z2 = helpers.observe(o.X, lm, ids2, rng)
+    Zn = np.array([[650.0, 900.0, 410.0], [0.3, -0.8, 1.7]])
+    phi2 = float(o.X[2]) - 5e-5
+    for f in (g, o):
+        f.update(Z2, RE, ids2, True)
+        f.augment(Zn, RE)
+        f.observeHeading(phi2, True)
+        f.update(Zn[:, 2:], RE, np.array([N + 3], dtype=np.int32), False)
+    _assert_state(g, o)
+    assert g.sync() == 0
