@@ -219,4 +219,72 @@ __global__ void __launch_bounds__(256, MINB) k_cov_update_multi(double* __restri
     }
 }
 
+
+// K consecutive heading updates (EKF.cpp:328-352 -> slam.h:700-725, each a rank-1 pass P -= a a^T with
+// FLT_MIN added on the diagonal, slam.h:719) applied in ONE pass over rows >= row_min of the upper
+// triangle:  P(i,j) <- ((P(i,j) - a0_i a0_j [+ eps]) - a1_i a1_j [+ eps]) ...  — the operations of K
+// launches of k_cov_update<1>, bit-identical.  The predicts between the heading updates of consecutive
+// control steps only rewrite rows 0..2 (EKF.cpp:439-443 on upper-triangle storage), which the caller
+// keeps current eagerly (k_rows012_update) and excludes here with row_min = 3; every other row sees
+// nothing but the K rank-1 terms, so their passes commute with the predicts and merge.
+// Panel rows 0..K-1 of A are the K vectors a = p / sqrt(S).
+template <int K, int T, int BATCH_ = 4, int MINB = 4, int HINT = 1>
+__global__ void __launch_bounds__(256, MINB) k_cov_update_multi1(double* __restrict__ P, size_t ld, int n,
+                                                                 const double* __restrict__ A, size_t lda, int nt,
+                                                                 double diag_eps, int row_min, Shard sh) {
+    constexpr int CP = T / 2, RG = 256 / CP, RPT = T / RG;
+    constexpr int BATCH = RPT > BATCH_ ? BATCH_ : RPT;
+    __shared__ double sRow[T][K];
+    __shared__ double2 sCol[K][CP];
+    int tr, tc;
+    shard_tile(blockIdx.x, nt, sh, tr, tc);
+    const int i0 = tr * T, j0 = tc * T;
+    for (int idx = threadIdx.x; idx < K * T; idx += 256) {
+        const int q = idx / T, ii = idx % T;
+        sRow[ii][q] = (i0 + ii < n) ? A[(size_t)q * lda + i0 + ii] : 0.0;
+    }
+    for (int idx = threadIdx.x; idx < K * CP; idx += 256) {
+        const int q = idx / CP, c = idx % CP;
+        const int jj = j0 + 2 * c;
+        const double* a = A + (size_t)q * lda;
+        sCol[q][c] = make_double2(jj < n ? a[jj] : 0.0, jj + 1 < n ? a[jj + 1] : 0.0);
+    }
+    const int cp = threadIdx.x % CP, rg = threadIdx.x / CP;
+    const int j = j0 + 2 * cp;
+    __syncthreads();
+    if (j >= n) return;
+    const bool diag_tile = (tr == tc);
+    const bool y_in = j + 1 < n;
+#pragma unroll 1
+    for (int b0 = 0; b0 < RPT; b0 += BATCH) {
+        double2 v[BATCH];
+#pragma unroll
+        for (int b = 0; b < BATCH; b++) {
+            const int i = i0 + rg + (b0 + b) * RG;
+            const bool act = (i < n) && (i >= row_min) && (!diag_tile || j + 1 >= i);
+            if (act) v[b] = cov_ld<HINT>(P + shard_lrow(sh, i) * ld + j);
+        }
+#pragma unroll
+        for (int q = 0; q < K; q++) {
+            const double2 c = sCol[q][cp];
+#pragma unroll
+            for (int b = 0; b < BATCH; b++) {
+                const int ii = rg + (b0 + b) * RG;
+                const int i = i0 + ii;
+                const double r = sRow[ii][q];
+                if (j >= i) v[b].x = v[b].x - r * c.x;
+                if (y_in) v[b].y = v[b].y - r * c.y;
+                if (j == i) v[b].x += diag_eps;
+                if (j + 1 == i) v[b].y += diag_eps;
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < BATCH; b++) {
+            const int i = i0 + rg + (b0 + b) * RG;
+            const bool act = (i < n) && (i >= row_min) && (!diag_tile || j + 1 >= i);
+            if (act) cov_st<HINT>(P + shard_lrow(sh, i) * ld + j, v[b]);
+        }
+    }
+}
+
 }  // namespace cslam

@@ -760,10 +760,10 @@ __global__ void __launch_bounds__(256) k_diag_follow(double* __restrict__ D, int
             d01 = d01 - a0[f] * a0[f + 1];
             d11 = d11 - a0[f + 1] * a0[f + 1];
         }
-    }
-    if (add_eps) {  // k_cov_update adds diag_eps on the diagonal (also when it is 0.0); k_cov_update_multi does not
-        d00 += diag_eps;
-        d11 += diag_eps;
+        if (add_eps) {  // k_cov_update / k_cov_update_multi1 add diag_eps on the diagonal after every term
+            d00 += diag_eps;  // (also when it is 0.0); k_cov_update_multi does not
+            d11 += diag_eps;
+        }
     }
     D[j] = d00;
     D[(size_t)dcap + j] = d01;
@@ -900,6 +900,31 @@ static int launch_cov_update_multi(cslam_ekf* h, int g, const int* live) {
         k_rows012_update_multi<<<dim3((n + 255) / 256, 3), 256, 0, h->stream>>>(h->R3, h->ld, n, h->A, h->lda, g);
         CSLAM_CUDA(cudaGetLastError());
     }
+    return CSLAM_OK;
+}
+
+// One pass for the k heading updates of k consecutive control steps (panel rows 0..k-1 of A); rows
+// 0..2 were already brought up to date term by term (k_rows012_update), see k_cov_update_multi1.
+static int launch_heading_multi(cslam_ekf* h, int k) {
+    const int n = h->n;
+    const int nt = (n + 127) / 128;
+    const long long tiles = shard_tile_count(nt, h->sh);
+    if (tiles == 0) return CSLAM_OK;
+    ProfScope prof(h);
+    count_launch();
+#define CSLAM_H1(K)                                                                                          \
+    case K:                                                                                                  \
+        k_cov_update_multi1<K, 128, 4, 4, 1><<<(unsigned)tiles, 256, 0, h->stream>>>(h->P, h->ld, n, h->A, h->lda, nt, \
+                                                                                     kFltMin, 3, h->sh);     \
+        break;
+    switch (k) {
+        CSLAM_H1(1) CSLAM_H1(2) CSLAM_H1(3) CSLAM_H1(4) CSLAM_H1(5) CSLAM_H1(6) CSLAM_H1(7) CSLAM_H1(8)
+        default:
+            set_last_error("launch_heading_multi: bad group size %d", k);
+            return CSLAM_ERR_BAD_ARG;
+    }
+#undef CSLAM_H1
+    CSLAM_CUDA(cudaGetLastError());
     return CSLAM_OK;
 }
 
@@ -1201,15 +1226,41 @@ int cslam_ekf_control_steps(cslam_ekf_t* h, int k, const double* v, const double
                 set_last_error("k_control_steps -> %s", cudaGetErrorString(e));
                 rc = CSLAM_ERR_CUDA;
             }
-        } else {  // big or sharded maps: the per-step kernels, still one call and no host round trip
-            for (int i = 0; i < kc && rc == CSLAM_OK; i++) {
-                rc = cslam_ekf_predict(h, v[base + i], swa[base + i], Q, wb, dt);
-                if (rc == CSLAM_OK) rc = cslam_ekf_observe_heading(h, phi ? phi[base + i] : 0.0, use_heading);
-                if (rc == CSLAM_OK && trace_dev) {
-                    cudaError_t e = cudaMemcpyAsync(trace_dev + 3 * (base + i), h->X[h->cur], 3 * sizeof(double),
-                                                    cudaMemcpyDeviceToDevice, h->stream);
-                    if (e != cudaSuccess) rc = CSLAM_ERR_CUDA;
+        } else {
+            // big or sharded maps: per step the O(n) kernels (predict, heading gain, rank-1 update of rows
+            // 0..2 and of the replicated caches), then ONE pass over the rest of the covariance for up to
+            // 8 heading updates (k_cov_update_multi1) instead of one pass per control step
+            for (int g0 = 0; g0 < kc && rc == CSLAM_OK; g0 += kSeqGroup) {
+                const int gk = std::min(kSeqGroup, kc - g0);
+                for (int i = 0; i < gk && rc == CSLAM_OK; i++) {
+                    const int st = base + g0 + i;
+                    rc = cslam_ekf_predict(h, v[st], swa[st], Q, wb, dt);
+                    if (rc == CSLAM_OK && use_heading) {
+                        double* Ai = h->A + (size_t)i * h->lda;  // panel row i of this group
+                        count_launch();
+                        k_heading_gain<<<(n + 255) / 256, 256, 0, h->stream>>>(h->X[h->cur], h->X[h->cur ^ 1], h->R3,
+                                                                               h->ld, n, phi[st], sigma * sigma, Ai);
+                        h->cur ^= 1;
+                        count_launch();
+                        k_rows012_update<<<dim3((n + 255) / 256, 3), 256, 0, h->stream>>>(h->R3, h->ld, n, Ai, h->lda, 1,
+                                                                                        kFltMin);
+                        if (cudaGetLastError() != cudaSuccess) rc = CSLAM_ERR_CUDA;
+                        if (rc == CSLAM_OK && h->sh.world > 1 && !h->diag_dirty) {
+                            const int nf = (n - 3) / 2;
+                            if (nf > 0) {
+                                count_launch();
+                                k_diag_follow<<<(nf + 255) / 256, 256, 0, h->stream>>>(h->D, h->dcap, nf, Ai, h->lda, 1, 1,
+                                                                                       kFltMin, true);
+                            }
+                        }
+                    }
+                    if (rc == CSLAM_OK && trace_dev) {
+                        cudaError_t e = cudaMemcpyAsync(trace_dev + 3 * st, h->X[h->cur], 3 * sizeof(double),
+                                                        cudaMemcpyDeviceToDevice, h->stream);
+                        if (e != cudaSuccess) rc = CSLAM_ERR_CUDA;
+                    }
                 }
+                if (rc == CSLAM_OK && use_heading) rc = launch_heading_multi(h, gk);
             }
         }
     }

@@ -110,6 +110,18 @@ def ekf_checks():
             f.predict(83.33, -0.01, QE, 73.0, 0.01)
             f.observeHeading(phi_meas, True)
         check("augment")
+        # k control steps in one call: per step predict + heading gain + eager rows 0..2 / cache update,
+        # the k heading passes over the rest of the sharded covariance merged into one
+        kk = 5
+        sw = 0.02 * np.sin(np.arange(kk))
+        ph = float(o.X[2]) + np.cumsum(83.33 * 0.01 * np.sin(sw) / 73.0) + 1e-4 * np.cos(np.arange(kk))
+        tr = g.controlSteps(np.full(kk, 83.33), sw, ph, True, QE, 73.0, 0.01)
+        for i in range(kk):
+            o.predict(83.33, sw[i], QE, 73.0, 0.01)
+            o.observeHeading(ph[i], True)
+        assert rel_err(tr[-1], o.X[:3]) < 1e-9
+        check("control steps (merged heading passes)")
+        same_gate(helpers.observe(o.X, lm, (rng.choice(N, size=6, replace=False) + 1).astype(np.int32), rng))
         ids3 = np.array([N + 1, N + 3, 7], dtype=np.int32)
         Z3 = np.stack([np.array([700.0, 300.0, Z[0, 0]]), np.array([0.4, 2.0, Z[1, 0]])])
         for f in (g, o):
