@@ -107,6 +107,9 @@ class ClockSampler:
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+QE_BENCH = 2.0 * np.diag([0.3 ** 2, (np.pi / 180.0) ** 2])  # test/main.cpp:127 (QE = 2Q)
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -660,6 +663,32 @@ def main():
     barrier()
     e2e_ms = t_e0.elapsed_time(t_e1)
 
+    # ---- a whole drive cycle of test/main.cpp (6 control steps = predict + observeHeading each, then one
+    # observation scan), stepwise calls vs cslam_ekf_control_steps (heading passes merged): extra info
+    drive = None
+    if world == 1 and not batch:
+        def cycle(merged, Z):
+            if merged:
+                ekf.controlSteps(np.zeros(6), np.zeros(6), np.zeros(6), True, QE_BENCH, 73.0, 0.01, want_trace=False)
+            else:
+                for _ in range(6):
+                    ekf.predict(0.0, 0.0, QE_BENCH, 73.0, 0.01)
+                    ekf.observeHeading(0.0, True)
+            ekf_scan(ekf, Z)
+        drive = {"control_steps_per_cycle": 6, "observations_per_cycle": m,
+                 "covariance_passes_per_cycle": {"stepwise": 7, "merged": 2}}
+        for name, merged in (("stepwise", False), ("merged", True)):
+            cycle(merged, scans[0][0])
+            ekf.sync()
+            d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                d0.record(stream)
+                for c in range(3):
+                    cycle(merged, scans[(c + 2) % len(scans)][0])
+                d1.record(stream)
+            torch.cuda.synchronize()
+            drive[f"ms_per_cycle_{name}"] = d0.elapsed_time(d1) / 3.0
+
     if world > 1:
         t = torch.tensor([ms, e2e_ms], device=f"cuda:{local}", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -741,6 +770,8 @@ def main():
         }
         if batch:
             out["observations_per_s"] = value * m
+        if drive is not None:
+            out["drive_cycle"] = drive
         if not args.no_cpu_baseline and world == 1:
             t1 = time.time()
             # the reference's own compiled sources (oracle/_ref) when they travelled with the snapshot,

@@ -196,18 +196,31 @@ __global__ void __launch_bounds__(256, MINB) k_cov_update_multi(double* __restri
             const bool act = (i < n) && (!diag_tile || j + 1 >= i);
             if (act) v[b] = cov_ld<HINT>(P + shard_lrow(sh, i) * ld + j);
         }
+        if (diag_tile) {  // only tiles on the diagonal need the j >= i mask
 #pragma unroll
-        for (int q = 0; q < M; q++) {
-            const double2 c0 = sCol0[q][cp], c1 = sCol1[q][cp];
+            for (int q = 0; q < M; q++) {
+                const double2 c0 = sCol0[q][cp], c1 = sCol1[q][cp];
 #pragma unroll
-            for (int b = 0; b < BATCH; b++) {
-                const int ii = rg + (b0 + b) * RG;
-                const int i = i0 + ii;
-                const double2 r = sRow[ii][q];
-                const double s0 = rank2_term(r.x, r.y, c0.x, c1.x);
-                const double s1 = rank2_term(r.x, r.y, c0.y, c1.y);
-                if (j >= i) v[b].x = v[b].x - s0;
-                if (y_in) v[b].y = v[b].y - s1;
+                for (int b = 0; b < BATCH; b++) {
+                    const int ii = rg + (b0 + b) * RG;
+                    const int i = i0 + ii;
+                    const double2 r = sRow[ii][q];
+                    const double s0 = rank2_term(r.x, r.y, c0.x, c1.x);
+                    const double s1 = rank2_term(r.x, r.y, c0.y, c1.y);
+                    if (j >= i) v[b].x = v[b].x - s0;
+                    if (y_in) v[b].y = v[b].y - s1;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < M; q++) {
+                const double2 c0 = sCol0[q][cp], c1 = sCol1[q][cp];
+#pragma unroll
+                for (int b = 0; b < BATCH; b++) {
+                    const double2 r = sRow[rg + (b0 + b) * RG][q];
+                    v[b].x = v[b].x - rank2_term(r.x, r.y, c0.x, c1.x);
+                    if (y_in) v[b].y = v[b].y - rank2_term(r.x, r.y, c0.y, c1.y);
+                }
             }
         }
 #pragma unroll
@@ -264,18 +277,31 @@ __global__ void __launch_bounds__(256, MINB) k_cov_update_multi1(double* __restr
             const bool act = (i < n) && (i >= row_min) && (!diag_tile || j + 1 >= i);
             if (act) v[b] = cov_ld<HINT>(P + shard_lrow(sh, i) * ld + j);
         }
+        if (diag_tile) {  // only tiles on the diagonal carry the per-term FLT_MIN and the j >= i mask
 #pragma unroll
-        for (int q = 0; q < K; q++) {
-            const double2 c = sCol[q][cp];
+            for (int q = 0; q < K; q++) {
+                const double2 c = sCol[q][cp];
 #pragma unroll
-            for (int b = 0; b < BATCH; b++) {
-                const int ii = rg + (b0 + b) * RG;
-                const int i = i0 + ii;
-                const double r = sRow[ii][q];
-                if (j >= i) v[b].x = v[b].x - r * c.x;
-                if (y_in) v[b].y = v[b].y - r * c.y;
-                if (j == i) v[b].x += diag_eps;
-                if (j + 1 == i) v[b].y += diag_eps;
+                for (int b = 0; b < BATCH; b++) {
+                    const int ii = rg + (b0 + b) * RG;
+                    const int i = i0 + ii;
+                    const double r = sRow[ii][q];
+                    if (j >= i) v[b].x = v[b].x - r * c.x;
+                    if (y_in) v[b].y = v[b].y - r * c.y;
+                    if (j == i) v[b].x += diag_eps;
+                    if (j + 1 == i) v[b].y += diag_eps;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < K; q++) {
+                const double2 c = sCol[q][cp];
+#pragma unroll
+                for (int b = 0; b < BATCH; b++) {
+                    const double r = sRow[rg + (b0 + b) * RG][q];
+                    v[b].x = v[b].x - r * c.x;
+                    if (y_in) v[b].y = v[b].y - r * c.y;
+                }
             }
         }
 #pragma unroll
