@@ -231,14 +231,18 @@ class PfScenario:
         self.lm = np.stack([rad * np.cos(ang) + 150.0, rad * np.sin(ang)])
 
     def controls(self):
+        """The 6 control steps between two observations (predict + observeHeading each, test/main.cpp:279-286)
+        handed over in one call: the controls and the measured heading do not depend on the filter."""
+        swas, phis = [], []
         for c in range(PF_CONTROLS_PER_OBS):
             swa = 0.02 * np.sin(0.3 * (self.cycle * PF_CONTROLS_PER_OBS + c))
-            self.pf.predict(self.v, swa, PF_Q, self.wb, self.dt)
             # nominal pose: slam.h:952-966 vehicleModel
             x, y, phi = self.pose
             self.pose = np.array([x + self.v * self.dt * np.cos(swa + phi), y + self.v * self.dt * np.sin(swa + phi),
                                   phi + self.v * self.dt * np.sin(swa) / self.wb])
-            self.pf.observeHeading(self.pose[2], True)
+            swas.append(swa)
+            phis.append(self.pose[2])
+        self.pf.controlSteps(np.full(PF_CONTROLS_PER_OBS, self.v), swas, phis, True, PF_Q, self.wb, self.dt)
 
     def init_map(self, xi_dev_ptr):
         """6 control steps, sample the pose (test/main.cpp:319-325), initialise every landmark."""

@@ -17,6 +17,7 @@
 // Built with -fmad=false and written in the oracle's operation order (matmul = ascending-k
 // accumulation from zero, PartialPivLU inverse, LLT) so weights and poses track
 // oracle/slam_oracle.hpp to rounding of libm calls only.
+#include <algorithm>
 #include <cstdlib>
 #include <new>
 #include <vector>
@@ -141,18 +142,8 @@ struct PfObs {  // kernel-parameter transport of one scan
 // ------------------------------------------------------------------------------------
 
 // PF.cpp:419-471 predict: P <- Gv P Gv^T + Gu Q Gu^T (3x3), deterministic pose advance (Q15).
-__global__ void __launch_bounds__(256) k_pf_predict(double* __restrict__ xv, double* __restrict__ pv, size_t pp,
-                                                    int np, double v, double swa, double q00, double q01,
-                                                    double q10, double q11, double wb, double dt) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= np) return;
-    double X[3], P[3][3];
-#pragma unroll
-    for (int i = 0; i < 3; i++) X[i] = xv[i * pp + p];
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = 0; j < 3; j++) P[i][j] = pv[(3 * i + j) * pp + p];
+__device__ __forceinline__ void pf_predict_regs(double (&X)[3], double (&P)[3][3], double v, double swa, double q00,
+                                                double q01, double q10, double q11, double wb, double dt) {
     const double phi = X[2];
     const double s = sin(swa + phi), c = cos(swa + phi);
     const double Gv[3][3] = {{1.0, 0.0, -v * dt * s}, {0.0, 1.0, v * dt * c}, {0.0, 0.0, 1.0}};
@@ -168,24 +159,15 @@ __global__ void __launch_bounds__(256) k_pf_predict(double* __restrict__ xv, dou
 #pragma unroll
     for (int i = 0; i < 3; i++)
 #pragma unroll
-        for (int j = 0; j < 3; j++) pv[(3 * i + j) * pp + p] = A[i][j] + B[i][j];
-    xv[0 * pp + p] = X[0] + v * dt * c;
-    xv[1 * pp + p] = X[1] + v * dt * s;
-    xv[2 * pp + p] = pi2pi(X[2] + v * dt * sin(swa) / wb);
+        for (int j = 0; j < 3; j++) P[i][j] = A[i][j] + B[i][j];
+    const double x0 = X[0] + v * dt * c, x1 = X[1] + v * dt * s;
+    X[2] = pi2pi(X[2] + v * dt * sin(swa) / wb);
+    X[0] = x0;
+    X[1] = x1;
 }
 
 // PF.cpp:382-417 observeHeading -> slam.h:700-725 josephUpdate on the 3x3 pose block, H = e_2^T.
-__global__ void __launch_bounds__(256) k_pf_heading(double* __restrict__ xv, double* __restrict__ pv, size_t pp,
-                                                    int np, double phi_meas, double Rh) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= np) return;
-    double X[3], P[3][3];
-#pragma unroll
-    for (int i = 0; i < 3; i++) X[i] = xv[i * pp + p];
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = 0; j < 3; j++) P[i][j] = pv[(3 * i + j) * pp + p];
+__device__ __forceinline__ void pf_heading_regs(double (&X)[3], double (&P)[3][3], double phi_meas, double Rh) {
     const double v = pi2pi(phi_meas - X[2]);
     const double H[1][3] = {{0.0, 0.0, 1.0}};
     double Ht[3][1], PHT[3][1], HPHT[1][1];
@@ -218,10 +200,70 @@ __global__ void __launch_bounds__(256) k_pf_heading(double* __restrict__ xv, dou
             const double wr = 0.0 + W[i] * Rh;
             double o = CPC[i][j] + (0.0 + wr * W[j]);
             if (i == j) o = o + kFltMin;
-            pv[(3 * i + j) * pp + p] = o;
+            P[i][j] = o;
         }
+}
+
+__device__ __forceinline__ void pf_load_pose(const double* __restrict__ xv, const double* __restrict__ pv, size_t pp,
+                                             int p, double (&X)[3], double (&P)[3][3]) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) X[i] = xv[i * pp + p];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) P[i][j] = pv[(3 * i + j) * pp + p];
+}
+__device__ __forceinline__ void pf_store_pose(double* __restrict__ xv, double* __restrict__ pv, size_t pp, int p,
+                                              const double (&X)[3], const double (&P)[3][3]) {
 #pragma unroll
     for (int i = 0; i < 3; i++) xv[i * pp + p] = X[i];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) pv[(3 * i + j) * pp + p] = P[i][j];
+}
+
+__global__ void __launch_bounds__(256) k_pf_predict(double* __restrict__ xv, double* __restrict__ pv, size_t pp,
+                                                    int np, double v, double swa, double q00, double q01,
+                                                    double q10, double q11, double wb, double dt) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= np) return;
+    double X[3], P[3][3];
+    pf_load_pose(xv, pv, pp, p, X, P);
+    pf_predict_regs(X, P, v, swa, q00, q01, q10, q11, wb, dt);
+    pf_store_pose(xv, pv, pp, p, X, P);
+}
+
+__global__ void __launch_bounds__(256) k_pf_heading(double* __restrict__ xv, double* __restrict__ pv, size_t pp,
+                                                    int np, double phi_meas, double Rh) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= np) return;
+    double X[3], P[3][3];
+    pf_load_pose(xv, pv, pp, p, X, P);
+    pf_heading_regs(X, P, phi_meas, Rh);
+    pf_store_pose(xv, pv, pp, p, X, P);
+}
+
+// k consecutive control steps of every particle (test/main.cpp:279-286 for k iterations of the driver
+// loop): the 12 pose values are loaded once, k x (predict, observeHeading) run in registers, and are
+// stored once — one launch and 2 x 104 B per particle instead of 2k launches and 2k x 208 B.
+constexpr int kPfMaxControlSteps = 16;
+struct PfControlPack {
+    double v[kPfMaxControlSteps], swa[kPfMaxControlSteps], phi[kPfMaxControlSteps];
+    int k, use_heading;
+    double q00, q01, q10, q11, wb, dt, rh;
+};
+__global__ void __launch_bounds__(256) k_pf_control_steps(double* __restrict__ xv, double* __restrict__ pv, size_t pp,
+                                                          int np, PfControlPack cp) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= np) return;
+    double X[3], P[3][3];
+    pf_load_pose(xv, pv, pp, p, X, P);
+    for (int st = 0; st < cp.k; st++) {
+        pf_predict_regs(X, P, cp.v[st], cp.swa[st], cp.q00, cp.q01, cp.q10, cp.q11, cp.wb, cp.dt);
+        if (cp.use_heading) pf_heading_regs(X, P, cp.phi[st], cp.rh);
+    }
+    pf_store_pose(xv, pv, pp, p, X, P);
 }
 
 // PF.cpp:502-544 sampleProposal.
@@ -997,6 +1039,33 @@ int cslam_pf_observe_heading(cslam_pf_t* h, double phi, int use_heading) {
     count_launch();
     k_pf_heading<<<nblk(h->np, 256), 256, 0, h->stream>>>(b.xv, b.pv, h->pp, h->np, phi, sigma * sigma);
     CSLAM_CUDA(cudaGetLastError());
+    return CSLAM_OK;
+}
+
+int cslam_pf_control_steps(cslam_pf_t* h, int k, const double* v, const double* swa, const double* phi,
+                           int use_heading, const double Q[4], double wb, double dt) {
+    if (int rc = check_pf(h)) return rc;
+    CSLAM_REQUIRE(k >= 0, CSLAM_ERR_BAD_ARG, "k < 0");
+    if (k == 0) return CSLAM_OK;
+    CSLAM_REQUIRE(v && swa && Q && (phi || !use_heading), CSLAM_ERR_BAD_ARG, "null argument");
+    const double sigma = 0.01F * kPi / 180.0F;  // PF.cpp:391
+    PfBuf& b = h->buf[h->cur];
+    for (int base = 0; base < k; base += kPfMaxControlSteps) {
+        PfControlPack cp;
+        memset(&cp, 0, sizeof(cp));
+        cp.k = std::min(kPfMaxControlSteps, k - base);
+        for (int i = 0; i < cp.k; i++) {
+            cp.v[i] = v[base + i];
+            cp.swa[i] = swa[base + i];
+            cp.phi[i] = phi ? phi[base + i] : 0.0;
+        }
+        cp.use_heading = use_heading ? 1 : 0;
+        cp.q00 = Q[0]; cp.q01 = Q[2]; cp.q10 = Q[1]; cp.q11 = Q[3];
+        cp.wb = wb; cp.dt = dt; cp.rh = sigma * sigma;
+        count_launch();
+        k_pf_control_steps<<<nblk(h->np, 256), 256, 0, h->stream>>>(b.xv, b.pv, h->pp, h->np, cp);
+        CSLAM_CUDA(cudaGetLastError());
+    }
     return CSLAM_OK;
 }
 

@@ -338,6 +338,14 @@ class PfGpuT {
     void observeHeading(double phi, bool useHeading = false) {
         report(cslam_pf_observe_heading(h_, phi, useHeading ? 1 : 0), "observeHeading");
     }
+    // k control steps (predict + observeHeading each) of every particle in one launch
+    void controlSteps(const std::vector<double>& v, const std::vector<double>& swa, const std::vector<double>& phi,
+                      bool useHeading, const MatT& Q, double wb, double dt) {
+        const double q[4] = {Q(0, 0), Q(1, 0), Q(0, 1), Q(1, 1)};
+        report(cslam_pf_control_steps(h_, (int)v.size(), v.data(), swa.data(), phi.data(), useHeading ? 1 : 0, q, wb,
+                                      dt),
+               "controlSteps");
+    }
     // Slam::sampleProposal(Particle_t&, Z, idf, R)         slam.h:881-884 / PF.cpp:502-544
     void sampleProposal(const MatT& Z, const std::vector<int>& idf, const MatT& R, const std::vector<double>& xi) {
         const int m = Z.cols();

@@ -115,6 +115,17 @@ class PF:
         check(self._lib.cslam_pf_observe_heading(self._h, float(phi), int(bool(useHeading))),
               "cslam_pf_observe_heading")
 
+    def controlSteps(self, v, swa, phi, useHeading, Q, wb, dt):
+        """k control steps (predict + observeHeading each) of every particle in one launch."""
+        v = np.ascontiguousarray(v, dtype=np.float64).reshape(-1)
+        swa = np.ascontiguousarray(swa, dtype=np.float64).reshape(-1)
+        phi = np.ascontiguousarray(phi, dtype=np.float64).reshape(-1)
+        assert swa.shape[0] == v.shape[0] and phi.shape[0] == v.shape[0]
+        q = _m2(Q)
+        check(self._lib.cslam_pf_control_steps(self._h, v.shape[0], dptr(v), dptr(swa), dptr(phi),
+                                               int(bool(useHeading)), dptr(q), float(wb), float(dt)),
+              "cslam_pf_control_steps")
+
     def sampleProposal(self, Z, idf, R, xi):
         """slam.h:881-884 / PF.cpp:502-544.  xi: [P][3] standard-normal draws."""
         Zm, zflat = _z(Z)

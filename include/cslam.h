@@ -181,6 +181,12 @@ int cslam_pf_num_features(const cslam_pf_t* h);
 int cslam_pf_predict(cslam_pf_t* h, double v, double swa, const double Q[4], double wb, double dt);
 /* Slam::observeHeading(Particle_t&,phi,use) for every particle     slam.h:796 -> PF.cpp:382-417 */
 int cslam_pf_observe_heading(cslam_pf_t* h, double phi, int use_heading);
+/* k consecutive control steps of every particle — per step Slam::predict then Slam::observeHeading,
+ * test/main.cpp:279-286 for k iterations of the driver loop — in ONE launch: the pose block of a particle
+ * is loaded once, stepped k times in registers and stored once.  Bit-identical to k calls of
+ * cslam_pf_predict + cslam_pf_observe_heading. */
+int cslam_pf_control_steps(cslam_pf_t* h, int k, const double* v, const double* swa, const double* phi,
+                           int use_heading, const double Q[4], double wb, double dt);
 /* Slam::sampleProposal(Particle_t&,Z,idf,R) for every particle     slam.h:881-884 -> PF.cpp:502-544.
  * xi: 3 standard-normal draws per particle, [p][3] (the values slam.h:753-764 would take
  * from Boost — an input).  xi_on_device != 0: xi is a device pointer. */

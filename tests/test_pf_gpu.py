@@ -170,3 +170,29 @@ def test_pf_argument_errors():
     with pytest.raises(cs.CslamError) as e:
         g.sampleProposal(np.array([[10.0, 11.0], [0.1, 0.1]]), np.array([1, 1], dtype=np.int32), R2, xi)
     assert e.value.code == 5
+
+
+@pytest.mark.parametrize("use_heading", [True, False])
+def test_control_steps_equal_stepwise_calls(use_heading):
+    """cslam_pf_control_steps (k x predict + observeHeading in registers, one launch) is bit-identical to
+    the 2k per-step launches and matches the oracle."""
+    import conan_slam_b200 as cs
+    npart = 1000
+    rng = np.random.default_rng(3)
+    a = cs.PF(num_particles=npart, capacity_landmarks=2, flags=oracle_py.FLAG_INTENDED)
+    b = cs.PF(num_particles=npart, capacity_landmarks=2, flags=oracle_py.FLAG_INTENDED)
+    o = oracle_py.OraclePF(npart, oracle_py.FLAG_INTENDED)
+    X0 = rng.normal(size=(npart, 3)) * np.array([5.0, 5.0, 0.05])
+    for f in (a, b, o):
+        f.set_poses(X0, None)
+    k = 19  # > 16: two launches
+    v = 83.33 + rng.normal(size=k)
+    swa = 0.05 * rng.normal(size=k)
+    phi = np.cumsum(v * 0.01 * np.sin(swa) / 73.0) + 1e-4 * rng.normal(size=k)
+    a.controlSteps(v, swa, phi, use_heading, QE, 73.0, 0.01)
+    for i in range(k):
+        for f in (b, o):
+            f.predict(v[i], swa[i], QE, 73.0, 0.01)
+            f.observeHeading(phi[i], use_heading)
+    assert np.array_equal(a.poses, b.poses) and np.array_equal(a.pose_covs, b.pose_covs)
+    assert rel_err(a.poses, o.poses) < TOL
