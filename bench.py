@@ -172,13 +172,15 @@ def make_scans(lm, rng, nscans, m):
     return scans
 
 
-def ekf_scan(ekf, Z, batch=False):
+def ekf_scan(ekf, Z, batch=False, want_indices=True):
     """The user-facing call sequence of one scan (test/main.cpp:193-195): gate, then update
     (batch=False: singleUpdate EKF.cpp:457-479; batch=True: one joint batchUpdate EKF.cpp:93-129)."""
     if not batch:
-        # one asynchronous submission, association indices stay on the device (cslam_ekf_scan);
-        # the indices are read back behind the gate kernel while the updates run
-        return ekf.scan(Z, RE, GATE1, GATE2)[0]
+        # one asynchronous submission, association indices stay on the device (cslam_ekf_scan); with
+        # want_indices they are read back behind the gate kernel while the updates run, without them the
+        # call never waits for the GPU (the number of applied updates is read once at the end)
+        r = ekf.scan(Z, RE, GATE1, GATE2, want_indices=want_indices)
+        return r[0] if want_indices else None
     jbest, is_new, _, _ = ekf.gate(Z, RE, GATE1, GATE2)
     sel = jbest > 0
     ekf.update(Z[:, sel], RE, jbest[sel], batch)
@@ -637,13 +639,16 @@ def main():
     ekf.profile_begin(args.steps * m + 8)
     sampler.start()
     updates = 0
+    assoc0 = 0 if batch else ekf.scan_associations()
     with torch.cuda.stream(stream):
         ev0.record(stream)
         for s in range(args.steps):
-            jb = ekf_scan(ekf, scans[(args.warmup + s) % len(scans)][0], batch)
-            updates += (1 if batch else int((jb > 0).sum()))
+            jb = ekf_scan(ekf, scans[(args.warmup + s) % len(scans)][0], batch, want_indices=False)
+            updates += (1 if batch else 0)
         ev1.record(stream)
     barrier()
+    if not batch:  # updates applied = observations the gate associated, counted on the device
+        updates = ekf.scan_associations() - assoc0
     clocks = sampler.stop()
     cov_ms, cov_launches, cov_bytes = ekf.profile_end()
     launches = lib.cslam_kernel_launches() - launches0

@@ -690,7 +690,7 @@ __global__ void __launch_bounds__(128) k_batch_w1(const double* __restrict__ PHT
 int launch_gate(const double* X, const double* P, const double* R3, const double* D, int dcap, size_t ld, int nf,
                 const double* Z, int m, const double R[4], double gate1, double gate2, double* part_nd,
                 double* part_out, int* part_j, unsigned* ticket, int* jbest, double* nbest, double* outer,
-                cudaStream_t stream);
+                unsigned long long* assoc_count, cudaStream_t stream);
 
 // ------------------------------------------------------------------------ accessors ----
 // sharded: every rank fills the entries it stores (zeros elsewhere) and the block is all-reduced
@@ -1047,6 +1047,8 @@ static int create_common(cslam_ekf_t** out, int capacity_landmarks, int device, 
     TRY(cudaMalloc(&h->gate.d_jbest, CSLAM_MAX_OBS * sizeof(int)));
     TRY(cudaMalloc(&h->gate.d_nbest, CSLAM_MAX_OBS * sizeof(double)));
     TRY(cudaMalloc(&h->gate.d_outer, CSLAM_MAX_OBS * sizeof(double)));
+    TRY(cudaMalloc(&h->assoc_count, sizeof(unsigned long long)));
+    TRY(cudaMemsetAsync(h->assoc_count, 0, sizeof(unsigned long long), h->stream));
     h->pinned_bytes = std::max<size_t>(h->ld * sizeof(double), 1 << 16);
     TRY(cudaMallocHost(&h->pinned, h->pinned_bytes));
     TRY(cudaMemsetAsync(h->X[0], 0, h->ld * sizeof(double), h->stream));
@@ -1114,6 +1116,7 @@ int cslam_ekf_destroy(cslam_ekf_t* h) {
     cudaFree(h->small); cudaFree(h->status); cudaFree(h->ticket);
     cudaFree(h->gate.part_nd); cudaFree(h->gate.part_out); cudaFree(h->gate.part_j);
     cudaFree(h->gate.d_jbest); cudaFree(h->gate.d_nbest); cudaFree(h->gate.d_outer);
+    cudaFree(h->assoc_count);
     if (h->pinned) cudaFreeHost(h->pinned);
     for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
     if (h->scan_ev) cudaEventDestroy(h->scan_ev);
@@ -1293,7 +1296,7 @@ int cslam_ekf_gate(cslam_ekf_t* h, const double* Z, int m, const double R[4], do
         if (int rc = launch_gate(h->X[h->cur], h->P, h->R3, h->sh.world > 1 ? h->D : nullptr, h->dcap, h->ld, nf,
                                  Z + 2 * base, mc, R, gate1, gate2, h->gate.part_nd, h->gate.part_out,
                                  h->gate.part_j, h->ticket + 1, h->gate.d_jbest, h->gate.d_nbest, h->gate.d_outer,
-                                 h->stream))
+                                 nullptr, h->stream))
             return rc;
         char* pin = static_cast<char*>(h->pinned);
         int* pj = reinterpret_cast<int*>(pin);
@@ -1374,7 +1377,7 @@ int cslam_ekf_scan(cslam_ekf_t* h, const double* Z, int m, const double R[4], do
     if (int rc = launch_gate(h->X[h->cur], h->P, h->R3, h->sh.world > 1 ? h->D : nullptr, h->dcap, h->ld, nf, Z, m, R,
                              gate1, gate2,
                              h->gate.part_nd, h->gate.part_out, h->gate.part_j, h->ticket + 1, h->gate.d_jbest,
-                             h->gate.d_nbest, h->gate.d_outer, h->stream))
+                             h->gate.d_nbest, h->gate.d_outer, h->assoc_count, h->stream))
         return rc;
     if (jbest || is_new) {  // optional read-back, queued behind the gate only: overlaps the updates
         char* pin = static_cast<char*>(h->pinned);
@@ -1395,6 +1398,16 @@ int cslam_ekf_scan(cslam_ekf_t* h, const double* Z, int m, const double R[4], do
             if (is_new) is_new[i] = (pj[i] == 0 && po[i] > gate2) ? 1 : 0;  // EKF.cpp:287-295
         }
     }
+    return CSLAM_OK;
+}
+
+int cslam_ekf_scan_associations(cslam_ekf_t* h, unsigned long long* total) {
+    if (int rc = check_handle(h)) return rc;
+    CSLAM_REQUIRE(total != nullptr, CSLAM_ERR_BAD_ARG, "total is null");
+    CSLAM_CUDA(cudaMemcpyAsync(h->pinned, h->assoc_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                               h->stream));
+    CSLAM_CUDA(cudaStreamSynchronize(h->stream));
+    *total = *static_cast<unsigned long long*>(h->pinned);
     return CSLAM_OK;
 }
 

@@ -51,6 +51,7 @@ struct cslam_ekf {
     int* status = nullptr;        // device: #skipped updates
     unsigned* ticket = nullptr;   // device: last-block tickets (predict, gate)
     cslam::GateScratch gate;
+    unsigned long long* assoc_count = nullptr;  // device: observations associated by fused scans since create
     void* pinned = nullptr;  // host staging
     size_t pinned_bytes = 0;
     cudaStream_t stream = nullptr;

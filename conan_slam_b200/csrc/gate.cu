@@ -43,7 +43,8 @@ __global__ void __launch_bounds__(kGateThreads) k_gate(const double* __restrict_
                                               size_t ld, int nf, GatePack gp, double* __restrict__ part_nd,
                                               double* __restrict__ part_out, int* __restrict__ part_j,
                                               unsigned* __restrict__ ticket, int* __restrict__ jbest,
-                                              double* __restrict__ nbest, double* __restrict__ outer) {
+                                              double* __restrict__ nbest, double* __restrict__ outer,
+                                              unsigned long long* __restrict__ assoc_count) {
     constexpr int NW = kGateThreads / 32;
     __shared__ double s_nd[NW][CSLAM_MAX_OBS];
     __shared__ double s_out[NW][CSLAM_MAX_OBS];
@@ -181,6 +182,9 @@ __global__ void __launch_bounds__(kGateThreads) k_gate(const double* __restrict_
             jbest[i] = (c.j == 0x7fffffff) ? 0 : c.j;
             nbest[i] = c.nd;
             outer[i] = c.out;
+            // running total of associated observations: lets an asynchronous driver (cslam_ekf_scan with
+            // no index read-back) learn how many updates its scans applied with ONE read at the end
+            if (assoc_count != nullptr && c.j != 0x7fffffff) atomicAdd(assoc_count, 1ULL);
         }
     }
     if (threadIdx.x == 0) *ticket = 0;
@@ -190,7 +194,7 @@ __global__ void __launch_bounds__(kGateThreads) k_gate(const double* __restrict_
 int launch_gate(const double* X, const double* P, const double* R3, const double* D, int dcap, size_t ld, int nf,
                 const double* Z, int m, const double R[4], double gate1, double gate2, double* part_nd,
                 double* part_out, int* part_j, unsigned* ticket, int* jbest, double* nbest, double* outer,
-                cudaStream_t stream) {
+                unsigned long long* assoc_count, cudaStream_t stream) {
     GatePack gp;
     memset(&gp, 0, sizeof(gp));
     memcpy(gp.z, Z, sizeof(double) * 2 * m);
@@ -201,7 +205,7 @@ int launch_gate(const double* X, const double* P, const double* R3, const double
     const int blocks = nf > 0 ? (nf + kGateThreads - 1) / kGateThreads : 1;
     count_launch();
     k_gate<<<blocks, kGateThreads, 0, stream>>>(X, P, R3, D, dcap, ld, nf, gp, part_nd, part_out, part_j, ticket, jbest, nbest,
-                                       outer);
+                                                outer, assoc_count);
     CSLAM_CUDA(cudaGetLastError());
     return CSLAM_OK;
 }

@@ -262,6 +262,12 @@ class EKF:
               "cslam_ekf_scan")
         return None
 
+    def scan_associations(self):
+        """Observations associated (= updates applied) by all fused scans so far; synchronises."""
+        total = C.c_ulonglong(0)
+        check(self._lib.cslam_ekf_scan_associations(self._h, C.byref(total)), "cslam_ekf_scan_associations")
+        return int(total.value)
+
     def dataAssociate(self, Z, R, gate1, gate2):
         """slam.h:482-487 / EKF.cpp:235-326.  ZN follows Q5: empty unless FLAG Q5_RETURN_ZN."""
         Zm, _ = _z(Z)

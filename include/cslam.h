@@ -126,6 +126,10 @@ int cslam_ekf_update(cslam_ekf_t* h, const double* Z, const int32_t* idf, int m,
  * computes the same indices from its replicated gate inputs; SPMD call contract). */
 int cslam_ekf_scan(cslam_ekf_t* h, const double* Z, int m, const double R[4], double gate1, double gate2,
                    int32_t* jbest, uint8_t* is_new);
+/* Running total of observations that cslam_ekf_scan associated (and therefore applied as updates) since
+ * the handle was created — the one read an asynchronous driver needs after a series of scans issued with
+ * jbest == NULL.  Synchronises the stream. */
+int cslam_ekf_scan_associations(cslam_ekf_t* h, unsigned long long* total);
 /* Slam::augment(X,P,Z,R)                                slam.h:190-191 -> EKF.cpp:9-26 -> :28-91 */
 int cslam_ekf_augment(cslam_ekf_t* h, const double* Z, int m, const double R[4]);
 

@@ -189,6 +189,7 @@ def test_fused_scan_equals_gate_then_update(N, m, flags):
     Zx = np.stack([rng.uniform(3000.0, 9000.0, size=extra), rng.uniform(-np.pi, np.pi, size=extra)])
     Z = np.concatenate([Z, Zx], axis=1)
     Z = Z[:, rng.permutation(m)]  # associated and spurious observations interleaved
+    total = 0
     for rep in range(2):  # second scan: asynchronous form, indices fetched by a separate gate
         jo, newo, _, _, idf_o, _ = o.gate(Z, RE, 50.0, 1000.0, dense=(N <= 40))
         o.update(Z[:, jo != 0], RE, idf_o, False)
@@ -198,6 +199,8 @@ def test_fused_scan_equals_gate_then_update(N, m, flags):
         else:
             assert g.scan(Z, RE, 50.0, 1000.0, want_indices=False) is None
         _assert_state(g, o)
+        total += int((jo != 0).sum())
+        assert g.scan_associations() == total  # device-side count of applied updates
     assert g.sync() == 0
 
 
