@@ -299,3 +299,53 @@ def test_sim_tape_matches_survey_counts():
     # deterministic
     tape2 = oracle_py.sim_tape(noise_seed=0)
     assert np.array_equal(tape["controls"], tape2["controls"]) and np.array_equal(tape["Z"], tape2["Z"])
+
+
+@pytest.mark.parametrize("flags", [0, oracle_py.FLAG_INTENDED])
+def test_sequential_updates_commute_with_one_deferred_covariance_pass(flags):
+    """The identity the fused scan rests on (k_cov_update_multi, k_gain_single kprev): observation q of a
+    scan may read P *before* the covariance passes of observations 0..q-1 if every entry it reads is
+    corrected by their rank-2 terms, and one pass then subtracts all terms in update order.  Pinned here
+    on the CPU: the oracle's sequential singleUpdate (EKF.cpp:457-479) against a numpy restatement that
+    defers the covariance pass to the end of the scan — X identical, P within rounding of a zero-initialised
+    versus first-term-initialised dot product (the only difference in operation order)."""
+    N, m = 40, 5
+    X, P, lm = helpers.synthetic_map(N, 77)
+    rng = np.random.default_rng(77)
+    ids = (rng.choice(N, size=m, replace=False) + 1).astype(np.int32)
+    Z = helpers.observe(X, lm, ids, rng)
+    o = oracle_py.OracleEKF(flags)
+    o.reset(X, P)
+    o.update(Z, helpers.RE, ids, False)
+
+    n = X.shape[0]
+    Xd, P0 = X.copy(), P.copy()
+    panels = []                                   # W1 of every observation so far (n x 2 each)
+
+    def view(rows, cols):                         # entries of "P after the pending updates", built from P0
+        V = P0[np.ix_(rows, cols)].copy()
+        for W1 in panels:
+            V = V - (W1[rows, 0:1] * W1[cols, 0][None, :] + W1[rows, 1:2] * W1[cols, 1][None, :])
+        return V
+
+    for q in range(m):
+        f = 3 + 2 * (ids[q] - 1)
+        cols = np.array([0, 1, 2, f, f + 1])
+        zhat, H = np_ref.observe_model(Xd, int(ids[q]))
+        Hs = H[:, cols]                           # the 5 non-zero columns of the sparse H
+        v = np.array([Z[0, q] - zhat[0], np_ref.pi2pi(Z[1, q] - zhat[1])])
+        Pc = view(cols, cols)
+        S = Hs @ Pc @ Hs.T + helpers.RE
+        S = (S + S.T) * 0.5
+        L = np.linalg.cholesky(S)
+        Li = np.linalg.inv(L)
+        G = Li.T if (flags & np_ref.Q1) else Li   # Q1: literal metric L^T L, intended S (slam.h:250-260)
+        W1 = (view(np.arange(n), cols) @ Hs.T) @ G
+        W = W1 @ G.T
+        Xd = Xd + W @ v
+        panels.append(W1)
+    Pd = P0.copy()
+    for W1 in panels:                             # ONE deferred pass, terms in update order
+        Pd = Pd - (W1[:, 0:1] * W1[:, 0][None, :] + W1[:, 1:2] * W1[:, 1][None, :])
+    assert helpers.rel_err(Xd, o.X) < 1e-11
+    assert helpers.rel_err(Pd, o.P) < 1e-11
