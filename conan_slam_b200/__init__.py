@@ -8,6 +8,7 @@ the in-tree built library (python -m conan_slam_b200.build).
 from ._lib import CslamError, FLAG_INTENDED, FLAG_REF_LITERAL, FLAGS, lib_path, load_library  # noqa: F401
 from .ekf import EKF, Association  # noqa: F401
 from .pf import PF  # noqa: F401
+from .world import SimWorld  # noqa: F401
 
 __all__ = ["EKF", "PF", "Association", "CslamError", "FLAGS", "FLAG_REF_LITERAL", "FLAG_INTENDED",
            "load_library", "lib_path"]

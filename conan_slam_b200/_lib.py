@@ -67,6 +67,9 @@ SIGNATURES = {
     "cslam_ekf_save": (C.c_int, [_vp, C.c_char_p]),
     "cslam_ekf_load": (C.c_int, [_vp, C.c_char_p]),
     "cslam_ekf_device_ptrs": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_size_t)]),
+    "cslam_world_create": (C.c_int, [C.POINTER(_vp), _dp, C.c_int, C.c_int]),
+    "cslam_world_destroy": (C.c_int, [_vp]),
+    "cslam_world_observe": (C.c_int, [_vp, _dp, C.c_double, C.c_int, _dp, _ip, C.POINTER(C.c_int)]),
     "cslam_pf_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.c_uint]),
     "cslam_pf_create_sharded": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.c_uint, C.c_int, C.c_int, _vp]),
     "cslam_pf_ipc_export": (C.c_int, [_vp, _vp]),

@@ -24,6 +24,7 @@ SOURCES = [
     ("ekf_dmma.cu", []),
     ("gate.cu", ["-fmad=false"]),
     ("pf.cu", ["-fmad=false"]),
+    ("sim.cu", ["-fmad=false"]),
 ]
 
 

@@ -57,6 +57,7 @@ extern "C" {
 
 typedef struct cslam_ekf cslam_ekf_t;
 typedef struct cslam_pf cslam_pf_t;
+typedef struct cslam_world cslam_world_t;
 
 const char* cslam_last_error(void);
 int cslam_version(void);
@@ -158,6 +159,20 @@ int cslam_ekf_profile_begin(cslam_ekf_t* h, int max_launches);
 int cslam_ekf_profile_end(cslam_ekf_t* h, double* ms, int* launches, double* bytes);
 /* Device pointers for zero-copy consumers (bench, visualisers): X (n doubles), P (row-major, ld). */
 int cslam_ekf_device_ptrs(cslam_ekf_t* h, void** dX, void** dP, size_t* ld);
+
+/* ----------------------------------------------- observation front-end (simulated world) ---- */
+
+/* Slam::getObservations(XTrue, LM, tags, maxRange) (slam.h:575-582 -> getVisibleLandmarks :608-683 ->
+ * computeRangeBearing :339-368) with the world's landmarks resident on the device — the O(N) step right
+ * before the filter hot path in test/main.cpp:177 ("next" row 2 of SURVEY.md §8f).  landmarks_2xN is
+ * the reference's LM (2 x N column-major: x_i, y_i interleaved).  observe() returns the visible
+ * landmarks in landmark order (as the reference's loop does): Z[2k], Z[2k+1] = range, unwrapped bearing;
+ * tags[k] = 1-based landmark number; *m_out = how many are visible (only the first max_out are written).
+ * Sensor noise (slam.h:168-178) stays with the caller: its draws are inputs. */
+int cslam_world_create(cslam_world_t** out, const double* landmarks_2xN, int num_landmarks, int device);
+int cslam_world_destroy(cslam_world_t* w);
+int cslam_world_observe(cslam_world_t* w, const double x_true[3], double max_range, int max_out, double* Z,
+                        int32_t* tags, int* m_out);
 
 /* -------------------------------------------------------- particle filter (FastSLAM) ---- */
 

@@ -169,6 +169,30 @@ void ORC(ekf_table)(void* h, const int* idz, int m, int* table, int table_len, i
 // (the reference's clock-seeded draws are not reproducible, so they are inputs).
 // controls[s] = (vn, swan, phi_true); observation steps have obs_ptr[s+1] > obs_ptr[s] or
 // obs_flag[s] = 1 with zero visible landmarks.
+// slam.h:575-582 getObservations for a world of N landmarks (LM 2 x N column-major); tags = 1..N.
+// Returns the number of visible landmarks; the first max_out are written (Z interleaved range, bearing).
+int ORC(get_observations)(const T* X3, const T* LM, int N, double rmax, int max_out, T* Z, int* tags_out) {
+    Vec<T> X(3);
+    for (int i = 0; i < 3; i++) X[i] = X3[i];
+    Mat<T> L(2, N);
+    std::vector<int> tags(N);
+    for (int i = 0; i < N; i++) {
+        L(0, i) = LM[2 * (size_t)i];
+        L(1, i) = LM[2 * (size_t)i + 1];
+        tags[i] = i + 1;
+    }
+    Mat<T> Zm;
+    std::vector<int> vis;
+    get_observations<T>(X, L, tags, (T)rmax, Zm, vis);
+    const int m = (int)vis.size();
+    for (int k = 0; k < m && k < max_out; k++) {
+        Z[2 * k] = Zm(0, k);
+        Z[2 * k + 1] = Zm(1, k);
+        tags_out[k] = vis[k];
+    }
+    return m;
+}
+
 int ORC(sim_tape)(int max_steps, unsigned long long noise_seed, T* controls, int* obs_flag, int* obs_ptr,
                  T* Zout, int* tags_out, int max_obs, T* consts /* [8] out */) {
     const T V = 83.33F, maxSWA = (float)(kPi / 4.0F), rateSWA = (float)(70.0F * kPi / 180.0F), wb = 73.0F;

@@ -303,6 +303,23 @@ def stratified_resample(w, u, flags=0):
     return keep, neff.value, cum
 
 
+def get_observations(XTrue, LM, rmax, max_out=None):
+    """slam.h:575-582 getObservations on a 2 x N world: (Z (2 x m), tags (m,), m_total)."""
+    L = lib()
+    lm = np.asarray(LM, dtype=np.float64).reshape(2, -1)
+    N = lm.shape[1]
+    cap = N if max_out is None else int(max_out)
+    flat = np.ascontiguousarray(lm.T).reshape(-1)
+    x = np.ascontiguousarray(XTrue, dtype=np.float64).reshape(-1)[:3].copy()
+    Z = np.zeros(2 * max(cap, 1))
+    tags = np.zeros(max(cap, 1), dtype=np.int32)
+    L.orc_get_observations.restype = C.c_int
+    L.orc_get_observations.argtypes = [_dp, _dp, C.c_int, C.c_double, C.c_int, _dp, _ip]
+    m = L.orc_get_observations(_d(x), _d(flat), N, float(rmax), cap, _d(Z), _i(tags))
+    k = min(m, cap)
+    return Z[:2 * k].reshape(k, 2).T.copy(), tags[:k].copy(), m
+
+
 def sim_tape(max_steps=40000, noise_seed=0, max_obs=400000):
     """Filter-independent half of test/main.cpp's loop.  Returns dict with controls [S,3]
     (vn, swan, phi_true), obs_flag [S], obs_ptr [S+1], Z [K,2], tags [K], and constants."""
