@@ -81,6 +81,8 @@ SIGNATURES = {
     "cslam_pf_num_features": (C.c_int, [_vp]),
     "cslam_pf_predict": (C.c_int, [_vp, C.c_double, C.c_double, _dp, C.c_double, C.c_double]),
     "cslam_pf_observe_heading": (C.c_int, [_vp, C.c_double, C.c_int]),
+    "cslam_pf_save": (C.c_int, [_vp, C.c_char_p]),
+    "cslam_pf_load": (C.c_int, [_vp, C.c_char_p]),
     "cslam_pf_control_steps": (C.c_int, [_vp, C.c_int, _dp, _dp, _dp, C.c_int, _dp, C.c_double, C.c_double]),
     "cslam_pf_sample_proposal": (C.c_int, [_vp, _dp, _ip, C.c_int, _dp, _vp, C.c_int]),
     "cslam_pf_feature_update": (C.c_int, [_vp, _dp, _ip, C.c_int, _dp]),

@@ -1285,6 +1285,90 @@ int cslam_pf_profile_end(cslam_pf_t* h, double* ms, int* resamples, double* byte
     return CSLAM_OK;
 }
 
+// Checkpoint of the particle set (the reference keeps std::vector<Particle_t> in the driver and has no
+// persistence): header {magic, version, flags, np, nf} + every SoA row of the current
+// buffer (w, xv[3], pv[9], xf[2*nf], pf[3*nf]), np doubles each.  Single-GPU handles.
+namespace {
+struct PfCkptHeader {
+    char magic[8];
+    uint32_t version;
+    uint32_t flags;
+    int32_t np;
+    int32_t nf;
+};
+const char kPfCkptMagic[8] = {'C', 'S', 'L', 'A', 'M', 'P', 'F', '1'};
+struct PfRows {
+    double* base;
+    int rows;
+};
+}  // namespace
+
+static int pf_ckpt_io(cslam_pf* h, FILE* f, bool save) {
+    PfBuf& b = h->buf[h->cur];
+    const PfRows groups[5] = {{b.w, 1}, {b.xv, 3}, {b.pv, 9}, {b.xf, 2 * h->nf}, {b.pf, 3 * h->nf}};
+    const size_t row_bytes = (size_t)h->np * sizeof(double);
+    const int slab = (int)std::max<size_t>(1, (size_t)(64u << 20) / row_bytes);  // rows per ~64 MB transfer
+    std::vector<double> host((size_t)slab * h->np);
+    for (const PfRows& g : groups) {
+        for (int r0 = 0; r0 < g.rows; r0 += slab) {
+            const int nr = std::min(slab, g.rows - r0);
+            if (save) {
+                CSLAM_CUDA(cudaMemcpy2D(host.data(), row_bytes, g.base + (size_t)r0 * h->pp, h->pp * sizeof(double),
+                                        row_bytes, nr, cudaMemcpyDeviceToHost));
+                CSLAM_REQUIRE(fwrite(host.data(), row_bytes, nr, f) == (size_t)nr, CSLAM_ERR_BAD_ARG,
+                              "short write to the checkpoint file");
+            } else {
+                CSLAM_REQUIRE(fread(host.data(), row_bytes, nr, f) == (size_t)nr, CSLAM_ERR_BAD_ARG,
+                              "truncated checkpoint file");
+                CSLAM_CUDA(cudaMemcpy2D(g.base + (size_t)r0 * h->pp, h->pp * sizeof(double), host.data(), row_bytes,
+                                        row_bytes, nr, cudaMemcpyHostToDevice));
+            }
+        }
+    }
+    return CSLAM_OK;
+}
+
+int cslam_pf_save(cslam_pf_t* h, const char* path) {
+    if (int rc = check_pf(h)) return rc;
+    CSLAM_REQUIRE(path != nullptr, CSLAM_ERR_BAD_ARG, "path is null");
+    CSLAM_REQUIRE(h->world == 1, CSLAM_ERR_UNSUPPORTED, "checkpoints are single-GPU (sharded: save per rank)");
+    CSLAM_CUDA(cudaStreamSynchronize(h->stream));
+    FILE* f = fopen(path, "wb");
+    CSLAM_REQUIRE(f != nullptr, CSLAM_ERR_BAD_ARG, "cannot open checkpoint file for writing");
+    PfCkptHeader hd;
+    memcpy(hd.magic, kPfCkptMagic, 8);
+    hd.version = 1;
+    hd.flags = h->flags;
+    hd.np = h->np;
+    hd.nf = h->nf;
+    int rc = fwrite(&hd, sizeof(hd), 1, f) == 1 ? CSLAM_OK : CSLAM_ERR_BAD_ARG;
+    if (rc == CSLAM_OK) rc = pf_ckpt_io(h, f, true);
+    if (fclose(f) != 0 && rc == CSLAM_OK) rc = CSLAM_ERR_BAD_ARG;
+    return rc;
+}
+
+int cslam_pf_load(cslam_pf_t* h, const char* path) {
+    if (int rc = check_pf(h)) return rc;
+    CSLAM_REQUIRE(path != nullptr, CSLAM_ERR_BAD_ARG, "path is null");
+    CSLAM_REQUIRE(h->world == 1, CSLAM_ERR_UNSUPPORTED, "checkpoints are single-GPU (sharded: load per rank)");
+    FILE* f = fopen(path, "rb");
+    CSLAM_REQUIRE(f != nullptr, CSLAM_ERR_BAD_ARG, "cannot open checkpoint file");
+    PfCkptHeader hd;
+    const bool ok = fread(&hd, sizeof(hd), 1, f) == 1 && memcmp(hd.magic, kPfCkptMagic, 8) == 0 && hd.version == 1 &&
+                    hd.np == h->np && hd.nf >= 0 && hd.nf <= h->nf_cap;
+    if (!ok) {
+        fclose(f);
+        set_last_error("cslam_pf_load: not a particle checkpoint of this library, or particle count / landmark "
+                       "capacity of the handle do not match");
+        return CSLAM_ERR_BAD_ARG;
+    }
+    CSLAM_CUDA(cudaStreamSynchronize(h->stream));
+    h->nf = hd.nf;
+    const int rc = pf_ckpt_io(h, f, false);
+    fclose(f);
+    return rc;
+}
+
 int cslam_pf_get_weights(cslam_pf_t* h, double* w) {
     if (int rc = check_pf(h)) return rc;
     CSLAM_REQUIRE(w != nullptr, CSLAM_ERR_BAD_ARG, "null");

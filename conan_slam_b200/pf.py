@@ -115,6 +115,13 @@ class PF:
         check(self._lib.cslam_pf_observe_heading(self._h, float(phi), int(bool(useHeading))),
               "cslam_pf_observe_heading")
 
+    def save(self, path):
+        """Checkpoint the whole particle set (the reference has no persistence)."""
+        check(self._lib.cslam_pf_save(self._h, str(path).encode()), "cslam_pf_save")
+
+    def load(self, path):
+        check(self._lib.cslam_pf_load(self._h, str(path).encode()), "cslam_pf_load")
+
     def controlSteps(self, v, swa, phi, useHeading, Q, wb, dt):
         """k control steps (predict + observeHeading each) of every particle in one launch."""
         v = np.ascontiguousarray(v, dtype=np.float64).reshape(-1)

@@ -238,6 +238,11 @@ int cslam_pf_get_pose_covs(cslam_pf_t* h, double* Pv);
 int cslam_pf_get_features(cslam_pf_t* h, int particle, double* XF, double* PF);
 int cslam_pf_set_weights(cslam_pf_t* h, const double* w);
 int cslam_pf_set_poses(cslam_pf_t* h, const double* X, const double* Pv);
+/* Checkpoint / restore of the whole particle set: header + every struct-of-arrays row of
+ * the current buffer.  load() needs a handle with the same particle count and enough landmark capacity.
+ * Single-GPU handles. */
+int cslam_pf_save(cslam_pf_t* h, const char* path);
+int cslam_pf_load(cslam_pf_t* h, const char* path);
 /* Slam::extractStatesFromParticles (slam.h:493-511): pose of the MINIMUM-weight particle (Q13). */
 int cslam_pf_extract_state(cslam_pf_t* h, double X[3], int* index);
 

@@ -196,3 +196,27 @@ def test_control_steps_equal_stepwise_calls(use_heading):
             f.observeHeading(phi[i], use_heading)
     assert np.array_equal(a.poses, b.poses) and np.array_equal(a.pose_covs, b.pose_covs)
     assert rel_err(a.poses, o.poses) < TOL
+
+
+def test_checkpoint_roundtrip(tmp_path):
+    """cslam_pf_save / _load: a restored particle set continues bit-identically."""
+    import conan_slam_b200 as cs
+    g, o, rng = _scenario(600, 5, oracle_py.FLAG_INTENDED, seed=21)
+    path = tmp_path / "pf.ckpt"
+    g.save(path)
+    g2 = cs.PF(num_particles=600, capacity_landmarks=9, flags=oracle_py.FLAG_INTENDED)
+    g2.load(path)
+    assert g2.num_features == g.num_features
+    assert np.array_equal(g2.weights, g.weights) and np.array_equal(g2.poses, g.poses)
+    assert np.array_equal(g2.pose_covs, g.pose_covs)
+    for p in (0, 17, 599):
+        a, b = g.features(p), g2.features(p)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    u = rng.normal(size=600) * 0.3
+    ka, na, da = g.resampleParticles(600, u, True)
+    kb, nb, db = g2.resampleParticles(600, u, True)
+    assert np.array_equal(ka, kb) and na == nb and da == db
+    assert np.array_equal(g2.poses, g.poses)
+    other = cs.PF(num_particles=512, capacity_landmarks=9)
+    with pytest.raises(Exception):
+        other.load(path)  # particle count mismatch
