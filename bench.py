@@ -549,7 +549,7 @@ def run_reference(args):
     out = {
         "impl": "reference", "metric": "EKF updates/sec", "value": val, "unit": "updates/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 4 * t_full * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32" if use_ref else "f64", "data": "synthetic",
         "config": {"workload": f"EKF-SLAM {N} landmarks (state dim {n}), range-bearing observations, sequential "
                                f"update: gate + gain + covariance, 4 observations per scan - the reference's dense "
                                f"CPU algorithm", "landmarks": N, "state_dim": n, "obs_per_step": 4},
