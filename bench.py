@@ -4,14 +4,20 @@
 Metric (BASELINE.json): EKF updates/sec at N landmarks (+ % of the HBM roofline).
 One EKF update = one full observation cycle for ONE range-bearing observation: Mahalanobis
 gating over all N landmarks + innovation / Kalman gain + in-place covariance update
-(SURVEY.md §8d).  One benchmark "step" = one scan of m = 4 observations: one gating pass shared
-by the scan, then 4 sequential (re-linearised) updates — EKF.cpp:235-326 + :457-479.
+(SURVEY.md §8d).  One benchmark "step" = one scan of m = 4 observations (cslam_ekf_scan): one gating
+pass shared by the scan, 4 sequential (re-linearised) gains, and their 4 covariance updates applied in
+one pass over the upper triangle — EKF.cpp:235-326 + :457-479, results bit-identical to 4 separate passes.
 
 Default workload (N = 1 GPU): the north-star headline, a 20,000-landmark map (n = 40,003,
 FP64 P = 12.8 GB, upper triangle streamed in place) — "C3-seq" of BASELINE.md.
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload ...] [--impl reference]
-N > 1 (torchrun, one rank per GPU): see --workload; default is the row-block-sharded covariance
-when available, else independent Monte-Carlo filter replicas (no data-path collective).
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+        [--batch]            C3 as worded in BASELINE.json: joint update of m = 32 observations (FP64 tensor cores)
+        [--landmarks 2000]   C2          [--landmarks 60000 under torchrun]  C5
+        [--workload pf]      C4: FastSLAM, 1M particles x 500 landmarks
+N > 1 (torchrun, one rank per GPU): the row-sharded covariance of ONE filter (strong scaling), or
+--multi replicas: independent Monte-Carlo filter replicas (no data-path collective, weak scaling).
+Extra fields of the JSON line: roofline (live CUDA-event timing of the dominant kernel), cpu_baseline
+(the reference's own sources on the host), drive_cycle (6 control steps + one scan, stepwise vs merged).
 """
 import argparse
 import ctypes as C
