@@ -48,6 +48,37 @@ def test_no_cpu_fallback_without_gpu(gpu_available):
     assert e.value.code == 3
     with pytest.raises(cs.CslamError):
         cs.PF(num_particles=8, capacity_landmarks=2)
+    with pytest.raises(cs.CslamError):
+        cs.SimWorld([[1.0, 2.0], [3.0, 4.0]])
+
+
+def test_null_handles_are_rejected_not_dereferenced():
+    """Every handle-taking compute entry returns CSLAM_ERR_BAD_ARG for a NULL handle (error convention of
+    include/cslam.h: status codes, never a crash, never a silent fallback)."""
+    from conan_slam_b200 import _lib
+    lib = _lib.load_library()
+    z = (C.c_double * 4)(1.0, 0.1, 2.0, 0.2)
+    r = (C.c_double * 4)(0.01, 0.0, 0.0, 0.0003)
+    ids = (C.c_int32 * 2)(1, 2)
+    tot = C.c_ulonglong(0)
+    m = C.c_int(0)
+    calls = [
+        lambda: lib.cslam_ekf_predict(None, 1.0, 0.0, r, 73.0, 0.01),
+        lambda: lib.cslam_ekf_observe_heading(None, 0.0, 1),
+        lambda: lib.cslam_ekf_control_steps(None, 1, z, z, z, 1, r, 73.0, 0.01, None),
+        lambda: lib.cslam_ekf_scan(None, z, 2, r, 50.0, 1000.0, None, None),
+        lambda: lib.cslam_ekf_update(None, z, ids, 2, r, 0),
+        lambda: lib.cslam_ekf_augment(None, z, 2, r),
+        lambda: lib.cslam_ekf_scan_associations(None, C.byref(tot)),
+        lambda: lib.cslam_ekf_save(None, b"/tmp/x"),
+        lambda: lib.cslam_pf_predict(None, 1.0, 0.0, r, 73.0, 0.01),
+        lambda: lib.cslam_pf_control_steps(None, 1, z, z, z, 1, r, 73.0, 0.01),
+        lambda: lib.cslam_pf_save(None, b"/tmp/x"),
+        lambda: lib.cslam_world_observe(None, z, 2000.0, 2, z, ids, C.byref(m)),
+    ]
+    for k, call in enumerate(calls):
+        assert call() == 1, f"call {k} did not report CSLAM_ERR_BAD_ARG"
+    assert b"null" in lib.cslam_last_error().lower() or b"bad argument" in lib.cslam_last_error().lower()
 
 
 def test_product_never_imports_oracle():
