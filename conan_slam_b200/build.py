@@ -44,7 +44,7 @@ def _stale(target, deps):
 
 def build(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
-    headers = [os.path.join(CSRC, h) for h in ("common.cuh", "cov_update.cuh", "ekf_handle.cuh", "nccl_dl.cuh")]
+    headers = [os.path.join(CSRC, h) for h in ("common.cuh", "shard_map.h", "cov_update.cuh", "ekf_handle.cuh", "nccl_dl.cuh")]
     headers += [os.path.join(HERE, "..", "include", "cslam.h"), __file__]
     objs = []
     nvcc = _nvcc()

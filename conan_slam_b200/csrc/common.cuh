@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include "../../include/cslam.h"
+#include "shard_map.h"
 
 namespace cslam {
 
@@ -40,19 +41,6 @@ __host__ __device__ __forceinline__ double pi2pi(double a) {
     if (a > kPi) a = a - 2.0 * kPi;
     if (a < -kPi) a = a + 2.0 * kPi;
     return a;
-}
-
-// Row sharding of the covariance over GPUs: block-cyclic 128-row tiles (tile tr belongs to rank
-// tr % world; local tile index tr / world).  world == 1 is the identity, so every kernel is
-// written shard-aware and the single-GPU path pays nothing.
-constexpr int kShardRows = 128;
-struct Shard {
-    int rank;
-    int world;
-};
-__host__ __device__ __forceinline__ bool shard_owns(Shard s, int i) { return ((i >> 7) % s.world) == s.rank; }
-__host__ __device__ __forceinline__ size_t shard_lrow(Shard s, int i) {
-    return (size_t)((i >> 7) / s.world) * kShardRows + (size_t)(i & 127);
 }
 
 // Symmetric read of the upper-triangle-authoritative covariance: P(i,j) == P(j,i).

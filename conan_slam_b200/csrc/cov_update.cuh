@@ -27,29 +27,6 @@ __device__ __forceinline__ void cov_st(double* p, double2 v) {
     }
 }
 
-// Linear tile index -> (tr, tc) over the tiles of the upper triangle that THIS RANK owns, row-major:
-// owned tile rows are tr = l*world + rank (l = 0,1,...), row tr holds the nt - tr tiles tc >= tr, so
-//   first(l) = l*(nt - rank) - world*l*(l-1)/2          (world = 1: the plain triangular index)
-__host__ __device__ __forceinline__ long long shard_first_tile(long long l, int nt, Shard sh) {
-    return l * (long long)(nt - sh.rank) - (long long)sh.world * l * (l - 1) / 2;
-}
-__device__ __forceinline__ void shard_tile(long long t, int nt, Shard sh, int& tr, int& tc) {
-    const double w = (double)sh.world;
-    const double b = (double)(nt - sh.rank) + 0.5 * w;
-    long long l = (long long)floor((b - sqrt(b * b - 2.0 * w * (double)t)) / w);
-    if (l < 0) l = 0;
-    while (shard_first_tile(l, nt, sh) > t) l--;
-    while (shard_first_tile(l + 1, nt, sh) <= t) l++;
-    tr = (int)l * sh.world + sh.rank;
-    tc = tr + (int)(t - shard_first_tile(l, nt, sh));
-}
-// number of owned tiles (host side)
-inline long long shard_tile_count(int nt, Shard sh) {
-    long long cnt = 0;
-    for (int tr = sh.rank; tr < nt; tr += sh.world) cnt += nt - tr;
-    return cnt;
-}
-
 // slam.h:260  P <- P - W1 W1^T over the UPPER TRIANGLE only, in place, FP64.
 // One CTA per T x T tile of the triangle (tiles with tc >= tr); thread = one 16-byte column
 // pair x T/RG rows, all loads of a batch issued before the first use so that every SM keeps
