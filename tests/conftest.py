@@ -11,6 +11,16 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # A fresh checkout has no built library (build artefacts are not tracked): build it once, in-tree,
+    # exactly as __graft_entry__.build() does.  Building is not a fallback — if nvcc is unavailable the
+    # tests that need the library fail loudly, as the product does.
+    try:
+        from conan_slam_b200 import _lib, build
+        if not os.path.exists(_lib.lib_path()):
+            build.build()
+            build.build_host()
+    except Exception as e:  # pragma: no cover
+        print(f"[conftest] could not build libcslam.so: {e}", file=sys.stderr)
 
 
 def _has_gpu():
