@@ -22,6 +22,7 @@ SOURCES = [
     ("util.cu", []),
     ("ekf.cu", ["-fmad=false"]),
     ("ekf_dmma.cu", []),
+    ("cov_tma.cu", []),
     ("gate.cu", ["-fmad=false"]),
     ("pf.cu", ["-fmad=false"]),
     ("sim.cu", ["-fmad=false"]),
@@ -44,7 +45,7 @@ def _stale(target, deps):
 
 def build(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
-    headers = [os.path.join(CSRC, h) for h in ("common.cuh", "shard_map.h", "cov_update.cuh", "ekf_handle.cuh", "nccl_dl.cuh")]
+    headers = [os.path.join(CSRC, h) for h in ("common.cuh", "shard_map.h", "cov_update.cuh", "ekf_handle.cuh", "nccl_dl.cuh", "ptx_async.cuh")]
     headers += [os.path.join(HERE, "..", "include", "cslam.h"), __file__]
     objs = []
     nvcc = _nvcc()

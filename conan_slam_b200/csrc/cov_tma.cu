@@ -1,0 +1,342 @@
+// cov_tma.cu — the streaming covariance pass of a GROUP of sequential updates,
+//     P <- P - sum_q a_q a_q^T      (slam.h:260 for the g observations of one scan, EKF.cpp:457-479;
+//                                    panel rows 2q, 2q+1 of A are W1 of observation q)
+// as a persistent TMA + FP64-tensor-core kernel for sm_100a.
+//
+// Why: the FMA form of this pass (k_cov_update_multi, cov_update.cuh) is issue-bound, not memory-bound
+// (ncu, round 1: 99 warp instructions per 512 bytes of P at g = 4 — address arithmetic, predicates,
+// 128-bit LDG/STG and 8g non-fused FP64 operations; issue slots 48 % busy, 0.87 of HBM at g = 4, 0.72 at
+// g = 8).  Here the covariance never passes through the load/store pipeline of the SM cores at all:
+//   * P tiles travel HBM -> shared memory -> HBM by tensor-map TMA (cp.async.bulk.tensor.2d, SASS
+//     UTMALDG / UTMASTG): one elected thread issues 4 KB boxes, a 5-stage ring of 32 KB sub-tiles
+//     (32 rows x 128 columns) keeps >= 64 KB of loads in flight per SM independent of the compute;
+//   * the rank-2g term is ONE contraction on the FP64 tensor cores (mma.sync m8n8k4 -> DMMA.8x8x4):
+//     2g/4 DMMAs per 8x8 block instead of 8g FP64 instructions per 16-byte pair x 32 lanes;
+//   * the accumulator fragments are read from / written to the swizzled tile with conflict-free
+//     128-bit LDS/STS; the row / column panels of the tile arrive by 1-D TMA bulk copies.
+// Per 32 KB sub-tile a warp issues ~75 instructions (g = 8) where the FMA kernel issued ~1400.
+//
+// Arithmetic: DMMA accumulates the 2g products with fused multiply-adds in k order on top of P(i,j);
+// the FMA kernel subtracts g separately rounded terms.  Both are correctly rounded evaluations of the
+// same expression; they differ in the last bits (~1e-16 relative), far inside the 1e-9 parity budget
+// (DESIGN.md §2).  Association decisions are taken by the gate kernel, never here.
+//
+// Layout facts the kernel relies on:
+//   * TMA box = 16 columns x 32 rows of doubles (128 B inner dimension, SWIZZLE_128B): the 16-byte chunk c
+//     of row r lands at chunk (c ^ (r & 7)) of that row's 128 bytes; stage and box bases are 1024-aligned.
+//   * DMMA fragment: lane l holds C[g][2t], C[g][2t+1] with g = l / 4, t = l % 4.  The 8 DMMA rows of a block
+//     are mapped to tile rows rho(g) = 4 (g & 1) + (g >> 1) so that the 8 lanes of a quarter-warp (two g) touch
+//     rows that differ in bit 2 -> after the swizzle their 16-byte chunks cover all 32 banks exactly once.
+//     The row panel is read with the same permutation (any row permutation is legal: the update is
+//     elementwise in (i, j) once A and C agree on it).
+//   * Row-panel row k starts at 132 k - 2 (k & 1) doubles: with the rho permutation the 16 lanes of a
+//     half-warp then hit 16 distinct 8-byte banks; column-panel rows have stride 132 (natural g order).
+//   * Everything inside a 128 x 128 tile of the upper triangle is updated, also the (unauthoritative)
+//     lower half of diagonal tiles and rows / columns between n and the capacity: nothing reads them
+//     before augmentation overwrites them (k_augment writes every upper entry of a new column).
+#include <stdlib.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "ptx_async.cuh"
+
+namespace cslam {
+
+using namespace ptx;
+
+constexpr int TM_T = 128;                          // tile edge (= shard block rows)
+constexpr int TM_SUB = 32;                         // rows per pipeline stage
+constexpr int TM_BOXC = 16;                        // columns per TMA box (128 B, the swizzle span)
+constexpr int TM_BOX_BYTES = TM_BOXC * TM_SUB * 8; // 4 KB
+constexpr int TM_STAGE_BYTES = TM_T * TM_SUB * 8;  // 32 KB = 8 boxes
+constexpr int TM_PITCH = 132;                      // panel row pitch (doubles)
+constexpr int TM_CONSUMERS = 8;                    // consumer warps, one 16-column box each
+constexpr int TM_THREADS = (TM_CONSUMERS + 1) * 32;
+
+template <int KS, int S>
+struct TmaSmem {
+    static constexpr int RP = 4 * KS;
+    static constexpr int ring_bytes = S * TM_STAGE_BYTES;
+    static constexpr int panel_doubles = RP * TM_PITCH;            // one panel (row or column) of one slot
+    static constexpr int panels_bytes = 2 * 2 * panel_doubles * 8;  // 2 slots x (row, column)
+    static constexpr int bar_count = 2 * S + 4;                     // full[S], done[S], pfull[2], pempty[2]
+    static constexpr int total = ring_bytes + panels_bytes + bar_count * 8;
+};
+
+__device__ __forceinline__ int tm_row_base(int k) { return TM_PITCH * k - 2 * (k & 1); }
+
+// KS = padded rank / 4 (1..4), S = ring depth.  r = actual number of panel rows (<= 4 KS).
+// grid = min(#SMs, tiles); CTA b handles tiles b, b + grid, ... of this rank's row-major triangle.
+template <int KS, int S>
+__global__ void __launch_bounds__(TM_THREADS, 1) k_cov_update_tma(const __grid_constant__ CUtensorMap tmP,
+                                                                 const double* __restrict__ A, size_t lda, int r,
+                                                                 int nt, long long tiles, Shard sh,
+                                                                 const int* __restrict__ live, int nlive, int dbg) {
+    using L = TmaSmem<KS, S>;
+    constexpr int RP = L::RP;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* ring = smem_raw;
+    double* panels = reinterpret_cast<double*>(smem_raw + L::ring_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L::ring_bytes + L::panels_bytes);
+
+    // fused scan: if no observation of the group passed the gate every panel is zero — skip the pass
+    if (live != nullptr) {
+        int any = 0;
+        for (int q = 0; q < nlive; q++) any |= live[q];
+        if (!any) return;
+    }
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t bar0 = smem_u32(bars);
+    const uint32_t bar_full = bar0, bar_done = bar0 + 8 * S, bar_pfull = bar0 + 16 * S, bar_pempty = bar0 + 16 * S + 16;
+    auto rowp = [&](int slot) { return panels + (size_t)slot * 2 * L::panel_doubles; };
+    auto colp = [&](int slot) { return panels + (size_t)slot * 2 * L::panel_doubles + L::panel_doubles; };
+
+    if (tid == 0) {
+        if ((smem_u32(smem_raw) & 1023u) != 0) __trap();  // SWIZZLE_128B needs 1024-byte aligned stages
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_done + 8 * s, TM_CONSUMERS);
+        }
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            mbar_init(bar_pfull + 8 * s, 1);
+            mbar_init(bar_pempty + 8 * s, TM_CONSUMERS);
+        }
+        mbar_fence_init();
+    }
+    // Panels start out zero: rows r..RP-1 (rank padding) stay zero for the whole kernel — the bulk copies only
+    // ever write rows < r.  The proxy fence orders these generic-proxy writes before the async-proxy copies.
+    for (int idx = tid; idx < 4 * L::panel_doubles / 2; idx += TM_THREADS)
+        reinterpret_cast<double2*>(panels)[idx] = make_double2(0.0, 0.0);
+    fence_proxy_async();
+    __syncthreads();
+
+    if (warp == TM_CONSUMERS) {
+        // ------------------------------------------------------------------ producer ----
+        if (lane != 0) return;
+        tmap_prefetch(&tmP);
+        const uint64_t pol_stream = policy_evict_first();  // P: touched once per pass
+        const uint64_t pol_keep = policy_evict_last();     // panels: re-read by every tile of a strip / column
+        const uint32_t ring_u32 = smem_u32(ring);
+        int cj[S], cr[S];  // tile coordinates of the sub-tile held by each stage
+        long long sub = 0, stored = 0;
+        int st = 0, st_store = 0;
+        uint32_t done_phase = 0;  // bit s = parity to wait for on done[s]
+        auto issue_store = [&]() {  // store the oldest not-yet-stored sub-tile (stage st_store)
+            mbar_wait(bar_done + 8 * st_store, (done_phase >> st_store) & 1u);
+            done_phase ^= 1u << st_store;
+            if (!(dbg & 2)) {
+#pragma unroll
+                for (int b = 0; b < 8; b++) {
+                    if (dbg & 1)
+                        tma_store_2d_nohint(&tmP, cj[st_store] + TM_BOXC * b, cr[st_store],
+                                            ring_u32 + st_store * TM_STAGE_BYTES + b * TM_BOX_BYTES);
+                    else
+                        tma_store_2d(&tmP, cj[st_store] + TM_BOXC * b, cr[st_store],
+                                     ring_u32 + st_store * TM_STAGE_BYTES + b * TM_BOX_BYTES, pol_stream);
+                }
+            }
+            bulk_commit();
+            st_store = st_store + 1 == S ? 0 : st_store + 1;
+            stored++;
+        };
+        int lt = 0;
+        for (long long t = blockIdx.x; t < tiles; t += gridDim.x, lt++) {
+            int tr, tc;
+            shard_tile(t, nt, sh, tr, tc);
+            const int slot = lt & 1;
+            if (lt >= 2) mbar_wait(bar_pempty + 8 * slot, ((lt >> 1) - 1) & 1);
+            const int i0 = tr * TM_T, j0 = tc * TM_T;
+            const int ilen = min(TM_T, (int)lda - i0), jlen = min(TM_T, (int)lda - j0);  // doubles, > 0, even
+            mbar_expect_tx(bar_pfull + 8 * slot, (uint32_t)(r * (ilen + jlen) * 8));
+            {
+                const uint32_t rp_u32 = smem_u32(rowp(slot)), cp_u32 = smem_u32(colp(slot));
+                for (int k = 0; k < r; k++) {
+                    bulk_g2s_hint(rp_u32 + 8 * tm_row_base(k), A + (size_t)k * lda + i0, (uint32_t)ilen * 8,
+                                  bar_pfull + 8 * slot, pol_keep);
+                    bulk_g2s_hint(cp_u32 + 8 * TM_PITCH * k, A + (size_t)k * lda + j0, (uint32_t)jlen * 8,
+                                  bar_pfull + 8 * slot, pol_keep);
+                }
+            }
+            const int lrow0 = (int)shard_lrow(sh, i0);
+#pragma unroll 1
+            for (int s = 0; s < TM_T / TM_SUB; s++) {
+                if (sub >= S) {  // the stage still holds sub-tile (sub - S): write it back first
+                    issue_store();
+                    bulk_wait_read<0>();
+                }
+                cj[st] = j0;
+                cr[st] = lrow0 + TM_SUB * s;
+                if (dbg & 4) {  // development ablation: no covariance loads
+                    mbar_arrive(bar_full + 8 * st);
+                } else {
+                    mbar_expect_tx(bar_full + 8 * st, TM_STAGE_BYTES);
+#pragma unroll
+                    for (int b = 0; b < 8; b++) {
+                        if (dbg & 1)
+                            tma_load_2d_nohint(ring_u32 + st * TM_STAGE_BYTES + b * TM_BOX_BYTES, &tmP, j0 + TM_BOXC * b,
+                                               lrow0 + TM_SUB * s, bar_full + 8 * st);
+                        else
+                            tma_load_2d(ring_u32 + st * TM_STAGE_BYTES + b * TM_BOX_BYTES, &tmP, j0 + TM_BOXC * b,
+                                        lrow0 + TM_SUB * s, bar_full + 8 * st, pol_stream);
+                    }
+                }
+                st = st + 1 == S ? 0 : st + 1;
+                sub++;
+            }
+        }
+        while (stored < sub) issue_store();
+        bulk_wait<0>();  // all writes performed before the kernel ends
+        return;
+    }
+
+    // ---------------------------------------------------------------------- consumers ----
+    const int g = lane >> 2, t = lane & 3;
+    const int rho = ((g & 1) << 2) | (g >> 1);
+    // fragment offsets inside this warp's box: row rho, 16-byte chunk (4 cb + t) ^ rho
+    const uint32_t off0 = (uint32_t)(rho * 128 + ((t ^ rho) << 4));
+    const uint32_t off1 = off0 ^ 64u;
+    const long long my_tiles = (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    int st = 0;
+    uint32_t full_phase = 0;
+    for (long long lt = 0; lt < my_tiles; lt++) {
+        const int slot = (int)(lt & 1);
+        mbar_wait(bar_pfull + 8 * slot, (uint32_t)((lt >> 1) & 1));
+        // negated column-panel fragments of this warp's 16 columns: constant over the tile
+        double nb[KS][2];
+        {
+            const double* cp = colp(slot) + TM_BOXC * warp + g;
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++)
+#pragma unroll
+                for (int cb = 0; cb < 2; cb++) nb[ks][cb] = -cp[TM_PITCH * (4 * ks + t) + 8 * cb];
+        }
+        const double* rp = rowp(slot) + rho;
+#pragma unroll 1
+        for (int s = 0; s < TM_T / TM_SUB; s++) {
+            mbar_wait(bar_full + 8 * st, (full_phase >> st) & 1u);
+            full_phase ^= 1u << st;
+            unsigned char* box = ring + st * TM_STAGE_BYTES + warp * TM_BOX_BYTES;
+            double2 acc[4][2];
+#pragma unroll
+            for (int rb = 0; rb < 4; rb++) {
+                acc[rb][0] = *reinterpret_cast<const double2*>(box + rb * 1024 + off0);
+                acc[rb][1] = *reinterpret_cast<const double2*>(box + rb * 1024 + off1);
+            }
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++) {
+                double a[4];
+#pragma unroll
+                for (int rb = 0; rb < 4; rb++) a[rb] = rp[tm_row_base(4 * ks + t) + TM_SUB * s + 8 * rb];
+#pragma unroll
+                for (int rb = 0; rb < 4; rb++) {
+                    dmma884(acc[rb][0].x, acc[rb][0].y, a[rb], nb[ks][0]);
+                    dmma884(acc[rb][1].x, acc[rb][1].y, a[rb], nb[ks][1]);
+                }
+            }
+#pragma unroll
+            for (int rb = 0; rb < 4; rb++) {
+                *reinterpret_cast<double2*>(box + rb * 1024 + off0) = acc[rb][0];
+                *reinterpret_cast<double2*>(box + rb * 1024 + off1) = acc[rb][1];
+            }
+            fence_proxy_async();  // the TMA store (async proxy) must see these generic-proxy writes
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_done + 8 * st);
+            st = st + 1 == S ? 0 : st + 1;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_pempty + 8 * slot);
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// Tensor map over the locally stored rows of P (row-major doubles, `rows` x `ld`): 16 x 32 boxes, 128-byte swizzle.
+int make_cov_tensor_map(void* out_map64, double* P, size_t ld, size_t rows) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    CSLAM_REQUIRE(enc != nullptr, CSLAM_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    CUtensorMap tm;
+    const cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(double)};
+    const cuuint32_t box[2] = {TM_BOXC, TM_SUB};
+    const cuuint32_t estr[2] = {1, 1};
+    CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+    if (const char* e = getenv("CSLAM_TMA_PROMO")) promo = (CUtensorMapL2promotion)atoi(e);  // development knob (0..3)
+    const CUresult rc = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, P, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) {
+        set_last_error("cuTensorMapEncodeTiled failed (CUresult %d; ld=%zu rows=%zu)", (int)rc, ld, rows);
+        return CSLAM_ERR_CUDA;
+    }
+    memcpy(out_map64, &tm, sizeof(tm));
+    return CSLAM_OK;
+}
+
+int g_tma_dbg = 0;  // development knobs of tools/cov_tma_bench.cu (1: no L2 hints, 2: no stores, 4: no loads)
+
+template <int KS, int S>
+static int launch_one(const CUtensorMap& tm, const double* A, size_t lda, int r, int nt, long long tiles, Shard sh,
+                      const int* live, int nlive, int num_sms, cudaStream_t stream) {
+    using L = TmaSmem<KS, S>;
+    static bool attr_set[64] = {};  // per device and instantiation: the attribute is set once, not per call
+    int dev = 0;
+    CSLAM_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        CSLAM_CUDA(cudaFuncSetAttribute(k_cov_update_tma<KS, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total));
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    const unsigned grid = (unsigned)std::min<long long>(num_sms, tiles);
+    count_launch();
+    k_cov_update_tma<KS, S><<<grid, TM_THREADS, L::total, stream>>>(tm, A, lda, r, nt, tiles, sh, live, nlive, g_tma_dbg);
+    CSLAM_CUDA(cudaGetLastError());
+    return CSLAM_OK;
+}
+
+// One pass P -= sum_{k < r} A[k] A[k]^T over this rank's tiles of the upper triangle (r <= 16).
+// map64: the 64-byte tensor map made by make_cov_tensor_map for this handle's P.
+int launch_cov_update_tma(const void* map64, int n, const double* A, size_t lda, int r, Shard sh, const int* live,
+                          int nlive, int num_sms, int stages, cudaStream_t stream) {
+    CSLAM_REQUIRE(r >= 1 && r <= 16, CSLAM_ERR_BAD_ARG, "TMA covariance pass: rank out of range (1..16)");
+    CUtensorMap tm;
+    memcpy(&tm, map64, sizeof(tm));
+    const int nt = (n + TM_T - 1) / TM_T;
+    const long long tiles = shard_tile_count(nt, sh);
+    if (tiles == 0) return CSLAM_OK;
+    const int ks = (r + 3) / 4;
+#define TM_CASE(KS_)                                                                                              \
+    case KS_:                                                                                                     \
+        if (stages == 4) return launch_one<KS_, 4>(tm, A, lda, r, nt, tiles, sh, live, nlive, num_sms, stream);   \
+        if (stages == 3) return launch_one<KS_, 3>(tm, A, lda, r, nt, tiles, sh, live, nlive, num_sms, stream);   \
+        if (stages == 2) return launch_one<KS_, 2>(tm, A, lda, r, nt, tiles, sh, live, nlive, num_sms, stream);   \
+        return launch_one<KS_, 5>(tm, A, lda, r, nt, tiles, sh, live, nlive, num_sms, stream);
+    switch (ks) {
+        TM_CASE(1) TM_CASE(2) TM_CASE(3) TM_CASE(4)
+    }
+#undef TM_CASE
+    return CSLAM_ERR_BAD_ARG;
+}
+
+}  // namespace cslam
