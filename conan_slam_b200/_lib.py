@@ -49,6 +49,8 @@ SIGNATURES = {
     "cslam_ekf_destroy": (C.c_int, [_vp]),
     "cslam_ekf_set_stream": (C.c_int, [_vp, _vp]),
     "cslam_ekf_sync": (C.c_int, [_vp, C.POINTER(C.c_int)]),
+    "cslam_ekf_flush": (C.c_int, [_vp]),
+    "cslam_ekf_pass_count": (C.c_int, [_vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_int)]),
     "cslam_ekf_n": (C.c_int, [_vp]),
     "cslam_ekf_num_landmarks": (C.c_int, [_vp]),
     "cslam_ekf_capacity": (C.c_int, [_vp]),
@@ -62,6 +64,7 @@ SIGNATURES = {
     "cslam_ekf_augment": (C.c_int, [_vp, _dp, C.c_int, _dp]),
     "cslam_ekf_get_state": (C.c_int, [_vp, _dp, C.c_int]),
     "cslam_ekf_get_cov_block": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _dp]),
+    "cslam_ekf_get_cov_gather": (C.c_int, [_vp, _ip, C.c_int, _dp]),
     "cslam_ekf_reset": (C.c_int, [_vp, _dp, C.c_int, _dp]),
     "cslam_ekf_get_landmark_covs": (C.c_int, [_vp, C.c_int, C.c_int, _dp]),
     "cslam_ekf_save": (C.c_int, [_vp, C.c_char_p]),

@@ -60,25 +60,34 @@ struct TmaSmem {
     static constexpr int ring_bytes = S * TM_STAGE_BYTES;
     static constexpr int panel_doubles = RP * TM_PITCH;            // one panel (row or column) of one slot
     static constexpr int panels_bytes = 2 * 2 * panel_doubles * 8;  // 2 slots x (row, column)
-    static constexpr int bar_count = 2 * S + 4;                     // full[S], done[S], pfull[2], pempty[2]
-    static constexpr int total = ring_bytes + panels_bytes + bar_count * 8;
+    static constexpr int bar_count = 2 * S + 4;                     // full[S], free[S], pfull[2], pempty[2]
+    static constexpr int info_bytes = 2 * 16 + 8 * S;               // per panel slot {j0, local row 0, diagonal?}; done[S] (dense variant)
+    static constexpr int total = ring_bytes + panels_bytes + bar_count * 8 + info_bytes;
 };
 
 __device__ __forceinline__ int tm_row_base(int k) { return TM_PITCH * k - 2 * (k & 1); }
 
 // KS = padded rank / 4 (1..4), S = ring depth.  r = actual number of panel rows (<= 4 KS).
 // grid = min(#SMs, tiles); CTA b handles tiles b, b + grid, ... of this rank's row-major triangle.
+// tmSrc / tmDst: tensor maps of the covariance the pass reads / writes (the same map for an in-place pass, the
+// two halves of a ping-pong pair otherwise).  diag_eps: added once to every diagonal element (the sum of the
+// FLT_MIN terms of the heading updates in this group, slam.h:719).
+// Roles: warp 8 lane 0 = producer (panel bulk copies + tile loads); warps 0..7 = consumers, each owns the 16-column
+// box `warp` of every stage: it waits for the stage, updates its box in place in shared memory, and its lane 0
+// stores the box back by TMA itself — eight independent store pipelines, no CTA-wide hand-over.
 template <int KS, int S>
-__global__ void __launch_bounds__(TM_THREADS, 1) k_cov_update_tma(const __grid_constant__ CUtensorMap tmP,
+__global__ void __launch_bounds__(TM_THREADS, 1) k_cov_update_tma(const __grid_constant__ CUtensorMap tmSrc,
+                                                                 const __grid_constant__ CUtensorMap tmDst,
                                                                  const double* __restrict__ A, size_t lda, int r,
                                                                  int nt, long long tiles, Shard sh,
-                                                                 const int* __restrict__ live, int nlive, int dbg) {
+                                                                 const int* __restrict__ live, int nlive,
+                                                                 double diag_eps, int dbg, int boxr) {
     using L = TmaSmem<KS, S>;
-    constexpr int RP = L::RP;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* ring = smem_raw;
     double* panels = reinterpret_cast<double*>(smem_raw + L::ring_bytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L::ring_bytes + L::panels_bytes);
+    int4* tinfo = reinterpret_cast<int4*>(smem_raw + L::ring_bytes + L::panels_bytes + L::bar_count * 8);
 
     // fused scan: if no observation of the group passed the gate every panel is zero — skip the pass
     if (live != nullptr) {
@@ -89,7 +98,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_cov_update_tma(const __grid_c
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t bar0 = smem_u32(bars);
-    const uint32_t bar_full = bar0, bar_done = bar0 + 8 * S, bar_pfull = bar0 + 16 * S, bar_pempty = bar0 + 16 * S + 16;
+    const uint32_t bar_full = bar0, bar_free = bar0 + 8 * S, bar_pfull = bar0 + 16 * S, bar_pempty = bar0 + 16 * S + 16;
     auto rowp = [&](int slot) { return panels + (size_t)slot * 2 * L::panel_doubles; };
     auto colp = [&](int slot) { return panels + (size_t)slot * 2 * L::panel_doubles + L::panel_doubles; };
 
@@ -98,7 +107,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_cov_update_tma(const __grid_c
 #pragma unroll
         for (int s = 0; s < S; s++) {
             mbar_init(bar_full + 8 * s, 1);
-            mbar_init(bar_done + 8 * s, TM_CONSUMERS);
+            mbar_init(bar_free + 8 * s, TM_CONSUMERS);
         }
 #pragma unroll
         for (int s = 0; s < 2; s++) {
@@ -117,32 +126,13 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_cov_update_tma(const __grid_c
     if (warp == TM_CONSUMERS) {
         // ------------------------------------------------------------------ producer ----
         if (lane != 0) return;
-        tmap_prefetch(&tmP);
+        tmap_prefetch(&tmSrc);
         const uint64_t pol_stream = policy_evict_first();  // P: touched once per pass
         const uint64_t pol_keep = policy_evict_last();     // panels: re-read by every tile of a strip / column
         const uint32_t ring_u32 = smem_u32(ring);
-        int cj[S], cr[S];  // tile coordinates of the sub-tile held by each stage
-        long long sub = 0, stored = 0;
-        int st = 0, st_store = 0;
-        uint32_t done_phase = 0;  // bit s = parity to wait for on done[s]
-        auto issue_store = [&]() {  // store the oldest not-yet-stored sub-tile (stage st_store)
-            mbar_wait(bar_done + 8 * st_store, (done_phase >> st_store) & 1u);
-            done_phase ^= 1u << st_store;
-            if (!(dbg & 2)) {
-#pragma unroll
-                for (int b = 0; b < 8; b++) {
-                    if (dbg & 1)
-                        tma_store_2d_nohint(&tmP, cj[st_store] + TM_BOXC * b, cr[st_store],
-                                            ring_u32 + st_store * TM_STAGE_BYTES + b * TM_BOX_BYTES);
-                    else
-                        tma_store_2d(&tmP, cj[st_store] + TM_BOXC * b, cr[st_store],
-                                     ring_u32 + st_store * TM_STAGE_BYTES + b * TM_BOX_BYTES, pol_stream);
-                }
-            }
-            bulk_commit();
-            st_store = st_store + 1 == S ? 0 : st_store + 1;
-            stored++;
-        };
+        long long sub = 0;
+        int st = 0;
+        uint32_t free_phase = 0;  // bit s = parity to wait for on free[s]
         int lt = 0;
         for (long long t = blockIdx.x; t < tiles; t += gridDim.x, lt++) {
             int tr, tc;
@@ -150,6 +140,8 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_cov_update_tma(const __grid_c
             const int slot = lt & 1;
             if (lt >= 2) mbar_wait(bar_pempty + 8 * slot, ((lt >> 1) - 1) & 1);
             const int i0 = tr * TM_T, j0 = tc * TM_T;
+            const int lrow0 = (int)shard_lrow(sh, i0);
+            tinfo[slot] = make_int4(j0, lrow0, tr == tc ? 1 : 0, 0);  // published by the arrive below (release)
             const int ilen = min(TM_T, (int)lda - i0), jlen = min(TM_T, (int)lda - j0);  // doubles, > 0, even
             mbar_expect_tx(bar_pfull + 8 * slot, (uint32_t)(r * (ilen + jlen) * 8));
             {
@@ -161,35 +153,28 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_cov_update_tma(const __grid_c
                                   bar_pfull + 8 * slot, pol_keep);
                 }
             }
-            const int lrow0 = (int)shard_lrow(sh, i0);
 #pragma unroll 1
             for (int s = 0; s < TM_T / TM_SUB; s++) {
-                if (sub >= S) {  // the stage still holds sub-tile (sub - S): write it back first
-                    issue_store();
-                    bulk_wait_read<0>();
+                if (sub >= S) {  // every consumer warp's store of the sub-tile that used this stage has left shared memory
+                    mbar_wait(bar_free + 8 * st, (free_phase >> st) & 1u);
+                    free_phase ^= 1u << st;
                 }
-                cj[st] = j0;
-                cr[st] = lrow0 + TM_SUB * s;
                 if (dbg & 4) {  // development ablation: no covariance loads
                     mbar_arrive(bar_full + 8 * st);
                 } else {
                     mbar_expect_tx(bar_full + 8 * st, TM_STAGE_BYTES);
+                    // row-group major: the 8 boxes that cover the same rows (1 KB contiguous per row) are requested
+                    // back to back
+                    for (int rg = 0; rg < TM_SUB; rg += boxr)
 #pragma unroll
-                    for (int b = 0; b < 8; b++) {
-                        if (dbg & 1)
-                            tma_load_2d_nohint(ring_u32 + st * TM_STAGE_BYTES + b * TM_BOX_BYTES, &tmP, j0 + TM_BOXC * b,
-                                               lrow0 + TM_SUB * s, bar_full + 8 * st);
-                        else
-                            tma_load_2d(ring_u32 + st * TM_STAGE_BYTES + b * TM_BOX_BYTES, &tmP, j0 + TM_BOXC * b,
-                                        lrow0 + TM_SUB * s, bar_full + 8 * st, pol_stream);
-                    }
+                        for (int b = 0; b < 8; b++)
+                            tma_load_2d(ring_u32 + st * TM_STAGE_BYTES + b * TM_BOX_BYTES + rg * 128, &tmSrc,
+                                        j0 + TM_BOXC * b, lrow0 + TM_SUB * s + rg, bar_full + 8 * st, pol_stream);
                 }
                 st = st + 1 == S ? 0 : st + 1;
                 sub++;
             }
         }
-        while (stored < sub) issue_store();
-        bulk_wait<0>();  // all writes performed before the kernel ends
         return;
     }
 
@@ -200,11 +185,14 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_cov_update_tma(const __grid_c
     const uint32_t off0 = (uint32_t)(rho * 128 + ((t ^ rho) << 4));
     const uint32_t off1 = off0 ^ 64u;
     const long long my_tiles = (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
-    int st = 0;
+    const uint64_t pol_stream = policy_evict_first();
+    if (lane == 0) tmap_prefetch(&tmDst);
+    int st = 0, prev_st = -1;
     uint32_t full_phase = 0;
     for (long long lt = 0; lt < my_tiles; lt++) {
         const int slot = (int)(lt & 1);
         mbar_wait(bar_pfull + 8 * slot, (uint32_t)((lt >> 1) & 1));
+        const int4 ti = tinfo[slot];
         // negated column-panel fragments of this warp's 16 columns: constant over the tile
         double nb[KS][2];
         {
@@ -237,12 +225,239 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_cov_update_tma(const __grid_c
                     dmma884(acc[rb][1].x, acc[rb][1].y, a[rb], nb[ks][1]);
                 }
             }
+            if (ti.z && diag_eps != 0.0) {  // diagonal tile: slam.h:719 on the diagonal elements
+#pragma unroll
+                for (int rb = 0; rb < 4; rb++) {
+                    const int row = TM_SUB * s + 8 * rb + rho;  // tile-relative
+#pragma unroll
+                    for (int cb = 0; cb < 2; cb++) {
+                        const int col = TM_BOXC * warp + 8 * cb + 2 * t;
+                        if (col == row) acc[rb][cb].x += diag_eps;
+                        if (col + 1 == row) acc[rb][cb].y += diag_eps;
+                    }
+                }
+            }
 #pragma unroll
             for (int rb = 0; rb < 4; rb++) {
                 *reinterpret_cast<double2*>(box + rb * 1024 + off0) = acc[rb][0];
                 *reinterpret_cast<double2*>(box + rb * 1024 + off1) = acc[rb][1];
             }
             fence_proxy_async();  // the TMA store (async proxy) must see these generic-proxy writes
+            __syncwarp();
+            if (lane == 0) {
+                if (!(dbg & 2))
+                    for (int rg = 0; rg < TM_SUB; rg += boxr)
+                        tma_store_2d(&tmDst, ti.x + TM_BOXC * warp, ti.y + TM_SUB * s + rg, smem_u32(box) + rg * 128,
+                                     pol_stream);
+                bulk_commit();
+                if (prev_st >= 0) {  // the previous store of this warp has left shared memory: its stage is free
+                    bulk_wait_read<1>();
+                    mbar_arrive(bar_free + 8 * prev_st);
+                }
+            }
+            prev_st = st;
+            st = st + 1 == S ? 0 : st + 1;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_pempty + 8 * slot);
+    }
+    if (lane == 0) bulk_wait<0>();  // all writes performed before the kernel ends
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Dense-row variant: a stage is 32 full rows of the tile (32 x 1 KB, no swizzle), ONE tensor-map load and ONE
+// tensor-map store per stage, both 1 KB contiguous per covariance row (DRAM-page friendly).  Roles: warps 0..7
+// consumers, warp 8 lane 0 loads, warp 9 lane 0 stores.  Bank conflicts of the fragment accesses (row pitch
+// 1 KB: the two DMMA rows of a quarter-warp would hit the same banks) are avoided by letting the lanes of odd
+// DMMA rows touch the warp's second 8-column block first and swapping the two registers afterwards.
+constexpr int TMD_THREADS = (TM_CONSUMERS + 2) * 32;
+template <int KS, int S>
+__global__ void __launch_bounds__(TMD_THREADS, 1) k_cov_update_tma_dense(const __grid_constant__ CUtensorMap tmSrc,
+                                                                        const __grid_constant__ CUtensorMap tmDst,
+                                                                        const double* __restrict__ A, size_t lda,
+                                                                        int r, int nt, long long tiles, Shard sh,
+                                                                        const int* __restrict__ live, int nlive,
+                                                                        double diag_eps, int dbg) {
+    using L = TmaSmem<KS, S>;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* ring = smem_raw;
+    double* panels = reinterpret_cast<double*>(smem_raw + L::ring_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L::ring_bytes + L::panels_bytes);
+    int4* tinfo = reinterpret_cast<int4*>(smem_raw + L::ring_bytes + L::panels_bytes + L::bar_count * 8);
+    uint64_t* bars_done = reinterpret_cast<uint64_t*>(tinfo + 2);  // done[S] lives behind the tile info (S <= 6)
+    if (live != nullptr) {
+        int any = 0;
+        for (int q = 0; q < nlive; q++) any |= live[q];
+        if (!any) return;
+    }
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t bar0 = smem_u32(bars);
+    const uint32_t bar_full = bar0, bar_free = bar0 + 8 * S, bar_pfull = bar0 + 16 * S, bar_pempty = bar0 + 16 * S + 16;
+    const uint32_t bar_done = smem_u32(bars_done);
+    auto rowp = [&](int slot) { return panels + (size_t)slot * 2 * L::panel_doubles; };
+    auto colp = [&](int slot) { return panels + (size_t)slot * 2 * L::panel_doubles + L::panel_doubles; };
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_free + 8 * s, 1);
+            mbar_init(bar_done + 8 * s, TM_CONSUMERS);
+        }
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            mbar_init(bar_pfull + 8 * s, 1);
+            mbar_init(bar_pempty + 8 * s, TM_CONSUMERS);
+        }
+        mbar_fence_init();
+    }
+    for (int idx = tid; idx < 4 * L::panel_doubles / 2; idx += TMD_THREADS)
+        reinterpret_cast<double2*>(panels)[idx] = make_double2(0.0, 0.0);
+    fence_proxy_async();
+    __syncthreads();
+
+    if (warp == TM_CONSUMERS) {  // ------------------------------------------------ loads ----
+        if (lane != 0) return;
+        tmap_prefetch(&tmSrc);
+        const uint64_t pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
+        const uint32_t ring_u32 = smem_u32(ring);
+        long long sub = 0;
+        int st = 0, lt = 0;
+        uint32_t free_phase = 0;
+        for (long long t = blockIdx.x; t < tiles; t += gridDim.x, lt++) {
+            int tr, tc;
+            shard_tile(t, nt, sh, tr, tc);
+            const int slot = lt & 1;
+            if (lt >= 2) mbar_wait(bar_pempty + 8 * slot, ((lt >> 1) - 1) & 1);
+            const int i0 = tr * TM_T, j0 = tc * TM_T;
+            const int lrow0 = (int)shard_lrow(sh, i0);
+            tinfo[slot] = make_int4(j0, lrow0, tr == tc ? 1 : 0, 0);
+            const int ilen = min(TM_T, (int)lda - i0), jlen = min(TM_T, (int)lda - j0);
+            mbar_expect_tx(bar_pfull + 8 * slot, (uint32_t)(r * (ilen + jlen) * 8));
+            const uint32_t rp_u32 = smem_u32(rowp(slot)), cp_u32 = smem_u32(colp(slot));
+            for (int k = 0; k < r; k++) {
+                bulk_g2s_hint(rp_u32 + 8 * TM_PITCH * k, A + (size_t)k * lda + i0, (uint32_t)ilen * 8,
+                              bar_pfull + 8 * slot, pol_keep);
+                bulk_g2s_hint(cp_u32 + 8 * TM_PITCH * k, A + (size_t)k * lda + j0, (uint32_t)jlen * 8,
+                              bar_pfull + 8 * slot, pol_keep);
+            }
+#pragma unroll 1
+            for (int s = 0; s < TM_T / TM_SUB; s++) {
+                if (sub >= S) {
+                    mbar_wait(bar_free + 8 * st, (free_phase >> st) & 1u);
+                    free_phase ^= 1u << st;
+                }
+                if (dbg & 4) {
+                    mbar_arrive(bar_full + 8 * st);
+                } else {
+                    mbar_expect_tx(bar_full + 8 * st, TM_STAGE_BYTES);
+                    if (dbg & 8)
+                        tma_load_2d_nohint(ring_u32 + st * TM_STAGE_BYTES, &tmSrc, j0, lrow0 + TM_SUB * s, bar_full + 8 * st);
+                    else
+                        tma_load_2d(ring_u32 + st * TM_STAGE_BYTES, &tmSrc, j0, lrow0 + TM_SUB * s, bar_full + 8 * st,
+                                    pol_stream);
+                }
+                st = st + 1 == S ? 0 : st + 1;
+                sub++;
+            }
+        }
+        return;
+    }
+    if (warp == TM_CONSUMERS + 1) {  // -------------------------------------------- stores ----
+        if (lane != 0) return;
+        tmap_prefetch(&tmDst);
+        const uint64_t pol_stream = policy_evict_first();
+        const uint32_t ring_u32 = smem_u32(ring);
+        int st = 0, prev_st = -1;
+        uint32_t done_phase = 0;
+        for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+            int tr, tc;
+            shard_tile(t, nt, sh, tr, tc);
+            const int j0 = tc * TM_T, lrow0 = (int)shard_lrow(sh, tr * TM_T);
+#pragma unroll 1
+            for (int s = 0; s < TM_T / TM_SUB; s++) {
+                mbar_wait(bar_done + 8 * st, (done_phase >> st) & 1u);
+                done_phase ^= 1u << st;
+                if (!(dbg & 2)) {
+                    if (dbg & 16)
+                        tma_store_2d_nohint(&tmDst, j0, lrow0 + TM_SUB * s, ring_u32 + st * TM_STAGE_BYTES);
+                    else
+                        tma_store_2d(&tmDst, j0, lrow0 + TM_SUB * s, ring_u32 + st * TM_STAGE_BYTES, pol_stream);
+                }
+                bulk_commit();
+                if (prev_st >= 0) {
+                    bulk_wait_read<1>();
+                    mbar_arrive(bar_free + 8 * prev_st);
+                }
+                prev_st = st;
+                st = st + 1 == S ? 0 : st + 1;
+            }
+        }
+        bulk_wait<0>();
+        return;
+    }
+    // ---------------------------------------------------------------------------- consumers ----
+    const int g = lane >> 2, t = lane & 3, odd = g & 1;
+    // lanes of odd DMMA rows read the warp's second 8-column block with the first instruction
+    const uint32_t offA = (uint32_t)(g * 1024 + (TM_BOXC * warp + 8 * odd + 2 * t) * 8);
+    const uint32_t offB = (uint32_t)(g * 1024 + (TM_BOXC * warp + 8 * (odd ^ 1) + 2 * t) * 8);
+    const long long my_tiles = (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    int st = 0;
+    uint32_t full_phase = 0;
+    for (long long lt = 0; lt < my_tiles; lt++) {
+        const int slot = (int)(lt & 1);
+        mbar_wait(bar_pfull + 8 * slot, (uint32_t)((lt >> 1) & 1));
+        const int4 ti = tinfo[slot];
+        double nb[KS][2];
+        {
+            const double* cp = colp(slot) + TM_BOXC * warp + g;
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++)
+#pragma unroll
+                for (int cb = 0; cb < 2; cb++) nb[ks][cb] = -cp[TM_PITCH * (4 * ks + t) + 8 * cb];
+        }
+        const double* rp = rowp(slot) + g;
+#pragma unroll 1
+        for (int s = 0; s < TM_T / TM_SUB; s++) {
+            mbar_wait(bar_full + 8 * st, (full_phase >> st) & 1u);
+            full_phase ^= 1u << st;
+            unsigned char* stage = ring + st * TM_STAGE_BYTES;
+            double2 acc[4][2];
+#pragma unroll
+            for (int rb = 0; rb < 4; rb++) {
+                const double2 va = *reinterpret_cast<const double2*>(stage + rb * 8192 + offA);
+                const double2 vb = *reinterpret_cast<const double2*>(stage + rb * 8192 + offB);
+                acc[rb][0] = odd ? vb : va;
+                acc[rb][1] = odd ? va : vb;
+            }
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++) {
+                double a[4];
+#pragma unroll
+                for (int rb = 0; rb < 4; rb++) a[rb] = rp[TM_PITCH * (4 * ks + t) + TM_SUB * s + 8 * rb];
+#pragma unroll
+                for (int rb = 0; rb < 4; rb++) {
+                    dmma884(acc[rb][0].x, acc[rb][0].y, a[rb], nb[ks][0]);
+                    dmma884(acc[rb][1].x, acc[rb][1].y, a[rb], nb[ks][1]);
+                }
+            }
+            if (ti.z && diag_eps != 0.0) {
+#pragma unroll
+                for (int rb = 0; rb < 4; rb++) {
+                    const int row = TM_SUB * s + 8 * rb + g;
+#pragma unroll
+                    for (int cb = 0; cb < 2; cb++) {
+                        const int col = TM_BOXC * warp + 8 * cb + 2 * t;
+                        if (col == row) acc[rb][cb].x += diag_eps;
+                        if (col + 1 == row) acc[rb][cb].y += diag_eps;
+                    }
+                }
+            }
+#pragma unroll
+            for (int rb = 0; rb < 4; rb++) {
+                *reinterpret_cast<double2*>(stage + rb * 8192 + offA) = odd ? acc[rb][1] : acc[rb][0];
+                *reinterpret_cast<double2*>(stage + rb * 8192 + offB) = odd ? acc[rb][0] : acc[rb][1];
+            }
+            fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_done + 8 * st);
             st = st + 1 == S ? 0 : st + 1;
@@ -273,6 +488,12 @@ static EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
+int g_tma_boxr = 32;  // development knob: rows per TMA box of the swizzled-box variant (8, 16 or 32)
+// 1 = dense-row variant (k_cov_update_tma_dense: one 32 KB tensor-map load / store per stage, measured slightly
+// faster on a B200), 0 = swizzled 16-column boxes with consumer-issued stores (k_cov_update_tma).
+// CSLAM_TMA_DENSE=0/1 overrides; the tensor maps of a handle are made for one variant.
+int g_tma_dense = getenv("CSLAM_TMA_DENSE") ? atoi(getenv("CSLAM_TMA_DENSE")) : 1;
+
 // Tensor map over the locally stored rows of P (row-major doubles, `rows` x `ld`): 16 x 32 boxes, 128-byte swizzle.
 int make_cov_tensor_map(void* out_map64, double* P, size_t ld, size_t rows) {
     EncodeTiledFn enc = encode_tiled_fn();
@@ -280,12 +501,12 @@ int make_cov_tensor_map(void* out_map64, double* P, size_t ld, size_t rows) {
     CUtensorMap tm;
     const cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(double)};
-    const cuuint32_t box[2] = {TM_BOXC, TM_SUB};
+    const cuuint32_t box[2] = {g_tma_dense ? (cuuint32_t)TM_T : (cuuint32_t)TM_BOXC, (cuuint32_t)(g_tma_dense ? TM_SUB : g_tma_boxr)};
     const cuuint32_t estr[2] = {1, 1};
     CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
     if (const char* e = getenv("CSLAM_TMA_PROMO")) promo = (CUtensorMapL2promotion)atoi(e);  // development knob (0..3)
     const CUresult rc = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, P, dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, g_tma_dense ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B, promo,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) {
         set_last_error("cuTensorMapEncodeTiled failed (CUresult %d; ld=%zu rows=%zu)", (int)rc, ld, rows);
@@ -295,10 +516,10 @@ int make_cov_tensor_map(void* out_map64, double* P, size_t ld, size_t rows) {
     return CSLAM_OK;
 }
 
-int g_tma_dbg = 0;  // development knobs of tools/cov_tma_bench.cu (1: no L2 hints, 2: no stores, 4: no loads)
+int g_tma_dbg = 0;  // development knobs of tools/cov_tma_bench.cu (2: no stores, 4: no loads)
 
 template <int KS, int S>
-static int launch_one(const CUtensorMap& tm, const double* A, size_t lda, int r, int nt, long long tiles, Shard sh,
+static int launch_one(const CUtensorMap& tm, const CUtensorMap& tmd, double diag_eps, const double* A, size_t lda, int r, int nt, long long tiles, Shard sh,
                       const int* live, int nlive, int num_sms, cudaStream_t stream) {
     using L = TmaSmem<KS, S>;
     static bool attr_set[64] = {};  // per device and instantiation: the attribute is set once, not per call
@@ -310,28 +531,44 @@ static int launch_one(const CUtensorMap& tm, const double* A, size_t lda, int r,
     }
     const unsigned grid = (unsigned)std::min<long long>(num_sms, tiles);
     count_launch();
-    k_cov_update_tma<KS, S><<<grid, TM_THREADS, L::total, stream>>>(tm, A, lda, r, nt, tiles, sh, live, nlive, g_tma_dbg);
+    if (g_tma_dense) {
+        static bool dense_attr[64] = {};
+        if (dev < 0 || dev >= 64 || !dense_attr[dev]) {
+            CSLAM_CUDA(cudaFuncSetAttribute(k_cov_update_tma_dense<KS, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            L::total));
+            if (dev >= 0 && dev < 64) dense_attr[dev] = true;
+        }
+        k_cov_update_tma_dense<KS, S><<<grid, TMD_THREADS, L::total, stream>>>(tm, tmd, A, lda, r, nt, tiles, sh, live,
+                                                                               nlive, diag_eps, g_tma_dbg);
+    } else {
+        k_cov_update_tma<KS, S><<<grid, TM_THREADS, L::total, stream>>>(tm, tmd, A, lda, r, nt, tiles, sh, live, nlive,
+                                                                        diag_eps, g_tma_dbg, g_tma_boxr);
+    }
     CSLAM_CUDA(cudaGetLastError());
     return CSLAM_OK;
 }
 
 // One pass P -= sum_{k < r} A[k] A[k]^T over this rank's tiles of the upper triangle (r <= 16).
-// map64: the 64-byte tensor map made by make_cov_tensor_map for this handle's P.
-int launch_cov_update_tma(const void* map64, int n, const double* A, size_t lda, int r, Shard sh, const int* live,
-                          int nlive, int num_sms, int stages, cudaStream_t stream) {
+// src_map / dst_map: tensor maps made by make_cov_tensor_map (the same one for an in-place pass).
+int launch_cov_update_tma(const void* src_map, const void* dst_map, int n, const double* A, size_t lda, int r,
+                          double diag_eps, Shard sh, const int* live, int nlive, int num_sms, int stages,
+                          cudaStream_t stream) {
     CSLAM_REQUIRE(r >= 1 && r <= 16, CSLAM_ERR_BAD_ARG, "TMA covariance pass: rank out of range (1..16)");
-    CUtensorMap tm;
-    memcpy(&tm, map64, sizeof(tm));
+    CUtensorMap tm, tmd;
+    memcpy(&tm, src_map, sizeof(tm));
+    memcpy(&tmd, dst_map, sizeof(tmd));
     const int nt = (n + TM_T - 1) / TM_T;
     const long long tiles = shard_tile_count(nt, sh);
     if (tiles == 0) return CSLAM_OK;
     const int ks = (r + 3) / 4;
 #define TM_CASE(KS_)                                                                                              \
     case KS_:                                                                                                     \
-        if (stages == 4) return launch_one<KS_, 4>(tm, A, lda, r, nt, tiles, sh, live, nlive, num_sms, stream);   \
-        if (stages == 3) return launch_one<KS_, 3>(tm, A, lda, r, nt, tiles, sh, live, nlive, num_sms, stream);   \
-        if (stages == 2) return launch_one<KS_, 2>(tm, A, lda, r, nt, tiles, sh, live, nlive, num_sms, stream);   \
-        return launch_one<KS_, 5>(tm, A, lda, r, nt, tiles, sh, live, nlive, num_sms, stream);
+        if (stages == 4) return launch_one<KS_, 4>(tm, tmd, diag_eps, A, lda, r, nt, tiles, sh, live, nlive, num_sms, stream);   \
+        if (stages == 3) return launch_one<KS_, 3>(tm, tmd, diag_eps, A, lda, r, nt, tiles, sh, live, nlive, num_sms, stream);   \
+        if (stages == 2) return launch_one<KS_, 2>(tm, tmd, diag_eps, A, lda, r, nt, tiles, sh, live, nlive, num_sms, stream);   \
+        if (stages == 6 && KS_ <= 2)                                                                              \
+            return launch_one<KS_, (KS_ <= 2 ? 6 : 5)>(tm, tmd, diag_eps, A, lda, r, nt, tiles, sh, live, nlive, num_sms, stream); \
+        return launch_one<KS_, 5>(tm, tmd, diag_eps, A, lda, r, nt, tiles, sh, live, nlive, num_sms, stream);
     switch (ks) {
         TM_CASE(1) TM_CASE(2) TM_CASE(3) TM_CASE(4)
     }

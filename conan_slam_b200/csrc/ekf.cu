@@ -456,9 +456,11 @@ __global__ void __launch_bounds__(256) k_cov_update_rank(double* __restrict__ P,
 // 0..len-1) and the new 2x2 diagonal block are written inside the pre-allocated P.
 //   P[i][len+k] = (Gv * P[0:3, i])_k ;  P[len:len+2, len:len+2] = Gv Pvv Gv^T + Gz R Gz^T
 // Sharded: every rank writes the rows it owns; rows 0..2 also go to the replicated panel R3.
+// D (nullable): replicated diagonal-block cache — the new landmark's 2x2 block is entered directly.
 __global__ void __launch_bounds__(256) k_augment(double* __restrict__ X, double* __restrict__ P,
                                                  double* __restrict__ R3, size_t ld, int len, double r, double b,
-                                                 double r00, double r10, double r01, double r11, Shard sh) {
+                                                 double r00, double r10, double r01, double r11, Shard sh,
+                                                 double* __restrict__ D, int dcap) {
     const double phi = X[2];
     const double s = sin(phi + b), c = cos(phi + b);
     const double g02 = -r * s, g12 = r * c;
@@ -503,6 +505,7 @@ __global__ void __launch_bounds__(256) k_augment(double* __restrict__ X, double*
                 for (int k = 0; k < 3; k++) x += GP[a][k] * Gv[d][k];
                 for (int k = 0; k < 2; k++) y += GR[a][k] * Gz[d][k];
                 if (shard_owns(sh, len + a)) P[shard_lrow(sh, len + a) * ld + len + d] = x + y;
+                if (D != nullptr) D[(size_t)(a + d) * dcap + (len - 3) / 2] = x + y;
             }
     }
 }
@@ -693,14 +696,18 @@ int launch_gate(const double* X, const double* P, const double* R3, const double
                 unsigned long long* assoc_count, cudaStream_t stream);
 
 // ------------------------------------------------------------------------ accessors ----
-// sharded: every rank fills the entries it stores (zeros elsewhere) and the block is all-reduced
-__global__ void k_gather_block(const double* __restrict__ P, size_t ld, int r0, int c0, int nr, int nc,
-                               double* __restrict__ out, Shard sh) {
+// sharded: every rank fills the entries it stores (zeros elsewhere) and the block is all-reduced.
+// Rows 0..2 are read from R3 (rank 0's copy; on a lazy handle the big array's rows 0..2 are not maintained).
+__global__ void k_gather_block(const double* __restrict__ P, const double* __restrict__ R3, size_t ld, int r0, int c0,
+                               int nr, int nc, double* __restrict__ out, Shard sh) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (size_t)nr * nc) return;
     const int i = r0 + (int)(idx / nc), j = c0 + (int)(idx % nc);
     const int lo = i <= j ? i : j, hi = i <= j ? j : i;
-    out[idx] = shard_owns(sh, lo) ? P[shard_lrow(sh, lo) * ld + hi] : 0.0;
+    if (lo < 3)
+        out[idx] = sh.rank == 0 ? R3[(size_t)lo * ld + hi] : 0.0;
+    else
+        out[idx] = shard_owns(sh, lo) ? P[shard_lrow(sh, lo) * ld + hi] : 0.0;
 }
 __global__ void k_scatter_upper(double* __restrict__ P, double* __restrict__ R3, size_t ld, int n,
                                 const double* __restrict__ in, Shard sh) {
@@ -716,6 +723,10 @@ __global__ void k_scatter_upper(double* __restrict__ P, double* __restrict__ R3,
 size_t dmma_panel_doubles(int n_cap);
 int launch_cov_update_dmma(double* P, size_t ld, int n, const double* A, size_t lda, int r, Shard sh,
                            double* panels, int n_cap, int chunk, cudaStream_t stream);
+
+}  // namespace cslam
+#include "ekf_lazy.cuh"
+namespace cslam {
 
 // ------------------------------------------------------------------------------------
 // Host-side launch helpers
@@ -824,6 +835,22 @@ static int launch_cov_update(cslam_ekf* h, double diag_eps, const int* live = nu
 
 static int launch_cov_update_rank(cslam_ekf* h, int r) {
     const int n = h->n;
+    if (h->lz.on) {
+        // lazy handle (nothing pending, see cslam_ekf_update): tensor-core pass on the current array; rows 0..2
+        // and the diagonal-block cache follow with the same FMA operations on every rank
+        if (!h->dmma_panels) {
+            const size_t bytes = dmma_panel_doubles(h->n_cap) * sizeof(double);
+            CSLAM_CUDA(cudaMalloc(&h->dmma_panels, bytes));
+            CSLAM_CUDA(cudaMemsetAsync(h->dmma_panels, 0, bytes, h->stream));
+        }
+        {
+            ProfScope prof(h);
+            if (int rc = launch_cov_update_dmma(lazy_P(h), h->ld, n, h->A, h->lda, r, h->sh, h->dmma_panels, h->n_cap, 0,
+                                                h->stream))
+                return rc;
+        }
+        return lazy_follow(h, h->A, r, 0ULL);
+    }
     h->diag_dirty = true;
     // large maps (and every sharded map): FP64 tensor-core kernel; small maps: plain FMA kernel
     if (n >= 1024 || h->sh.world > 1) {
@@ -848,8 +875,11 @@ static int launch_cov_update_rank(cslam_ekf* h, int r) {
     ProfScope prof(h);
     const int nt = (n + 63) / 64;
     const size_t smem = (size_t)2 * r * 64 * sizeof(double);
-    CSLAM_CUDA(cudaFuncSetAttribute(k_cov_update_rank<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    2 * kMaxRank * 64 * (int)sizeof(double)));
+    if (!h->attr_rank) {  // once per handle (device), not per call
+        CSLAM_CUDA(cudaFuncSetAttribute(k_cov_update_rank<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        2 * kMaxRank * 64 * (int)sizeof(double)));
+        h->attr_rank = true;
+    }
     count_launch();
     k_cov_update_rank<64><<<(unsigned)shard_tile_count(nt, h->sh), 256, smem, h->stream>>>(h->P, h->ld, n, h->A,
                                                                                           h->lda, r, nt, h->sh);
@@ -1059,14 +1089,45 @@ static int create_common(cslam_ekf_t** out, int capacity_landmarks, int device, 
     TRY(cudaMemsetAsync(h->status, 0, sizeof(int), h->stream));
     TRY(cudaMemsetAsync(h->ticket, 0, 4 * sizeof(unsigned), h->stream));
     h->R3 = h->P;  // one GPU, or rank 0 of a sharded handle: rows 0..2 are the first rows of P
-    if (world > 1) {
-        if (rank != 0) {
+    {  // deferred covariance passes (ekf_lazy.cuh): large and sharded maps; CSLAM_LAZY=0/1 overrides
+        const char* e = getenv("CSLAM_LAZY");
+        h->lz.on = e ? atoi(e) != 0 : (h->n_cap >= 2048 || world > 1);
+    }
+    if (world > 1 || h->lz.on) {
+        if (rank != 0 || h->lz.on) {  // lazy handles keep rows 0..2 in their own panel on EVERY rank
             TRY(cudaMalloc(&h->R3, 3 * h->ld * sizeof(double)));
             TRY(cudaMemsetAsync(h->R3, 0, 3 * h->ld * sizeof(double), h->stream));
         }
         TRY(cudaMalloc(&h->colbuf, (size_t)kMaxRank * h->lda * sizeof(double)));
         h->dcap = std::max(capacity_landmarks, 1);
         TRY(cudaMalloc(&h->D, 3 * (size_t)h->dcap * sizeof(double)));
+        TRY(cudaMemsetAsync(h->D, 0, 3 * (size_t)h->dcap * sizeof(double), h->stream));
+    }
+    if (h->lz.on) {
+        LazyState& L = h->lz;
+        L.Pbuf[0] = h->P;
+        TRY(cudaDeviceGetAttribute(&L.num_sms, cudaDevAttrMultiProcessorCount, device));
+        TRY(cudaStreamCreateWithFlags(&L.pass_stream, cudaStreamNonBlocking));
+        TRY(cudaEventCreateWithFlags(&L.ev_chain, cudaEventDisableTiming));
+        TRY(cudaEventCreateWithFlags(&L.ev_pass, cudaEventDisableTiming));
+        if (const char* e = getenv("CSLAM_TMA_STAGES")) L.stages = atoi(e);
+        // ping-pong pair: the pass of bank k streams array a -> array b while the gains of the following scans
+        // read array a, so the chain never waits for a running pass.  Costs a second covariance array; taken
+        // when it fits comfortably (CSLAM_PINGPONG=0/1 overrides).
+        size_t free_b = 0, total_b = 0;
+        TRY(cudaMemGetInfo(&free_b, &total_b));
+        const char* e = getenv("CSLAM_PINGPONG");
+        L.pingpong = e ? atoi(e) != 0 : (free_b > pbytes + pbytes / 8 + ((size_t)2 << 30));
+        if (L.pingpong) {
+            TRY(cudaMalloc(&L.Pbuf[1], pbytes));
+            TRY(cudaMemsetAsync(L.Pbuf[1], 0, pbytes, h->stream));
+        }
+        for (int b = 0; b < (L.pingpong ? 2 : 1); b++)
+            if (make_cov_tensor_map(L.map[b], L.Pbuf[b], h->ld, (size_t)h->local_rows_cap) != CSLAM_OK)
+                return fail(CSLAM_ERR_CUDA);
+        if (!L.pingpong) memcpy(L.map[1], L.map[0], sizeof(L.map[0]));
+    }
+    if (world > 1) {
         const NcclApi* api = nccl_api();
         if (!api) return fail(CSLAM_ERR_NCCL);
         ncclUniqueId id;
@@ -1105,6 +1166,15 @@ int cslam_ekf_destroy(cslam_ekf_t* h) {
     if (!h) return CSLAM_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->lz.pass_stream) {
+        cudaStreamSynchronize(h->lz.pass_stream);
+        cudaStreamDestroy(h->lz.pass_stream);
+    }
+    if (h->lz.ev_chain) cudaEventDestroy(h->lz.ev_chain);
+    if (h->lz.ev_pass) cudaEventDestroy(h->lz.ev_pass);
+    cudaFree(h->lz.Pbuf[1]);
+    cudaFree(h->trace_dev);
+    cudaFree(h->acc_dev);
     if (h->comm) {
         const NcclApi* api = nccl_api();
         if (api) api->CommDestroy(h->comm);
@@ -1134,8 +1204,21 @@ int cslam_ekf_set_stream(cslam_ekf_t* h, void* cuda_stream) {
     return CSLAM_OK;
 }
 
+int cslam_ekf_flush(cslam_ekf_t* h) {
+    if (int rc = check_handle(h)) return rc;
+    return lazy_flush_all(h);
+}
+
+int cslam_ekf_pass_count(cslam_ekf_t* h, unsigned long long* passes, int* pending_rows) {
+    if (int rc = check_handle(h)) return rc;
+    if (passes) *passes = h->lz.passes;
+    if (pending_rows) *pending_rows = h->lz.on ? h->lz.np : 0;
+    return CSLAM_OK;
+}
+
 int cslam_ekf_sync(cslam_ekf_t* h, int* skipped_updates) {
     if (int rc = check_handle(h)) return rc;
+    if (int rc = lazy_flush_all(h)) return rc;
     if (skipped_updates) {
         CSLAM_CUDA(cudaMemcpyAsync(h->pinned, h->status, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CSLAM_CUDA(cudaStreamSynchronize(h->stream));
@@ -1168,6 +1251,7 @@ int cslam_ekf_predict(cslam_ekf_t* h, double v, double swa, const double Q[4], d
 int cslam_ekf_observe_heading(cslam_ekf_t* h, double phi, int use_heading) {
     if (int rc = check_handle(h)) return rc;
     if (!use_heading) return CSLAM_OK;  // EKF.cpp:332-335
+    if (h->lz.on) return lazy_heading(h, phi);
     const int n = h->n;
     const double sigma = 0.01F * kPi / 180.0F;  // EKF.cpp:337
     count_launch();
@@ -1182,16 +1266,31 @@ int cslam_ekf_observe_heading(cslam_ekf_t* h, double phi, int use_heading) {
 // all-reduce.  Needed only after reset / augment / a tensor-core joint update; the FMA-path updates
 // keep it current themselves (k_diag_follow).
 static int refresh_diag_cache(cslam_ekf* h) {
-    if (h->sh.world == 1 || !h->diag_dirty) return CSLAM_OK;
+    if ((h->sh.world == 1 && !h->lz.on) || !h->diag_dirty) return CSLAM_OK;
+    if (int rc = lazy_flush_all(h)) return rc;
     const int nf = (h->n - 3) / 2;
     CSLAM_CUDA(cudaMemsetAsync(h->D, 0, 3 * (size_t)h->dcap * sizeof(double), h->stream));
     if (nf > 0) {
         count_launch();
-        k_diag_pack<<<(nf + 255) / 256, 256, 0, h->stream>>>(h->P, h->ld, nf, h->D, h->dcap, h->sh);
+        k_diag_pack<<<(nf + 255) / 256, 256, 0, h->stream>>>(lazy_P(h), h->ld, nf, h->D, h->dcap, h->sh);
         CSLAM_CUDA(cudaGetLastError());
     }
-    if (int rc = allreduce_sum(h, h->D, 3 * (size_t)h->dcap)) return rc;
+    if (h->sh.world > 1)
+        if (int rc = allreduce_sum(h, h->D, 3 * (size_t)h->dcap)) return rc;
     h->diag_dirty = false;
+    return CSLAM_OK;
+}
+
+// device scratch owned by the handle: grown when a call needs more, never allocated per call
+static int ensure_scratch(cslam_ekf* h, double** buf, size_t* cap, size_t doubles) {
+    if (*cap >= doubles) return CSLAM_OK;
+    CSLAM_CUDA(cudaStreamSynchronize(h->stream));
+    cudaFree(*buf);
+    *buf = nullptr;
+    *cap = 0;
+    const size_t want = std::max<size_t>(doubles, 4096);
+    CSLAM_CUDA(cudaMalloc(buf, want * sizeof(double)));
+    *cap = want;
     return CSLAM_OK;
 }
 
@@ -1203,9 +1302,27 @@ int cslam_ekf_control_steps(cslam_ekf_t* h, int k, const double* v, const double
     CSLAM_REQUIRE(v && swa && Q && (phi || !use_heading), CSLAM_ERR_BAD_ARG, "null argument");
     const double sigma = 0.01F * kPi / 180.0F;  // EKF.cpp:337
     double* trace_dev = nullptr;
-    if (pose_trace) CSLAM_CUDA(cudaMalloc(&trace_dev, (size_t)3 * k * sizeof(double)));
+    if (pose_trace) {
+        if (int rc = ensure_scratch(h, &h->trace_dev, &h->trace_cap, (size_t)3 * k)) return rc;
+        trace_dev = h->trace_dev;
+    }
     int rc = CSLAM_OK;
-    for (int base = 0; base < k && rc == CSLAM_OK; base += kMaxControlSteps) {
+    if (h->lz.on) {
+        // lazy handle: per step the O(n) kernels only (predict on rows 0..2, heading gain, R3 / D follow); the
+        // rank-1 terms join the pending bank and are applied by the next pass together with whatever else
+        // is pending — a whole drive cycle of test/main.cpp streams the covariance once
+        for (int st = 0; st < k && rc == CSLAM_OK; st++) {
+            rc = cslam_ekf_predict(h, v[st], swa[st], Q, wb, dt);
+            if (rc == CSLAM_OK && use_heading) rc = lazy_heading(h, phi[st]);
+            if (rc == CSLAM_OK && trace_dev) {
+                cudaError_t e = cudaMemcpyAsync(trace_dev + 3 * st, h->X[h->cur], 3 * sizeof(double),
+                                                cudaMemcpyDeviceToDevice, h->stream);
+                if (e != cudaSuccess) rc = CSLAM_ERR_CUDA;
+            }
+        }
+        k = rc == CSLAM_OK ? k : 0;
+    }
+    for (int base = 0; base < k && rc == CSLAM_OK && !h->lz.on; base += kMaxControlSteps) {
         const int kc = std::min(kMaxControlSteps, k - base);
         const int n = h->n;
         int width = 0;
@@ -1276,10 +1393,6 @@ int cslam_ekf_control_steps(cslam_ekf_t* h, int k, const double* v, const double
             rc = CSLAM_ERR_CUDA;
         }
     }
-    if (trace_dev) {
-        cudaStreamSynchronize(h->stream);
-        cudaFree(trace_dev);
-    }
     return rc;
 }
 
@@ -1293,7 +1406,7 @@ int cslam_ekf_gate(cslam_ekf_t* h, const double* Z, int m, const double R[4], do
         if (int rc = refresh_diag_cache(h)) return rc;
     for (int base = 0; base < m; base += CSLAM_MAX_OBS) {
         const int mc = std::min(CSLAM_MAX_OBS, m - base);
-        if (int rc = launch_gate(h->X[h->cur], h->P, h->R3, h->sh.world > 1 ? h->D : nullptr, h->dcap, h->ld, nf,
+        if (int rc = launch_gate(h->X[h->cur], h->P, h->R3, (h->sh.world > 1 || h->lz.on) ? h->D : nullptr, h->dcap, h->ld, nf,
                                  Z + 2 * base, mc, R, gate1, gate2, h->gate.part_nd, h->gate.part_out,
                                  h->gate.part_j, h->ticket + 1, h->gate.d_jbest, h->gate.d_nbest, h->gate.d_outer,
                                  nullptr, h->stream))
@@ -1325,8 +1438,9 @@ int cslam_ekf_update(cslam_ekf_t* h, const double* Z, const int32_t* idf, int m,
     const bool sharded = h->sh.world > 1;
     for (int i = 0; i < m; i++)
         CSLAM_REQUIRE(idf[i] >= 1 && idf[i] <= nf, CSLAM_ERR_BAD_ARG, "idf out of range (1-based map slots)");
-    if (!batch) return sequential_updates(h, Z, idf, nullptr, m, R);
+    if (!batch) return h->lz.on ? lazy_sequential(h, Z, idf, nullptr, m, R) : sequential_updates(h, Z, idf, nullptr, m, R);
     CSLAM_REQUIRE(m <= CSLAM_MAX_BATCH_OBS, CSLAM_ERR_UNSUPPORTED, "joint update supports at most 32 observations");
+    if (int rc = lazy_flush_all(h)) return rc;  // the joint update reads its 2m columns from the up-to-date array
     ObsPack ob;
     memset(&ob, 0, sizeof(ob));
     memcpy(ob.z, Z, sizeof(double) * 2 * m);
@@ -1336,14 +1450,18 @@ int cslam_ekf_update(cslam_ekf_t* h, const double* Z, const int32_t* idf, int m,
     const int r = 2 * m;
     count_launch();
     k_batch_prep<<<1, CSLAM_MAX_BATCH_OBS, 0, h->stream>>>(h->X[h->cur], ob, h->small);
-    if (sharded) {
+    if (sharded || h->lz.on) {
         ColList cl;
         cl.n = r;
         for (int k = 0; k < m; k++) {
             cl.c[2 * k] = 3 + 2 * (idf[k] - 1);
             cl.c[2 * k + 1] = cl.c[2 * k] + 1;
         }
-        if (int rc = exchange_columns(h, cl)) return rc;
+        if (h->lz.on) {
+            if (int rc = lazy_snapshot(h, cl, nullptr)) return rc;
+        } else {
+            if (int rc = exchange_columns(h, cl)) return rc;
+        }
         count_launch();
         k_batch_pht<true><<<dim3((n + 127) / 128, m), 128, 0, h->stream>>>(h->P, h->R3, h->colbuf, h->ld, n, m,
                                                                             h->small, h->PHT, h->lda);
@@ -1353,7 +1471,10 @@ int cslam_ekf_update(cslam_ekf_t* h, const double* Z, const int32_t* idf, int m,
                                                                              h->small, h->PHT, h->lda);
     }
     const int chol_smem = 2 * kMaxRank * (kMaxRank + 1) * (int)sizeof(double);
-    CSLAM_CUDA(cudaFuncSetAttribute(k_batch_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, chol_smem));
+    if (!h->attr_chol) {  // once per handle (device), not per call
+        CSLAM_CUDA(cudaFuncSetAttribute(k_batch_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, chol_smem));
+        h->attr_chol = true;
+    }
     count_launch();
     k_batch_chol<<<1, 256, chol_smem, h->stream>>>(h->PHT, h->lda, m, R[0], R[1], R[2], R[3], h->flags, h->small,
                                                    h->status);
@@ -1374,7 +1495,7 @@ int cslam_ekf_scan(cslam_ekf_t* h, const double* Z, int m, const double R[4], do
     const int n = h->n, nf = (n - 3) / 2;
     if (int rc = refresh_diag_cache(h)) return rc;
     // dataAssociate at the pre-update state for the whole scan (test/main.cpp:193), indices stay in d_jbest
-    if (int rc = launch_gate(h->X[h->cur], h->P, h->R3, h->sh.world > 1 ? h->D : nullptr, h->dcap, h->ld, nf, Z, m, R,
+    if (int rc = launch_gate(h->X[h->cur], h->P, h->R3, (h->sh.world > 1 || h->lz.on) ? h->D : nullptr, h->dcap, h->ld, nf, Z, m, R,
                              gate1, gate2,
                              h->gate.part_nd, h->gate.part_out, h->gate.part_j, h->ticket + 1, h->gate.d_jbest,
                              h->gate.d_nbest, h->gate.d_outer, h->assoc_count, h->stream))
@@ -1387,7 +1508,9 @@ int cslam_ekf_scan(cslam_ekf_t* h, const double* Z, int m, const double R[4], do
     }
     // singleUpdate (EKF.cpp:457-479): re-linearised per observation, in observation order
     if (nf > 0) {
-        if (int rc = sequential_updates(h, Z, nullptr, h->gate.d_jbest, m, R)) return rc;
+        if (int rc = h->lz.on ? lazy_sequential(h, Z, nullptr, h->gate.d_jbest, m, R)
+                              : sequential_updates(h, Z, nullptr, h->gate.d_jbest, m, R))
+            return rc;
     }
     if (jbest || is_new) {
         CSLAM_CUDA(cudaEventSynchronize(h->scan_ev));
@@ -1417,15 +1540,19 @@ int cslam_ekf_augment(cslam_ekf_t* h, const double* Z, int m, const double R[4])
     if (m == 0) return CSLAM_OK;
     CSLAM_REQUIRE(Z && R, CSLAM_ERR_BAD_ARG, "null argument");
     CSLAM_REQUIRE(h->n + 2 * m <= h->n_cap, CSLAM_ERR_CAPACITY, "landmark capacity exceeded");
+    // lazy handle: the new columns are written into the up-to-date array (pending panel rows end at the old n)
+    if (int rc = lazy_flush_all(h)) return rc;
+    const bool dcache = h->lz.on && !h->diag_dirty;  // enter the new 2x2 blocks into the cache directly
     for (int i = 0; i < m; i++) {
         const int len = h->n;
         count_launch();
-        k_augment<<<(len + 255) / 256, 256, 0, h->stream>>>(h->X[h->cur], h->P, h->R3, h->ld, len, Z[2 * i],
-                                                            Z[2 * i + 1], R[0], R[1], R[2], R[3], h->sh);
+        k_augment<<<(len + 255) / 256, 256, 0, h->stream>>>(h->X[h->cur], lazy_P(h), h->R3, h->ld, len, Z[2 * i],
+                                                            Z[2 * i + 1], R[0], R[1], R[2], R[3], h->sh,
+                                                            dcache ? h->D : nullptr, h->dcap);
         CSLAM_CUDA(cudaGetLastError());
         h->n += 2;
     }
-    h->diag_dirty = true;
+    if (!dcache) h->diag_dirty = true;
     return CSLAM_OK;
 }
 
@@ -1443,20 +1570,54 @@ int cslam_ekf_get_cov_block(cslam_ekf_t* h, int r0, int c0, int nr, int nc, doub
     CSLAM_REQUIRE(out && r0 >= 0 && c0 >= 0 && nr >= 0 && nc >= 0 && r0 + nr <= h->n && c0 + nc <= h->n,
                   CSLAM_ERR_BAD_ARG, "block out of range");
     if (nr == 0 || nc == 0) return CSLAM_OK;
-    double* tmp = nullptr;
+    if (int rc = lazy_flush_all(h)) return rc;
     const size_t cnt = (size_t)nr * nc;
-    CSLAM_CUDA(cudaMalloc(&tmp, cnt * sizeof(double)));
+    if (int rc = ensure_scratch(h, &h->acc_dev, &h->acc_cap, cnt)) return rc;
+    double* tmp = h->acc_dev;
     count_launch();
-    k_gather_block<<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(h->P, h->ld, r0, c0, nr, nc, tmp, h->sh);
-    cudaError_t e = cudaGetLastError();
-    int rc = CSLAM_OK;
-    if (e == cudaSuccess && h->sh.world > 1) rc = allreduce_sum(h, tmp, cnt);  // collective: all ranks call
-    if (e == cudaSuccess && rc == CSLAM_OK)
-        e = cudaMemcpyAsync(out, tmp, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    cudaFree(tmp);
-    if (rc) return rc;
-    CSLAM_CUDA(e);
+    k_gather_block<<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(lazy_P(h), h->R3, h->ld, r0, c0, nr, nc, tmp,
+                                                                         h->sh);
+    CSLAM_CUDA(cudaGetLastError());
+    if (h->sh.world > 1)
+        if (int rc = allreduce_sum(h, tmp, cnt)) return rc;  // collective: all ranks call
+    CSLAM_CUDA(cudaMemcpyAsync(out, tmp, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CSLAM_CUDA(cudaStreamSynchronize(h->stream));
+    return CSLAM_OK;
+}
+
+// Arbitrary principal sub-matrix: out[a * k + b] = P(idx[a], idx[b]) — the joint marginal of a set of state
+// entries (e.g. the pose and a handful of landmarks) without reading P back.
+__global__ void k_gather_sub(const double* __restrict__ P, const double* __restrict__ R3, size_t ld,
+                             const int* __restrict__ idx, int k, double* __restrict__ out, Shard sh) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)k * k) return;
+    const int i = idx[t / k], j = idx[t % k];
+    const int lo = i <= j ? i : j, hi = i <= j ? j : i;
+    if (lo < 3)
+        out[t] = sh.rank == 0 ? R3[(size_t)lo * ld + hi] : 0.0;
+    else
+        out[t] = shard_owns(sh, lo) ? P[shard_lrow(sh, lo) * ld + hi] : 0.0;
+}
+
+int cslam_ekf_get_cov_gather(cslam_ekf_t* h, const int32_t* idx, int k, double* out) {
+    if (int rc = check_handle(h)) return rc;
+    CSLAM_REQUIRE(k >= 0 && k <= 8192, CSLAM_ERR_BAD_ARG, "k out of range (0..8192)");
+    if (k == 0) return CSLAM_OK;
+    CSLAM_REQUIRE(idx && out, CSLAM_ERR_BAD_ARG, "null argument");
+    for (int a = 0; a < k; a++) CSLAM_REQUIRE(idx[a] >= 0 && idx[a] < h->n, CSLAM_ERR_BAD_ARG, "state index out of range");
+    if (int rc = lazy_flush_all(h)) return rc;
+    const size_t cnt = (size_t)k * k;
+    // scratch: k*k doubles of output followed by the k indices
+    if (int rc = ensure_scratch(h, &h->acc_dev, &h->acc_cap, cnt + (size_t)(k + 1) / 2)) return rc;
+    int* didx = reinterpret_cast<int*>(h->acc_dev + cnt);
+    CSLAM_CUDA(cudaMemcpyAsync(didx, idx, (size_t)k * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    count_launch();
+    k_gather_sub<<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(lazy_P(h), h->R3, h->ld, didx, k, h->acc_dev, h->sh);
+    CSLAM_CUDA(cudaGetLastError());
+    if (h->sh.world > 1)
+        if (int rc = allreduce_sum(h, h->acc_dev, cnt)) return rc;  // collective: all ranks call
+    CSLAM_CUDA(cudaMemcpyAsync(out, h->acc_dev, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CSLAM_CUDA(cudaStreamSynchronize(h->stream));
     return CSLAM_OK;
 }
 
@@ -1485,20 +1646,17 @@ int cslam_ekf_get_landmark_covs(cslam_ekf_t* h, int first_landmark, int count, d
                   "landmark range out of bounds (1-based ids)");
     if (count == 0) return CSLAM_OK;
     CSLAM_REQUIRE(out != nullptr, CSLAM_ERR_BAD_ARG, "out is null");
-    double* tmp = nullptr;
+    if (int rc = lazy_flush_all(h)) return rc;
     const size_t cnt = 3 * (size_t)count;
-    CSLAM_CUDA(cudaMalloc(&tmp, cnt * sizeof(double)));
+    if (int rc = ensure_scratch(h, &h->acc_dev, &h->acc_cap, cnt)) return rc;
+    double* tmp = h->acc_dev;
     count_launch();
-    k_landmark_covs<<<(count + 255) / 256, 256, 0, h->stream>>>(h->P, h->ld, first_landmark - 1, count, tmp, h->sh);
-    cudaError_t e = cudaGetLastError();
-    int rc = CSLAM_OK;
-    if (e == cudaSuccess && h->sh.world > 1) rc = allreduce_sum(h, tmp, cnt);  // collective: all ranks call
-    if (e == cudaSuccess && rc == CSLAM_OK)
-        e = cudaMemcpyAsync(out, tmp, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    cudaFree(tmp);
-    if (rc) return rc;
-    CSLAM_CUDA(e);
+    k_landmark_covs<<<(count + 255) / 256, 256, 0, h->stream>>>(lazy_P(h), h->ld, first_landmark - 1, count, tmp, h->sh);
+    CSLAM_CUDA(cudaGetLastError());
+    if (h->sh.world > 1)
+        if (int rc = allreduce_sum(h, tmp, cnt)) return rc;  // collective: all ranks call
+    CSLAM_CUDA(cudaMemcpyAsync(out, tmp, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CSLAM_CUDA(cudaStreamSynchronize(h->stream));
     return CSLAM_OK;
 }
 
@@ -1520,7 +1678,9 @@ int cslam_ekf_save(cslam_ekf_t* h, const char* path) {
     if (int rc = check_handle(h)) return rc;
     CSLAM_REQUIRE(path != nullptr, CSLAM_ERR_BAD_ARG, "path is null");
     CSLAM_REQUIRE(h->sh.world == 1, CSLAM_ERR_UNSUPPORTED, "checkpoints are single-GPU (sharded: save per block)");
+    if (int rc = lazy_flush_all(h)) return rc;
     CSLAM_CUDA(cudaStreamSynchronize(h->stream));
+    const double* Psrc = lazy_P(h);
     FILE* f = fopen(path, "wb");
     CSLAM_REQUIRE(f != nullptr, CSLAM_ERR_BAD_ARG, "cannot open checkpoint file for writing");
     const int n = h->n;
@@ -1539,8 +1699,11 @@ int cslam_ekf_save(cslam_ekf_t* h, const char* path) {
     std::vector<double> rows((size_t)slab * n);
     for (int i0 = 0; ok && i0 < n; i0 += slab) {
         const int nr = std::min(slab, n - i0);
-        e = cudaMemcpy2D(rows.data(), (size_t)n * sizeof(double), h->P + (size_t)i0 * h->ld, h->ld * sizeof(double),
+        e = cudaMemcpy2D(rows.data(), (size_t)n * sizeof(double), Psrc + (size_t)i0 * h->ld, h->ld * sizeof(double),
                          (size_t)n * sizeof(double), nr, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && i0 == 0 && h->R3 != Psrc)  // lazy handle: rows 0..2 live in their own panel
+            e = cudaMemcpy2D(rows.data(), (size_t)n * sizeof(double), h->R3, h->ld * sizeof(double),
+                             (size_t)n * sizeof(double), std::min(3, nr), cudaMemcpyDeviceToHost);
         ok = e == cudaSuccess;
         for (int r = 0; ok && r < nr; r++) {
             const int i = i0 + r;
@@ -1569,8 +1732,33 @@ int cslam_ekf_load(cslam_ekf_t* h, const char* path) {
         set_last_error("cslam_ekf_load: not a checkpoint of this library, or it exceeds the handle's capacity");
         return CSLAM_ERR_BAD_ARG;
     }
+    // validate BEFORE touching device state: quirk mode and exact length (a truncated file must not leave a
+    // half-overwritten handle behind)
+    if (hd.flags != h->flags) {
+        fclose(f);
+        set_last_error("cslam_ekf_load: checkpoint written with flags 0x%x, handle created with 0x%x", hd.flags, h->flags);
+        return CSLAM_ERR_BAD_ARG;
+    }
+    {
+        const long long want = (long long)sizeof(hd) + 8LL * hd.n + 4LL * hd.n * ((long long)hd.n + 1);
+        long long have = -1;
+        if (fseek(f, 0, SEEK_END) == 0) have = ftell(f);
+        if (have != want || fseek(f, (long)sizeof(hd), SEEK_SET) != 0) {
+            fclose(f);
+            set_last_error("cslam_ekf_load: checkpoint length %lld, expected %lld (truncated or corrupt)", have, want);
+            return CSLAM_ERR_BAD_ARG;
+        }
+    }
     const int n = hd.n;
     CSLAM_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->lz.on) {  // the state is replaced: drop pending terms, array 0 becomes current
+        LazyState& L = h->lz;
+        CSLAM_CUDA(cudaStreamSynchronize(L.pass_stream));
+        L.stable = L.newest = 0;
+        L.np = L.infl_rows = 0;
+        L.eps_mask = L.infl_eps_mask = 0;
+        L.pass_pending_wait = false;
+    }
     std::vector<double> x((size_t)n);
     ok = fread(x.data(), sizeof(double), n, f) == (size_t)n;
     cudaError_t e = cudaSuccess;
@@ -1594,6 +1782,7 @@ int cslam_ekf_load(cslam_ekf_t* h, const char* path) {
         return CSLAM_ERR_CUDA;
     }
     CSLAM_REQUIRE(ok, CSLAM_ERR_BAD_ARG, "truncated checkpoint file");
+    if (h->R3 != h->P) CSLAM_CUDA(cudaMemcpy(h->R3, h->P, 3 * h->ld * sizeof(double), cudaMemcpyDeviceToDevice));
     h->n = n;
     h->diag_dirty = true;
     CSLAM_CUDA(cudaMemsetAsync(h->status, 0, sizeof(int), h->stream));
@@ -1610,23 +1799,26 @@ int cslam_ekf_reset(cslam_ekf_t* h, const double* X, int n, const double* P) {
     h->cur = 0;
     h->n = n;
     h->diag_dirty = true;
+    if (h->lz.on) {  // drop whatever is pending or in flight: the state is replaced
+        LazyState& L = h->lz;
+        CSLAM_CUDA(cudaStreamSynchronize(L.pass_stream));
+        L.stable = L.newest = 0;
+        L.np = L.infl_rows = 0;
+        L.eps_mask = L.infl_eps_mask = 0;
+        L.pass_pending_wait = false;
+    }
     CSLAM_CUDA(cudaMemsetAsync(h->P, 0, (size_t)h->local_rows_cap * h->ld * sizeof(double), h->stream));
     if (h->R3 != h->P) CSLAM_CUDA(cudaMemsetAsync(h->R3, 0, 3 * h->ld * sizeof(double), h->stream));
     CSLAM_CUDA(cudaMemsetAsync(h->status, 0, sizeof(int), h->stream));
     CSLAM_CUDA(cudaStreamSynchronize(h->stream));
     if (P) {
-        double* tmp = nullptr;
         const size_t cnt = (size_t)n * n;
-        CSLAM_CUDA(cudaMalloc(&tmp, cnt * sizeof(double)));
-        cudaError_t e = cudaMemcpyAsync(tmp, P, cnt * sizeof(double), cudaMemcpyHostToDevice, h->stream);
-        if (e == cudaSuccess) {
-            count_launch();
-            k_scatter_upper<<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(h->P, h->R3, h->ld, n, tmp, h->sh);
-            e = cudaGetLastError();
-        }
-        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-        cudaFree(tmp);
-        CSLAM_CUDA(e);
+        if (int rc = ensure_scratch(h, &h->acc_dev, &h->acc_cap, cnt)) return rc;
+        CSLAM_CUDA(cudaMemcpyAsync(h->acc_dev, P, cnt * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        count_launch();
+        k_scatter_upper<<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(h->P, h->R3, h->ld, n, h->acc_dev, h->sh);
+        CSLAM_CUDA(cudaGetLastError());
+        CSLAM_CUDA(cudaStreamSynchronize(h->stream));
     }
     return CSLAM_OK;
 }
@@ -1649,6 +1841,7 @@ int cslam_ekf_profile_end(cslam_ekf_t* h, double* ms, int* launches, double* byt
     if (int rc = check_handle(h)) return rc;
     h->prof = false;
     CSLAM_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->lz.pass_stream) CSLAM_CUDA(cudaStreamSynchronize(h->lz.pass_stream));
     double total = 0.0;
     for (int i = 0; i + 1 < h->prof_used; i += 2) {
         float t = 0.f;
@@ -1663,8 +1856,9 @@ int cslam_ekf_profile_end(cslam_ekf_t* h, double* ms, int* launches, double* byt
 
 int cslam_ekf_device_ptrs(cslam_ekf_t* h, void** dX, void** dP, size_t* ld) {
     if (int rc = check_handle(h)) return rc;
+    if (int rc = lazy_flush_all(h)) return rc;
     if (dX) *dX = h->X[h->cur];
-    if (dP) *dP = h->P;
+    if (dP) *dP = lazy_P(h);  // lazy handles: rows 0..2 live in their own panel, not in this array
     if (ld) *ld = h->ld;
     return CSLAM_OK;
 }

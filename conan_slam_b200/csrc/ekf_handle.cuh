@@ -21,6 +21,37 @@ struct BatchSmall {  // device-resident scratch of the joint update (EKF.cpp:93-
     int f[CSLAM_MAX_BATCH_OBS];
 };
 
+// Deferred covariance passes ("lazy" engine, large and sharded maps; ekf_lazy.cuh).  The big array holds
+//   P_dev = P_true + (sum of the pending rank-1 terms)  for rows >= 3,
+// while X, rows 0..2 (R3) and the landmarks' 2x2 diagonal blocks (D) are always current.  Heading updates and
+// landmark updates append their panel rows to a BANK of kLazyBank rows; one TMA / tensor-core pass
+// (cov_tma.cu) applies a whole bank — e.g. the six heading updates and the four observations of one
+// test/main.cpp drive cycle in ONE read + write of the covariance instead of two (round 1) or ten (reference).
+// Gains read the few entries of P they need from a column snapshot and bring them up to date with the
+// pending terms themselves.  The pass runs on its own stream and overlaps the gate / gain chain of the
+// following scans; with a ping-pong pair of arrays the chain never waits for a pass that is still running.
+constexpr int kLazyBank = 16;  // panel rows per bank = rank of one pass (cov_tma.cu: KS <= 4)
+struct LazyState {
+    bool on = false;
+    bool pingpong = false;
+    double* Pbuf[2] = {nullptr, nullptr};  // Pbuf[0] == h->P; Pbuf[1] only with pingpong
+    unsigned char map[2][128];             // tensor maps of Pbuf[0 / 1] (64 bytes used, copied by value per launch)
+    int stable = 0;   // array the chain stream may read: never written by a pass in flight when pingpong
+    int newest = 0;   // array that holds the newest state once every launched pass has completed
+    int bank = 0;     // bank that receives new panel rows: rows [bank * kLazyBank, +kLazyBank) of h->A
+    int np = 0;       // rows pending in `bank`
+    unsigned eps_mask = 0;       // bit k: pending row k is a heading term (diagonal += FLT_MIN, slam.h:719)
+    int infl_rows = 0;           // rows of the OTHER bank that the pass in flight applies and `stable` lacks
+    unsigned infl_eps_mask = 0;
+    bool pass_pending_wait = false;  // a pass was launched and the chain stream has not waited for it yet
+    cudaStream_t pass_stream = nullptr;
+    cudaEvent_t ev_chain = nullptr;  // "every reader of the array the next pass overwrites is done"
+    cudaEvent_t ev_pass = nullptr;   // completion of the most recently launched pass
+    int num_sms = 0;
+    int stages = 4;
+    unsigned long long passes = 0;   // passes launched since create (diagnostics)
+};
+
 struct GateScratch {
     double* part_nd = nullptr;   // [blocks][m]
     double* part_out = nullptr;  // [blocks][m]
@@ -66,6 +97,12 @@ struct cslam_ekf {
     double* D = nullptr;         // [3][dcap] replicated cache of the 2x2 diagonal blocks (gating)
     int dcap = 0;
     bool diag_dirty = true;
+    cslam::LazyState lz;
+    double* trace_dev = nullptr;  // pose trace of cslam_ekf_control_steps (grown on demand, never per call)
+    size_t trace_cap = 0;
+    double* acc_dev = nullptr;    // scratch of the accessors (cov block / landmark marginals), grown on demand
+    size_t acc_cap = 0;
+    bool attr_chol = false, attr_rank = false;  // cudaFuncSetAttribute done for this handle's device
     // diagnostics: event pairs around covariance-update launches
     bool prof = false;
     std::vector<cudaEvent_t> prof_ev;
@@ -78,12 +115,14 @@ namespace cslam {
 struct ProfScope {  // records start/stop events around one covariance-update launch when profiling
     cslam_ekf* h;
     bool on;
-    explicit ProfScope(cslam_ekf* h_) : h(h_), on(h_->prof && h_->prof_used + 2 <= (int)h_->prof_ev.size()) {
-        if (on) cudaEventRecord(h->prof_ev[h->prof_used], h->stream);
+    cudaStream_t st;
+    explicit ProfScope(cslam_ekf* h_, cudaStream_t stream = nullptr)
+        : h(h_), on(h_->prof && h_->prof_used + 2 <= (int)h_->prof_ev.size()), st(stream ? stream : h_->stream) {
+        if (on) cudaEventRecord(h->prof_ev[h->prof_used], st);
     }
     ~ProfScope() {
         if (on) {
-            cudaEventRecord(h->prof_ev[h->prof_used + 1], h->stream);
+            cudaEventRecord(h->prof_ev[h->prof_used + 1], st);
             h->prof_used += 2;
             h->prof_bytes += 8.0 * (double)h->n * ((double)h->n + 1.0) / (double)h->sh.world;
         }

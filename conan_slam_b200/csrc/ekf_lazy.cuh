@@ -1,0 +1,366 @@
+// ekf_lazy.cuh — deferred covariance passes for large and sharded maps (included by ekf.cu, same
+// -fmad=false translation unit).  See LazyState in ekf_handle.cuh for the invariant:
+//     P_dev(rows >= 3) = P_true + sum of the pending rank-1 terms,   X, R3 (rows 0..2), D (2x2 blocks) current.
+// Every Kalman update of the reference is  P <- P - W1 W1^T  (slam.h:260; the Joseph form of the heading
+// update slam.h:718 reduces to the same shape, see k_heading_gain), so a sequence of updates — the k heading
+// updates of k control steps (EKF.cpp:328-352) and the m sequential landmark updates of a scan
+// (EKF.cpp:457-479) — is a sum of rank-1 terms that ONE pass over the covariance can apply.  What an update
+// needs of P_true is tiny: rows 0..2 (kept current eagerly), the observed landmark's two columns (read from a
+// column snapshot and corrected by the pending terms inside the gain kernel) and, for gating, the landmarks'
+// 2x2 diagonal blocks (kept current eagerly).  Nothing else of P is ever read between passes.
+#pragma once
+#include <algorithm>
+
+#include "common.cuh"
+#include "cov_update.cuh"
+#include "ekf_handle.cuh"
+
+namespace cslam {
+
+// defined in cov_tma.cu
+int make_cov_tensor_map(void* out_map64, double* P, size_t ld, size_t rows);
+int launch_cov_update_tma(const void* src_map, const void* dst_map, int n, const double* A, size_t lda, int r,
+                          double diag_eps, Shard sh, const int* live, int nlive, int num_sms, int stages,
+                          cudaStream_t stream);
+
+constexpr int kSeqGroupLazy = 8;  // observations per column snapshot (2 x 8 columns exchanged at once)
+
+// Pending rank-1 terms as a gain kernel sees them: first the rows of the bank that the pass in flight is
+// applying (the column snapshot was taken from the array that pass READS), then the rows of the current bank.
+struct PendView {
+    const double* A0;
+    int n0;
+    unsigned eps0;
+    const double* A1;
+    int n1;
+    unsigned eps1;
+    int r3_from;  // rows 0..2 are current up to the start of the running group: they lack terms >= r3_from only
+};
+__device__ __forceinline__ const double* pend_row(const PendView& pv, size_t lda, int t) {
+    return t < pv.n0 ? pv.A0 + (size_t)t * lda : pv.A1 + (size_t)(t - pv.n0) * lda;
+}
+__device__ __forceinline__ bool pend_eps(const PendView& pv, int t) {
+    return t < pv.n0 ? ((pv.eps0 >> t) & 1u) != 0 : ((pv.eps1 >> (t - pv.n0)) & 1u) != 0;
+}
+
+// Column snapshot: colbuf[k][i] = P_dev(i, c_k) for the listed columns (symmetric read of the upper triangle;
+// rows 0..2 come from the always-current R3).  Sharded: every rank contributes what it stores, zeros
+// elsewhere, and an all-reduce completes the columns (x + 0 is exact).  idf_dev (nullable): fused scan —
+// column k belongs to observation k/2 whose 1-based landmark index sits in device memory (0 = none).
+__global__ void __launch_bounds__(256) k_col_pack_lazy(const double* __restrict__ P, const double* __restrict__ R3,
+                                                       size_t ld, int n, ColList cl, double* __restrict__ colbuf,
+                                                       size_t lda, Shard sh, const int* __restrict__ idf_dev) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;
+    if (i >= n) return;
+    int c = cl.c[k];
+    if (idf_dev != nullptr) {
+        const int j = idf_dev[k >> 1];
+        c = j > 0 ? 3 + 2 * (j - 1) + (k & 1) : -1;
+    }
+    double v = 0.0;
+    if (c < 0) {
+    } else if (i < 3) {
+        if (sh.rank == 0) v = R3[(size_t)i * ld + c];
+    } else if (i <= c) {
+        if (shard_owns(sh, i)) v = P[shard_lrow(sh, i) * ld + c];
+    } else {
+        if (shard_owns(sh, c)) v = P[shard_lrow(sh, c) * ld + i];
+    }
+    colbuf[(size_t)k * lda + i] = v;
+}
+
+// slam.h:243-259 for one observation (sparse H), reading P through the column snapshot and the pending terms.
+// Writes Xout = Xin + W v and the two panel rows W1 (Aout, Aout + lda) that join the pending terms.
+__global__ void __launch_bounds__(256) k_gain_lazy(const double* Xin, double* Xout, const double* __restrict__ R3,
+                                                   const double* __restrict__ colbuf, size_t ld, size_t lda, int n,
+                                                   double zr, double zb, int idf, double r00, double r10, double r01,
+                                                   double r11, unsigned flags, PendView pv, double* Aout,
+                                                   int* __restrict__ status, const int* __restrict__ idf_dev) {
+    __shared__ GainSmall g;
+    __shared__ double sPc[5][5];
+    __shared__ double sAc[2 * kLazyBank][5];  // a_t[c] for the five columns c in {0, 1, 2, f, f+1}
+    if (idf_dev != nullptr) idf = *idf_dev;
+    const int i0 = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    if (idf == 0) {  // no landmark passed the gate: X is carried over, zero panel rows are a no-op update
+        for (int i = i0; i < n; i += stride) {
+            Xout[i] = Xin[i];
+            Aout[i] = 0.0;
+            Aout[lda + i] = 0.0;
+        }
+        return;
+    }
+    const int f = 3 + 2 * (idf - 1);
+    const int nterm = pv.n0 + pv.n1;
+    for (int idx = threadIdx.x; idx < nterm * 5; idx += blockDim.x) {
+        const int t = idx / 5, b = idx % 5;
+        sAc[t][b] = pend_row(pv, lda, t)[b < 3 ? b : f + (b - 3)];
+    }
+    __syncthreads();
+    if (threadIdx.x < 25) {  // the 5x5 block of P_true at {0, 1, 2, f, f+1}
+        const int a = threadIdx.x / 5, b = threadIdx.x % 5;
+        const int lo = min(a, b), hi = max(a, b);  // block indices; columns: lo/hi < 3 ? itself : f + (x - 3)
+        double v;
+        int t0;
+        if (lo < 3) {
+            v = R3[(size_t)lo * ld + (hi < 3 ? hi : f + (hi - 3))];
+            t0 = pv.r3_from;
+        } else {  // both in {f, f+1}: P(f + lo - 3, f + hi - 3) = snapshot column (hi - 3), row f + lo - 3
+            v = colbuf[(size_t)(hi - 3) * lda + f + (lo - 3)];
+            t0 = 0;
+        }
+        for (int t = t0; t < nterm; t++) {
+            v = v - sAc[t][lo] * sAc[t][hi];
+            if (lo == hi && pend_eps(pv, t)) v += kFltMin;
+        }
+        sPc[a][b] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double Pc[5][5];
+        for (int a = 0; a < 5; a++)
+            for (int b = 0; b < 5; b++) Pc[a][b] = sPc[a][b];
+        const double R[4] = {r00, r10, r01, r11};
+        gain_prologue(Xin, Pc, f, zr, zb, R, flags, g);
+        if (!g.ok && blockIdx.x == 0) atomicAdd(status, 1);
+    }
+    __syncthreads();
+    for (int i = i0; i < n; i += stride) {
+        double pc[5];  // P_true(i, c) for c in {0, 1, 2, f, f+1}
+#pragma unroll
+        for (int b = 0; b < 3; b++) pc[b] = i <= b ? R3[(size_t)i * ld + b] : R3[(size_t)b * ld + i];
+        pc[3] = colbuf[i];
+        pc[4] = colbuf[lda + i];
+        // the snapshot columns lack every pending term (rows 0..2 of them came from R3: only the group's own)
+        for (int t = (i < 3 ? pv.r3_from : 0); t < pv.r3_from; t++) {
+            const double ai = pend_row(pv, lda, t)[i];
+            pc[3] = pc[3] - ai * sAc[t][3];
+            pc[4] = pc[4] - ai * sAc[t][4];
+            if (pend_eps(pv, t)) {
+                if (i == f) pc[3] += kFltMin;
+                if (i == f + 1) pc[4] += kFltMin;
+            }
+        }
+        for (int t = pv.r3_from; t < nterm; t++) {
+            const double ai = pend_row(pv, lda, t)[i];
+#pragma unroll
+            for (int b = 0; b < 5; b++) pc[b] = pc[b] - ai * sAc[t][b];
+            if (pend_eps(pv, t)) {
+                if (i < 3) pc[i] += kFltMin;
+                if (i == f) pc[3] += kFltMin;
+                if (i == f + 1) pc[4] += kFltMin;
+            }
+        }
+        double pht[2];
+        for (int k = 0; k < 2; k++)
+            pht[k] = (((pc[0] * g.H[k][0] + pc[1] * g.H[k][1]) + pc[2] * g.H[k][2]) + pc[3] * g.H[k][3]) + pc[4] * g.H[k][4];
+        const double w1_0 = pht[0] * g.G[0][0] + pht[1] * g.G[1][0];
+        const double w1_1 = pht[0] * g.G[0][1] + pht[1] * g.G[1][1];
+        const double w_0 = w1_0 * g.G[0][0] + w1_1 * g.G[0][1];
+        const double w_1 = w1_0 * g.G[1][0] + w1_1 * g.G[1][1];
+        Xout[i] = Xin[i] + (w_0 * g.V[0] + w_1 * g.V[1]);
+        Aout[i] = w1_0;
+        Aout[lda + i] = w1_1;
+    }
+}
+
+// Rows 0..2 (R3) and the landmarks' diagonal blocks (D) follow `cnt` new rank-1 terms (rows Ab, Ab + lda, ...)
+// in order: same operations on every rank, so the replicas stay bit-identical.  epsm bit q: term q is a
+// heading update (diagonal += FLT_MIN, slam.h:719).
+__global__ void __launch_bounds__(256) k_follow_lazy(double* __restrict__ R3, double* __restrict__ D, int dcap,
+                                                     size_t ld, size_t lda, int n, int nf,
+                                                     const double* __restrict__ Ab, int cnt, unsigned long long epsm) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int nrow = j < 3 ? j + 1 : 3;  // rows i <= j of the upper triangle
+    double o[3];
+    for (int i = 0; i < nrow; i++) o[i] = R3[(size_t)i * ld + j];
+    const bool lm = j >= 3 && ((j - 3) & 1) == 0 && (j - 3) / 2 < nf;  // first coordinate of a landmark
+    const int l = (j - 3) / 2;
+    double d00 = 0.0, d01 = 0.0, d11 = 0.0;
+    if (lm) {
+        d00 = D[l];
+        d01 = D[(size_t)dcap + l];
+        d11 = D[2 * (size_t)dcap + l];
+    }
+    for (int q = 0; q < cnt; q++) {
+        const double* a = Ab + (size_t)q * lda;
+        const double aj = a[j];
+        const bool eps = (epsm >> q) & 1ULL;
+        for (int i = 0; i < nrow; i++) {
+            o[i] = o[i] - a[i] * aj;
+            if (eps && i == j) o[i] += kFltMin;
+        }
+        if (lm) {
+            const double aj1 = a[j + 1];
+            d00 = d00 - aj * aj;
+            d01 = d01 - aj * aj1;
+            d11 = d11 - aj1 * aj1;
+            if (eps) {
+                d00 += kFltMin;
+                d11 += kFltMin;
+            }
+        }
+    }
+    for (int i = 0; i < nrow; i++) R3[(size_t)i * ld + j] = o[i];
+    if (lm) {
+        D[l] = d00;
+        D[(size_t)dcap + l] = d01;
+        D[2 * (size_t)dcap + l] = d11;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------
+static inline double* lazy_bank(cslam_ekf* h, int bank) { return h->A + (size_t)bank * kLazyBank * h->lda; }
+static inline double* lazy_P(cslam_ekf* h) { return h->lz.on ? h->lz.Pbuf[h->lz.stable] : h->P; }
+
+// Launch one pass for the rows pending in the current bank (if any).  Chain stream: waits for the pass BEFORE
+// this one (it produced the array that becomes `stable`, and it read the bank that becomes current).
+static int lazy_flush(cslam_ekf* h) {
+    LazyState& L = h->lz;
+    if (!L.on || L.np == 0) return CSLAM_OK;
+    // everything the chain has read from the array this pass overwrites must be done
+    CSLAM_CUDA(cudaEventRecord(L.ev_chain, h->stream));
+    CSLAM_CUDA(cudaStreamWaitEvent(L.pass_stream, L.ev_chain, 0));
+    const int src = L.newest, dst = L.pingpong ? (L.newest ^ 1) : L.newest;
+    const double eps = (double)__builtin_popcount(L.eps_mask) * kFltMin;
+    {
+        ProfScope prof(h, L.pass_stream);
+        if (int rc = launch_cov_update_tma(L.map[src], L.map[dst], h->n, lazy_bank(h, L.bank), h->lda, L.np, eps, h->sh,
+                                           nullptr, 0, L.num_sms, L.stages, L.pass_stream))
+            return rc;
+    }
+    if (L.pass_pending_wait) CSLAM_CUDA(cudaStreamWaitEvent(h->stream, L.ev_pass, 0));  // the previous pass
+    CSLAM_CUDA(cudaEventRecord(L.ev_pass, L.pass_stream));                               // ... now this one
+    L.pass_pending_wait = true;
+    L.stable = src;
+    L.newest = dst;
+    L.infl_rows = L.np;
+    L.infl_eps_mask = L.eps_mask;
+    L.bank ^= 1;
+    L.np = 0;
+    L.eps_mask = 0;
+    L.passes++;
+    return CSLAM_OK;
+}
+
+// Before the chain reads the covariance array: in-place mode has to wait for the pass in flight (it is
+// modifying the array); with a ping-pong pair `stable` is never written while it is the read side.
+static int lazy_acquire_read(cslam_ekf* h) {
+    LazyState& L = h->lz;
+    if (!L.on || L.pingpong || !L.pass_pending_wait) return CSLAM_OK;
+    CSLAM_CUDA(cudaStreamWaitEvent(h->stream, L.ev_pass, 0));
+    L.pass_pending_wait = false;
+    L.infl_rows = 0;
+    L.infl_eps_mask = 0;
+    return CSLAM_OK;
+}
+
+// Apply everything: afterwards (in chain-stream order) lazy_P(h) holds P_true for rows >= 3.
+static int lazy_flush_all(cslam_ekf* h) {
+    LazyState& L = h->lz;
+    if (!L.on) return CSLAM_OK;
+    if (int rc = lazy_flush(h)) return rc;
+    if (L.pass_pending_wait) {
+        CSLAM_CUDA(cudaStreamWaitEvent(h->stream, L.ev_pass, 0));
+        L.pass_pending_wait = false;
+    }
+    L.stable = L.newest;
+    L.infl_rows = 0;
+    L.infl_eps_mask = 0;
+    return CSLAM_OK;
+}
+
+static int lazy_follow(cslam_ekf* h, const double* rows, int cnt, unsigned long long epsm) {
+    const int nf = (h->n - 3) / 2;
+    count_launch();
+    k_follow_lazy<<<(h->n + 255) / 256, 256, 0, h->stream>>>(h->R3, h->D, h->dcap, h->ld, h->lda, h->n, nf, rows, cnt,
+                                                            epsm);
+    CSLAM_CUDA(cudaGetLastError());
+    return CSLAM_OK;
+}
+
+// EKF.cpp:328-352 in lazy mode: the gain needs only rows 0..2; the rank-1 term joins the pending bank.
+static int lazy_heading(cslam_ekf* h, double phi) {
+    LazyState& L = h->lz;
+    if (L.np + 1 > kLazyBank)
+        if (int rc = lazy_flush(h)) return rc;
+    const int n = h->n;
+    const double sigma = 0.01F * kPi / 180.0F;  // EKF.cpp:337
+    double* row = lazy_bank(h, L.bank) + (size_t)L.np * h->lda;
+    count_launch();
+    k_heading_gain<<<(n + 255) / 256, 256, 0, h->stream>>>(h->X[h->cur], h->X[h->cur ^ 1], h->R3, h->ld, n, phi,
+                                                           sigma * sigma, row);
+    CSLAM_CUDA(cudaGetLastError());
+    h->cur ^= 1;
+    if (int rc = lazy_follow(h, row, 1, 1ULL)) return rc;
+    L.eps_mask |= 1u << L.np;
+    L.np += 1;
+    if (L.np == kLazyBank) return lazy_flush(h);
+    return CSLAM_OK;
+}
+
+static int allreduce_sum(cslam_ekf* h, double* buf, size_t count);
+
+// Column snapshot of `ncols` columns (host list or device indices) from the array the chain may read.
+static int lazy_snapshot(cslam_ekf* h, const ColList& cl, const int* idf_dev) {
+    if (int rc = lazy_acquire_read(h)) return rc;
+    count_launch();
+    k_col_pack_lazy<<<dim3((h->n + 255) / 256, cl.n), 256, 0, h->stream>>>(lazy_P(h), h->R3, h->ld, h->n, cl, h->colbuf,
+                                                                           h->lda, h->sh, idf_dev);
+    CSLAM_CUDA(cudaGetLastError());
+    if (h->sh.world > 1) return allreduce_sum(h, h->colbuf, (size_t)cl.n * h->lda);
+    return CSLAM_OK;
+}
+
+// singleUpdate (EKF.cpp:457-479) in lazy mode: per group of observations one column snapshot, per
+// observation one gain kernel (re-linearised at the X the previous observation produced), then R3 / D
+// follow; the 2g panel rows join the pending bank and a pass is launched whenever a bank is full.
+static int lazy_sequential(cslam_ekf* h, const double* Z, const int32_t* idf_host, const int* idf_dev, int m,
+                           const double R[4]) {
+    LazyState& L = h->lz;
+    const int n = h->n;
+    int base = 0;
+    while (base < m) {
+        if (kLazyBank - L.np < 2)
+            if (int rc = lazy_flush(h)) return rc;
+        const int g = std::min({m - base, (kLazyBank - L.np) / 2, kSeqGroupLazy});
+        ColList cl;
+        cl.n = 2 * g;
+        for (int k = 0; k < g; k++) {
+            cl.c[2 * k] = idf_host ? 3 + 2 * (idf_host[base + k] - 1) : 0;
+            cl.c[2 * k + 1] = cl.c[2 * k] + 1;
+        }
+        if (int rc = lazy_snapshot(h, cl, idf_dev ? idf_dev + base : nullptr)) return rc;
+        const int np0 = L.np;
+        double* bank = lazy_bank(h, L.bank);
+        for (int k = 0; k < g; k++) {
+            const int i = base + k;
+            PendView pv;
+            pv.A0 = lazy_bank(h, L.bank ^ 1);
+            pv.n0 = L.infl_rows;
+            pv.eps0 = L.infl_eps_mask;
+            pv.A1 = bank;
+            pv.n1 = np0 + 2 * k;
+            pv.eps1 = L.eps_mask;
+            pv.r3_from = L.infl_rows + np0;
+            count_launch();
+            k_gain_lazy<<<(n + 255) / 256, 256, 0, h->stream>>>(
+                h->X[h->cur], h->X[h->cur ^ 1], h->R3, h->colbuf + (size_t)2 * k * h->lda, h->ld, h->lda, n, Z[2 * i],
+                Z[2 * i + 1], idf_host ? idf_host[i] : 0, R[0], R[1], R[2], R[3], h->flags, pv,
+                bank + (size_t)(np0 + 2 * k) * h->lda, h->status, idf_dev ? idf_dev + i : nullptr);
+            CSLAM_CUDA(cudaGetLastError());
+            h->cur ^= 1;
+        }
+        if (int rc = lazy_follow(h, bank + (size_t)np0 * h->lda, 2 * g, 0ULL)) return rc;
+        L.np = np0 + 2 * g;
+        base += g;
+        if (L.np == kLazyBank)
+            if (int rc = lazy_flush(h)) return rc;
+    }
+    return CSLAM_OK;
+}
+
+}  // namespace cslam

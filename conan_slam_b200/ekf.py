@@ -103,6 +103,16 @@ class EKF:
         check(self._lib.cslam_ekf_sync(self._h, C.byref(skipped)), "cslam_ekf_sync")
         return skipped.value
 
+    def flush(self):
+        """Apply every pending (deferred) covariance term, asynchronously in stream order (cslam_ekf_flush)."""
+        check(self._lib.cslam_ekf_flush(self._h), "cslam_ekf_flush")
+
+    def pass_count(self):
+        """(covariance passes launched since create, panel rows still pending)."""
+        p, r = C.c_ulonglong(0), C.c_int(0)
+        check(self._lib.cslam_ekf_pass_count(self._h, C.byref(p), C.byref(r)), "cslam_ekf_pass_count")
+        return int(p.value), int(r.value)
+
     def profile_begin(self, max_launches=4096):
         check(self._lib.cslam_ekf_profile_begin(self._h, int(max_launches)), "cslam_ekf_profile_begin")
 
@@ -159,6 +169,15 @@ class EKF:
     def cov_block(self, r0, c0, nr, nc):
         out = np.empty((nr, nc), dtype=np.float64)
         check(self._lib.cslam_ekf_get_cov_block(self._h, r0, c0, nr, nc, dptr(out)), "cslam_ekf_get_cov_block")
+        return out
+
+    def cov_gather(self, idx):
+        """Principal sub-matrix P[idx][:, idx] (0-based state indices) without reading P back."""
+        idx = np.ascontiguousarray(idx, dtype=np.int32).reshape(-1)
+        k = idx.shape[0]
+        out = np.empty((k, k), dtype=np.float64)
+        if k:
+            check(self._lib.cslam_ekf_get_cov_gather(self._h, iptr(idx), k, dptr(out)), "cslam_ekf_get_cov_gather")
         return out
 
     @property

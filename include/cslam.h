@@ -87,6 +87,16 @@ int cslam_ekf_destroy(cslam_ekf_t* h);
 int cslam_ekf_set_stream(cslam_ekf_t* h, void* cuda_stream);
 /* Wait for the stream; *skipped_updates (nullable) = updates skipped as non-SPD since create/reset. */
 int cslam_ekf_sync(cslam_ekf_t* h, int* skipped_updates);
+/* Large (capacity >= 1023 landmarks) and sharded handles DEFER the covariance passes: every Kalman update of the
+ * reference is P <- P - W1 W1^T (slam.h:260; the heading update slam.h:718 has the same shape), so the
+ * updates of consecutive calls — the heading updates of the control steps and the sequential landmark
+ * updates of a scan — accumulate as panel rows and ONE pass over the covariance applies up to 16 of them
+ * (X, rows 0..2 of P and the landmarks' 2x2 diagonal blocks are always current; gains read the few other
+ * entries of P they need through the pending terms).  Results are those of the eager sequence up to rounding.
+ * cslam_ekf_flush applies everything that is pending (asynchronously, in stream order); accessors, augment,
+ * the joint update, save and sync do so themselves.  pass_count: passes launched so far / rows pending. */
+int cslam_ekf_flush(cslam_ekf_t* h);
+int cslam_ekf_pass_count(cslam_ekf_t* h, unsigned long long* passes, int* pending_rows);
 int cslam_ekf_n(const cslam_ekf_t* h);             /* state dimension n = X.rows()            */
 int cslam_ekf_num_landmarks(const cslam_ekf_t* h); /* (n-3)/2                                  */
 int cslam_ekf_capacity(const cslam_ekf_t* h);
@@ -139,6 +149,10 @@ int cslam_ekf_augment(cslam_ekf_t* h, const double* Z, int m, const double R[4])
  * lower triangle mirrored from the authoritative upper one. */
 int cslam_ekf_get_state(cslam_ekf_t* h, double* X, int max_n);
 int cslam_ekf_get_cov_block(cslam_ekf_t* h, int r0, int c0, int nr, int nc, double* out);
+/* Principal sub-matrix of P for an arbitrary set of k <= 8192 state indices (0-based positions in X): the joint
+ * marginal of the pose and a few landmarks without reading P back; out is dense row-major k x k.  Collective
+ * on sharded handles. */
+int cslam_ekf_get_cov_gather(cslam_ekf_t* h, const int32_t* idx, int k, double* out);
 /* Landmark marginals without reading P back (visualisation of the uncertainty ellipses, README.md:15-22;
  * "next" row of SURVEY.md §8f): for the 1-based landmarks first .. first+count-1 the 2x2 diagonal block
  * packed as out[3*k + {0,1,2}] = (P_ff, P_f,f+1, P_f+1,f+1).  Collective on sharded handles. */

@@ -14,9 +14,10 @@ using namespace cslam;
 
 namespace cslam {
 int make_cov_tensor_map(void* out_map64, double* P, size_t ld, size_t rows);
-int launch_cov_update_tma(const void* map64, int n, const double* A, size_t lda, int r, Shard sh, const int* live,
-                          int nlive, int num_sms, int stages, cudaStream_t stream);
-extern int g_tma_dbg;
+int launch_cov_update_tma(const void* src_map, const void* dst_map, int n, const double* A, size_t lda, int r,
+                          double diag_eps, Shard sh, const int* live, int nlive, int num_sms, int stages,
+                          cudaStream_t stream);
+extern int g_tma_dbg, g_tma_boxr, g_tma_dense;
 }  // namespace cslam
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA %s at line %d\n", cudaGetErrorString(e), __LINE__); exit(1);} } while (0)
@@ -72,6 +73,9 @@ static void run_ref_g(int g, double* P, size_t ld, int n, const double* A, size_
 }
 
 int main(int argc, char** argv) {
+    if (getenv("TMA_BOXR")) g_tma_boxr = atoi(getenv("TMA_BOXR"));
+    if (getenv("TMA_DENSE")) g_tma_dense = atoi(getenv("TMA_DENSE"));
+    else g_tma_dense = 0;
     const int n = argc > 1 ? atoi(argv[1]) : 40003;
     const int reps = argc > 2 ? atoi(argv[2]) : 10;
     const Shard sh{argc > 4 ? atoi(argv[4]) : 0, argc > 3 ? atoi(argv[3]) : 1};
@@ -89,14 +93,15 @@ int main(int argc, char** argv) {
     CK(cudaMalloc(&P2, ld * rows * sizeof(double)));
     CK(cudaMalloc(&A, 16 * ld * sizeof(double)));
     CK(cudaMalloc(&dres, 16));
-    unsigned char map[128];
+    unsigned char map[128], map1[128];
     if (make_cov_tensor_map(map, P2, ld, rows) != 0) { printf("tensor map: %s\n", cslam_last_error()); return 1; }
+    if (make_cov_tensor_map(map1, P1, ld, rows) != 0) { printf("tensor map: %s\n", cslam_last_error()); return 1; }
     const unsigned gi = (unsigned)((rows * ld + 255) / 256);
     k_init_panel<<<(unsigned)((16 * ld + 255) / 256), 256>>>(A, ld, n, 16);
     CK(cudaDeviceSynchronize());
     const double gb = 8.0 * n * ((double)n + 1.0) / 1e9 / sh.world;
-    printf("n=%d ld=%zu rows=%zu world=%d rank=%d SMs=%d, algorithmic bytes per pass %.3f GB\n", n, ld, rows, sh.world,
-           sh.rank, sms, gb);
+    printf("n=%d ld=%zu rows=%zu world=%d rank=%d SMs=%d boxr=%d dense=%d, algorithmic bytes per pass %.3f GB\n", n, ld, rows, sh.world,
+           sh.rank, sms, g_tma_boxr, g_tma_dense, gb);
     int bad = 0;
     for (int g = 2; g <= 8; g++) {
         k_init<<<gi, 256>>>(P1, ld, rows, n, sh);
@@ -104,7 +109,7 @@ int main(int argc, char** argv) {
         CK(cudaMemset(dres, 0, 16));
         run_ref_g(g, P1, ld, n, A, ld, sh);
         CK(cudaDeviceSynchronize());
-        if (launch_cov_update_tma(map, n, A, ld, 2 * g, sh, nullptr, 0, sms, 5, 0) != 0) {
+        if (launch_cov_update_tma(map, map, n, A, ld, 2 * g, 0.0, sh, nullptr, 0, sms, 5, 0) != 0) {
             printf("launch: %s\n", cslam_last_error());
             return 1;
         }
@@ -121,13 +126,13 @@ int main(int argc, char** argv) {
     if (bad) { printf("PARITY FAILED\n"); return 2; }
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    auto time_tma = [&](int g, int stages, int dbg) {
+    auto time_tma = [&](int g, int stages, int dbg, bool pp = false) {
         g_tma_dbg = dbg;
         float ms = 0.f;
-        launch_cov_update_tma(map, n, A, ld, 2 * g, sh, nullptr, 0, sms, stages, 0);
+        launch_cov_update_tma(pp ? map1 : map, map, n, A, ld, 2 * g, 0.0, sh, nullptr, 0, sms, stages, 0);
         CK(cudaDeviceSynchronize());
         CK(cudaEventRecord(e0));
-        for (int i = 0; i < reps; i++) launch_cov_update_tma(map, n, A, ld, 2 * g, sh, nullptr, 0, sms, stages, 0);
+        for (int i = 0; i < reps; i++) launch_cov_update_tma(pp ? map1 : map, map, n, A, ld, 2 * g, 0.0, sh, nullptr, 0, sms, stages, 0);
         CK(cudaEventRecord(e1));
         CK(cudaDeviceSynchronize());
         CK(cudaEventElapsedTime(&ms, e0, e1));
@@ -145,17 +150,25 @@ int main(int argc, char** argv) {
         CK(cudaEventElapsedTime(&ms_ref, e0, e1));
         ms_ref /= reps;
         printf("n=%d g=%d : FMA pass %8.4f ms %7.1f GB/s | TMA+DMMA pass (stages 2..5):", n, g, ms_ref, gb / (ms_ref * 1e-3));
-        for (int stages = 2; stages <= 5; stages++) {
+        for (int stages = 2; stages <= 6; stages++) {
+            if (stages == 6 && g > 4) continue;
             const float ms = time_tma(g, stages, 0);
             printf("  S%d %7.4f ms %6.1f GB/s", stages, ms, gb / (ms * 1e-3));
         }
-        printf("\n");
+        const float ms_pp = time_tma(g, 4, 0, true);
+        printf("  | out of place (P1 -> P2) S4 %7.4f ms %6.1f GB/s\n", ms_pp, gb / (ms_pp * 1e-3));
     }
-    for (int dbg = 1; dbg <= 6; dbg++) {
-        if (dbg == 3 || dbg == 5) continue;
+    for (int dbg = 8; dbg <= 24; dbg += 8)
+        for (int g = 4; g <= 8; g += 4) {
+            const float ms = time_tma(g, 4, dbg);
+            const float ms5 = time_tma(g, 5, dbg);
+            printf("n=%d g=%d dbg=%d (8 loads without L2 hint, 16 stores without, 24 neither): S4 %8.4f ms %7.1f GB/s  S5 %8.4f ms %7.1f GB/s\n",
+                   n, g, dbg, ms, gb / (ms * 1e-3), ms5, gb / (ms5 * 1e-3));
+        }
+    for (int dbg = 2; dbg <= 6; dbg += 2) {
         for (int stages = 3; stages <= 5; stages += 2) {
             const float ms = time_tma(4, stages, dbg);
-            printf("n=%d g=4 stages=%d dbg=%d (1 no L2 hints, 2 no stores, 4 no loads, 6 neither): %8.4f ms, %7.1f GB/s of the full pass\n",
+            printf("n=%d g=4 stages=%d dbg=%d (2 no stores, 4 no loads, 6 neither): %8.4f ms, %7.1f GB/s of the full pass\n",
                    n, stages, dbg, ms, gb / (ms * 1e-3));
         }
     }
