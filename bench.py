@@ -385,9 +385,12 @@ def ref_ekf_update_rate(N, budget_s=20.0):
     }
 
 
-def run_pf(args):
-    """--workload pf: C4 of BASELINE.json — FastSLAM, 1M particles x 500 landmarks, m_obs = 4 known
-    associations per observation cycle, resampling every cycle; particles split over the GPUs."""
+def pf_case(args, steps, warmup, spread="balanced", with_cpu=True, quiet=False):
+    """C4 of BASELINE.json — FastSLAM, P particles x Nf landmarks, m_obs known associations per observation
+    cycle, resampling every cycle; particles split over the GPUs.  Returns the result dict (rank 0) or None.
+    spread: "balanced" = weights as the filter produces them; "realistic" = log-normal weight spread injected
+    before every resampling (neff ~ 0.1-0.3 P, survivors cross rank boundaries); "adversarial" = all the
+    weight mass on rank 0's particles (every other rank fetches ALL its survivors over NVLink)."""
     import torch
     import torch.distributed as dist
 
@@ -397,10 +400,8 @@ def run_pf(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _lib.load_library()
-    P, nfeat, m_obs = args.particles, args.pf_landmarks, args.obs
+    P, nfeat, m_obs = args.particles, args.pf_landmarks, args.pf_obs
     assert P % (32 * world) == 0
     Pl = P // world
     stream = torch.cuda.Stream(device=local)
@@ -418,6 +419,12 @@ def run_pf(args):
     u_h = torch.empty(Pl, dtype=torch.float64).pin_memory()
     xi_h.copy_(xi)
     u_h.copy_(u)
+    # weight modulation for the non-balanced cases (applied on the device right before resampling)
+    wmod = None
+    if spread == "realistic":
+        wmod = torch.exp(1.6 * torch.randn(Pl, dtype=torch.float64, device=f"cuda:{local}", generator=gen))
+    elif spread == "adversarial":
+        wmod = torch.full((Pl,), 1.0 if rank == 0 else 1e-300, dtype=torch.float64, device=f"cuda:{local}")
     torch.cuda.synchronize()
     sc.init_map(xi.data_ptr())
 
@@ -427,39 +434,46 @@ def run_pf(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        sc.cycle_step(xi.data_ptr(), u.data_ptr())
+    def cycle(want_keep=False, host_draws=False):
+        sc.controls()
+        Z, ids = sc.observation()
+        pf.sampleProposal(Z, ids, PF_R, xi_h.numpy() if host_draws else xi.data_ptr())
+        pf.featureUpdate(Z, ids, PF_R)
+        if wmod is not None:
+            pf.scale_weights_device(wmod.data_ptr())
+        out = pf.resampleParticles(float("inf"), u_h.numpy() if host_draws else u.data_ptr(), True, want_keep=want_keep,
+                                   want_neff=want_keep)
+        sc.cycle += 1
+        return out
+
+    for _ in range(warmup):
+        cycle()
     pf.sync()
     sampler = ClockSampler(local)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     launches0 = lib.cslam_kernel_launches()
-    pf.profile_begin(args.steps + 4)
+    pf.profile_begin(steps + 4)
     sampler.start()
     did = []
     with torch.cuda.stream(stream):
         ev0.record(stream)
-        for _ in range(args.steps):
-            did.append(sc.cycle_step(xi.data_ptr(), u.data_ptr())[2])
+        for _ in range(steps):
+            did.append(cycle()[2])
         ev1.record(stream)
     barrier()
     clocks = sampler.stop()
     g_ms, g_cnt, g_bytes = pf.profile_end()
     launches = lib.cslam_kernel_launches() - launches0
     ms = ev0.elapsed_time(ev1)
-    # end to end: the step's random draws come from pinned HOST memory, the weights go back to the host
+    # end to end: the step's random draws come from pinned HOST memory, the result (pose of the extracted
+    # particle) goes back to the host every step
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    xi_np, u_np = xi_h.numpy(), u_h.numpy()
     with torch.cuda.stream(stream):
         e0.record(stream)
-        for _ in range(args.steps):
-            sc.controls()
-            Z, ids = sc.observation()
-            pf.sampleProposal(Z, ids, PF_R, xi_np)
-            pf.featureUpdate(Z, ids, PF_R)
-            pf.resampleParticles(float("inf"), u_np, True, want_keep=False)
-            sc.cycle += 1
+        for _ in range(steps):
+            cycle(host_draws=True)
             Xe, _ = pf.extractStatesFromParticles()  # D2H of the step's result
         e1.record(stream)
     barrier()
@@ -467,50 +481,75 @@ def run_pf(args):
     w = pf.weights
     ok = bool(all(did)) and bool(np.all(np.isfinite(w))) and pf.sync() == 0
     # one extra untimed cycle with the indices read back: how many survivors cross rank boundaries
-    keep, neff_last, _ = sc.cycle_step(xi.data_ptr(), u.data_ptr(), want_keep=True)
+    keep, neff_last, _ = cycle(want_keep=True)
     remote_frac = float(np.mean((keep // Pl) != rank))
     distinct = int(np.unique(keep).shape[0])
-    log(f"[bench r{rank}] neff={neff_last:.1f} of {P}, remote survivors {100 * remote_frac:.1f} %, "
-        f"{distinct} distinct sources for {Pl} slots")
+    if not quiet:
+        log(f"[bench r{rank}] PF {spread}: neff={neff_last:.1f} of {P}, remote survivors {100 * remote_frac:.1f} %, "
+            f"{distinct} distinct sources for {Pl} slots")
+    remote_all = remote_frac
     if world > 1:
         t = torch.tensor([ms, e2e_ms], device=f"cuda:{local}", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_ms = float(t[0]), float(t[1])
-        c = torch.tensor([launches], device=f"cuda:{local}", dtype=torch.float64)
+        c = torch.tensor([launches, remote_frac], device=f"cuda:{local}", dtype=torch.float64)
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
         launches = int(c[0])
-    if rank == 0:
-        peak, peak_src = measured_peaks()
-        value = P * args.steps / (ms * 1e-3)
-        bytes_step = PF_CONTROLS_PER_OBS * 2 * 208 + m_obs * 96 + 2 * (nfeat * 40 + 13 * 8)
-        ach = (g_bytes / g_cnt) / (g_ms / g_cnt * 1e-3) / 1e9 if g_cnt else 0.0
-        out = {
-            "metric": "PF particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"particle filter (FastSLAM) {P} particles x {nfeat} landmarks, {m_obs} known "
-                                   f"associations per observation cycle (6 predict+heading, sampleProposal, "
-                                   f"featureUpdate), resampling every cycle, particles split over {world} GPU(s)",
-                       "particles": P, "landmarks": nfeat, "obs_per_step": m_obs, "mode": "INTENDED",
-                       "l2": f"inputs larger than L2 ({Pl * nfeat * 40 / 1e9:.1f} GB of particle state per GPU)",
-                       "parallelism": "particles block-partitioned; NCCL all-gather of scan tops + cumulative weights; "
-                                      "survivors read from peers over NVLink inside the gather kernel"
-                       if world > 1 else "single GPU"},
-            "clocks": clocks,
-            "e2e": {"value": P * args.steps / (e2e_ms * 1e-3), "unit": "particle-steps/s",
-                    "h2d_bytes_per_step": int(Pl * 4 * 8 + m_obs * 28 + 6 * 40), "d2h_bytes_per_step": 48},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_gather_rows (PF.cpp:494-498 survivor copy)", "achieved": ach,
-                         "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src, "traffic": None,
-                         "algorithmic_bytes_per_launch": g_bytes / max(1, g_cnt), "launches_timed": g_cnt,
-                         "avg_launch_ms": g_ms / max(1, g_cnt),
-                         "whole_step_frac": bytes_step * Pl / (ms / args.steps * 1e-3) / 1e9 / peak},
-            "valid": ok, "neff": neff_last, "remote_survivor_frac_rank0": remote_frac,
-            "distinct_sources_rank0": distinct,
-        }
-        if not args.no_cpu_baseline and world == 1:
-            out["cpu_baseline"] = cpu_pf_rate(nfeat, m_obs, 1)
-            out["cpu_baseline"]["all_cores"] = cpu_pf_rate(nfeat, m_obs, os.cpu_count() or 1, particles=8000)
+        remote_all = float(c[1]) / world
+    pf.close()
+    del xi, u, wmod
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    peak, peak_src = measured_peaks()
+    value = P * steps / (ms * 1e-3)
+    bytes_particle = 2 * (nfeat * 40 + 13 * 8)
+    bytes_step = PF_CONTROLS_PER_OBS * 2 * 208 + m_obs * 96 + bytes_particle
+    ach = (g_bytes / g_cnt) / (g_ms / g_cnt * 1e-3) / 1e9 if g_cnt else 0.0
+    out = {
+        "metric": "PF particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": world,
+        "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"particle filter (FastSLAM) {P} particles x {nfeat} landmarks, {m_obs} known "
+                               f"associations per observation cycle (6 predict+heading, sampleProposal, "
+                               f"featureUpdate), resampling every cycle, particles split over {world} GPU(s)",
+                   "particles": P, "landmarks": nfeat, "obs_per_step": m_obs, "mode": "INTENDED",
+                   "weight_spread": spread,
+                   "l2": f"inputs larger than L2 ({Pl * nfeat * 40 / 1e9:.1f} GB of particle state per GPU)",
+                   "parallelism": "particles block-partitioned; one all-gather of per-rank scan totals + cumulative "
+                                  "weights; survivors read from peers over NVLink inside the gather kernel"
+                   if world > 1 else "single GPU"},
+        "clocks": clocks,
+        "e2e": {"value": P * steps / (e2e_ms * 1e-3), "unit": "particle-steps/s",
+                "h2d_bytes_per_step": int(Pl * 4 * 8 + m_obs * 28 + 6 * 40), "d2h_bytes_per_step": 48},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "k_gather_rows (PF.cpp:494-498 survivor copy)", "achieved": ach,
+                     "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src, "traffic": None,
+                     "algorithmic_bytes_per_launch": g_bytes / max(1, g_cnt), "launches_timed": g_cnt,
+                     "avg_launch_ms": g_ms / max(1, g_cnt), "per": "GPU",
+                     "whole_step_frac": bytes_step * Pl / (ms / steps * 1e-3) / 1e9 / peak},
+        "valid": ok, "neff": neff_last, "remote_survivor_frac_rank0": remote_frac,
+        "remote_survivor_frac_all_ranks": remote_all,
+        "nvlink_bytes_per_step_per_gpu": remote_all * Pl * bytes_particle / 2,
+        "distinct_sources_rank0": distinct,
+    }
+    if with_cpu and world == 1:
+        out["cpu_baseline"] = cpu_pf_rate(nfeat, m_obs, 1)
+        out["cpu_baseline"]["all_cores"] = cpu_pf_rate(nfeat, m_obs, os.cpu_count() or 1, particles=8000)
+    return out
+
+
+def run_pf(args):
+    """--workload pf: the PF half of the metric as the whole run."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    out = pf_case(args, args.steps, args.warmup, spread=args.pf_spread, with_cpu=not args.no_cpu_baseline)
+    if out is not None:
         emit(out)
     if world > 1:
         dist.destroy_process_group()
@@ -556,14 +595,344 @@ def run_reference(args):
         "impl": "reference", "metric": "EKF updates/sec", "value": val, "unit": "updates/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 4 * t_full * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32" if use_ref else "f64", "data": "synthetic",
+        "extrapolated": True,
+        "extrapolation": ("the value is EXTRAPOLATED: the reference's dense O(n^2)-per-update and O(N n^2)-per-scan "
+                          "code is timed on a bounded smaller map and scaled by its own complexity (see "
+                          "cpu_baseline.sample); a full-size step would take hours"),
         "config": {"workload": f"EKF-SLAM {N} landmarks (state dim {n}), range-bearing observations, sequential "
                                f"update: gate + gain + covariance, 4 observations per scan - the reference's dense "
-                               f"CPU algorithm", "landmarks": N, "state_dim": n, "obs_per_step": 4},
+                               f"CPU algorithm", "landmarks": N, "state_dim": n, "obs_per_step": 4,
+                   "mode": "reference arithmetic (FP32)" if use_ref else "INTENDED (SURVEY Appendix A)",
+                   "l2": "n/a (CPU)", "parallelism": "single host thread (the reference has none)"},
         "cpu_baseline": base,
         "e2e": {"value": val, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(out)
+
+
+class Ctx:
+    """Process-level context of one bench run (one rank)."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+
+        import conan_slam_b200 as cs
+        from conan_slam_b200 import _lib
+        self.torch, self.dist, self.cs = torch, dist, cs
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        self.lib = _lib.load_library()
+        self.sharded = self.world > 1 and args.multi == "sharded"
+        self.dev = f"cuda:{self.local}"
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def allmax(self, *vals):
+        if self.world == 1:
+            return [float(v) for v in vals]
+        t = self.torch.tensor(list(vals), device=self.dev, dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    def allsum(self, *vals):
+        if self.world == 1:
+            return [float(v) for v in vals]
+        t = self.torch.tensor(list(vals), device=self.dev, dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return [float(x) for x in t]
+
+
+class EkfBench:
+    """One synthetic N-landmark EKF-SLAM filter on this rank's GPU (or its shard of it) + the timed loops."""
+
+    def __init__(self, ctx, N, nscans):
+        cs, torch = ctx.cs, ctx.torch
+        self.ctx, self.N, self.n = ctx, N, 3 + 2 * N
+        self.stream = torch.cuda.Stream(device=ctx.local)
+        t0 = time.time()
+        if ctx.sharded:
+            from conan_slam_b200 import dist as cdist
+            nid = cdist.nccl_unique_id(device=ctx.dev)
+            # one filter, covariance row-sharded over the ranks: identical inputs on every rank (SPMD)
+            self.ekf, self.lm, self.rng = build_ekf(N, ctx.local, cs.FLAG_INTENDED, seed=N, stream=self.stream.cuda_stream,
+                                                    rank=ctx.rank, world=ctx.world, nccl_id=nid)
+        else:
+            self.ekf, self.lm, self.rng = build_ekf(N, ctx.local, cs.FLAG_INTENDED, seed=N + 1000 * ctx.rank,
+                                                    stream=self.stream.cuda_stream)
+        log(f"[bench r{ctx.rank}] built {N}-landmark map (n={self.n}, P={8.0 * self.n * self.n / 1e9:.2f} GB) "
+            f"in {time.time() - t0:.1f}s")
+        self.nscans = nscans
+        self.scan_cache = {}
+
+    def scans(self, m):
+        if m not in self.scan_cache:
+            self.scan_cache[m] = make_scans(self.lm, self.rng, self.nscans, m)
+        return self.scan_cache[m]
+
+    def close(self):
+        self.ekf.close()
+        self.ctx.torch.cuda.empty_cache()
+
+    # ---- parity against the CPU oracle on the marginal of the observed + a sample of other landmarks ----
+    def parity(self, m, batch, nscan=3):
+        """The filter restricted to an index set I that contains the pose and every observed landmark evolves
+        exactly like the full filter (every update touches P(i,j) through rows/columns of I only), so the CPU
+        oracle can replay the same calls on the |I|-dimensional marginal: state and covariance within 1e-9
+        relative, association indices exactly (north_star).  Test infrastructure used as the CHECKER only,
+        outside every timed region."""
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import oracle_py
+            ekf, N = self.ekf, self.N
+            scans = self.scans(m)[:nscan]
+            rng = np.random.Generator(np.random.MT19937(99))
+            lms = sorted(set(int(j) for _, ids in scans for j in ids) | set(int(j) for j in rng.choice(N, 48, replace=False) + 1))
+            idx = [0, 1, 2] + [c for j in lms for c in (3 + 2 * (j - 1), 4 + 2 * (j - 1))]
+            slot = {j: k + 1 for k, j in enumerate(lms)}  # global landmark id -> oracle map slot
+            X = ekf.X
+            orc = oracle_py.OracleEKF(self.ctx.cs.FLAG_INTENDED)
+            orc.reset(X[idx], ekf.cov_gather(idx))
+            same_idx = True
+            for f in (orc, ekf):  # two control steps first: predict + heading (EKF.cpp:406-455, 328-352)
+                for k in range(2):
+                    f.predict(20.0, 0.01 * (k + 1), QE_BENCH, 73.0, 0.01)
+                    f.observeHeading(1e-4, True)
+            for Z, ids in scans:
+                jo = orc.gate(Z, RE, GATE1, GATE2)[0]
+                jo_glob = np.array([lms[j - 1] if j > 0 else 0 for j in jo], dtype=np.int32)
+                if batch:
+                    jg = ekf.gate(Z, RE, GATE1, GATE2)[0]
+                    ekf.update(Z[:, jg > 0], RE, jg[jg > 0], True)
+                    orc.update(Z[:, jo > 0], RE, jo[jo > 0], True)
+                else:
+                    jg = ekf.scan(Z, RE, GATE1, GATE2)[0]
+                    orc.update(Z[:, jo > 0], RE, jo[jo > 0], False)
+                same_idx = same_idx and bool(np.array_equal(jg, jo_glob)) and bool(np.array_equal(jg, ids))
+            Xg, Pg = ekf.X[idx], ekf.cov_gather(idx)
+            Xo, Po = orc.X, orc.P
+            iu = np.triu_indices(len(idx))
+            ex = float(np.max(np.abs(Xg - Xo)) / max(np.max(np.abs(Xo)), 1e-300))
+            ep = float(np.max(np.abs(Pg[iu] - Po[iu])) / max(np.max(np.abs(Po[iu])), 1e-300))
+            return {"checked_against": "CPU oracle (oracle/slam_oracle.hpp, FP64) on the marginal of the pose, the observed "
+                                       f"landmarks and 48 random landmarks ({len(idx)} state entries, full covariance block)",
+                    "calls": f"2 x (predict + observeHeading), {nscan} scans of {m} observations "
+                             f"({'gate + joint batchUpdate' if batch else 'fused gate + sequential update'})",
+                    "state_max_rel_err": ex, "cov_max_rel_err": ep, "indices_equal": same_idx,
+                    "tolerance": 1e-9, "ok": bool(ex < 1e-9 and ep < 1e-9 and same_idx)}
+        except Exception as e:  # pragma: no cover - reported, never fatal for the timing
+            return {"ok": False, "error": f"{type(e).__name__}: {e}"}
+
+    # ---- device-timed throughput (state resident in HBM) + live kernel timing ----
+    def timed(self, m, steps, warmup, batch=False, strict=False):
+        ctx, ekf, torch = self.ctx, self.ekf, self.ctx.torch
+        scans = self.scans(m)
+        for s in range(warmup):
+            ekf_scan(ekf, scans[s % len(scans)][0], batch)
+            if strict:
+                ekf.flush()
+        ekf.sync()
+        sampler = ClockSampler(ctx.local)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ctx.barrier()
+        launches0 = ctx.lib.cslam_kernel_launches()
+        passes0 = ekf.pass_count()[0]
+        ekf.profile_begin(steps * max(1, m) + 8)
+        sampler.start()
+        updates = 0
+        assoc0 = 0 if batch else ekf.scan_associations()
+        with torch.cuda.stream(self.stream):
+            ev0.record(self.stream)
+            for s in range(steps):
+                ekf_scan(ekf, scans[(warmup + s) % len(scans)][0], batch, want_indices=False)
+                if strict:
+                    ekf.flush()
+                updates += (1 if batch else 0)
+            ekf.flush()  # every deferred covariance term is applied INSIDE the timed region
+            ev1.record(self.stream)
+        ctx.barrier()
+        if not batch:  # updates applied = observations the gate associated, counted on the device
+            updates = ekf.scan_associations() - assoc0
+        clocks = sampler.stop()
+        cov_ms, cov_launches, cov_bytes = ekf.profile_end()
+        launches = ctx.lib.cslam_kernel_launches() - launches0
+        ms = ev0.elapsed_time(ev1)
+        skipped = ekf.sync()
+        ms, = ctx.allmax(ms)
+        if ctx.world > 1:
+            u, l = ctx.allsum(updates, launches)
+            launches = int(l)
+            if not ctx.sharded:
+                updates = int(u)
+        return {"ms": ms, "updates": updates, "cov_ms": cov_ms, "cov_launches": cov_launches, "cov_bytes": cov_bytes,
+                "launches": int(launches), "clocks": clocks, "skipped": skipped, "steps": steps,
+                "passes": ekf.pass_count()[0] - passes0}
+
+    # ---- end to end through the public API: host observations in, state + indices out ----
+    def e2e(self, m, steps, batch=False):
+        ctx, ekf, torch = self.ctx, self.ekf, self.ctx.torch
+        scans = self.scans(m)
+        X_host = None
+        ctx.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        upd = 0
+        with torch.cuda.stream(self.stream):
+            e0.record(self.stream)
+            for s in range(steps):
+                Z = scans[(s + 1) % len(scans)][0]
+                jb = ekf_scan(ekf, Z, batch)
+                X_host = ekf.X  # D2H read of the step's result (n doubles through pinned staging)
+                upd += (1 if batch else int((jb > 0).sum()))
+            ekf.flush()
+            e1.record(self.stream)
+        ctx.barrier()
+        ms = e0.elapsed_time(e1)
+        ms, = ctx.allmax(ms)
+        if ctx.world > 1 and not ctx.sharded:
+            upd = int(ctx.allsum(upd)[0])
+        return {"ms": ms, "updates": upd, "X": X_host}
+
+    # ---- a whole drive cycle of test/main.cpp: 6 control steps (predict + observeHeading) + one scan ----
+    def drive(self, m, cycles=4):
+        ctx, ekf, torch = self.ctx, self.ekf, self.ctx.torch
+        scans = self.scans(m)
+
+        def cycle(Z):
+            ekf.controlSteps(np.zeros(6), np.zeros(6), np.zeros(6), True, QE_BENCH, 73.0, 0.01, want_trace=False)
+            ekf_scan(ekf, Z, want_indices=False)
+        cycle(scans[0][0])
+        ekf.sync()
+        p0 = ekf.pass_count()[0]
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(self.stream):
+            d0.record(self.stream)
+            for c in range(cycles):
+                cycle(scans[(c + 2) % len(scans)][0])
+            ekf.flush()
+            d1.record(self.stream)
+        torch.cuda.synchronize()
+        return {"control_steps_per_cycle": 6, "observations_per_cycle": m, "cycles_timed": cycles,
+                "ms_per_cycle": d0.elapsed_time(d1) / cycles,
+                "covariance_passes_per_cycle": (ekf.pass_count()[0] - p0) / cycles,
+                "round1_ms_per_cycle": {"stepwise (7 passes)": 14.4, "merged heading passes (2 passes)": 4.6},
+                "note": "heading and landmark updates are deferred rank-1 terms: one pass per 16 of them"}
+
+
+def ekf_roofline(ctx, n, N, m, t, batch, strict, peak, peak_src):
+    shards = ctx.world if ctx.sharded else 1
+    cov_ms, cov_launches, cov_bytes = t["cov_ms"], t["cov_launches"], t["cov_bytes"]
+    ach = (cov_bytes / cov_launches) / (cov_ms / cov_launches * 1e-3) / 1e9 if cov_launches else 0.0
+    upd_local = t["updates"] if (ctx.sharded or ctx.world == 1) else t["updates"] / ctx.world
+    if batch:
+        r_rank = 2 * m
+        flops = float(r_rank) * n * (n + 1) / shards
+        tpeak, tsrc = dmma_peak()
+        t_launch = cov_ms / max(1, cov_launches) * 1e-3
+        return {
+            "bound": "tensor", "kernel": "k_cov_update_dmma (slam.h:260, rank-2m update on FP64 tensor cores, "
+                                         "DMMA.8x8x4) incl. its panel-tiling kernel",
+            "achieved": flops / t_launch / 1e12 if cov_launches else 0.0, "peak": tpeak, "unit": "TFLOP/s",
+            "frac": (flops / t_launch / 1e12) / tpeak if cov_launches else 0.0, "peak_source": tsrc,
+            "traffic": ncu_traffic("k_cov_update_dmma", n) if ctx.world == 1 else None,
+            "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": 8.0 * n * (n + 1) / shards,
+            "hbm_gbs_same_launch": (cov_bytes / cov_launches) / t_launch / 1e9 if cov_launches else 0.0,
+            "hbm_frac_same_launch": ((cov_bytes / cov_launches) / t_launch / 1e9) / peak if cov_launches else 0.0,
+            "per": "GPU", "launches_timed": cov_launches, "avg_launch_ms": cov_ms / max(1, cov_launches),
+        }
+    rows = 2 * (1 if strict else min(m, 8))
+    per_pass = upd_local / max(1, cov_launches)
+    alg_update_bytes = (8.0 * n * (n + 1)) / shards + 112.0 * n  # SURVEY §8d: cov R+W + 5 P columns + X + gating
+    lazy = n >= 2048 or ctx.world > 1
+    kname = "k_cov_update_tma_dense" if lazy else "k_cov_update_multi"
+    return {
+        "bound": "hbm",
+        "kernel": (f"{kname} (slam.h:260 for every pending update — up to 16 panel rows = 8 sequential landmark updates "
+                   f"per launch — in ONE tensor-map TMA read + write of the upper triangle, rank-r term on the FP64 "
+                   f"tensor cores)" if lazy else f"{kname} (slam.h:260, upper-triangle update)"),
+        "updates_per_launch": per_pass, "panel_rows_per_update": 2,
+        "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak if peak else 0.0,
+        "peak_source": peak_src, "traffic": ncu_traffic(kname, n) if ctx.world == 1 else None,
+        "algorithmic_bytes_per_launch": 8.0 * n * (n + 1) / shards, "per": "GPU",
+        "launches_timed": cov_launches, "avg_launch_ms": cov_ms / max(1, cov_launches),
+        "whole_update_frac": (alg_update_bytes * upd_local / (t["ms"] * 1e-3) / 1e9) / peak if peak else 0.0,
+        "whole_update_frac_note": "SURVEY §8d bytes assume one covariance pass per update; deferred passes apply "
+                                  f"{per_pass:.1f} updates per pass, hence > 1" if per_pass > 1.01 else None,
+    }
+
+
+def ekf_result(ctx, eb, m, steps, warmup, batch=False, strict=False, with_e2e=True, with_parity=True):
+    """One EKF workload on an existing EkfBench: parity check, device-timed loop, end-to-end loop -> result dict."""
+    N, n = eb.N, eb.n
+    par = eb.parity(m, batch) if with_parity else None
+    t = eb.timed(m, steps, warmup, batch, strict)
+    e = eb.e2e(m, steps, batch) if with_e2e else None
+    if ctx.rank != 0:
+        return None
+    peak, peak_src = measured_peaks()
+    value = t["updates"] / (t["ms"] * 1e-3)
+    r_rank = 2 * m
+    upd_kind = (f"batched JOINT update of {m} observations per scan (rank {r_rank}): gate + stacked gain + "
+                f"tensor-core covariance update" if batch else
+                f"sequential update: gate + gain + covariance, {m} observation{'s' if m > 1 else ''} per scan" +
+                (", one covariance pass per update (flush after every scan)" if strict else ""))
+    sharded, world = ctx.sharded, ctx.world
+    out = {
+        "metric": "EKF updates/sec", "value": value, "unit": "updates/s", "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": t["ms"] / steps, "higher_is_better": True,
+        "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {
+            "workload": (f"EKF-SLAM {N} landmarks (state dim {n}, FP64 P {8.0 * n * n / 1e9:.2f} GB), "
+                         f"range-bearing observations, {upd_kind}" +
+                         (f", covariance row-sharded over {world} GPUs" if sharded else
+                          (f", {world} independent filter replicas" if world > 1 else ""))),
+            "landmarks": N, "state_dim": n, "obs_per_step": m, "mode": "INTENDED (SURVEY Appendix A)",
+            "l2": f"inputs larger than L2 ({4.0 * n * n / 1e9 / (world if sharded else 1):.1f} GB of upper "
+                  f"triangle streamed per GPU per covariance pass)",
+            "parallelism": ("row-sharded covariance (block-cyclic 128-row tiles), NCCL all-reduce of the observed "
+                            "columns per scan, gains / gating overlapped with the covariance pass" if sharded else
+                            ("replicas only (one independent filter per GPU)" if world > 1 else "single GPU")),
+        },
+        "clocks": t["clocks"],
+        "gpu_launches": t["launches"],
+        "covariance_passes": t["passes"],
+        "roofline": ekf_roofline(ctx, n, N, m, t, batch, strict, peak, peak_src),
+        "skipped_updates": t["skipped"],
+    }
+    if e is not None:
+        out["e2e"] = {"value": e["updates"] / (e["ms"] * 1e-3), "unit": "updates/s",
+                      "h2d_bytes_per_step": int(2 * m * 8 + 4 * 8 + 2 * 8 + m * 4 + 4 * 8),
+                      "d2h_bytes_per_step": int(n * 8 + m * (4 + 8 + 8))}
+        out["state_checksum"] = float(np.sum(e["X"][:3])) if e["X"] is not None else None
+    if par is not None:
+        out["parity_check"] = par
+    if batch:
+        out["observations_per_s"] = value * m
+    return out
+
+
+def guarded(name, fn):
+    """Extras never take the headline down: failures are reported in place."""
+    try:
+        t0 = time.time()
+        r = fn()
+        if isinstance(r, dict):
+            r["wall_s"] = round(time.time() - t0, 1)
+        return r
+    except Exception as e:  # pragma: no cover
+        import traceback
+        log(f"[bench] extra '{name}' failed: {traceback.format_exc()}")
+        return {"error": f"{type(e).__name__}: {e}"}
 
 
 def main():
@@ -576,13 +945,17 @@ def main():
     ap.add_argument("--obs", type=int, default=None, help="observations per scan (default 4; 32 with --batch)")
     ap.add_argument("--batch", action="store_true",
                     help="C3 of BASELINE.json: one JOINT update of all observations of a scan (rank 2m, FP64 tensor cores)")
+    ap.add_argument("--strict", action="store_true", help="one covariance pass per scan (flush after every scan)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="headline only (no C2 / C3-batch / per-observation / PF / C5 blocks)")
     ap.add_argument("--multi", default="sharded", choices=["sharded", "replicas"],
                     help="N>1: row-sharded covariance of ONE filter (strong scaling) or independent filter replicas")
     ap.add_argument("--workload", default="ekf", choices=["ekf", "pf"],
                     help="ekf: the headline (BASELINE.json metric, first half); pf: particle-steps/sec (C4)")
     ap.add_argument("--particles", type=int, default=1 << 20)
     ap.add_argument("--pf-landmarks", type=int, default=500)
+    ap.add_argument("--pf-obs", type=int, default=4)
+    ap.add_argument("--pf-spread", default="balanced", choices=["balanced", "realistic", "adversarial"])
     args = ap.parse_args()
     _capture_stdout()
     if args.obs is None:
@@ -592,202 +965,56 @@ def main():
         run_reference(args)
         return
     if args.workload == "pf":
+        args.pf_obs = args.obs if args.obs != 32 else args.pf_obs
         run_pf(args)
         return
 
-    import torch
-    import torch.distributed as dist
-
-    import conan_slam_b200 as cs
-    from conan_slam_b200 import _lib
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    lib = _lib.load_library()
-
+    ctx = Ctx(args)
     N, m = args.landmarks, args.obs
-    n = 3 + 2 * N
-    stream = torch.cuda.Stream(device=local)
-    t0 = time.time()
-    sharded = world > 1 and args.multi == "sharded"
-    if sharded:
-        from conan_slam_b200 import dist as cdist
-        nid = cdist.nccl_unique_id(device=f"cuda:{local}")
-        # one filter, covariance row-sharded over the ranks: identical inputs on every rank (SPMD)
-        ekf, lm, rng = build_ekf(N, local, cs.FLAG_INTENDED, seed=N, stream=stream.cuda_stream, rank=rank,
-                                 world=world, nccl_id=nid)
-    else:
-        ekf, lm, rng = build_ekf(N, local, cs.FLAG_INTENDED, seed=N + 1000 * rank, stream=stream.cuda_stream)
-    log(f"[bench r{rank}] built {N}-landmark map (n={n}, P={8.0 * n * n / 1e9:.2f} GB) in {time.time() - t0:.1f}s")
-    scans = make_scans(lm, rng, max(8, args.steps + args.warmup), m)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- device-timed throughput (state resident in HBM) + live kernel timing ----
-    batch = bool(args.batch)
-    for s in range(args.warmup):
-        ekf_scan(ekf, scans[s % len(scans)][0], batch)
-    ekf.sync()
-    sampler = ClockSampler(local)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    launches0 = lib.cslam_kernel_launches()
-    ekf.profile_begin(args.steps * m + 8)
-    sampler.start()
-    updates = 0
-    assoc0 = 0 if batch else ekf.scan_associations()
-    with torch.cuda.stream(stream):
-        ev0.record(stream)
-        for s in range(args.steps):
-            jb = ekf_scan(ekf, scans[(args.warmup + s) % len(scans)][0], batch, want_indices=False)
-            updates += (1 if batch else 0)
-        ev1.record(stream)
-    barrier()
-    if not batch:  # updates applied = observations the gate associated, counted on the device
-        updates = ekf.scan_associations() - assoc0
-    clocks = sampler.stop()
-    cov_ms, cov_launches, cov_bytes = ekf.profile_end()
-    launches = lib.cslam_kernel_launches() - launches0
-    ms = ev0.elapsed_time(ev1)
-    skipped = ekf.sync()
-
-    # ---- end to end through the public API: host observations in, state + indices out ----
-    X_host = None
-    barrier()
-    t_e0 = torch.cuda.Event(enable_timing=True)
-    t_e1 = torch.cuda.Event(enable_timing=True)
-    e2e_updates = 0
-    with torch.cuda.stream(stream):
-        t_e0.record(stream)
-        for s in range(args.steps):
-            Z = scans[(s + 1) % len(scans)][0]
-            jb = ekf_scan(ekf, Z, batch)
-            X_host = ekf.X  # D2H read of the step's result (n doubles through pinned staging)
-            e2e_updates += (1 if batch else int((jb > 0).sum()))
-        t_e1.record(stream)
-    barrier()
-    e2e_ms = t_e0.elapsed_time(t_e1)
-
-    # ---- a whole drive cycle of test/main.cpp (6 control steps = predict + observeHeading each, then one
-    # observation scan), stepwise calls vs cslam_ekf_control_steps (heading passes merged): extra info
-    drive = None
-    if world == 1 and not batch:
-        def cycle(merged, Z):
-            if merged:
-                ekf.controlSteps(np.zeros(6), np.zeros(6), np.zeros(6), True, QE_BENCH, 73.0, 0.01, want_trace=False)
+    extras_on = not args.no_extras and not args.batch and not args.strict and args.multi == "sharded" and N == 20000
+    eb = EkfBench(ctx, N, max(8, args.steps + args.warmup))
+    out = ekf_result(ctx, eb, m, args.steps, args.warmup, batch=args.batch, strict=args.strict)
+    extras = {}
+    if ctx.world == 1 and not args.batch:
+        d = guarded("drive_cycle", lambda: eb.drive(m))
+        if ctx.rank == 0:
+            out["drive_cycle"] = d
+    if extras_on:
+        # ---- the rest of the measurement contract in the same run ----
+        if ctx.world == 1:
+            extras["c3_obs1"] = guarded("c3_obs1", lambda: ekf_result(ctx, eb, 1, 12, 3, strict=True, with_parity=False))
+            extras["c3_batch"] = guarded("c3_batch", lambda: ekf_result(ctx, eb, 32, 6, 3, batch=True))
+            extras["c3_obs8"] = guarded("c3_obs8", lambda: ekf_result(ctx, eb, 8, 10, 3, with_parity=False, with_e2e=False))
+    eb.close()
+    if extras_on:
+        if ctx.world == 1:
+            def c2():
+                e2 = EkfBench(ctx, 2000, 64)
+                r = ekf_result(ctx, e2, 4, 200, 10)
+                e2.close()
+                return r
+            extras["c2"] = guarded("c2", c2)
+        if ctx.world >= 2:
+            def c5():
+                e5 = EkfBench(ctx, 60000, 16)
+                r = ekf_result(ctx, e5, 4, 8, 3)
+                e5.close()
+                return r
+            free_gb = ctx.torch.cuda.mem_get_info()[0] / 1e9
+            need_gb = 2 * 8.0 * 120003 ** 2 / 1e9 / ctx.world * 1.15
+            if free_gb > need_gb / 2 + 4:  # one array is the minimum; the ping-pong twin is taken when it fits
+                extras["c5"] = guarded("c5", c5)
             else:
-                for _ in range(6):
-                    ekf.predict(0.0, 0.0, QE_BENCH, 73.0, 0.01)
-                    ekf.observeHeading(0.0, True)
-            ekf_scan(ekf, Z)
-        drive = {"control_steps_per_cycle": 6, "observations_per_cycle": m,
-                 "covariance_passes_per_cycle": {"stepwise": 7, "merged": 2}}
-        for name, merged in (("stepwise", False), ("merged", True)):
-            cycle(merged, scans[0][0])
-            ekf.sync()
-            d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            with torch.cuda.stream(stream):
-                d0.record(stream)
-                for c in range(3):
-                    cycle(merged, scans[(c + 2) % len(scans)][0])
-                d1.record(stream)
-            torch.cuda.synchronize()
-            drive[f"ms_per_cycle_{name}"] = d0.elapsed_time(d1) / 3.0
-
-    if world > 1:
-        t = torch.tensor([ms, e2e_ms], device=f"cuda:{local}", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms = float(t[0]), float(t[1])
-        cnt = torch.tensor([updates, e2e_updates, launches], device=f"cuda:{local}", dtype=torch.float64)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-        if sharded:  # every rank took part in the SAME updates: count them once
-            launches = int(cnt[2])
-        else:
-            updates, e2e_updates, launches = int(cnt[0]), int(cnt[1]), int(cnt[2])
-
-    if rank == 0:
-        peak, peak_src = measured_peaks()
-        value = updates / (ms * 1e-3)
-        e2e_value = e2e_updates / (e2e_ms * 1e-3)
-        ach = (cov_bytes / cov_launches) / (cov_ms / cov_launches * 1e-3) / 1e9 if cov_launches else 0.0
-        shards = world if sharded else 1   # per-GPU figures: each rank streams 1/world of the triangle
-        alg_update_bytes = (8.0 * n * (n + 1)) / shards + 112.0 * n  # cov R+W + 5 P columns + X + gating
-        r_rank = 2 * m
-        if batch:
-            # joint update: bytes 8n(n+1) + (3+2m)*8n + 88N, flops 2*r*n(n+1)/2
-            alg_update_bytes = (8.0 * n * (n + 1)) / shards + (3 + r_rank) * 8.0 * n + 88.0 * N
-            flops = float(r_rank) * n * (n + 1) / shards
-            tpeak, tsrc = dmma_peak()
-            t_launch = cov_ms / max(1, cov_launches) * 1e-3
-            roof = {
-                "bound": "tensor", "kernel": "k_cov_update_dmma (slam.h:260, rank-2m update on FP64 tensor cores, "
-                                             "DMMA.8x8x4) incl. its panel-tiling kernel",
-                "achieved": flops / t_launch / 1e12 if cov_launches else 0.0, "peak": tpeak, "unit": "TFLOP/s",
-                "frac": (flops / t_launch / 1e12) / tpeak if cov_launches else 0.0, "peak_source": tsrc,
-                "traffic": ncu_traffic("k_cov_update_dmma", n) if world == 1 else None,
-                "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": 8.0 * n * (n + 1) / shards,
-                "hbm_gbs_same_launch": (cov_bytes / cov_launches) / t_launch / 1e9 if cov_launches else 0.0,
-                "hbm_frac_same_launch": ((cov_bytes / cov_launches) / t_launch / 1e9) / peak if cov_launches else 0.0,
-                "per": "GPU", "launches_timed": cov_launches, "avg_launch_ms": cov_ms / max(1, cov_launches),
-            }
-        else:
-            mg = min(m, 8)  # sequential updates of a scan share one pass in groups of up to 8
-            kname = f"k_cov_update_multi<{mg},128>" if mg > 1 else "k_cov_update<2,128>"
-            roof = {
-                "bound": "hbm",
-                "kernel": (f"{kname} (slam.h:260 for the {mg} sequential updates of a scan, ONE read + write of the "
-                           f"upper triangle)" if mg > 1 else f"{kname} (slam.h:260, upper-triangle rank-2 update)"),
-                "updates_per_launch": mg,
-                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "peak_source": peak_src, "traffic": ncu_traffic(kname, n) if world == 1 else None,
-                "algorithmic_bytes_per_launch": 8.0 * n * (n + 1) / shards, "per": "GPU",
-                "launches_timed": cov_launches, "avg_launch_ms": cov_ms / max(1, cov_launches),
-                "whole_update_frac": (alg_update_bytes * (updates if (sharded or world == 1) else updates / world)
-                                      / (ms * 1e-3) / 1e9) / peak,
-            }
-        upd_kind = (f"batched JOINT update of {m} observations per scan (rank {r_rank}): gate + stacked gain + "
-                    f"tensor-core covariance update" if batch else
-                    f"sequential update: gate + gain + covariance, {m} observations per scan")
-        out = {
-            "metric": "EKF updates/sec", "value": value, "unit": "updates/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {
-                "workload": (f"EKF-SLAM {N} landmarks (state dim {n}, FP64 P {8.0 * n * n / 1e9:.2f} GB), "
-                             f"range-bearing observations, {upd_kind}" +
-                             (f", covariance row-sharded over {world} GPUs" if sharded else
-                              (f", {world} independent filter replicas" if world > 1 else ""))),
-                "landmarks": N, "state_dim": n, "obs_per_step": m, "mode": "INTENDED (SURVEY Appendix A)",
-                "l2": f"inputs larger than L2 ({4.0 * n * n / 1e9 / (world if sharded else 1):.1f} GB of upper "
-                      f"triangle streamed per GPU per update)",
-                "parallelism": ("row-sharded covariance (block-cyclic 128-row tiles), NCCL all-reduce of the observed "
-                                "columns per update" if sharded else
-                                ("replicas only (one independent filter per GPU)" if world > 1 else "single GPU")),
-            },
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "updates/s",
-                    "h2d_bytes_per_step": int(2 * m * 8 + 4 * 8 + 2 * 8 + m * 4 + 4 * 8),
-                    "d2h_bytes_per_step": int(n * 8 + m * (4 + 8 + 8))},
-            "gpu_launches": int(launches),
-            "roofline": roof,
-            "skipped_updates": skipped,
-            "state_checksum": float(np.sum(X_host[:3])) if X_host is not None else None,
-        }
-        if batch:
-            out["observations_per_s"] = value * m
-        if drive is not None:
-            out["drive_cycle"] = drive
-        if not args.no_cpu_baseline and world == 1:
+                extras["c5"] = {"skipped": f"60,000 landmarks need {need_gb / 2:.0f} GB per GPU, {free_gb:.0f} GB free"}
+        pf_steps = 6
+        extras["pf_c4"] = guarded("pf_c4", lambda: pf_case(args, pf_steps, 3, "balanced", with_cpu=not args.no_cpu_baseline, quiet=True))
+        extras["pf_c4_realistic"] = guarded("pf_c4_realistic", lambda: pf_case(args, pf_steps, 3, "realistic", with_cpu=False, quiet=True))
+        if ctx.world > 1:
+            extras["pf_c4_adversarial"] = guarded("pf_c4_adversarial", lambda: pf_case(args, pf_steps, 3, "adversarial", with_cpu=False, quiet=True))
+    if ctx.rank == 0:
+        if extras:
+            out["extras"] = {k: v for k, v in extras.items() if v is not None}
+        if not args.no_cpu_baseline and ctx.world == 1:
             t1 = time.time()
             # the reference's own compiled sources (oracle/_ref) when they travelled with the snapshot,
             # else the oracle port; the multi-threaded port beside it as a generous baseline
@@ -797,10 +1024,11 @@ def main():
             out["cpu_baseline"]["oracle_port_all_cores"] = {
                 "cores": mt["cores"], "value": mt["value"], "kind": "port",
                 "update_only_updates_per_s": mt["update_only_updates_per_s"]}
+            out["cpu_baseline"]["extrapolated"] = True
             log(f"[bench] cpu baseline took {time.time() - t1:.1f}s")
         emit(out)
-    if world > 1:
-        dist.destroy_process_group()
+    if ctx.world > 1:
+        ctx.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -98,7 +98,9 @@ SIGNATURES = {
     "cslam_pf_get_poses": (C.c_int, [_vp, _dp]),
     "cslam_pf_get_pose_covs": (C.c_int, [_vp, _dp]),
     "cslam_pf_get_features": (C.c_int, [_vp, C.c_int, _dp, _dp]),
+    "cslam_pf_get_features_all": (C.c_int, [_vp, _dp, _dp]),
     "cslam_pf_set_weights": (C.c_int, [_vp, _dp]),
+    "cslam_pf_scale_weights": (C.c_int, [_vp, _vp, C.c_int]),
     "cslam_pf_set_poses": (C.c_int, [_vp, _dp, _dp]),
     "cslam_pf_extract_state": (C.c_int, [_vp, _dp, C.POINTER(C.c_int)]),
 }

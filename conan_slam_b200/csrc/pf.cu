@@ -70,6 +70,8 @@ struct cslam_pf {
     cslam::PfBuf peer[2][8];               // IPC-mapped buffers of every rank (self = own pointers)
     bool peers_ready = false;
     const double** d_peer_tab = nullptr;   // device copy of the peers' base pointers
+    double* acc_dev = nullptr;             // accessor scratch (AoS <-> SoA staging), grown on demand, never per call
+    size_t acc_cap = 0;
     // diagnostics: CUDA events around the gather-copy launches of each resample
     bool prof = false;
     std::vector<cudaEvent_t> prof_ev;
@@ -748,7 +750,7 @@ static int run_scan(cslam_pf* h, const double* in, int mode, const double* div) 
         double* totals = (l + 1 < h->levels) ? h->scan[l + 1] : h->d_small + 7;
         count_launch();
         k_scan_level<<<nblk(len, 256), 256, 0, h->stream>>>(src, len, h->scan[l], totals, l == 0 ? mode : 0, div);
-        src = h->scan[l + 1];  // level l+1's INPUT is the totals array; it is scanned in place
+        if (l + 1 < h->levels) src = h->scan[l + 1];  // level l+1's INPUT is the totals array; it is scanned in place
         len = (len + 31) / 32;
     }
     if (L < h->levels) {
@@ -987,6 +989,7 @@ int cslam_pf_destroy(cslam_pf_t* h) {
     for (int l = 0; l < 5; l++) { cudaFree(h->scan[l]); cudaFree(h->gscan[l]); }
     cudaFree(h->cum_global);
     cudaFree(h->d_peer_tab);
+    cudaFree(h->acc_dev);
     cudaFree(h->comb); cudaFree(h->wn); cudaFree(h->keep); cudaFree(h->d_in);
     cudaFree(h->d_small); cudaFree(h->d_ismall);
     if (h->pinned) cudaFreeHost(h->pinned);
@@ -1201,16 +1204,22 @@ int cslam_pf_resample(cslam_pf_t* h, const double* u, int u_on_device, double nu
         k_fill_keep<<<nblk(np, 256), 256, 0, h->stream>>>(h->keep, np, h->d_ismall);
     }
     CSLAM_CUDA(cudaGetLastError());
-    // neff decides on the host whether the gather runs (PF.cpp:490): one 8-byte read-back
-    CSLAM_CUDA(cudaMemcpyAsync(h->pinned, S + 2, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CSLAM_CUDA(cudaStreamSynchronize(h->stream));
-    const double ne = 1.0 / *static_cast<double*>(h->pinned);
+    // neff decides whether the gather runs (PF.cpp:490: neff < numEffective).  With numEffective = +inf
+    // ("resample every step") the decision does not depend on neff: no read-back, the call never waits for
+    // the GPU unless the caller asks for neff or the indices.
+    const bool always = resample_on && isinf(num_effective) && num_effective > 0;
+    double ne = 0.0;
+    if (!always || neff) {
+        CSLAM_CUDA(cudaMemcpyAsync(h->pinned, S + 2, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CSLAM_CUDA(cudaStreamSynchronize(h->stream));
+        ne = 1.0 / *static_cast<double*>(h->pinned);
+    }
     if (neff) *neff = ne;
     if (keep) {
         CSLAM_CUDA(cudaMemcpyAsync(keep, h->keep, (size_t)np * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CSLAM_CUDA(cudaStreamSynchronize(h->stream));
     }
-    const bool doit = (ne < num_effective) && resample_on;
+    const bool doit = always || ((ne < num_effective) && resample_on);
     if (resampled) *resampled = doit ? 1 : 0;
     if (doit) {
         PfBuf& d = h->buf[h->cur ^ 1];
@@ -1253,6 +1262,23 @@ int cslam_pf_resample(cslam_pf_t* h, const double* u, int u_on_device, double nu
         CSLAM_CUDA(cudaGetLastError());
         h->cur ^= 1;
     }
+    return CSLAM_OK;
+}
+
+// w[p] *= factor[p] (device or host vector of np doubles): importance-weight modulation by an external
+// likelihood term; bench.py uses it to study resampling under realistic / adversarial weight spreads.
+__global__ void __launch_bounds__(256) k_scale_w(double* __restrict__ w, const double* __restrict__ f, int np) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < np) w[i] = w[i] * f[i];
+}
+int cslam_pf_scale_weights(cslam_pf_t* h, const double* factor, int on_device) {
+    if (int rc = check_pf(h)) return rc;
+    CSLAM_REQUIRE(factor != nullptr, CSLAM_ERR_BAD_ARG, "factor is null");
+    const double* df = nullptr;
+    if (int rc = stage_in(h, factor, (size_t)h->np, on_device, &df)) return rc;
+    count_launch();
+    k_scale_w<<<nblk(h->np, 256), 256, 0, h->stream>>>(h->buf[h->cur].w, df, h->np);
+    CSLAM_CUDA(cudaGetLastError());
     return CSLAM_OK;
 }
 
@@ -1377,32 +1403,37 @@ int cslam_pf_get_weights(cslam_pf_t* h, double* w) {
     return CSLAM_OK;
 }
 
+static int pf_scratch(cslam_pf* h, size_t doubles) {  // accessor staging owned by the handle
+    if (h->acc_cap >= doubles) return CSLAM_OK;
+    CSLAM_CUDA(cudaStreamSynchronize(h->stream));
+    cudaFree(h->acc_dev);
+    h->acc_dev = nullptr;
+    h->acc_cap = 0;
+    const size_t want = std::max<size_t>(doubles, 4096);
+    CSLAM_CUDA(cudaMalloc(&h->acc_dev, want * sizeof(double)));
+    h->acc_cap = want;
+    return CSLAM_OK;
+}
 static int get_aos(cslam_pf* h, const double* soa, int k, double* out) {
-    double* tmp = nullptr;
     const size_t cnt = (size_t)h->np * k;
-    CSLAM_CUDA(cudaMalloc(&tmp, cnt * sizeof(double)));
+    if (cnt == 0) return CSLAM_OK;
+    if (int rc = pf_scratch(h, cnt)) return rc;
     count_launch();
-    k_soa_to_aos<<<nblk(cnt, 256), 256, 0, h->stream>>>(soa, tmp, h->pp, h->np, k);
-    cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaMemcpyAsync(out, tmp, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    cudaFree(tmp);
-    CSLAM_CUDA(e);
+    k_soa_to_aos<<<nblk(cnt, 256), 256, 0, h->stream>>>(soa, h->acc_dev, h->pp, h->np, k);
+    CSLAM_CUDA(cudaGetLastError());
+    CSLAM_CUDA(cudaMemcpyAsync(out, h->acc_dev, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CSLAM_CUDA(cudaStreamSynchronize(h->stream));
     return CSLAM_OK;
 }
 static int set_aos(cslam_pf* h, double* soa, int k, const double* in) {
-    double* tmp = nullptr;
     const size_t cnt = (size_t)h->np * k;
-    CSLAM_CUDA(cudaMalloc(&tmp, cnt * sizeof(double)));
-    cudaError_t e = cudaMemcpyAsync(tmp, in, cnt * sizeof(double), cudaMemcpyHostToDevice, h->stream);
-    if (e == cudaSuccess) {
-        count_launch();
-        k_aos_to_soa<<<nblk(cnt, 256), 256, 0, h->stream>>>(tmp, soa, h->pp, h->np, k);
-        e = cudaGetLastError();
-    }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    cudaFree(tmp);
-    CSLAM_CUDA(e);
+    if (cnt == 0) return CSLAM_OK;
+    if (int rc = pf_scratch(h, cnt)) return rc;
+    CSLAM_CUDA(cudaMemcpyAsync(h->acc_dev, in, cnt * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    count_launch();
+    k_aos_to_soa<<<nblk(cnt, 256), 256, 0, h->stream>>>(h->acc_dev, soa, h->pp, h->np, k);
+    CSLAM_CUDA(cudaGetLastError());
+    CSLAM_CUDA(cudaStreamSynchronize(h->stream));
     return CSLAM_OK;
 }
 
@@ -1420,8 +1451,8 @@ int cslam_pf_get_features(cslam_pf_t* h, int particle, double* XF, double* PF) {
     if (int rc = check_pf(h)) return rc;
     CSLAM_REQUIRE(XF && PF && particle >= 0 && particle < h->np, CSLAM_ERR_BAD_ARG, "bad argument");
     if (h->nf == 0) return CSLAM_OK;
-    double* tmp = nullptr;
-    CSLAM_CUDA(cudaMalloc(&tmp, (size_t)6 * h->nf * sizeof(double)));
+    if (int rc = pf_scratch(h, (size_t)6 * h->nf)) return rc;
+    double* tmp = h->acc_dev;
     count_launch();
     k_get_features<<<nblk(h->nf, 128), 128, 0, h->stream>>>(h->buf[h->cur].xf, h->buf[h->cur].pf, h->pp, particle,
                                                             h->nf, tmp, tmp + 2 * h->nf);
@@ -1430,8 +1461,19 @@ int cslam_pf_get_features(cslam_pf_t* h, int particle, double* XF, double* PF) {
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(PF, tmp + 2 * h->nf, (size_t)4 * h->nf * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    cudaFree(tmp);
     CSLAM_CUDA(e);
+    return CSLAM_OK;
+}
+// Slam::extractFeaturesFromParticles (slam.h:517-539): the feature estimates of EVERY particle, particle
+// after particle — XF[p][f][2] (the reference concatenates the 2 x nf blocks column-wise in particle order) and,
+// optionally, their packed 2x2 covariances PFp[p][f][3] = (xx, xy, yy).  Either pointer may be NULL.
+int cslam_pf_get_features_all(cslam_pf_t* h, double* XF, double* PFp) {
+    if (int rc = check_pf(h)) return rc;
+    if (h->nf == 0) return CSLAM_OK;
+    if (XF)
+        if (int rc = get_aos(h, h->buf[h->cur].xf, 2 * h->nf, XF)) return rc;
+    if (PFp)
+        if (int rc = get_aos(h, h->buf[h->cur].pf, 3 * h->nf, PFp)) return rc;
     return CSLAM_OK;
 }
 int cslam_pf_set_weights(cslam_pf_t* h, const double* w) {

@@ -152,18 +152,32 @@ class PF:
         check(self._lib.cslam_pf_feature_update(self._h, dptr(zflat), iptr(idf), Zm.shape[1], dptr(r)),
               "cslam_pf_feature_update")
 
-    def resampleParticles(self, numEffective, u, resampleStatus=False, want_keep=True):
+    def resampleParticles(self, numEffective, u, resampleStatus=False, want_keep=True, want_neff=True):
         """slam.h:871-872 / PF.cpp:473-500 (+546-596).  u: one deviate per slot.
-        Returns (keep, neff, resampled)."""
+        Returns (keep, neff, resampled).  want_keep = want_neff = False with numEffective = inf: no read-back,
+        the call does not wait for the GPU (neff is then returned as None)."""
         n = self.num_particles
         ptr, on_dev, keepalive = _draws(u, n)
         keep = np.zeros(n, dtype=np.int32) if want_keep else None
         neff = C.c_double(0)
         did = C.c_int(0)
         check(self._lib.cslam_pf_resample(self._h, ptr, on_dev, float(numEffective), int(bool(resampleStatus)),
-                                          iptr(keep) if want_keep else None, C.byref(neff), C.byref(did)),
+                                          iptr(keep) if want_keep else None, C.byref(neff) if want_neff else None,
+                                          C.byref(did)),
               "cslam_pf_resample")
-        return keep, neff.value, bool(did.value)
+        return keep, (neff.value if want_neff else None), bool(did.value)
+
+    def extractFeaturesFromParticles(self):
+        """slam.h:517-539: the 2 x (P * nf) concatenation of every particle's feature estimates, particle order."""
+        n, nf = self.num_particles, self.num_features
+        out = np.zeros((n, nf, 2), dtype=np.float64)
+        if nf:
+            check(self._lib.cslam_pf_get_features_all(self._h, dptr(out), None), "cslam_pf_get_features_all")
+        return np.ascontiguousarray(out.reshape(n * nf, 2).T)
+
+    def scale_weights_device(self, dev_ptr):
+        """w[p] *= factor[p] with factor a DEVICE vector of num_particles doubles (cslam_pf_scale_weights)."""
+        check(self._lib.cslam_pf_scale_weights(self._h, C.c_void_p(int(dev_ptr)), 1), "cslam_pf_scale_weights")
 
     def addOneNewFeature(self, Z, R):
         """slam.h:134 / PF.cpp:9-60 for every particle."""

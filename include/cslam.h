@@ -231,7 +231,8 @@ int cslam_pf_feature_update(cslam_pf_t* h, const double* Z, const int32_t* idf, 
  *   -> stratifiedResample PF.cpp:546-577 (+ stratifiedRandom :579-596).
  * u: one deviate per slot (an input).  keep (nullable, host, P int32) receives the
  * selected 0-based source index per slot; *neff the effective particle count; *resampled
- * whether the gather-copy ran (neff < num_effective && resample_on). */
+ * whether the gather-copy ran (neff < num_effective && resample_on).  With num_effective = +infinity
+ * ("resample every step") and keep == neff == NULL the call is fully asynchronous (no read-back). */
 int cslam_pf_resample(cslam_pf_t* h, const double* u, int u_on_device, double num_effective, int resample_on,
                       int32_t* keep, double* neff, int* resampled);
 /* Slam::addOneNewFeature(Particle_t&,Z,R) for every particle       slam.h:134 -> PF.cpp:9-60 */
@@ -250,7 +251,12 @@ int cslam_pf_get_weights(cslam_pf_t* h, double* w);
 int cslam_pf_get_poses(cslam_pf_t* h, double* X);
 int cslam_pf_get_pose_covs(cslam_pf_t* h, double* Pv);
 int cslam_pf_get_features(cslam_pf_t* h, int particle, double* XF, double* PF);
+/* Slam::extractFeaturesFromParticles (slam.h:517-539): the feature estimates of every particle in particle
+ * order, XF[p][f][2], and optionally their packed 2x2 covariances PFp[p][f][3] = (xx, xy, yy).  Either may be NULL. */
+int cslam_pf_get_features_all(cslam_pf_t* h, double* XF, double* PFp);
 int cslam_pf_set_weights(cslam_pf_t* h, const double* w);
+/* w[p] *= factor[p] (np doubles, host or device): an external likelihood term on the importance weights. */
+int cslam_pf_scale_weights(cslam_pf_t* h, const double* factor, int on_device);
 int cslam_pf_set_poses(cslam_pf_t* h, const double* X, const double* Pv);
 /* Checkpoint / restore of the whole particle set: header + every struct-of-arrays row of
  * the current buffer.  load() needs a handle with the same particle count and enough landmark capacity.
