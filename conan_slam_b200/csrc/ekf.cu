@@ -1439,7 +1439,14 @@ int cslam_ekf_update(cslam_ekf_t* h, const double* Z, const int32_t* idf, int m,
     for (int i = 0; i < m; i++)
         CSLAM_REQUIRE(idf[i] >= 1 && idf[i] <= nf, CSLAM_ERR_BAD_ARG, "idf out of range (1-based map slots)");
     if (!batch) return h->lz.on ? lazy_sequential(h, Z, idf, nullptr, m, R) : sequential_updates(h, Z, idf, nullptr, m, R);
-    CSLAM_REQUIRE(m <= CSLAM_MAX_BATCH_OBS, CSLAM_ERR_UNSUPPORTED, "joint update supports at most 32 observations");
+    if (m > CSLAM_MAX_BATCH_OBS) {
+        // One joint update handles rank <= 64.  More observations are applied as successive joint updates of up to
+        // 32 each (every chunk linearised at the state the previous chunk produced) — documented in cslam.h; the
+        // reference's batchUpdate has no such limit but its driver never sees more than 7 landmarks at once.
+        for (int b = 0; b < m; b += CSLAM_MAX_BATCH_OBS)
+            if (int rc = cslam_ekf_update(h, Z + 2 * b, idf + b, std::min(CSLAM_MAX_BATCH_OBS, m - b), R, 1)) return rc;
+        return CSLAM_OK;
+    }
     if (int rc = lazy_flush_all(h)) return rc;  // the joint update reads its 2m columns from the up-to-date array
     ObsPack ob;
     memset(&ob, 0, sizeof(ob));

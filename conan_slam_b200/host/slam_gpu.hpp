@@ -16,11 +16,17 @@
 //     population level (PfGpuT below): the reference's per-particle virtuals are called in driver
 //     loops over a host std::vector<Particle_t>, one PfGpuT call replaces one such loop.
 //
-// Error convention mirrors the reference (EKF.cpp:22-25 etc.): failures are printed and the call
-// returns; nothing throws across the adaptor.  There is no CPU fallback.
+// Error convention: the C ABI never throws; THIS adaptor does.  The reference swallows exceptions and
+// prints (EKF.cpp:22-25 etc.), which is harmless there because a failed step leaves its host state as it
+// was; here a failed device call (capacity exceeded, CUDA error) would leave the driver running on a filter
+// that silently skipped a step, so every failure raises cslam_host::Error (std::runtime_error) with the
+// library's message.  Numerically skipped updates (non-SPD S, slam.h:252-255) are NOT failures: they are
+// counted and reported by skippedUpdates(), as in the reference they are silent.  There is no CPU fallback.
 #pragma once
 #include <cstdint>
 #include <iostream>
+#include <stdexcept>
+#include <string>
 #include <vector>
 
 #include "cslam.h"
@@ -70,8 +76,12 @@ struct AssociationT {  // slam.h:438-443
     std::vector<int> idf;
 };
 
-inline void report(int rc, const char* where) {  // reference style: print and continue
-    if (rc != CSLAM_OK) std::cout << cslam_last_error() << "\t" << where << std::endl;
+struct Error : std::runtime_error {
+    int code;
+    Error(int rc, const std::string& what) : std::runtime_error(what), code(rc) {}
+};
+inline void report(int rc, const char* where) {  // a failed device call is fatal for the step: raise
+    if (rc != CSLAM_OK) throw Error(rc, std::string(where) + ": " + cslam_last_error());
 }
 
 template <class Vec, class MatT>
@@ -244,9 +254,22 @@ class EkfGpuT {
         out.ZN.resize(zn.empty() ? 0 : 2, (int)zn.size());
         for (size_t k = 0; k < zn.size(); k++) { out.ZN(0, (int)k) = Z(0, zn[k]); out.ZN(1, (int)k) = Z(1, zn[k]); }
         const int nf = (X.rows() - 3) / 2;
+        // the slots handed out here are only valid if the following augment() fits: check BEFORE touching the table
+        if (nf + (int)idn.size() > cslam_ekf_capacity(h_))
+            throw Error(CSLAM_ERR_CAPACITY, "dataAssociateTable: " + std::to_string(idn.size()) + " new landmarks do not fit "
+                                            "the handle's capacity of " + std::to_string(cslam_ekf_capacity(h_)));
         for (size_t k = 0; k < idn.size(); k++) table[(size_t)idn[k] - 1] = nf + (int)k + 1;
         return out;
     }
+    // The device copy of X, P is authoritative after the first call: the caller's X and P are OUTPUTS (X always,
+    // P while n <= p_writeback_max).  A driver that edits its X / P in place (pose reset, covariance inflation)
+    // must hand the new state over explicitly.
+    void reseed(const Vec& X, const MatT& P) {
+        seeded_ = false;
+        push(X, P);
+    }
+    // true when P is no longer written back after each call (n > p_writeback_max): use fetchCovariance()
+    bool covarianceWritebackSuppressed() const { return cslam_ekf_n(h_) > p_writeback_max; }
     // explicit covariance read-back for maps above p_writeback_max
     void fetchCovariance(MatT& P) {
         const int n = cslam_ekf_n(h_);

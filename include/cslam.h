@@ -124,7 +124,9 @@ int cslam_ekf_gate(cslam_ekf_t* h, const double* Z, int m, const double R[4], do
                    int32_t* jbest, uint8_t* is_new, double* nbest, double* outer);
 /* Slam::update(X,P,Z,R,idf,batch)                       slam.h:938-943 -> EKF.cpp:481-496
  *   batch=0: singleUpdate EKF.cpp:457-479 (re-linearised per observation)
- *   batch=1: batchUpdate  EKF.cpp:93-129  (one joint rank-2m update; m <= CSLAM_MAX_BATCH_OBS)
+ *   batch=1: batchUpdate  EKF.cpp:93-129  (one joint rank-2m update for m <= CSLAM_MAX_BATCH_OBS = 32; more
+ *            observations are applied as successive joint updates of 32, each chunk linearised at the state
+ *            the previous one produced — an explicit, documented deviation: the reference has no rank limit)
  * both through Slam::choleskyUpdate slam.h:235-266.  Asynchronous. m == 0 is a no-op. */
 int cslam_ekf_update(cslam_ekf_t* h, const double* Z, const int32_t* idf, int m, const double R[4], int batch);
 /* One observation cycle with NO host round trip between association and update — the call pair

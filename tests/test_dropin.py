@@ -42,3 +42,35 @@ def test_dropin_gpu_matches_reference_class(tmp_path):
     assert np.max(np.abs(tr_ref[:, 2] - tr_gpu[:, 2])) < 2e-4
     assert X_ref.shape == X_gpu.shape and X_ref.shape[0] > 3
     assert np.max(np.abs(X_ref - X_gpu)) / np.max(np.abs(X_ref)) < 5e-4
+
+
+def _run_pf(which, n, path):
+    out = subprocess.run([EXE, which, str(n), path], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr + out.stdout
+    raw = np.fromfile(path, dtype=np.float32)
+    n_, nf = int(raw[0]), int(raw[1])
+    return raw[2:].reshape(n_, -1), nf, out.stdout
+
+
+@pytest.mark.gpu
+def test_dropin_pf_gpu_matches_reference_class(tmp_path):
+    """`class PFGpu : public Slam` with the reference's PER-PARTICLE virtual signatures (slam.h:134, 549-552, 688,
+    796, 858-863, 881-884): the driver loops of test/main.cpp:279-327 — predict / observeHeading over every
+    particle, pose sampling on the host + addOneNewFeature, sampleProposal + featureUpdate — run once on the
+    reference's own `PF` class (CPU, FP32) and once on `PFGpu` (population on the device, FP64)."""
+    if not os.path.exists(EXE):
+        pytest.skip("oracle/_ref/dropin_main was not prebuilt")
+    n = 64
+    ref, nf_r, _ = _run_pf("pfref", n, str(tmp_path / "pfref.bin"))
+    gpu, nf_g, out = _run_pf("pfgpu", n, str(tmp_path / "pfgpu.bin"))
+    assert nf_r == nf_g == 4 and ref.shape == gpu.shape
+    X_r, X_g = ref[:, 1:4], gpu[:, 1:4]
+    assert np.max(np.abs(X_r[:, :2] - X_g[:, :2])) / np.max(np.abs(X_r[:, :2])) < 1e-3      # FP32 reference vs FP64 device
+    assert np.max(np.abs(X_r[:, 2] - X_g[:, 2])) < 1e-4
+    assert np.max(np.abs(ref[:, 4:13] - gpu[:, 4:13])) < 1e-6                                # P = 0 after the proposal
+    xf_r, xf_g = ref[:, 13:13 + 2 * nf_r], gpu[:, 13:13 + 2 * nf_r]
+    assert np.max(np.abs(xf_r - xf_g)) / np.max(np.abs(xf_r)) < 2e-3
+    pf_r, pf_g = ref[:, 13 + 2 * nf_r:], gpu[:, 13 + 2 * nf_r:]
+    assert np.max(np.abs(pf_r - pf_g)) / np.max(np.abs(pf_r)) < 2e-2
+    assert np.max(np.abs(ref[:, 0] - gpu[:, 0])) < 1e-6                                     # weights (underflow to ~0, Q7)
+    assert "resampled, sum of weights 1.0000" in out

@@ -98,6 +98,7 @@ def test_one_pass_per_drive_cycle_and_inplace_mode_identical():
         with _env(CSLAM_PINGPONG=pingpong):
             g = cs.EKF(capacity_landmarks=N, device=0, flags=cs.FLAG_INTENDED)
         g.reset(X, P)
+        g.gate(Z, helpers.RE, GATE1, GATE2)  # builds the diagonal-block cache once (it is stale after a reset)
         p0 = g.pass_count()[0]
         for c in range(4):
             g.controlSteps(np.zeros(6), np.full(6, 0.01), np.full(6, X[2] + 1e-4), True, helpers.QE, 73.0, 0.01,
