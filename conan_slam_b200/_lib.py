@@ -58,6 +58,7 @@ SIGNATURES = {
     "cslam_ekf_observe_heading": (C.c_int, [_vp, C.c_double, C.c_int]),
     "cslam_ekf_control_steps": (C.c_int, [_vp, C.c_int, _dp, _dp, _dp, C.c_int, _dp, C.c_double, C.c_double, _dp]),
     "cslam_ekf_gate": (C.c_int, [_vp, _dp, C.c_int, _dp, C.c_double, C.c_double, _ip, _u8p, _dp, _dp]),
+    "cslam_ekf_observe_step": (C.c_int, [_vp, _dp, _ip, C.c_int, _dp, C.c_int, _dp, C.c_int]),
     "cslam_ekf_scan": (C.c_int, [_vp, _dp, C.c_int, _dp, C.c_double, C.c_double, _ip, _u8p]),
     "cslam_ekf_scan_associations": (C.c_int, [_vp, C.POINTER(C.c_ulonglong)]),
     "cslam_ekf_update": (C.c_int, [_vp, _dp, _ip, C.c_int, _dp, C.c_int]),

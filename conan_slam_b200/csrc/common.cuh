@@ -6,6 +6,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX 3: ranges cost nothing unless a tool (nsys / ncu) is attached
+
 #include "../../include/cslam.h"
 #include "shard_map.h"
 
@@ -13,6 +15,14 @@ namespace cslam {
 
 void set_last_error(const char* fmt, ...);
 void count_launch();  // every kernel launch of the library is counted (bench.py: gpu_launches)
+
+// One NVTX range per C-ABI call (the reference has no tracing at all): timelines show
+// cslam_ekf_scan / cslam_pf_resample / ... around the kernels they launch.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+#define CSLAM_NVTX_RANGE() ::cslam::NvtxRange nvtx_range__(__func__)
 
 #define CSLAM_CUDA(call)                                                                        \
     do {                                                                                        \

@@ -60,8 +60,8 @@ struct TmaSmem {
     static constexpr int ring_bytes = S * TM_STAGE_BYTES;
     static constexpr int panel_doubles = RP * TM_PITCH;            // one panel (row or column) of one slot
     static constexpr int panels_bytes = 2 * 2 * panel_doubles * 8;  // 2 slots x (row, column)
-    static constexpr int bar_count = 2 * S + 4;                     // full[S], free[S], pfull[2], pempty[2]
-    static constexpr int info_bytes = 2 * 16 + 8 * S;               // per panel slot {j0, local row 0, diagonal?}; done[S] (dense variant)
+    static constexpr int bar_count = 2 * S + 4;                     // full[S], free[S], pfull[2], pempty[2] (even: an int4 follows)
+    static constexpr int info_bytes = 2 * 16;                       // per panel slot: {j0, local row 0, diagonal tile?}
     static constexpr int total = ring_bytes + panels_bytes + bar_count * 8 + info_bytes;
 };
 
@@ -265,12 +265,31 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_cov_update_tma(const __grid_c
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Dense-row variant: a stage is 32 full rows of the tile (32 x 1 KB, no swizzle), ONE tensor-map load and ONE
-// tensor-map store per stage, both 1 KB contiguous per covariance row (DRAM-page friendly).  Roles: warps 0..7
-// consumers, warp 8 lane 0 loads, warp 9 lane 0 stores.  Bank conflicts of the fragment accesses (row pitch
-// 1 KB: the two DMMA rows of a quarter-warp would hit the same banks) are avoided by letting the lanes of odd
-// DMMA rows touch the warp's second 8-column block first and swapping the two registers afterwards.
-constexpr int TMD_THREADS = (TM_CONSUMERS + 2) * 32;
+// Dense-row variant (the default): a stage is 32 full rows of the tile (32 x 1 KB, no swizzle), ONE tensor-map
+// load and ONE tensor-map store per stage, both 1 KB contiguous per covariance row.
+// Roles: warps 0..7 consumers (each the 16-column slice `warp` of every stage), warp 8 lane 0 loads (panels +
+// tiles), warps 9..9+TMD_STORERS-1 lane 0 store: store thread j owns the sub-tiles u = j (mod TMD_STORERS), issues
+// the store when the consumers are done and waits for ITS OWN store to have left shared memory before it frees
+// the stage — frees are prompt and TMD_STORERS stores are in flight (measured: one store thread that frees a
+// stage only when it issues the next store costs a whole stage of the ring).
+// Shared-memory budget (227 KB): the ring wants every byte — B200 needs ~50 KB of loads AND ~50 KB of stores in
+// flight per SM to saturate HBM — so the column panel is single-buffered: the consumers copy their fragments
+// into registers at the start of a tile and hand the buffer back at once; the row panel (re-read by every
+// sub-tile) is double-buffered.
+// Bank conflicts of the fragment accesses (row pitch 1 KB: the two DMMA rows of a quarter-warp would hit the
+// same banks) are avoided by letting the lanes of odd DMMA rows touch the warp's second 8-column block first
+// and swapping the two registers afterwards.
+constexpr int TMD_STORERS = 2;
+constexpr int TMD_THREADS = (TM_CONSUMERS + 1 + TMD_STORERS) * 32;
+template <int KS, int S>
+struct TmdSmem {
+    static constexpr int RP = 4 * KS;
+    static constexpr int ring_bytes = S * TM_STAGE_BYTES;
+    static constexpr int panel_doubles = RP * TM_PITCH;
+    static constexpr int panels_bytes = 3 * panel_doubles * 8;  // row panel x 2 slots, column panel x 1
+    static constexpr int bar_count = (3 * S + 6 + 1) / 2 * 2;    // full, done, free [S]; pfull[2], pempty[2], cfull, cempty (even: int4 behind)
+    static constexpr int total = ring_bytes + panels_bytes + bar_count * 8 + 2 * 16;
+};
 template <int KS, int S>
 __global__ void __launch_bounds__(TMD_THREADS, 1) k_cov_update_tma_dense(const __grid_constant__ CUtensorMap tmSrc,
                                                                         const __grid_constant__ CUtensorMap tmDst,
@@ -278,13 +297,12 @@ __global__ void __launch_bounds__(TMD_THREADS, 1) k_cov_update_tma_dense(const _
                                                                         int r, int nt, long long tiles, Shard sh,
                                                                         const int* __restrict__ live, int nlive,
                                                                         double diag_eps, int dbg) {
-    using L = TmaSmem<KS, S>;
+    using L = TmdSmem<KS, S>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* ring = smem_raw;
     double* panels = reinterpret_cast<double*>(smem_raw + L::ring_bytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L::ring_bytes + L::panels_bytes);
     int4* tinfo = reinterpret_cast<int4*>(smem_raw + L::ring_bytes + L::panels_bytes + L::bar_count * 8);
-    uint64_t* bars_done = reinterpret_cast<uint64_t*>(tinfo + 2);  // done[S] lives behind the tile info (S <= 6)
     if (live != nullptr) {
         int any = 0;
         for (int q = 0; q < nlive; q++) any |= live[q];
@@ -292,10 +310,10 @@ __global__ void __launch_bounds__(TMD_THREADS, 1) k_cov_update_tma_dense(const _
     }
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t bar0 = smem_u32(bars);
-    const uint32_t bar_full = bar0, bar_free = bar0 + 8 * S, bar_pfull = bar0 + 16 * S, bar_pempty = bar0 + 16 * S + 16;
-    const uint32_t bar_done = smem_u32(bars_done);
-    auto rowp = [&](int slot) { return panels + (size_t)slot * 2 * L::panel_doubles; };
-    auto colp = [&](int slot) { return panels + (size_t)slot * 2 * L::panel_doubles + L::panel_doubles; };
+    const uint32_t bar_full = bar0, bar_done = bar0 + 8 * S, bar_free = bar0 + 16 * S, bar_pfull = bar0 + 24 * S,
+                   bar_pempty = bar_pfull + 16, bar_cfull = bar_pfull + 32, bar_cempty = bar_pfull + 40;
+    auto rowp = [&](int slot) { return panels + (size_t)slot * L::panel_doubles; };
+    double* colp = panels + 2 * (size_t)L::panel_doubles;
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < S; s++) {
@@ -308,9 +326,12 @@ __global__ void __launch_bounds__(TMD_THREADS, 1) k_cov_update_tma_dense(const _
             mbar_init(bar_pfull + 8 * s, 1);
             mbar_init(bar_pempty + 8 * s, TM_CONSUMERS);
         }
+        mbar_init(bar_cfull, 1);
+        mbar_init(bar_cempty, TM_CONSUMERS);
         mbar_fence_init();
     }
-    for (int idx = tid; idx < 4 * L::panel_doubles / 2; idx += TMD_THREADS)
+    // panels start out zero: rows r..RP-1 (rank padding) stay zero, the bulk copies only write rows < r
+    for (int idx = tid; idx < 3 * L::panel_doubles / 2; idx += TMD_THREADS)
         reinterpret_cast<double2*>(panels)[idx] = make_double2(0.0, 0.0);
     fence_proxy_async();
     __syncthreads();
@@ -327,34 +348,31 @@ __global__ void __launch_bounds__(TMD_THREADS, 1) k_cov_update_tma_dense(const _
             int tr, tc;
             shard_tile(t, nt, sh, tr, tc);
             const int slot = lt & 1;
-            if (lt >= 2) mbar_wait(bar_pempty + 8 * slot, ((lt >> 1) - 1) & 1);
             const int i0 = tr * TM_T, j0 = tc * TM_T;
             const int lrow0 = (int)shard_lrow(sh, i0);
-            tinfo[slot] = make_int4(j0, lrow0, tr == tc ? 1 : 0, 0);
-            const int ilen = min(TM_T, (int)lda - i0), jlen = min(TM_T, (int)lda - j0);
-            mbar_expect_tx(bar_pfull + 8 * slot, (uint32_t)(r * (ilen + jlen) * 8));
-            const uint32_t rp_u32 = smem_u32(rowp(slot)), cp_u32 = smem_u32(colp(slot));
-            for (int k = 0; k < r; k++) {
-                bulk_g2s_hint(rp_u32 + 8 * TM_PITCH * k, A + (size_t)k * lda + i0, (uint32_t)ilen * 8,
-                              bar_pfull + 8 * slot, pol_keep);
-                bulk_g2s_hint(cp_u32 + 8 * TM_PITCH * k, A + (size_t)k * lda + j0, (uint32_t)jlen * 8,
-                              bar_pfull + 8 * slot, pol_keep);
-            }
+            const int ilen = min(TM_T, (int)lda - i0), jlen = min(TM_T, (int)lda - j0);  // doubles, > 0, even
+            if (lt >= 2) mbar_wait(bar_pempty + 8 * slot, ((lt >> 1) - 1) & 1);
+            tinfo[slot] = make_int4(j0, lrow0, tr == tc ? 1 : 0, 0);  // published by the arrive below (release)
+            mbar_expect_tx(bar_pfull + 8 * slot, (uint32_t)(r * ilen * 8));
+            const uint32_t rp_u32 = smem_u32(rowp(slot)), cp_u32 = smem_u32(colp);
+            for (int k = 0; k < r; k++)
+                bulk_g2s_hint(rp_u32 + 8 * TM_PITCH * k, A + (size_t)k * lda + i0, (uint32_t)ilen * 8, bar_pfull + 8 * slot,
+                              pol_keep);
+            if (lt >= 1) mbar_wait(bar_cempty, (uint32_t)((lt - 1) & 1));  // fragments of the previous tile are in registers
+            mbar_expect_tx(bar_cfull, (uint32_t)(r * jlen * 8));
+            for (int k = 0; k < r; k++)
+                bulk_g2s_hint(cp_u32 + 8 * TM_PITCH * k, A + (size_t)k * lda + j0, (uint32_t)jlen * 8, bar_cfull, pol_keep);
 #pragma unroll 1
             for (int s = 0; s < TM_T / TM_SUB; s++) {
                 if (sub >= S) {
                     mbar_wait(bar_free + 8 * st, (free_phase >> st) & 1u);
                     free_phase ^= 1u << st;
                 }
-                if (dbg & 4) {
+                if (dbg & 4) {  // development ablation: no covariance loads
                     mbar_arrive(bar_full + 8 * st);
                 } else {
                     mbar_expect_tx(bar_full + 8 * st, TM_STAGE_BYTES);
-                    if (dbg & 8)
-                        tma_load_2d_nohint(ring_u32 + st * TM_STAGE_BYTES, &tmSrc, j0, lrow0 + TM_SUB * s, bar_full + 8 * st);
-                    else
-                        tma_load_2d(ring_u32 + st * TM_STAGE_BYTES, &tmSrc, j0, lrow0 + TM_SUB * s, bar_full + 8 * st,
-                                    pol_stream);
+                    tma_load_2d(ring_u32 + st * TM_STAGE_BYTES, &tmSrc, j0, lrow0 + TM_SUB * s, bar_full + 8 * st, pol_stream);
                 }
                 st = st + 1 == S ? 0 : st + 1;
                 sub++;
@@ -362,37 +380,33 @@ __global__ void __launch_bounds__(TMD_THREADS, 1) k_cov_update_tma_dense(const _
         }
         return;
     }
-    if (warp == TM_CONSUMERS + 1) {  // -------------------------------------------- stores ----
+    if (warp > TM_CONSUMERS) {  // ------------------------------------------------- stores ----
         if (lane != 0) return;
+        const int me = warp - TM_CONSUMERS - 1;
         tmap_prefetch(&tmDst);
         const uint64_t pol_stream = policy_evict_first();
         const uint32_t ring_u32 = smem_u32(ring);
-        int st = 0, prev_st = -1;
+        int st = 0;
+        long long sub = 0;
         uint32_t done_phase = 0;
         for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
             int tr, tc;
             shard_tile(t, nt, sh, tr, tc);
             const int j0 = tc * TM_T, lrow0 = (int)shard_lrow(sh, tr * TM_T);
 #pragma unroll 1
-            for (int s = 0; s < TM_T / TM_SUB; s++) {
-                mbar_wait(bar_done + 8 * st, (done_phase >> st) & 1u);
-                done_phase ^= 1u << st;
-                if (!(dbg & 2)) {
-                    if (dbg & 16)
-                        tma_store_2d_nohint(&tmDst, j0, lrow0 + TM_SUB * s, ring_u32 + st * TM_STAGE_BYTES);
-                    else
-                        tma_store_2d(&tmDst, j0, lrow0 + TM_SUB * s, ring_u32 + st * TM_STAGE_BYTES, pol_stream);
+            for (int s = 0; s < TM_T / TM_SUB; s++, sub++) {
+                if ((int)(sub % TMD_STORERS) == me) {
+                    mbar_wait(bar_done + 8 * st, (done_phase >> st) & 1u);
+                    if (!(dbg & 2)) tma_store_2d(&tmDst, j0, lrow0 + TM_SUB * s, ring_u32 + st * TM_STAGE_BYTES, pol_stream);
+                    bulk_commit();
+                    bulk_wait_read<0>();  // this store has left shared memory: the stage is free
+                    mbar_arrive(bar_free + 8 * st);
                 }
-                bulk_commit();
-                if (prev_st >= 0) {
-                    bulk_wait_read<1>();
-                    mbar_arrive(bar_free + 8 * prev_st);
-                }
-                prev_st = st;
+                done_phase ^= 1u << st;  // every storer tracks the phase of every stage
                 st = st + 1 == S ? 0 : st + 1;
             }
         }
-        bulk_wait<0>();
+        bulk_wait<0>();  // all writes performed before the kernel ends
         return;
     }
     // ---------------------------------------------------------------------------- consumers ----
@@ -405,16 +419,21 @@ __global__ void __launch_bounds__(TMD_THREADS, 1) k_cov_update_tma_dense(const _
     uint32_t full_phase = 0;
     for (long long lt = 0; lt < my_tiles; lt++) {
         const int slot = (int)(lt & 1);
-        mbar_wait(bar_pfull + 8 * slot, (uint32_t)((lt >> 1) & 1));
-        const int4 ti = tinfo[slot];
+        // negated column-panel fragments of this warp's 16 columns: constant over the tile, kept in registers;
+        // the buffer goes straight back to the producer
+        mbar_wait(bar_cfull, (uint32_t)(lt & 1));
         double nb[KS][2];
         {
-            const double* cp = colp(slot) + TM_BOXC * warp + g;
+            const double* cp = colp + TM_BOXC * warp + g;
 #pragma unroll
             for (int ks = 0; ks < KS; ks++)
 #pragma unroll
                 for (int cb = 0; cb < 2; cb++) nb[ks][cb] = -cp[TM_PITCH * (4 * ks + t) + 8 * cb];
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_cempty);
+        mbar_wait(bar_pfull + 8 * slot, (uint32_t)((lt >> 1) & 1));
+        const int4 ti = tinfo[slot];
         const double* rp = rowp(slot) + g;
 #pragma unroll 1
         for (int s = 0; s < TM_T / TM_SUB; s++) {
@@ -440,7 +459,7 @@ __global__ void __launch_bounds__(TMD_THREADS, 1) k_cov_update_tma_dense(const _
                     dmma884(acc[rb][1].x, acc[rb][1].y, a[rb], nb[ks][1]);
                 }
             }
-            if (ti.z && diag_eps != 0.0) {
+            if (ti.z && diag_eps != 0.0) {  // diagonal tile: slam.h:719 on the diagonal elements
 #pragma unroll
                 for (int rb = 0; rb < 4; rb++) {
                     const int row = TM_SUB * s + 8 * rb + g;
@@ -457,7 +476,7 @@ __global__ void __launch_bounds__(TMD_THREADS, 1) k_cov_update_tma_dense(const _
                 *reinterpret_cast<double2*>(stage + rb * 8192 + offA) = odd ? acc[rb][1] : acc[rb][0];
                 *reinterpret_cast<double2*>(stage + rb * 8192 + offB) = odd ? acc[rb][0] : acc[rb][1];
             }
-            fence_proxy_async();
+            fence_proxy_async();  // the TMA store (async proxy) must see these generic-proxy writes
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_done + 8 * st);
             st = st + 1 == S ? 0 : st + 1;
@@ -535,10 +554,10 @@ static int launch_one(const CUtensorMap& tm, const CUtensorMap& tmd, double diag
         static bool dense_attr[64] = {};
         if (dev < 0 || dev >= 64 || !dense_attr[dev]) {
             CSLAM_CUDA(cudaFuncSetAttribute(k_cov_update_tma_dense<KS, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            L::total));
+                                            TmdSmem<KS, S>::total));
             if (dev >= 0 && dev < 64) dense_attr[dev] = true;
         }
-        k_cov_update_tma_dense<KS, S><<<grid, TMD_THREADS, L::total, stream>>>(tm, tmd, A, lda, r, nt, tiles, sh, live,
+        k_cov_update_tma_dense<KS, S><<<grid, TMD_THREADS, TmdSmem<KS, S>::total, stream>>>(tm, tmd, A, lda, r, nt, tiles, sh, live,
                                                                                nlive, diag_eps, g_tma_dbg);
     } else {
         k_cov_update_tma<KS, S><<<grid, TM_THREADS, L::total, stream>>>(tm, tmd, A, lda, r, nt, tiles, sh, live, nlive,

@@ -564,15 +564,15 @@ __global__ void __launch_bounds__(128) k_batch_pht(const double* __restrict__ P,
 
 // slam.h:244-255: S = H PHT + RR, symmetrise, lower Cholesky, L^-1, finiteness check,
 // G = L^-1 (literal) or L^-T (Q1), u = G G^T V.  One CTA, r <= 64, everything in shared memory.
-__global__ void __launch_bounds__(256) k_batch_chol(const double* __restrict__ PHT, size_t lda, int m, double r00,
-                                                    double r10, double r01, double r11, unsigned flags,
-                                                    BatchSmall* __restrict__ sm, int* __restrict__ status) {
+// chol_smem: 2 * kMaxRank * (kMaxRank + 1) doubles of shared memory; tvec: kMaxRank doubles; okp: one int.
+// Any block size (loops stride by blockDim.x); shared by k_batch_chol and the single-CTA observation step.
+__device__ void batch_chol_body(const double* PHT, size_t lda, int m, double r00, double r10, double r01, double r11,
+                                unsigned flags, BatchSmall* sm, int* status, double* chol_smem, double* tvec,
+                                int* okp) {
     const int r = 2 * m;
-    extern __shared__ double chol_smem[];
     double(*S)[kMaxRank + 1] = reinterpret_cast<double(*)[kMaxRank + 1]>(chol_smem);
     double(*Li)[kMaxRank + 1] = reinterpret_cast<double(*)[kMaxRank + 1]>(chol_smem + kMaxRank * (kMaxRank + 1));
-    __shared__ double tvec[kMaxRank];
-    __shared__ int ok;
+    int& ok = *okp;
     const double R[2][2] = {{r00, r01}, {r10, r11}};
     for (int idx = threadIdx.x; idx < r * r; idx += blockDim.x) {
         const int a = idx / r, b = idx % r;
@@ -658,6 +658,14 @@ __global__ void __launch_bounds__(256) k_batch_chol(const double* __restrict__ P
         sm->u[k] = s;
     }
 }
+__global__ void __launch_bounds__(256) k_batch_chol(const double* __restrict__ PHT, size_t lda, int m, double r00,
+                                                    double r10, double r01, double r11, unsigned flags,
+                                                    BatchSmall* __restrict__ sm, int* __restrict__ status) {
+    extern __shared__ double chol_smem[];
+    __shared__ double tvec[kMaxRank];
+    __shared__ int ok;
+    batch_chol_body(PHT, lda, m, r00, r10, r01, r11, flags, sm, status, chol_smem, tvec, &ok);
+}
 
 // slam.h:257-259: W1 = PHT G (panel A), Xout = Xin + PHT u  (= X + W1 G^T V).
 // grid.y selects a chunk of 8 output ranks so accumulators stay in registers.
@@ -687,6 +695,128 @@ __global__ void __launch_bounds__(128) k_batch_w1(const double* __restrict__ PHT
     for (int l = 0; l < 8; l++)
         if (l0 + l < r) A[(size_t)(l0 + l) * lda + i] = acc[l];
     if (blockIdx.y == 0) Xout[i] = Xin[i] + dx;
+}
+
+// Small maps (the reference's own 30-landmark world, n <= kSmallN): the whole observation step of
+// test/main.cpp:186-189 — update(X, P, ZF, RE, IDF, batch = true) (EKF.cpp:93-129 -> slam.h:235-266) followed by
+// augment(X, P, ZN, RE) (EKF.cpp:9-91) — in ONE launch of ONE CTA (the control steps are
+// k_control_steps).  At n = 63 each of the 5 + mn kernels of the separate calls is pure launch latency; here the
+// phases are separated by __syncthreads.  Every phase performs the operations of the kernel it replaces in the
+// same order (k_batch_prep, k_batch_pht, k_batch_chol, k_batch_w1, k_cov_update_rank, k_augment), so the result
+// is bit-identical to the separate calls.  X is NOT __restrict__ (threads communicate through it).
+struct StepPack {
+    ObsPack ob;                              // associated observations (may be empty)
+    double zn[2 * CSLAM_MAX_BATCH_OBS];      // new landmarks (range, bearing)
+    int mn;
+};
+__global__ void __launch_bounds__(1024) k_observe_step_small(const double* Xin, double* Xout, double* P, size_t ld, int n,
+                                                             StepPack sp, unsigned flags, BatchSmall* sm, double* PHT,
+                                                             double* A, size_t lda, int* status) {
+    extern __shared__ double chol_smem[];
+    __shared__ double tvec[kMaxRank];
+    __shared__ int ok;
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int m = sp.ob.m, r = 2 * m;
+    double* X = const_cast<double*>(Xin);  // with no associated observation the state stays in its buffer
+    if (m > 0) {
+        X = Xout;
+        // ---- k_batch_prep
+        if (tid < m) {
+            const int f = 3 + 2 * (sp.ob.idf[tid] - 1);
+            const ObsLin o = observe_lin(Xin[0], Xin[1], Xin[2], Xin[f], Xin[f + 1]);
+            for (int a = 0; a < 2; a++) {
+                for (int c = 0; c < 3; c++) sm->hu[tid][a][c] = o.hu[a][c];
+                sm->lu[tid][a][0] = o.lu[a][0];
+                sm->lu[tid][a][1] = o.lu[a][1];
+            }
+            sm->f[tid] = f;
+            sm->V[2 * tid] = sp.ob.z[2 * tid] - o.zr;
+            sm->V[2 * tid + 1] = pi2pi(sp.ob.z[2 * tid + 1] - o.zb);
+        }
+        __syncthreads();
+        // ---- k_batch_pht<false>
+        for (int idx = tid; idx < m * n; idx += T) {
+            const int k = idx / n, i = idx % n;
+            const int f = sm->f[k];
+            const double p0 = psym(P, ld, i < 3 ? i : 0, i < 3 ? 0 : i);
+            const double p1 = i < 3 ? psym(P, ld, i, 1) : P[ld + i];
+            const double p2 = i < 3 ? psym(P, ld, i, 2) : P[2 * ld + i];
+            const double p3 = psym(P, ld, i, f), p4 = psym(P, ld, i, f + 1);
+            for (int a = 0; a < 2; a++)
+                PHT[(size_t)(2 * k + a) * lda + i] =
+                    (((p0 * sm->hu[k][a][0] + p1 * sm->hu[k][a][1]) + p2 * sm->hu[k][a][2]) + p3 * sm->lu[k][a][0]) +
+                    p4 * sm->lu[k][a][1];
+        }
+        __syncthreads();
+        // ---- k_batch_chol
+        batch_chol_body(PHT, lda, m, sp.ob.R[0], sp.ob.R[1], sp.ob.R[2], sp.ob.R[3], flags, sm, status, chol_smem, tvec, &ok);
+        __syncthreads();
+        // ---- k_batch_w1: W1 = PHT G (ascending k from 0.0), Xout = Xin + PHT u
+        for (int i = tid; i < n; i += T) {
+            double dx = 0;
+            for (int k = 0; k < r; k++) dx += PHT[(size_t)k * lda + i] * sm->u[k];
+            for (int l = 0; l < r; l++) {
+                double acc = 0;
+                for (int k = 0; k < r; k++) acc += PHT[(size_t)k * lda + i] * sm->G[k * r + l];
+                A[(size_t)l * lda + i] = acc;
+            }
+            Xout[i] = Xin[i] + dx;
+        }
+        __syncthreads();
+        // ---- k_cov_update_rank: P(i, j) -= sum_k A[k][i] A[k][j] over the upper triangle
+        for (int idx = tid; idx < n * n; idx += T) {
+            const int i = idx / n, j = idx % n;
+            if (j < i) continue;
+            double s0 = 0.0;
+            for (int k = 0; k < r; k++) s0 += A[(size_t)k * lda + i] * A[(size_t)k * lda + j];
+            P[(size_t)i * ld + j] -= s0;
+        }
+        __syncthreads();
+    }
+    // ---- k_augment, one new landmark after the other
+    for (int q = 0; q < sp.mn; q++) {
+        const int len = n + 2 * q;
+        const double rr = sp.zn[2 * q], b = sp.zn[2 * q + 1];
+        const double phi = X[2];
+        const double sn = sin(phi + b), cs = cos(phi + b);
+        const double g02 = -rr * sn, g12 = rr * cs;
+        for (int i = tid; i < len; i += T) {
+            const double p0 = psym(P, ld, 0, i), p1 = psym(P, ld, 1, i), p2 = psym(P, ld, 2, i);
+            P[(size_t)i * ld + len] = p0 + g02 * p2;
+            P[(size_t)i * ld + len + 1] = p1 + g12 * p2;
+        }
+        if (tid == 0) {
+            X[len] = X[0] + rr * cs;
+            X[len + 1] = X[1] + rr * sn;
+            double Pv[3][3];
+            for (int a = 0; a < 3; a++)
+                for (int d = 0; d < 3; d++) Pv[a][d] = psym(P, ld, a, d);
+            const double Gv[2][3] = {{1, 0, g02}, {0, 1, g12}};
+            const double Gz[2][2] = {{cs, -rr * sn}, {sn, rr * cs}};
+            const double R[2][2] = {{sp.ob.R[0], sp.ob.R[2]}, {sp.ob.R[1], sp.ob.R[3]}};
+            double GP[2][3], GR[2][2];
+            for (int a = 0; a < 2; a++)
+                for (int d = 0; d < 3; d++) {
+                    double acc = 0;
+                    for (int k = 0; k < 3; k++) acc += Gv[a][k] * Pv[k][d];
+                    GP[a][d] = acc;
+                }
+            for (int a = 0; a < 2; a++)
+                for (int d = 0; d < 2; d++) {
+                    double acc = 0;
+                    for (int k = 0; k < 2; k++) acc += Gz[a][k] * R[k][d];
+                    GR[a][d] = acc;
+                }
+            for (int a = 0; a < 2; a++)
+                for (int d = a; d < 2; d++) {
+                    double x = 0, y = 0;
+                    for (int k = 0; k < 3; k++) x += GP[a][k] * Gv[d][k];
+                    for (int k = 0; k < 2; k++) y += GR[a][k] * Gz[d][k];
+                    P[(size_t)(len + a) * ld + len + d] = x + y;
+                }
+        }
+        __syncthreads();
+    }
 }
 
 // gating kernel lives in gate.cu (separate TU, compiled with -fmad=false)
@@ -1154,15 +1284,18 @@ using namespace cslam;
 extern "C" {
 
 int cslam_ekf_create(cslam_ekf_t** out, int capacity_landmarks, int device, unsigned flags) {
+    CSLAM_NVTX_RANGE();
     return create_common(out, capacity_landmarks, device, flags, 0, 1, nullptr);
 }
 
 int cslam_ekf_create_sharded(cslam_ekf_t** out, int capacity_landmarks, int device, unsigned flags, int rank,
                              int world, const void* nccl_unique_id) {
+    CSLAM_NVTX_RANGE();
     return create_common(out, capacity_landmarks, device, flags, rank, world, nccl_unique_id);
 }
 
 int cslam_ekf_destroy(cslam_ekf_t* h) {
+    CSLAM_NVTX_RANGE();
     if (!h) return CSLAM_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
@@ -1196,6 +1329,7 @@ int cslam_ekf_destroy(cslam_ekf_t* h) {
 }
 
 int cslam_ekf_set_stream(cslam_ekf_t* h, void* cuda_stream) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_handle(h)) return rc;
     CSLAM_CUDA(cudaStreamSynchronize(h->stream));
     if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -1205,11 +1339,13 @@ int cslam_ekf_set_stream(cslam_ekf_t* h, void* cuda_stream) {
 }
 
 int cslam_ekf_flush(cslam_ekf_t* h) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_handle(h)) return rc;
     return lazy_flush_all(h);
 }
 
 int cslam_ekf_pass_count(cslam_ekf_t* h, unsigned long long* passes, int* pending_rows) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_handle(h)) return rc;
     if (passes) *passes = h->lz.passes;
     if (pending_rows) *pending_rows = h->lz.on ? h->lz.np : 0;
@@ -1217,6 +1353,7 @@ int cslam_ekf_pass_count(cslam_ekf_t* h, unsigned long long* passes, int* pendin
 }
 
 int cslam_ekf_sync(cslam_ekf_t* h, int* skipped_updates) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_handle(h)) return rc;
     if (int rc = lazy_flush_all(h)) return rc;
     if (skipped_updates) {
@@ -1234,6 +1371,7 @@ int cslam_ekf_num_landmarks(const cslam_ekf_t* h) { return h ? (h->n - 3) / 2 : 
 int cslam_ekf_capacity(const cslam_ekf_t* h) { return h ? h->cap_landmarks : -1; }
 
 int cslam_ekf_predict(cslam_ekf_t* h, double v, double swa, const double Q[4], double wb, double dt) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_handle(h)) return rc;
     CSLAM_REQUIRE(Q != nullptr, CSLAM_ERR_BAD_ARG, "Q is null");
     const int n = h->n;
@@ -1249,6 +1387,7 @@ int cslam_ekf_predict(cslam_ekf_t* h, double v, double swa, const double Q[4], d
 }
 
 int cslam_ekf_observe_heading(cslam_ekf_t* h, double phi, int use_heading) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_handle(h)) return rc;
     if (!use_heading) return CSLAM_OK;  // EKF.cpp:332-335
     if (h->lz.on) return lazy_heading(h, phi);
@@ -1296,6 +1435,7 @@ static int ensure_scratch(cslam_ekf* h, double** buf, size_t* cap, size_t double
 
 int cslam_ekf_control_steps(cslam_ekf_t* h, int k, const double* v, const double* swa, const double* phi,
                             int use_heading, const double Q[4], double wb, double dt, double* pose_trace) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_handle(h)) return rc;
     CSLAM_REQUIRE(k >= 0, CSLAM_ERR_BAD_ARG, "k < 0");
     if (k == 0) return CSLAM_OK;
@@ -1398,6 +1538,7 @@ int cslam_ekf_control_steps(cslam_ekf_t* h, int k, const double* v, const double
 
 int cslam_ekf_gate(cslam_ekf_t* h, const double* Z, int m, const double R[4], double gate1, double gate2,
                    int32_t* jbest, uint8_t* is_new, double* nbest, double* outer) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_handle(h)) return rc;
     CSLAM_REQUIRE(m >= 0, CSLAM_ERR_BAD_ARG, "m < 0");
     CSLAM_REQUIRE(m == 0 || (Z && R && jbest), CSLAM_ERR_BAD_ARG, "null argument");
@@ -1430,6 +1571,7 @@ int cslam_ekf_gate(cslam_ekf_t* h, const double* Z, int m, const double R[4], do
 }
 
 int cslam_ekf_update(cslam_ekf_t* h, const double* Z, const int32_t* idf, int m, const double R[4], int batch) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_handle(h)) return rc;
     CSLAM_REQUIRE(m >= 0, CSLAM_ERR_BAD_ARG, "m < 0");
     if (m == 0) return CSLAM_OK;  // test/main.cpp:188 calls update with an empty ZF
@@ -1493,8 +1635,49 @@ int cslam_ekf_update(cslam_ekf_t* h, const double* Z, const int32_t* idf, int m,
     return launch_cov_update_rank(h, r);
 }
 
+int cslam_ekf_observe_step(cslam_ekf_t* h, const double* ZF, const int32_t* idf, int mf, const double* ZN, int mn,
+                           const double R[4], int batch) {
+    if (int rc = check_handle(h)) return rc;
+    CSLAM_REQUIRE(mf >= 0 && mn >= 0, CSLAM_ERR_BAD_ARG, "negative count");
+    CSLAM_REQUIRE(R && (mf == 0 || (ZF && idf)) && (mn == 0 || ZN), CSLAM_ERR_BAD_ARG, "null argument");
+    const int n = h->n, nf = (n - 3) / 2;
+    const bool fused = batch && !h->lz.on && h->sh.world == 1 && n + 2 * mn <= kSmallN && mf <= CSLAM_MAX_BATCH_OBS &&
+                       mn <= CSLAM_MAX_BATCH_OBS && (mf > 0 || mn > 0);
+    if (!fused) {  // big / sharded maps and sequential updates: the two calls of test/main.cpp:188-189
+        if (int rc = cslam_ekf_update(h, ZF, idf, mf, R, batch)) return rc;
+        return cslam_ekf_augment(h, ZN, mn, R);
+    }
+    for (int i = 0; i < mf; i++)
+        CSLAM_REQUIRE(idf[i] >= 1 && idf[i] <= nf, CSLAM_ERR_BAD_ARG, "idf out of range (1-based map slots)");
+    CSLAM_REQUIRE(n + 2 * mn <= h->n_cap, CSLAM_ERR_CAPACITY, "landmark capacity exceeded");
+    StepPack sp;
+    memset(&sp, 0, sizeof(sp));
+    if (mf > 0) {
+        memcpy(sp.ob.z, ZF, sizeof(double) * 2 * mf);
+        memcpy(sp.ob.idf, idf, sizeof(int) * mf);
+    }
+    sp.ob.m = mf;
+    memcpy(sp.ob.R, R, sizeof(double) * 4);
+    if (mn > 0) memcpy(sp.zn, ZN, sizeof(double) * 2 * mn);
+    sp.mn = mn;
+    const int chol_smem = 2 * kMaxRank * (kMaxRank + 1) * (int)sizeof(double);
+    if (!h->attr_step) {
+        CSLAM_CUDA(cudaFuncSetAttribute(k_observe_step_small, cudaFuncAttributeMaxDynamicSharedMemorySize, chol_smem));
+        h->attr_step = true;
+    }
+    count_launch();
+    k_observe_step_small<<<1, 1024, chol_smem, h->stream>>>(h->X[h->cur], h->X[h->cur ^ 1], h->P, h->ld, n, sp, h->flags,
+                                                            h->small, h->PHT, h->A, h->lda, h->status);
+    CSLAM_CUDA(cudaGetLastError());
+    if (mf > 0) h->cur ^= 1;
+    h->n += 2 * mn;
+    h->diag_dirty = true;
+    return CSLAM_OK;
+}
+
 int cslam_ekf_scan(cslam_ekf_t* h, const double* Z, int m, const double R[4], double gate1, double gate2,
                    int32_t* jbest, uint8_t* is_new) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_handle(h)) return rc;
     CSLAM_REQUIRE(m >= 0 && m <= CSLAM_MAX_OBS, CSLAM_ERR_BAD_ARG, "m out of range (0..CSLAM_MAX_OBS)");
     if (m == 0) return CSLAM_OK;
@@ -1532,6 +1715,7 @@ int cslam_ekf_scan(cslam_ekf_t* h, const double* Z, int m, const double R[4], do
 }
 
 int cslam_ekf_scan_associations(cslam_ekf_t* h, unsigned long long* total) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_handle(h)) return rc;
     CSLAM_REQUIRE(total != nullptr, CSLAM_ERR_BAD_ARG, "total is null");
     CSLAM_CUDA(cudaMemcpyAsync(h->pinned, h->assoc_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
@@ -1542,6 +1726,7 @@ int cslam_ekf_scan_associations(cslam_ekf_t* h, unsigned long long* total) {
 }
 
 int cslam_ekf_augment(cslam_ekf_t* h, const double* Z, int m, const double R[4]) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_handle(h)) return rc;
     CSLAM_REQUIRE(m >= 0, CSLAM_ERR_BAD_ARG, "m < 0");
     if (m == 0) return CSLAM_OK;
@@ -1564,6 +1749,7 @@ int cslam_ekf_augment(cslam_ekf_t* h, const double* Z, int m, const double R[4])
 }
 
 int cslam_ekf_get_state(cslam_ekf_t* h, double* X, int max_n) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_handle(h)) return rc;
     CSLAM_REQUIRE(X != nullptr && max_n >= h->n, CSLAM_ERR_BAD_ARG, "buffer too small");
     CSLAM_CUDA(cudaMemcpyAsync(h->pinned, h->X[h->cur], h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -1573,6 +1759,7 @@ int cslam_ekf_get_state(cslam_ekf_t* h, double* X, int max_n) {
 }
 
 int cslam_ekf_get_cov_block(cslam_ekf_t* h, int r0, int c0, int nr, int nc, double* out) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_handle(h)) return rc;
     CSLAM_REQUIRE(out && r0 >= 0 && c0 >= 0 && nr >= 0 && nc >= 0 && r0 + nr <= h->n && c0 + nc <= h->n,
                   CSLAM_ERR_BAD_ARG, "block out of range");
@@ -1607,6 +1794,7 @@ __global__ void k_gather_sub(const double* __restrict__ P, const double* __restr
 }
 
 int cslam_ekf_get_cov_gather(cslam_ekf_t* h, const int32_t* idx, int k, double* out) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_handle(h)) return rc;
     CSLAM_REQUIRE(k >= 0 && k <= 8192, CSLAM_ERR_BAD_ARG, "k out of range (0..8192)");
     if (k == 0) return CSLAM_OK;
@@ -1647,6 +1835,7 @@ __global__ void __launch_bounds__(256) k_landmark_covs(const double* __restrict_
 }
 
 int cslam_ekf_get_landmark_covs(cslam_ekf_t* h, int first_landmark, int count, double* out) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_handle(h)) return rc;
     const int nf = (h->n - 3) / 2;
     CSLAM_REQUIRE(first_landmark >= 1 && count >= 0 && first_landmark - 1 + count <= nf, CSLAM_ERR_BAD_ARG,
@@ -1682,6 +1871,7 @@ const char kCkptMagic[8] = {'C', 'S', 'L', 'A', 'M', 'E', 'K', 'F'};
 }  // namespace
 
 int cslam_ekf_save(cslam_ekf_t* h, const char* path) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_handle(h)) return rc;
     CSLAM_REQUIRE(path != nullptr, CSLAM_ERR_BAD_ARG, "path is null");
     CSLAM_REQUIRE(h->sh.world == 1, CSLAM_ERR_UNSUPPORTED, "checkpoints are single-GPU (sharded: save per block)");
@@ -1727,6 +1917,7 @@ int cslam_ekf_save(cslam_ekf_t* h, const char* path) {
 }
 
 int cslam_ekf_load(cslam_ekf_t* h, const char* path) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_handle(h)) return rc;
     CSLAM_REQUIRE(path != nullptr, CSLAM_ERR_BAD_ARG, "path is null");
     CSLAM_REQUIRE(h->sh.world == 1, CSLAM_ERR_UNSUPPORTED, "checkpoints are single-GPU (sharded: load per block)");
@@ -1797,6 +1988,7 @@ int cslam_ekf_load(cslam_ekf_t* h, const char* path) {
 }
 
 int cslam_ekf_reset(cslam_ekf_t* h, const double* X, int n, const double* P) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_handle(h)) return rc;
     CSLAM_REQUIRE(X && n >= 3 && n <= h->n_cap && ((n - 3) % 2 == 0), CSLAM_ERR_BAD_ARG, "bad state size");
     // everything on the handle's stream: the legacy default stream does not order against it
@@ -1831,6 +2023,7 @@ int cslam_ekf_reset(cslam_ekf_t* h, const double* X, int n, const double* P) {
 }
 
 int cslam_ekf_profile_begin(cslam_ekf_t* h, int max_launches) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_handle(h)) return rc;
     CSLAM_REQUIRE(max_launches > 0 && max_launches <= (1 << 20), CSLAM_ERR_BAD_ARG, "max_launches out of range");
     while ((int)h->prof_ev.size() < 2 * max_launches) {
@@ -1845,6 +2038,7 @@ int cslam_ekf_profile_begin(cslam_ekf_t* h, int max_launches) {
 }
 
 int cslam_ekf_profile_end(cslam_ekf_t* h, double* ms, int* launches, double* bytes) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_handle(h)) return rc;
     h->prof = false;
     CSLAM_CUDA(cudaStreamSynchronize(h->stream));
@@ -1862,6 +2056,7 @@ int cslam_ekf_profile_end(cslam_ekf_t* h, double* ms, int* launches, double* byt
 }
 
 int cslam_ekf_device_ptrs(cslam_ekf_t* h, void** dX, void** dP, size_t* ld) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_handle(h)) return rc;
     if (int rc = lazy_flush_all(h)) return rc;
     if (dX) *dX = h->X[h->cur];

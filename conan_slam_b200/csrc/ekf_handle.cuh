@@ -48,7 +48,7 @@ struct LazyState {
     cudaEvent_t ev_chain = nullptr;  // "every reader of the array the next pass overwrites is done"
     cudaEvent_t ev_pass = nullptr;   // completion of the most recently launched pass
     int num_sms = 0;
-    int stages = 4;
+    int stages = 5;
     unsigned long long passes = 0;   // passes launched since create (diagnostics)
 };
 
@@ -102,7 +102,7 @@ struct cslam_ekf {
     size_t trace_cap = 0;
     double* acc_dev = nullptr;    // scratch of the accessors (cov block / landmark marginals), grown on demand
     size_t acc_cap = 0;
-    bool attr_chol = false, attr_rank = false;  // cudaFuncSetAttribute done for this handle's device
+    bool attr_chol = false, attr_rank = false, attr_step = false;  // cudaFuncSetAttribute done for this handle's device
     // diagnostics: event pairs around covariance-update launches
     bool prof = false;
     std::vector<cudaEvent_t> prof_ev;

@@ -920,16 +920,19 @@ static int pf_create_common(cslam_pf_t** out, int num_particles, int capacity_la
 }
 
 int cslam_pf_create(cslam_pf_t** out, int num_particles, int capacity_landmarks, int device, unsigned flags) {
+    CSLAM_NVTX_RANGE();
     return pf_create_common(out, num_particles, capacity_landmarks, device, flags, 0, 1, nullptr);
 }
 
 int cslam_pf_create_sharded(cslam_pf_t** out, int num_particles_local, int capacity_landmarks, int device,
                             unsigned flags, int rank, int world, const void* nccl_unique_id) {
+    CSLAM_NVTX_RANGE();
     return pf_create_common(out, num_particles_local, capacity_landmarks, device, flags, rank, world, nccl_unique_id);
 }
 
 // 10 cudaIpcMemHandle_t (64 bytes each): {w, xv, pv, xf, pf} of both ping-pong buffers
 int cslam_pf_ipc_export(cslam_pf_t* h, void* out640) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_pf(h)) return rc;
     CSLAM_REQUIRE(out640 != nullptr, CSLAM_ERR_BAD_ARG, "null");
     cudaIpcMemHandle_t* hs = static_cast<cudaIpcMemHandle_t*>(out640);
@@ -944,6 +947,7 @@ int cslam_pf_ipc_export(cslam_pf_t* h, void* out640) {
 }
 // all: world x 640 bytes in rank order (every rank's export).  Maps the peers' buffers (NVLink P2P).
 int cslam_pf_ipc_import(cslam_pf_t* h, const void* all, int world) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_pf(h)) return rc;
     CSLAM_REQUIRE(all != nullptr && world == h->world, CSLAM_ERR_BAD_ARG, "bad argument");
     const cudaIpcMemHandle_t* hs = static_cast<const cudaIpcMemHandle_t*>(all);
@@ -965,6 +969,7 @@ int cslam_pf_ipc_import(cslam_pf_t* h, const void* all, int world) {
 }
 
 int cslam_pf_destroy(cslam_pf_t* h) {
+    CSLAM_NVTX_RANGE();
     if (!h) return CSLAM_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
@@ -1000,6 +1005,7 @@ int cslam_pf_destroy(cslam_pf_t* h) {
 }
 
 int cslam_pf_set_stream(cslam_pf_t* h, void* cuda_stream) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_pf(h)) return rc;
     CSLAM_CUDA(cudaStreamSynchronize(h->stream));
     if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -1009,6 +1015,7 @@ int cslam_pf_set_stream(cslam_pf_t* h, void* cuda_stream) {
 }
 
 int cslam_pf_sync(cslam_pf_t* h, int* skipped_updates) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_pf(h)) return rc;
     if (skipped_updates) {
         CSLAM_CUDA(cudaMemcpyAsync(h->pinned, h->d_ismall + 2, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -1024,6 +1031,7 @@ int cslam_pf_num_particles(const cslam_pf_t* h) { return h ? h->np : -1; }
 int cslam_pf_num_features(const cslam_pf_t* h) { return h ? h->nf : -1; }
 
 int cslam_pf_predict(cslam_pf_t* h, double v, double swa, const double Q[4], double wb, double dt) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_pf(h)) return rc;
     CSLAM_REQUIRE(Q != nullptr, CSLAM_ERR_BAD_ARG, "Q is null");
     PfBuf& b = h->buf[h->cur];
@@ -1035,6 +1043,7 @@ int cslam_pf_predict(cslam_pf_t* h, double v, double swa, const double Q[4], dou
 }
 
 int cslam_pf_observe_heading(cslam_pf_t* h, double phi, int use_heading) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_pf(h)) return rc;
     if (!use_heading) return CSLAM_OK;
     const double sigma = 0.01F * kPi / 180.0F;  // PF.cpp:391
@@ -1047,6 +1056,7 @@ int cslam_pf_observe_heading(cslam_pf_t* h, double phi, int use_heading) {
 
 int cslam_pf_control_steps(cslam_pf_t* h, int k, const double* v, const double* swa, const double* phi,
                            int use_heading, const double Q[4], double wb, double dt) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_pf(h)) return rc;
     CSLAM_REQUIRE(k >= 0, CSLAM_ERR_BAD_ARG, "k < 0");
     if (k == 0) return CSLAM_OK;
@@ -1088,6 +1098,7 @@ static int check_obs(cslam_pf* h, const double* Z, const int32_t* idf, int m, co
 
 int cslam_pf_sample_proposal(cslam_pf_t* h, const double* Z, const int32_t* idf, int m, const double R[4],
                              const double* xi, int xi_on_device) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_pf(h)) return rc;
     if (int rc = check_obs(h, Z, idf, m, R, true)) return rc;
     CSLAM_REQUIRE(xi != nullptr, CSLAM_ERR_BAD_ARG, "xi is null");
@@ -1104,6 +1115,7 @@ int cslam_pf_sample_proposal(cslam_pf_t* h, const double* Z, const int32_t* idf,
 }
 
 int cslam_pf_feature_update(cslam_pf_t* h, const double* Z, const int32_t* idf, int m, const double R[4]) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_pf(h)) return rc;
     if (int rc = check_obs(h, Z, idf, m, R, true)) return rc;
     if (m == 0) return CSLAM_OK;
@@ -1118,6 +1130,7 @@ int cslam_pf_feature_update(cslam_pf_t* h, const double* Z, const int32_t* idf, 
 }
 
 int cslam_pf_add_features(cslam_pf_t* h, const double* Z, int m, const double R[4]) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_pf(h)) return rc;
     if (int rc = check_obs(h, Z, nullptr, m, R, false)) return rc;
     if (m == 0) return CSLAM_OK;
@@ -1133,6 +1146,7 @@ int cslam_pf_add_features(cslam_pf_t* h, const double* Z, int m, const double R[
 }
 
 int cslam_pf_sample_pose(cslam_pf_t* h, const double* xi, int xi_on_device) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_pf(h)) return rc;
     CSLAM_REQUIRE(xi != nullptr, CSLAM_ERR_BAD_ARG, "xi is null");
     const double* dxi = nullptr;
@@ -1146,6 +1160,7 @@ int cslam_pf_sample_pose(cslam_pf_t* h, const double* xi, int xi_on_device) {
 
 int cslam_pf_resample(cslam_pf_t* h, const double* u, int u_on_device, double num_effective, int resample_on,
                       int32_t* keep, double* neff, int* resampled) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_pf(h)) return rc;
     CSLAM_REQUIRE(u != nullptr, CSLAM_ERR_BAD_ARG, "u is null");
     const int np = h->np;
@@ -1272,6 +1287,7 @@ __global__ void __launch_bounds__(256) k_scale_w(double* __restrict__ w, const d
     if (i < np) w[i] = w[i] * f[i];
 }
 int cslam_pf_scale_weights(cslam_pf_t* h, const double* factor, int on_device) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_pf(h)) return rc;
     CSLAM_REQUIRE(factor != nullptr, CSLAM_ERR_BAD_ARG, "factor is null");
     const double* df = nullptr;
@@ -1283,6 +1299,7 @@ int cslam_pf_scale_weights(cslam_pf_t* h, const double* factor, int on_device) {
 }
 
 int cslam_pf_profile_begin(cslam_pf_t* h, int max_resamples) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_pf(h)) return rc;
     CSLAM_REQUIRE(max_resamples > 0 && max_resamples <= (1 << 16), CSLAM_ERR_BAD_ARG, "out of range");
     while ((int)h->prof_ev.size() < 2 * max_resamples) {
@@ -1295,6 +1312,7 @@ int cslam_pf_profile_begin(cslam_pf_t* h, int max_resamples) {
     return CSLAM_OK;
 }
 int cslam_pf_profile_end(cslam_pf_t* h, double* ms, int* resamples, double* bytes) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_pf(h)) return rc;
     h->prof = false;
     CSLAM_CUDA(cudaStreamSynchronize(h->stream));
@@ -1355,6 +1373,7 @@ static int pf_ckpt_io(cslam_pf* h, FILE* f, bool save) {
 }
 
 int cslam_pf_save(cslam_pf_t* h, const char* path) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_pf(h)) return rc;
     CSLAM_REQUIRE(path != nullptr, CSLAM_ERR_BAD_ARG, "path is null");
     CSLAM_REQUIRE(h->world == 1, CSLAM_ERR_UNSUPPORTED, "checkpoints are single-GPU (sharded: save per rank)");
@@ -1374,6 +1393,7 @@ int cslam_pf_save(cslam_pf_t* h, const char* path) {
 }
 
 int cslam_pf_load(cslam_pf_t* h, const char* path) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_pf(h)) return rc;
     CSLAM_REQUIRE(path != nullptr, CSLAM_ERR_BAD_ARG, "path is null");
     CSLAM_REQUIRE(h->world == 1, CSLAM_ERR_UNSUPPORTED, "checkpoints are single-GPU (sharded: load per rank)");
@@ -1396,6 +1416,7 @@ int cslam_pf_load(cslam_pf_t* h, const char* path) {
 }
 
 int cslam_pf_get_weights(cslam_pf_t* h, double* w) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_pf(h)) return rc;
     CSLAM_REQUIRE(w != nullptr, CSLAM_ERR_BAD_ARG, "null");
     CSLAM_CUDA(cudaMemcpyAsync(w, h->buf[h->cur].w, (size_t)h->np * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -1438,16 +1459,19 @@ static int set_aos(cslam_pf* h, double* soa, int k, const double* in) {
 }
 
 int cslam_pf_get_poses(cslam_pf_t* h, double* X) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_pf(h)) return rc;
     CSLAM_REQUIRE(X != nullptr, CSLAM_ERR_BAD_ARG, "null");
     return get_aos(h, h->buf[h->cur].xv, 3, X);
 }
 int cslam_pf_get_pose_covs(cslam_pf_t* h, double* Pv) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_pf(h)) return rc;
     CSLAM_REQUIRE(Pv != nullptr, CSLAM_ERR_BAD_ARG, "null");
     return get_aos(h, h->buf[h->cur].pv, 9, Pv);
 }
 int cslam_pf_get_features(cslam_pf_t* h, int particle, double* XF, double* PF) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_pf(h)) return rc;
     CSLAM_REQUIRE(XF && PF && particle >= 0 && particle < h->np, CSLAM_ERR_BAD_ARG, "bad argument");
     if (h->nf == 0) return CSLAM_OK;
@@ -1468,6 +1492,7 @@ int cslam_pf_get_features(cslam_pf_t* h, int particle, double* XF, double* PF) {
 // after particle — XF[p][f][2] (the reference concatenates the 2 x nf blocks column-wise in particle order) and,
 // optionally, their packed 2x2 covariances PFp[p][f][3] = (xx, xy, yy).  Either pointer may be NULL.
 int cslam_pf_get_features_all(cslam_pf_t* h, double* XF, double* PFp) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_pf(h)) return rc;
     if (h->nf == 0) return CSLAM_OK;
     if (XF)
@@ -1477,6 +1502,7 @@ int cslam_pf_get_features_all(cslam_pf_t* h, double* XF, double* PFp) {
     return CSLAM_OK;
 }
 int cslam_pf_set_weights(cslam_pf_t* h, const double* w) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_pf(h)) return rc;
     CSLAM_REQUIRE(w != nullptr, CSLAM_ERR_BAD_ARG, "null");
     CSLAM_CUDA(cudaMemcpyAsync(h->buf[h->cur].w, w, (size_t)h->np * sizeof(double), cudaMemcpyHostToDevice, h->stream));
@@ -1484,6 +1510,7 @@ int cslam_pf_set_weights(cslam_pf_t* h, const double* w) {
     return CSLAM_OK;
 }
 int cslam_pf_set_poses(cslam_pf_t* h, const double* X, const double* Pv) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_pf(h)) return rc;
     CSLAM_REQUIRE(X != nullptr, CSLAM_ERR_BAD_ARG, "null");
     if (int rc = set_aos(h, h->buf[h->cur].xv, 3, X)) return rc;
@@ -1492,6 +1519,7 @@ int cslam_pf_set_poses(cslam_pf_t* h, const double* X, const double* Pv) {
 }
 
 int cslam_pf_extract_state(cslam_pf_t* h, double X[3], int* index) {
+    CSLAM_NVTX_RANGE();
     if (int rc = check_pf(h)) return rc;
     CSLAM_REQUIRE(X != nullptr, CSLAM_ERR_BAD_ARG, "null");
     const int nw = (h->np + 31) / 32;

@@ -91,6 +91,7 @@ using namespace cslam;
 extern "C" {
 
 int cslam_world_create(cslam_world_t** out, const double* landmarks_2xN, int num_landmarks, int device) {
+    CSLAM_NVTX_RANGE();
     CSLAM_REQUIRE(out != nullptr && num_landmarks >= 0 && (landmarks_2xN != nullptr || num_landmarks == 0),
                   CSLAM_ERR_BAD_ARG, "bad argument");
     *out = nullptr;
@@ -136,6 +137,7 @@ int cslam_world_create(cslam_world_t** out, const double* landmarks_2xN, int num
 }
 
 int cslam_world_destroy(cslam_world_t* w) {
+    CSLAM_NVTX_RANGE();
     if (!w) return CSLAM_OK;
     cudaSetDevice(w->device);
     if (w->stream) cudaStreamSynchronize(w->stream);
@@ -148,6 +150,7 @@ int cslam_world_destroy(cslam_world_t* w) {
 
 int cslam_world_observe(cslam_world_t* w, const double x_true[3], double max_range, int max_out, double* Z,
                         int32_t* tags, int* m_out) {
+    CSLAM_NVTX_RANGE();
     CSLAM_REQUIRE(w != nullptr && x_true != nullptr && m_out != nullptr && max_out >= 0, CSLAM_ERR_BAD_ARG,
                   "bad argument");
     CSLAM_REQUIRE(max_out == 0 || (Z != nullptr && tags != nullptr), CSLAM_ERR_BAD_ARG, "null output");

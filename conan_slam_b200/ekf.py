@@ -232,6 +232,23 @@ class EKF:
             zc = np.ascontiguousarray(zflat[2 * b:2 * (b + _lib.MAX_OBS)])
             check(self._lib.cslam_ekf_augment(self._h, dptr(zc), zc.shape[0] // 2, dptr(r)), "cslam_ekf_augment")
 
+    def observeStep(self, ZF, R, idf, ZN, batch=True):
+        """update(ZF, R, idf, batch) followed by augment(ZN, R) (test/main.cpp:188-189) as one call: on small
+        maps one single-CTA launch (cslam_ekf_observe_step), bit-identical to the two calls."""
+        Zf, zf = _z(ZF)
+        Zn, zn = _z(ZN)
+        idf = np.ascontiguousarray(idf, dtype=np.int32).reshape(-1)
+        mf, mn = Zf.shape[1], Zn.shape[1]
+        assert idf.shape[0] == mf
+        if mf > _lib.MAX_OBS or mn > _lib.MAX_OBS:
+            self.update(ZF, R, idf, batch)
+            self.augment(ZN, R)
+            return
+        r = _m2(R)
+        check(self._lib.cslam_ekf_observe_step(self._h, dptr(zf) if mf else None, iptr(idf) if mf else None, mf,
+                                               dptr(zn) if mn else None, mn, dptr(r), int(bool(batch))),
+              "cslam_ekf_observe_step")
+
     def gate(self, Z, R, gate1, gate2):
         """Per-observation gating decisions (jbest, is_new, nbest, outer)."""
         Zm, zflat = _z(Z)

@@ -3,10 +3,14 @@
 // control loop, known-association table logic, update / augment calls.  Config 1 of
 // BASELINE.json ("bit-match run": noise switches off, FP64).
 //
-//   sim_main [--flags N] [--max-steps N] [--trace FILE] [--gated] [--print-every K]
+//   sim_main [--flags N] [--max-steps N] [--trace FILE] [--gated] [--print-every K] [--fused] [--no-cov-writeback]
+// --fused: the control steps between two observations in ONE launch (cslam_ekf_control_steps) and the observation
+// step (joint update + augmentation) in ONE launch (cslam_ekf_observe_step); --no-cov-writeback: P stays on the
+// device (the driver only prints X, test/main.cpp:134-137), the host copy of P is not refreshed after each call.
 //
 // --trace writes, per control step, (x, y, phi, n) of the ESTIMATE as 4 doubles, then the final
 // full state X; tests/test_host_cpp.py compares it with the CPU oracle replaying the same tape.
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -113,7 +117,7 @@ void getObservations(const DVec& X, const DMat& LM, double rmax, DMat& Z, std::v
 int main(int argc, char** argv) {
     unsigned flags = CSLAM_FLAG_REF_LITERAL;
     int max_steps = 1 << 30, print_every = 2000;
-    bool gated = false, fused = false;
+    bool gated = false, fused = false, no_writeback = false;
     std::string trace;
     for (int i = 1; i < argc; i++) {
         if (!strcmp(argv[i], "--flags") && i + 1 < argc) flags = (unsigned)atoi(argv[++i]);
@@ -122,6 +126,7 @@ int main(int argc, char** argv) {
         else if (!strcmp(argv[i], "--print-every") && i + 1 < argc) print_every = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--gated")) gated = true;
         else if (!strcmp(argv[i], "--fused")) fused = true;  // control steps between observations in one call
+        else if (!strcmp(argv[i], "--no-cov-writeback")) no_writeback = true;
     }
     DMat LM(2, 30), WP(2, 5);
     for (int i = 0; i < 30; i++) { LM(0, i) = kLm1[i]; LM(1, i) = kLm2[i]; }
@@ -130,6 +135,7 @@ int main(int argc, char** argv) {
     // std::shared_ptr<Slam> ekfSlam(new EKF(LM, WP));            test/main.cpp:89
     EkfGpu ekfSlam(LM.cols(), LM.cols(), 0, flags);
     ekfSlam.mSwitchAssociationKnown = !gated;
+    if (no_writeback) ekfSlam.p_writeback_max = 0;
     const double sigmaV = 0.3F, sigmaSWA = (float)(1.0F * kPi / 180.0F);
     const double sigmaR = 0.1F, sigmaB = (float)(1.0F * kPi / 180.0F);
     const double velocity = 83.33F, wheelBase = 73.0F, maxRange = 2000.0F, atWaypoint = 1.0F;
@@ -150,6 +156,7 @@ int main(int argc, char** argv) {
     for (auto& v : RE.a) v *= 8;
 
     FILE* tf = trace.empty() ? nullptr : fopen(trace.c_str(), "wb");
+    const auto t_start = std::chrono::steady_clock::now();
     std::vector<double> pend_v, pend_s, pend_p;
     int indexlooper = 0;
     while (iwp <= WP.cols() && iwp > 0 && indexlooper < max_steps) {
@@ -191,8 +198,12 @@ int main(int argc, char** argv) {
             if (Z.size() > 0) {
                 if (ekfSlam.mSwitchAssociationKnown) {
                     auto a = ekfSlam.dataAssociateTable(X, Z, visible, ekfSlam.mTABLE);   // :186
-                    ekfSlam.update(X, P, a.ZF, RE, a.idf, ekfSlam.mSwitchBatchUpdate);    // :188
-                    ekfSlam.augment(X, P, a.ZN, RE);                                      // :189
+                    if (fused) {  // :188-189 as one single-CTA launch (cslam_ekf_observe_step)
+                        ekfSlam.observeStep(X, P, a.ZF, RE, a.idf, a.ZN, ekfSlam.mSwitchBatchUpdate);
+                    } else {
+                        ekfSlam.update(X, P, a.ZF, RE, a.idf, ekfSlam.mSwitchBatchUpdate);    // :188
+                        ekfSlam.augment(X, P, a.ZN, RE);                                      // :189
+                    }
                 } else {
                     auto a = ekfSlam.dataAssociate(X, P, Z, RE, ekfSlam.mGateReject, ekfSlam.mGateAugment);  // :194
                     ekfSlam.update(X, P, a.ZF, RE, a.idf, ekfSlam.mSwitchBatchUpdate);    // :195
@@ -205,7 +216,9 @@ int main(int argc, char** argv) {
             fwrite(rec, sizeof(double), 4, tf);
         }
     }
-    std::printf("done: %d control steps, n=%d, skipped updates=%d\nX", indexlooper, X.rows(), ekfSlam.skippedUpdates());
+    const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+    std::printf("done: %d control steps, n=%d, skipped updates=%d, loop wall time %.3f s\nX", indexlooper, X.rows(),
+                ekfSlam.skippedUpdates(), wall);
     for (int i = 0; i < X.rows(); i++) std::printf(" %.12g", X(i));
     std::printf("\n");
     if (tf) {

@@ -176,6 +176,27 @@ class EkfGpuT {
         }
         pull(X, P);
     }
+    // update(X, P, ZF, R, idf, batch) immediately followed by augment(X, P, ZN, R) — test/main.cpp:188-189 — as one
+    // call (cslam_ekf_observe_step): one single-CTA launch on small maps, bit-identical to the two calls.
+    void observeStep(Vec& X, MatT& P, const MatT& ZF, const MatT& R, const std::vector<int>& idf, const MatT& ZN,
+                     bool batch = true) {
+        const int mf = ZF.cols(), mn = ZN.cols();
+        if (mf > CSLAM_MAX_BATCH_OBS || mn > CSLAM_MAX_BATCH_OBS) {
+            update(X, P, ZF, R, idf, batch);
+            augment(X, P, ZN, R);
+            return;
+        }
+        push(X, P);
+        std::vector<double> zf((size_t)2 * mf), zn((size_t)2 * mn);
+        for (int i = 0; i < mf; i++) { zf[2 * i] = ZF(0, i); zf[2 * i + 1] = ZF(1, i); }
+        for (int i = 0; i < mn; i++) { zn[2 * i] = ZN(0, i); zn[2 * i + 1] = ZN(1, i); }
+        std::vector<int32_t> ids(idf.begin(), idf.end());
+        const double r[4] = {R(0, 0), R(1, 0), R(0, 1), R(1, 1)};
+        report(cslam_ekf_observe_step(h_, mf ? zf.data() : nullptr, mf ? ids.data() : nullptr, mf,
+                                      mn ? zn.data() : nullptr, mn, r, batch ? 1 : 0),
+               "observeStep");
+        pull(X, P);
+    }
     // Slam::dataAssociate  slam.h:482-487 / EKF.cpp:235-326 (Q5: ZN empty unless CSLAM_FLAG_Q5_RETURN_ZN)
     AssociationT<MatT> dataAssociate(const Vec& X, const MatT& P, const MatT& Z, const MatT& R, double gate1,
                                     double gate2) {

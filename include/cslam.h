@@ -129,6 +129,13 @@ int cslam_ekf_gate(cslam_ekf_t* h, const double* Z, int m, const double R[4], do
  *            the previous one produced — an explicit, documented deviation: the reference has no rank limit)
  * both through Slam::choleskyUpdate slam.h:235-266.  Asynchronous. m == 0 is a no-op. */
 int cslam_ekf_update(cslam_ekf_t* h, const double* Z, const int32_t* idf, int m, const double R[4], int batch);
+/* The observation step of test/main.cpp:186-189 with known associations — update(X, P, ZF, RE, IDF, batch)
+ * (EKF.cpp:481-496) immediately followed by augment(X, P, ZN, RE) (EKF.cpp:9-26) — as ONE call.  On small maps
+ * (n + 2*mn <= 1024, single GPU, batch = 1: the reference's own 30-landmark world and its default switch
+ * slam.h:101) the joint update and all augmentations run in ONE single-CTA launch instead of 5 + mn
+ * (SURVEY.md §8f row 1), bit-identical to the two separate calls; otherwise it is exactly those two calls. */
+int cslam_ekf_observe_step(cslam_ekf_t* h, const double* ZF, const int32_t* idf, int mf, const double* ZN, int mn,
+                           const double R[4], int batch);
 /* One observation cycle with NO host round trip between association and update — the call pair
  * test/main.cpp:193-195 (dataAssociate EKF.cpp:235-326, then update with batch=false -> singleUpdate
  * EKF.cpp:457-479) as one asynchronous submission: the gate kernel leaves the association indices in

@@ -52,6 +52,9 @@ def ekf_checks():
         g.reset(X, P)
         o.reset(X, P)
         rng = np.random.default_rng(N)
+        # observed landmarks lie inside the reference's sensor range (slam.h:79): far landmarks make S cancel by
+        # many orders of magnitude and any re-association of the arithmetic visible at the 1e-9 level
+        near = np.argsort(np.hypot(lm[0] - X[0], lm[1] - X[1]))[:32]
 
         def check(tag):
             ex = rel_err(g.X, o.X)
@@ -65,7 +68,7 @@ def ekf_checks():
             f.predict(83.33, 0.02, QE, 73.0, 0.01)
             f.observeHeading(float(X[2]) + 1e-4, True)
         check("predict+heading")
-        ids = (rng.choice(N, size=5, replace=False) + 1).astype(np.int32)
+        ids = (rng.choice(near, size=5, replace=False) + 1).astype(np.int32)
         Z = helpers.observe(o.X, lm, ids, rng)
         jg = g.gate(Z, RE, 50.0, 1000.0)[0]
         jo = o.gate(Z, RE, 50.0, 1000.0)[0]
@@ -89,7 +92,7 @@ def ekf_checks():
         check("heading + single update (cache follows rank-1 and rank-2 passes)")
         same_gate()
         # fused scan on the sharded handle: 10 observations (two groups), one of them passing no gate
-        ids_s = (rng.choice(N, size=9, replace=False) + 1).astype(np.int32)
+        ids_s = (rng.choice(near, size=9, replace=False) + 1).astype(np.int32)
         Zs = np.concatenate([helpers.observe(o.X, lm, ids_s, rng)[:, :5], np.array([[9000.0], [1.0]]),
                              helpers.observe(o.X, lm, ids_s, rng)[:, 5:]], axis=1)
         jo = o.gate(Zs, RE, 50.0, 1000.0)[0]
@@ -97,8 +100,8 @@ def ekf_checks():
         jg, _ = g.scan(Zs, RE, 50.0, 1000.0)
         assert np.array_equal(jg, jo) and jo[5] == 0, (jg, jo)
         check("fused scan (sharded)")
-        same_gate(helpers.observe(o.X, lm, (rng.choice(N, size=6, replace=False) + 1).astype(np.int32), rng))
-        ids2 = (rng.choice(N, size=16, replace=False) + 1).astype(np.int32)
+        same_gate(helpers.observe(o.X, lm, (rng.choice(near, size=6, replace=False) + 1).astype(np.int32), rng))
+        ids2 = (rng.choice(near, size=16, replace=False) + 1).astype(np.int32)
         Z2 = helpers.observe(o.X, lm, ids2, rng)
         for f in (g, o):
             f.update(Z2, RE, ids2, True)
@@ -121,7 +124,7 @@ def ekf_checks():
             o.observeHeading(ph[i], True)
         assert rel_err(tr[-1], o.X[:3]) < 1e-9
         check("control steps (merged heading passes)")
-        same_gate(helpers.observe(o.X, lm, (rng.choice(N, size=6, replace=False) + 1).astype(np.int32), rng))
+        same_gate(helpers.observe(o.X, lm, (rng.choice(near, size=6, replace=False) + 1).astype(np.int32), rng))
         ids3 = np.array([N + 1, N + 3, 7], dtype=np.int32)
         Z3 = np.stack([np.array([700.0, 300.0, Z[0, 0]]), np.array([0.4, 2.0, Z[1, 0]])])
         for f in (g, o):

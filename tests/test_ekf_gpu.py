@@ -2,8 +2,8 @@
 
 Bar (BASELINE.json north_star): state / landmark / covariance estimates within 1e-9 relative
 in FP64; association indices exactly equal.  Inputs are seeded; sizes are what the dense oracle
-finishes in seconds; full-size behaviour is covered by size-independent properties
-(test_ekf_properties_gpu.py).
+finishes in seconds; the benchmarked sizes (2,000 landmarks with the full covariance, 20,000 landmarks on the
+marginal of the observed landmarks) are covered by tests/test_ekf_lazy.py.
 """
 import numpy as np
 import pytest
@@ -380,3 +380,42 @@ def test_tile_boundary_sizes(N):
         f.update(Zn[:, 2:], RE, np.array([N + 3], dtype=np.int32), False)
     _assert_state(g, o)
     assert g.sync() == 0
+
+
+@pytest.mark.gpu
+def test_observe_step_equals_update_then_augment():
+    """cslam_ekf_observe_step: on a small map the joint update and the augmentations of one
+    observation step (test/main.cpp:188-189) run in ONE single-CTA launch — bit-identical to the two calls,
+    and within 1e-9 of the oracle."""
+    import conan_slam_b200 as cs
+    N = 25
+    X, P, lm = helpers.synthetic_map(N, 31)
+    rng = np.random.default_rng(8)
+    for flags in (0, cs.FLAG_INTENDED):
+        a = cs.EKF(capacity_landmarks=N + 6, device=0, flags=flags)
+        b = cs.EKF(capacity_landmarks=N + 6, device=0, flags=flags)
+        o = oracle_py.OracleEKF(flags)
+        for f in (a, b, o):
+            f.reset(X, P)
+        launches = []
+        for case in range(4):
+            mf = [3, 0, 5, 2][case]
+            mn = [2, 3, 0, 1][case]
+            ids = (rng.choice(N, size=mf, replace=False) + 1).astype(np.int32)
+            ZF = helpers.observe(o.X, lm, ids, rng) if mf else np.zeros((2, 0))
+            ZN = np.stack([rng.uniform(200, 1500, size=mn), rng.uniform(-1.5, 1.5, size=mn)]) if mn else np.zeros((2, 0))
+            l0 = cs.load_library().cslam_kernel_launches()
+            a.observeStep(ZF, helpers.RE, ids, ZN, True)
+            launches.append(cs.load_library().cslam_kernel_launches() - l0)
+            for f in (b, o):
+                f.update(ZF, helpers.RE, ids, True)
+                f.augment(ZN, helpers.RE)
+            assert a.n == b.n == o.n
+            assert np.array_equal(a.X, b.X)
+            assert np.array_equal(np.triu(a.P), np.triu(b.P))
+        assert launches == [1, 1, 1, 1], launches
+        iu = np.triu_indices(o.n)
+        assert helpers.rel_err(a.X, o.X) < 1e-9 and helpers.rel_err(a.P[iu], o.P[iu]) < 1e-9
+        assert a.sync() == 0
+        a.close()
+        b.close()

@@ -75,7 +75,6 @@ static void run_ref_g(int g, double* P, size_t ld, int n, const double* A, size_
 int main(int argc, char** argv) {
     if (getenv("TMA_BOXR")) g_tma_boxr = atoi(getenv("TMA_BOXR"));
     if (getenv("TMA_DENSE")) g_tma_dense = atoi(getenv("TMA_DENSE"));
-    else g_tma_dense = 0;
     const int n = argc > 1 ? atoi(argv[1]) : 40003;
     const int reps = argc > 2 ? atoi(argv[2]) : 10;
     const Shard sh{argc > 4 ? atoi(argv[4]) : 0, argc > 3 ? atoi(argv[3]) : 1};
@@ -155,8 +154,8 @@ int main(int argc, char** argv) {
             const float ms = time_tma(g, stages, 0);
             printf("  S%d %7.4f ms %6.1f GB/s", stages, ms, gb / (ms * 1e-3));
         }
-        const float ms_pp = time_tma(g, 4, 0, true);
-        printf("  | out of place (P1 -> P2) S4 %7.4f ms %6.1f GB/s\n", ms_pp, gb / (ms_pp * 1e-3));
+        const float ms_pp = time_tma(g, 5, 0, true);
+        printf("  | out of place (P1 -> P2) S5 %7.4f ms %6.1f GB/s\n", ms_pp, gb / (ms_pp * 1e-3));
     }
     for (int dbg = 8; dbg <= 24; dbg += 8)
         for (int g = 4; g <= 8; g += 4) {
