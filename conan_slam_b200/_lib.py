@@ -74,6 +74,10 @@ SIGNATURES = {
     "cslam_world_create": (C.c_int, [C.POINTER(_vp), _dp, C.c_int, C.c_int]),
     "cslam_world_destroy": (C.c_int, [_vp]),
     "cslam_world_observe": (C.c_int, [_vp, _dp, C.c_double, C.c_int, _dp, _ip, C.POINTER(C.c_int)]),
+    "cslam_world_observe_associate": (C.c_int, [_vp, _dp, C.c_double, C.c_int, C.c_int, _dp, _ip, C.POINTER(C.c_int), _dp,
+                                                C.POINTER(C.c_int)]),
+    "cslam_world_get_table": (C.c_int, [_vp, _ip]),
+    "cslam_world_reset_table": (C.c_int, [_vp]),
     "cslam_pf_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.c_uint]),
     "cslam_pf_create_sharded": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.c_uint, C.c_int, C.c_int, _vp]),
     "cslam_pf_ipc_export": (C.c_int, [_vp, _vp]),

@@ -42,3 +42,27 @@ class SimWorld:
               "cslam_world_observe")
         k = min(m.value, cap)
         return Z[:2 * k].reshape(k, 2).T.copy(), tags[:k].copy(), m.value
+
+    def observeAndAssociate(self, XTrue, maxRange, num_map_landmarks, max_out=None):
+        """getObservations + dataAssociateTable (test/main.cpp:177-186) on the device, one read-back: returns
+        (ZF (2 x mf), idf (mf,), ZN (2 x mn)); the association table (mTABLE) stays on the device."""
+        x = np.ascontiguousarray(XTrue, dtype=np.float64).reshape(-1)[:3].copy()
+        cap = self.num_landmarks if max_out is None else int(max_out)
+        ZF = np.zeros(2 * max(cap, 1), dtype=np.float64)
+        ZN = np.zeros(2 * max(cap, 1), dtype=np.float64)
+        idf = np.zeros(max(cap, 1), dtype=np.int32)
+        mf, mn = C.c_int(0), C.c_int(0)
+        check(self._lib.cslam_world_observe_associate(self._h, dptr(x), float(maxRange), int(num_map_landmarks), cap,
+                                                      dptr(ZF), iptr(idf), C.byref(mf), dptr(ZN), C.byref(mn)),
+              "cslam_world_observe_associate")
+        kf, kn = min(mf.value, cap), min(mn.value, cap)
+        return ZF[:2 * kf].reshape(kf, 2).T.copy(), idf[:kf].copy(), ZN[:2 * kn].reshape(kn, 2).T.copy()
+
+    @property
+    def table(self):
+        t = np.zeros(max(self.num_landmarks, 1), dtype=np.int32)
+        check(self._lib.cslam_world_get_table(self._h, iptr(t)), "cslam_world_get_table")
+        return t[:self.num_landmarks]
+
+    def reset_table(self):
+        check(self._lib.cslam_world_reset_table(self._h), "cslam_world_reset_table")

@@ -197,6 +197,18 @@ int cslam_world_destroy(cslam_world_t* w);
 int cslam_world_observe(cslam_world_t* w, const double x_true[3], double max_range, int max_out, double* Z,
                         int32_t* tags, int* m_out);
 
+/* getObservations + Slam::dataAssociateTable(X, Z, idz, table) (slam.h:454-457 -> EKF.cpp:146-233), i.e.
+ * test/main.cpp:177-186, without leaving the device in between ("next" row 2 of SURVEY.md §8f, second half): the
+ * association table (the reference's mTABLE, slam.h:105) lives on the device; the visible landmarks are split into
+ * known ones (ZF, idf = 1-based map slots) and new ones (ZN, which receive the slots num_map_landmarks + 1, ... in
+ * list order, EKF.cpp:212-226) and ONE read-back returns both lists.  *mf / *mn are the true counts (at most
+ * max_out entries are written to each list).  Follow with cslam_ekf_update + cslam_ekf_augment or
+ * cslam_ekf_observe_step. */
+int cslam_world_observe_associate(cslam_world_t* w, const double x_true[3], double max_range, int num_map_landmarks,
+                                  int max_out, double* ZF, int32_t* idf, int* mf, double* ZN, int* mn);
+int cslam_world_get_table(cslam_world_t* w, int32_t* table);
+int cslam_world_reset_table(cslam_world_t* w);
+
 /* -------------------------------------------------------- particle filter (FastSLAM) ---- */
 
 /* Replaces `new PF(LM, WP)` + Slam::initializeParticles(n) (slam.h:688 -> PF.cpp:319-341):

@@ -64,3 +64,45 @@ def test_front_end_feeds_the_filter():
     assert g.n == o.n and helpers.rel_err(g.X, o.X) < 1e-9
     iu = np.triu_indices(o.n)
     assert helpers.rel_err(g.P[iu], o.P[iu]) < 1e-9
+
+
+@pytest.mark.parametrize("N", [30, 700, 4000])
+def test_device_association_table_matches_host_bookkeeping(N):
+    """getObservations + dataAssociateTable (test/main.cpp:177-186, EKF.cpp:146-233) on the device
+    (cslam_world_observe_associate, table resident on the GPU) against the front end + the host bookkeeping
+    of the adaptor: same known / new split, same map slots, same table after every scan."""
+    import conan_slam_b200 as cs
+    rng = np.random.default_rng(N)
+    side = 10000.0 * np.sqrt(N / 30.0)
+    lm = rng.uniform(-side / 2, side / 2, size=(2, N))
+    w_dev, w_host = cs.SimWorld(lm), cs.SimWorld(lm)
+    table = np.zeros(N, dtype=np.int64)
+    nf = 0
+    for t in range(8):
+        pose = np.array([rng.uniform(-side / 4, side / 4), rng.uniform(-side / 4, side / 4), rng.uniform(-np.pi, np.pi)])
+        rmax = [2500.0, 4000.0, 1e9][t % 3]
+        Z, tags, _ = w_host.getObservations(pose, rmax)
+
+        book_nf = nf  # EKF.cpp:212: new landmarks receive the slots nf + 1, nf + 2, ... in list order
+        zf, zn, idf, idn = [], [], [], []
+        for i, ident in enumerate(tags):
+            if table[ident - 1] == 0:
+                zn.append(i); idn.append(ident)
+            else:
+                zf.append(i); idf.append(int(table[ident - 1]))
+        for k, ident in enumerate(idn):
+            table[ident - 1] = book_nf + k + 1
+        ZFd, idfd, ZNd = w_dev.observeAndAssociate(pose, rmax, nf)
+        assert np.array_equal(idfd, np.asarray(idf, dtype=np.int32))
+        assert ZFd.shape[1] == len(zf) and ZNd.shape[1] == len(zn)
+        if zf:
+            assert np.array_equal(ZFd, Z[:, zf])
+        if zn:
+            assert np.array_equal(ZNd, Z[:, zn])
+        nf += len(zn)
+        assert np.array_equal(w_dev.table, table.astype(np.int32))
+    assert nf > 0
+    w_dev.reset_table()
+    assert not w_dev.table.any()
+    for f in (w_dev, w_host):
+        f.close()
