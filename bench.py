@@ -921,6 +921,43 @@ def ekf_result(ctx, eb, m, steps, warmup, batch=False, strict=False, with_e2e=Tr
     return out
 
 
+def c1_loop():
+    """C1 of BASELINE.json: the reference's own simulated waypoint loop (test/main.cpp:132-200, 30-landmark world,
+    22,018 control steps, 3,259 observation steps) replayed by the C++ host driver through the drop-in adaptor:
+    stepwise calls vs the fused forms (k control steps per launch, cslam_ekf_control_steps; joint update +
+    augmentation per launch, cslam_ekf_observe_step).  Beside it the reference's own binary (test/main.cpp
+    compiled unmodified, oracle/_ref/slam_ref, stdout to /dev/null) on one host core — a baseline, not a target:
+    at n = 53 everything is launch- and PCIe-latency-bound."""
+    import re
+    import subprocess
+    exe = os.path.join(ROOT, "conan_slam_b200", "lib", "sim_main")
+    if not os.path.exists(exe):
+        return {"skipped": "conan_slam_b200/lib/sim_main not built"}
+    out = {"control_steps": None}
+
+    def run(flags):
+        r = subprocess.run([exe, "--print-every", "0"] + flags, capture_output=True, text=True, timeout=300)
+        m = re.search(r"done: (\d+) control steps, n=(\d+), skipped updates=(\d+), loop wall time ([0-9.]+) s", r.stdout)
+        if r.returncode != 0 or not m:
+            raise RuntimeError(f"sim_main {flags}: rc={r.returncode} {r.stdout[-200:]} {r.stderr[-200:]}")
+        out["control_steps"], out["final_state_dim"] = int(m.group(1)), int(m.group(2))
+        return float(m.group(4))
+    out["loop_s_stepwise_calls"] = run([])
+    out["loop_s_fused"] = run(["--fused"])
+    out["loop_s_fused_no_cov_writeback"] = run(["--fused", "--no-cov-writeback"])
+    out["control_steps_per_s_fused"] = out["control_steps"] / out["loop_s_fused"]
+    ref = os.path.join(ROOT, "oracle", "_ref", "slam_ref")
+    if os.path.exists(ref):
+        t0 = time.perf_counter()
+        with open(os.devnull, "w") as dn:
+            rc = subprocess.run([ref], stdout=dn, stderr=dn, timeout=600).returncode
+        out["cpu_baseline"] = {"value": time.perf_counter() - t0, "unit": "s per loop (whole process)", "cores": 1,
+                               "kind": "reference", "rc": rc,
+                               "sample": "the reference's own test/main.cpp + EKF.cpp (oracle/_ref/slam_ref, FP32, "
+                                         "Eigen stand-in), full loop, stdout discarded"}
+    return out
+
+
 def guarded(name, fn):
     """Extras never take the headline down: failures are reported in place."""
     try:
@@ -994,6 +1031,8 @@ def main():
                 e2.close()
                 return r
             extras["c2"] = guarded("c2", c2)
+            if ctx.rank == 0:
+                extras["c1_loop"] = guarded("c1_loop", c1_loop)
         if ctx.world >= 2:
             def c5():
                 e5 = EkfBench(ctx, 60000, 16)

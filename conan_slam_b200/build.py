@@ -45,7 +45,9 @@ def _stale(target, deps):
 
 def build(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
-    headers = [os.path.join(CSRC, h) for h in ("common.cuh", "shard_map.h", "cov_update.cuh", "ekf_handle.cuh", "nccl_dl.cuh", "ptx_async.cuh")]
+    # every header of csrc/ is a dependency of every object (a stale object with an old signature links, but
+    # fails to LOAD: undefined symbol)
+    headers = sorted(os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith((".cuh", ".h")))
     headers += [os.path.join(HERE, "..", "include", "cslam.h"), __file__]
     objs = []
     nvcc = _nvcc()

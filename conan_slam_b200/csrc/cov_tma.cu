@@ -281,23 +281,31 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_cov_update_tma(const __grid_c
 // and swapping the two registers afterwards.
 constexpr int TMD_STORERS = 2;
 constexpr int TMD_THREADS = (TM_CONSUMERS + 1 + TMD_STORERS) * 32;
-template <int KS, int S>
+template <int KS, int S, int SUB>
 struct TmdSmem {
     static constexpr int RP = 4 * KS;
-    static constexpr int ring_bytes = S * TM_STAGE_BYTES;
+    static constexpr int stage_bytes = SUB * TM_T * 8;  // SUB rows x 1 KB
+    static constexpr int ring_bytes = S * stage_bytes;
     static constexpr int panel_doubles = RP * TM_PITCH;
     static constexpr int panels_bytes = 3 * panel_doubles * 8;  // row panel x 2 slots, column panel x 1
     static constexpr int bar_count = (3 * S + 6 + 1) / 2 * 2;    // full, done, free [S]; pfull[2], pempty[2], cfull, cempty (even: int4 behind)
     static constexpr int total = ring_bytes + panels_bytes + bar_count * 8 + 2 * 16;
 };
-template <int KS, int S>
+// SUB = rows per pipeline stage (16 or 32): the ring holds S x SUB KB.
+template <int KS, int S, int SUB>
 __global__ void __launch_bounds__(TMD_THREADS, 1) k_cov_update_tma_dense(const __grid_constant__ CUtensorMap tmSrc,
                                                                         const __grid_constant__ CUtensorMap tmDst,
                                                                         const double* __restrict__ A, size_t lda,
                                                                         int r, int nt, long long tiles, Shard sh,
                                                                         const int* __restrict__ live, int nlive,
-                                                                        double diag_eps, int dbg) {
-    using L = TmdSmem<KS, S>;
+                                                                        double diag_eps, int dbg, double* Pdst,
+                                                                        size_t ld, int rows_cap) {
+    // Pdst != nullptr: "direct store" mode — the consumers write their accumulator fragments straight to global
+    // memory (streaming 16-byte stores) instead of handing the stage to a TMA store; a stage is then free as soon
+    // as it has been read into registers.
+    using L = TmdSmem<KS, S, SUB>;
+    constexpr int RB = SUB / 8;               // 8-row DMMA blocks per stage and warp
+    constexpr int STAGE = L::stage_bytes;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* ring = smem_raw;
     double* panels = reinterpret_cast<double*>(smem_raw + L::ring_bytes);
@@ -318,7 +326,7 @@ __global__ void __launch_bounds__(TMD_THREADS, 1) k_cov_update_tma_dense(const _
 #pragma unroll
         for (int s = 0; s < S; s++) {
             mbar_init(bar_full + 8 * s, 1);
-            mbar_init(bar_free + 8 * s, 1);
+            mbar_init(bar_free + 8 * s, Pdst != nullptr ? TM_CONSUMERS : 1);
             mbar_init(bar_done + 8 * s, TM_CONSUMERS);
         }
 #pragma unroll
@@ -363,7 +371,7 @@ __global__ void __launch_bounds__(TMD_THREADS, 1) k_cov_update_tma_dense(const _
             for (int k = 0; k < r; k++)
                 bulk_g2s_hint(cp_u32 + 8 * TM_PITCH * k, A + (size_t)k * lda + j0, (uint32_t)jlen * 8, bar_cfull, pol_keep);
 #pragma unroll 1
-            for (int s = 0; s < TM_T / TM_SUB; s++) {
+            for (int s = 0; s < TM_T / SUB; s++) {
                 if (sub >= S) {
                     mbar_wait(bar_free + 8 * st, (free_phase >> st) & 1u);
                     free_phase ^= 1u << st;
@@ -371,8 +379,8 @@ __global__ void __launch_bounds__(TMD_THREADS, 1) k_cov_update_tma_dense(const _
                 if (dbg & 4) {  // development ablation: no covariance loads
                     mbar_arrive(bar_full + 8 * st);
                 } else {
-                    mbar_expect_tx(bar_full + 8 * st, TM_STAGE_BYTES);
-                    tma_load_2d(ring_u32 + st * TM_STAGE_BYTES, &tmSrc, j0, lrow0 + TM_SUB * s, bar_full + 8 * st, pol_stream);
+                    mbar_expect_tx(bar_full + 8 * st, STAGE);
+                    tma_load_2d(ring_u32 + st * STAGE, &tmSrc, j0, lrow0 + SUB * s, bar_full + 8 * st, pol_stream);
                 }
                 st = st + 1 == S ? 0 : st + 1;
                 sub++;
@@ -381,7 +389,7 @@ __global__ void __launch_bounds__(TMD_THREADS, 1) k_cov_update_tma_dense(const _
         return;
     }
     if (warp > TM_CONSUMERS) {  // ------------------------------------------------- stores ----
-        if (lane != 0) return;
+        if (lane != 0 || Pdst != nullptr) return;
         const int me = warp - TM_CONSUMERS - 1;
         tmap_prefetch(&tmDst);
         const uint64_t pol_stream = policy_evict_first();
@@ -394,10 +402,10 @@ __global__ void __launch_bounds__(TMD_THREADS, 1) k_cov_update_tma_dense(const _
             shard_tile(t, nt, sh, tr, tc);
             const int j0 = tc * TM_T, lrow0 = (int)shard_lrow(sh, tr * TM_T);
 #pragma unroll 1
-            for (int s = 0; s < TM_T / TM_SUB; s++, sub++) {
+            for (int s = 0; s < TM_T / SUB; s++, sub++) {
                 if ((int)(sub % TMD_STORERS) == me) {
                     mbar_wait(bar_done + 8 * st, (done_phase >> st) & 1u);
-                    if (!(dbg & 2)) tma_store_2d(&tmDst, j0, lrow0 + TM_SUB * s, ring_u32 + st * TM_STAGE_BYTES, pol_stream);
+                    if (!(dbg & 2)) tma_store_2d(&tmDst, j0, lrow0 + SUB * s, ring_u32 + st * STAGE, pol_stream);
                     bulk_commit();
                     bulk_wait_read<0>();  // this store has left shared memory: the stage is free
                     mbar_arrive(bar_free + 8 * st);
@@ -436,33 +444,37 @@ __global__ void __launch_bounds__(TMD_THREADS, 1) k_cov_update_tma_dense(const _
         const int4 ti = tinfo[slot];
         const double* rp = rowp(slot) + g;
 #pragma unroll 1
-        for (int s = 0; s < TM_T / TM_SUB; s++) {
+        for (int s = 0; s < TM_T / SUB; s++) {
             mbar_wait(bar_full + 8 * st, (full_phase >> st) & 1u);
             full_phase ^= 1u << st;
-            unsigned char* stage = ring + st * TM_STAGE_BYTES;
-            double2 acc[4][2];
+            unsigned char* stage = ring + st * STAGE;
+            double2 acc[RB][2];
 #pragma unroll
-            for (int rb = 0; rb < 4; rb++) {
+            for (int rb = 0; rb < RB; rb++) {
                 const double2 va = *reinterpret_cast<const double2*>(stage + rb * 8192 + offA);
                 const double2 vb = *reinterpret_cast<const double2*>(stage + rb * 8192 + offB);
                 acc[rb][0] = odd ? vb : va;
                 acc[rb][1] = odd ? va : vb;
             }
+            if (Pdst != nullptr) {  // direct-store mode: the stage has been read, hand it back at once
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_free + 8 * st);
+            }
 #pragma unroll
             for (int ks = 0; ks < KS; ks++) {
-                double a[4];
+                double a[RB];
 #pragma unroll
-                for (int rb = 0; rb < 4; rb++) a[rb] = rp[TM_PITCH * (4 * ks + t) + TM_SUB * s + 8 * rb];
+                for (int rb = 0; rb < RB; rb++) a[rb] = rp[TM_PITCH * (4 * ks + t) + SUB * s + 8 * rb];
 #pragma unroll
-                for (int rb = 0; rb < 4; rb++) {
+                for (int rb = 0; rb < RB; rb++) {
                     dmma884(acc[rb][0].x, acc[rb][0].y, a[rb], nb[ks][0]);
                     dmma884(acc[rb][1].x, acc[rb][1].y, a[rb], nb[ks][1]);
                 }
             }
             if (ti.z && diag_eps != 0.0) {  // diagonal tile: slam.h:719 on the diagonal elements
 #pragma unroll
-                for (int rb = 0; rb < 4; rb++) {
-                    const int row = TM_SUB * s + 8 * rb + g;
+                for (int rb = 0; rb < RB; rb++) {
+                    const int row = SUB * s + 8 * rb + g;
 #pragma unroll
                     for (int cb = 0; cb < 2; cb++) {
                         const int col = TM_BOXC * warp + 8 * cb + 2 * t;
@@ -471,14 +483,27 @@ __global__ void __launch_bounds__(TMD_THREADS, 1) k_cov_update_tma_dense(const _
                     }
                 }
             }
+            if (Pdst != nullptr) {
+                // lane (g, t) owns columns 2t, 2t+1 of row g of each 8x8 block: 64 contiguous bytes per row and block
+                const int col0 = ti.x + TM_BOXC * warp + 2 * t;
+                double* prow = Pdst + (size_t)(ti.y + SUB * s + g) * ld + col0;
 #pragma unroll
-            for (int rb = 0; rb < 4; rb++) {
-                *reinterpret_cast<double2*>(stage + rb * 8192 + offA) = odd ? acc[rb][1] : acc[rb][0];
-                *reinterpret_cast<double2*>(stage + rb * 8192 + offB) = odd ? acc[rb][0] : acc[rb][1];
+                for (int rb = 0; rb < RB; rb++) {
+                    if (ti.y + SUB * s + 8 * rb + g < rows_cap && !(dbg & 2)) {
+                        if (col0 < (int)ld) __stcs(reinterpret_cast<double2*>(prow + (size_t)8 * rb * ld), acc[rb][0]);
+                        if (col0 + 8 < (int)ld) __stcs(reinterpret_cast<double2*>(prow + (size_t)8 * rb * ld + 8), acc[rb][1]);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int rb = 0; rb < RB; rb++) {
+                    *reinterpret_cast<double2*>(stage + rb * 8192 + offA) = odd ? acc[rb][1] : acc[rb][0];
+                    *reinterpret_cast<double2*>(stage + rb * 8192 + offB) = odd ? acc[rb][0] : acc[rb][1];
+                }
+                fence_proxy_async();  // the TMA store (async proxy) must see these generic-proxy writes
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_done + 8 * st);
             }
-            fence_proxy_async();  // the TMA store (async proxy) must see these generic-proxy writes
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_done + 8 * st);
             st = st + 1 == S ? 0 : st + 1;
         }
         __syncwarp();
@@ -507,6 +532,7 @@ static EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
+int g_tma_sub = getenv("CSLAM_TMA_SUB") ? atoi(getenv("CSLAM_TMA_SUB")) : 32;  // rows per stage of the dense variant (16 | 32)
 int g_tma_boxr = 32;  // development knob: rows per TMA box of the swizzled-box variant (8, 16 or 32)
 // 1 = dense-row variant (k_cov_update_tma_dense: one 32 KB tensor-map load / store per stage, measured slightly
 // faster on a B200), 0 = swizzled 16-column boxes with consumer-issued stores (k_cov_update_tma).
@@ -520,7 +546,7 @@ int make_cov_tensor_map(void* out_map64, double* P, size_t ld, size_t rows) {
     CUtensorMap tm;
     const cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(double)};
-    const cuuint32_t box[2] = {g_tma_dense ? (cuuint32_t)TM_T : (cuuint32_t)TM_BOXC, (cuuint32_t)(g_tma_dense ? TM_SUB : g_tma_boxr)};
+    const cuuint32_t box[2] = {g_tma_dense ? (cuuint32_t)TM_T : (cuuint32_t)TM_BOXC, (cuuint32_t)(g_tma_dense ? g_tma_sub : g_tma_boxr)};
     const cuuint32_t estr[2] = {1, 1};
     CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
     if (const char* e = getenv("CSLAM_TMA_PROMO")) promo = (CUtensorMapL2promotion)atoi(e);  // development knob (0..3)
@@ -537,8 +563,20 @@ int make_cov_tensor_map(void* out_map64, double* P, size_t ld, size_t rows) {
 
 int g_tma_dbg = 0;  // development knobs of tools/cov_tma_bench.cu (2: no stores, 4: no loads)
 
+struct DirectStore {  // destination array of the direct-store mode
+    double* P;
+    size_t ld;
+    int rows;
+};
+// 1 (default) = direct-store mode of the dense variant: tensor-map TMA loads, the consumers store their accumulator
+// fragments with streaming 16-byte stores; 0 = tensor-map TMA stores through the ring.  Measured on a B200
+// (tools/cov_tma_bench.cu, N = 20k): both land at 2.12-2.25 ms per pass; direct stores need only a 2-deep ring
+// (64 KB), which leaves room on every SM for the gate / gain kernels that run beside the pass.
+int g_tma_direct = getenv("CSLAM_TMA_DIRECT") ? atoi(getenv("CSLAM_TMA_DIRECT")) : 1;
+
+
 template <int KS, int S>
-static int launch_one(const CUtensorMap& tm, const CUtensorMap& tmd, double diag_eps, const double* A, size_t lda, int r, int nt, long long tiles, Shard sh,
+static int launch_one(const CUtensorMap& tm, const CUtensorMap& tmd, DirectStore ds, double diag_eps, const double* A, size_t lda, int r, int nt, long long tiles, Shard sh,
                       const int* live, int nlive, int num_sms, cudaStream_t stream) {
     using L = TmaSmem<KS, S>;
     static bool attr_set[64] = {};  // per device and instantiation: the attribute is set once, not per call
@@ -550,15 +588,25 @@ static int launch_one(const CUtensorMap& tm, const CUtensorMap& tmd, double diag
     }
     const unsigned grid = (unsigned)std::min<long long>(num_sms, tiles);
     count_launch();
-    if (g_tma_dense) {
+    if (g_tma_dense && g_tma_sub == 16) {
+        constexpr int S16 = 2 * S > 8 ? 8 : 2 * S;  // same ring bytes with half-size stages (at most 8)
         static bool dense_attr[64] = {};
         if (dev < 0 || dev >= 64 || !dense_attr[dev]) {
-            CSLAM_CUDA(cudaFuncSetAttribute(k_cov_update_tma_dense<KS, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            TmdSmem<KS, S>::total));
+            CSLAM_CUDA(cudaFuncSetAttribute(k_cov_update_tma_dense<KS, S16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            TmdSmem<KS, S16, 16>::total));
             if (dev >= 0 && dev < 64) dense_attr[dev] = true;
         }
-        k_cov_update_tma_dense<KS, S><<<grid, TMD_THREADS, TmdSmem<KS, S>::total, stream>>>(tm, tmd, A, lda, r, nt, tiles, sh, live,
-                                                                               nlive, diag_eps, g_tma_dbg);
+        k_cov_update_tma_dense<KS, S16, 16><<<grid, TMD_THREADS, TmdSmem<KS, S16, 16>::total, stream>>>(
+            tm, tmd, A, lda, r, nt, tiles, sh, live, nlive, diag_eps, g_tma_dbg, g_tma_direct ? ds.P : nullptr, ds.ld, ds.rows);
+    } else if (g_tma_dense) {
+        static bool dense_attr[64] = {};
+        if (dev < 0 || dev >= 64 || !dense_attr[dev]) {
+            CSLAM_CUDA(cudaFuncSetAttribute(k_cov_update_tma_dense<KS, S, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            TmdSmem<KS, S, 32>::total));
+            if (dev >= 0 && dev < 64) dense_attr[dev] = true;
+        }
+        k_cov_update_tma_dense<KS, S, 32><<<grid, TMD_THREADS, TmdSmem<KS, S, 32>::total, stream>>>(
+            tm, tmd, A, lda, r, nt, tiles, sh, live, nlive, diag_eps, g_tma_dbg, g_tma_direct ? ds.P : nullptr, ds.ld, ds.rows);
     } else {
         k_cov_update_tma<KS, S><<<grid, TM_THREADS, L::total, stream>>>(tm, tmd, A, lda, r, nt, tiles, sh, live, nlive,
                                                                         diag_eps, g_tma_dbg, g_tma_boxr);
@@ -571,7 +619,8 @@ static int launch_one(const CUtensorMap& tm, const CUtensorMap& tmd, double diag
 // src_map / dst_map: tensor maps made by make_cov_tensor_map (the same one for an in-place pass).
 int launch_cov_update_tma(const void* src_map, const void* dst_map, int n, const double* A, size_t lda, int r,
                           double diag_eps, Shard sh, const int* live, int nlive, int num_sms, int stages,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, double* dst_ptr, size_t dst_ld, int dst_rows) {
+    const DirectStore ds{dst_ptr, dst_ld, dst_rows};
     CSLAM_REQUIRE(r >= 1 && r <= 16, CSLAM_ERR_BAD_ARG, "TMA covariance pass: rank out of range (1..16)");
     CUtensorMap tm, tmd;
     memcpy(&tm, src_map, sizeof(tm));
@@ -582,12 +631,12 @@ int launch_cov_update_tma(const void* src_map, const void* dst_map, int n, const
     const int ks = (r + 3) / 4;
 #define TM_CASE(KS_)                                                                                              \
     case KS_:                                                                                                     \
-        if (stages == 4) return launch_one<KS_, 4>(tm, tmd, diag_eps, A, lda, r, nt, tiles, sh, live, nlive, num_sms, stream);   \
-        if (stages == 3) return launch_one<KS_, 3>(tm, tmd, diag_eps, A, lda, r, nt, tiles, sh, live, nlive, num_sms, stream);   \
-        if (stages == 2) return launch_one<KS_, 2>(tm, tmd, diag_eps, A, lda, r, nt, tiles, sh, live, nlive, num_sms, stream);   \
+        if (stages == 4) return launch_one<KS_, 4>(tm, tmd, ds, diag_eps, A, lda, r, nt, tiles, sh, live, nlive, num_sms, stream);   \
+        if (stages == 3) return launch_one<KS_, 3>(tm, tmd, ds, diag_eps, A, lda, r, nt, tiles, sh, live, nlive, num_sms, stream);   \
+        if (stages == 2) return launch_one<KS_, 2>(tm, tmd, ds, diag_eps, A, lda, r, nt, tiles, sh, live, nlive, num_sms, stream);   \
         if (stages == 6 && KS_ <= 2)                                                                              \
-            return launch_one<KS_, (KS_ <= 2 ? 6 : 5)>(tm, tmd, diag_eps, A, lda, r, nt, tiles, sh, live, nlive, num_sms, stream); \
-        return launch_one<KS_, 5>(tm, tmd, diag_eps, A, lda, r, nt, tiles, sh, live, nlive, num_sms, stream);
+            return launch_one<KS_, (KS_ <= 2 ? 6 : 5)>(tm, tmd, ds, diag_eps, A, lda, r, nt, tiles, sh, live, nlive, num_sms, stream); \
+        return launch_one<KS_, 5>(tm, tmd, ds, diag_eps, A, lda, r, nt, tiles, sh, live, nlive, num_sms, stream);
     switch (ks) {
         TM_CASE(1) TM_CASE(2) TM_CASE(3) TM_CASE(4)
     }

@@ -15,6 +15,7 @@
 // 2*n doubles), then every rank forms the gain and streams its own rows.
 #include <limits>
 #include <new>
+#include <string>
 #include <vector>
 
 #include "common.cuh"
@@ -1856,54 +1857,74 @@ int cslam_ekf_get_landmark_covs(cslam_ekf_t* h, int first_landmark, int count, d
     return CSLAM_OK;
 }
 
-// Checkpoint (the reference has none: X, P and mTABLE live in the driver).  File = header
-// {magic, version, n, flags} + X[n] + the upper triangle of P row by row (row i: n - i doubles),
-// i.e. the device layout minus padding; 8*n*(n+1)/2 bytes instead of 8*n*n.  Single-GPU handles.
+// Checkpoint (the reference has none: X, P and mTABLE live in the driver).  One file per rank:
+//   header {magic, version, flags, n, rank, world} + X[n] + rows 0..2 of P (3 x n, replicated on every rank)
+//   + every covariance row i >= 3 this rank stores, ascending, from the diagonal on (n - i doubles each)
+// — the device layout minus padding, 4 n (n+1) bytes of covariance in total over the ranks.  A sharded handle
+// writes / reads  <path>.r<rank>of<world>  (every rank calls with the same path), a single-GPU handle <path>.
 namespace {
 struct CkptHeader {
     char magic[8];
     uint32_t version;
     uint32_t flags;
     int32_t n;
+    int32_t rank;
+    int32_t world;
     int32_t reserved;
 };
 const char kCkptMagic[8] = {'C', 'S', 'L', 'A', 'M', 'E', 'K', 'F'};
+std::string ckpt_path(const cslam_ekf* h, const char* path) {
+    std::string p(path);
+    if (h->sh.world > 1) p += ".r" + std::to_string(h->sh.rank) + "of" + std::to_string(h->sh.world);
+    return p;
+}
+long long ckpt_bytes(const cslam_ekf* h, int n) {
+    long long rows = 0;
+    for (int i = 3; i < n; i++)
+        if (shard_owns(h->sh, i)) rows += n - i;
+    return (long long)sizeof(CkptHeader) + 8LL * n + 8LL * 3 * n + 8LL * rows;
+}
 }  // namespace
 
 int cslam_ekf_save(cslam_ekf_t* h, const char* path) {
     CSLAM_NVTX_RANGE();
     if (int rc = check_handle(h)) return rc;
     CSLAM_REQUIRE(path != nullptr, CSLAM_ERR_BAD_ARG, "path is null");
-    CSLAM_REQUIRE(h->sh.world == 1, CSLAM_ERR_UNSUPPORTED, "checkpoints are single-GPU (sharded: save per block)");
     if (int rc = lazy_flush_all(h)) return rc;
     CSLAM_CUDA(cudaStreamSynchronize(h->stream));
     const double* Psrc = lazy_P(h);
-    FILE* f = fopen(path, "wb");
+    const std::string file = ckpt_path(h, path);
+    FILE* f = fopen(file.c_str(), "wb");
     CSLAM_REQUIRE(f != nullptr, CSLAM_ERR_BAD_ARG, "cannot open checkpoint file for writing");
     const int n = h->n;
     CkptHeader hd;
+    memset(&hd, 0, sizeof(hd));
     memcpy(hd.magic, kCkptMagic, 8);
-    hd.version = 1;
+    hd.version = 2;
     hd.flags = h->flags;
     hd.n = n;
-    hd.reserved = 0;
+    hd.rank = h->sh.rank;
+    hd.world = h->sh.world;
     bool ok = fwrite(&hd, sizeof(hd), 1, f) == 1;
-    std::vector<double> host((size_t)std::max<size_t>(n, 1 << 20));
+    std::vector<double> host((size_t)std::max(3 * n, 1));
     cudaError_t e = cudaMemcpy(host.data(), h->X[h->cur], n * sizeof(double), cudaMemcpyDeviceToHost);
     ok = ok && e == cudaSuccess && fwrite(host.data(), sizeof(double), n, f) == (size_t)n;
-    // rows in slabs of ~8 MB through a 2D copy (pitch = ld), upper part written per row
-    const int slab = std::max(1, (int)((size_t)(1 << 20) / std::max(n, 1)));
-    std::vector<double> rows((size_t)slab * n);
-    for (int i0 = 0; ok && i0 < n; i0 += slab) {
-        const int nr = std::min(slab, n - i0);
-        e = cudaMemcpy2D(rows.data(), (size_t)n * sizeof(double), Psrc + (size_t)i0 * h->ld, h->ld * sizeof(double),
+    if (ok) {  // rows 0..2: the always-current panel (aliases P on an eager single-GPU handle)
+        e = cudaMemcpy2D(host.data(), (size_t)n * sizeof(double), h->R3, h->ld * sizeof(double), (size_t)n * sizeof(double), 3,
+                         cudaMemcpyDeviceToHost);
+        ok = e == cudaSuccess && fwrite(host.data(), sizeof(double), (size_t)3 * n, f) == (size_t)3 * n;
+    }
+    // owned rows in slabs of 128 (a shard block is contiguous in local storage), upper part written per row
+    std::vector<double> rows((size_t)kShardRows * n);
+    for (int i0 = 0; ok && i0 < n; i0 += kShardRows) {
+        if (!shard_owns(h->sh, i0)) continue;
+        const int nr = std::min(kShardRows, n - i0);
+        e = cudaMemcpy2D(rows.data(), (size_t)n * sizeof(double), Psrc + shard_lrow(h->sh, i0) * h->ld, h->ld * sizeof(double),
                          (size_t)n * sizeof(double), nr, cudaMemcpyDeviceToHost);
-        if (e == cudaSuccess && i0 == 0 && h->R3 != Psrc)  // lazy handle: rows 0..2 live in their own panel
-            e = cudaMemcpy2D(rows.data(), (size_t)n * sizeof(double), h->R3, h->ld * sizeof(double),
-                             (size_t)n * sizeof(double), std::min(3, nr), cudaMemcpyDeviceToHost);
         ok = e == cudaSuccess;
         for (int r = 0; ok && r < nr; r++) {
             const int i = i0 + r;
+            if (i < 3) continue;
             ok = fwrite(rows.data() + (size_t)r * n + i, sizeof(double), n - i, f) == (size_t)(n - i);
         }
     }
@@ -1920,25 +1941,26 @@ int cslam_ekf_load(cslam_ekf_t* h, const char* path) {
     CSLAM_NVTX_RANGE();
     if (int rc = check_handle(h)) return rc;
     CSLAM_REQUIRE(path != nullptr, CSLAM_ERR_BAD_ARG, "path is null");
-    CSLAM_REQUIRE(h->sh.world == 1, CSLAM_ERR_UNSUPPORTED, "checkpoints are single-GPU (sharded: load per block)");
-    FILE* f = fopen(path, "rb");
+    const std::string file = ckpt_path(h, path);
+    FILE* f = fopen(file.c_str(), "rb");
     CSLAM_REQUIRE(f != nullptr, CSLAM_ERR_BAD_ARG, "cannot open checkpoint file");
     CkptHeader hd;
-    bool ok = fread(&hd, sizeof(hd), 1, f) == 1 && memcmp(hd.magic, kCkptMagic, 8) == 0 && hd.version == 1;
+    bool ok = fread(&hd, sizeof(hd), 1, f) == 1 && memcmp(hd.magic, kCkptMagic, 8) == 0 && hd.version == 2;
     if (!ok || hd.n < 3 || hd.n > h->n_cap || (hd.n - 3) % 2 != 0) {
         fclose(f);
         set_last_error("cslam_ekf_load: not a checkpoint of this library, or it exceeds the handle's capacity");
         return CSLAM_ERR_BAD_ARG;
     }
-    // validate BEFORE touching device state: quirk mode and exact length (a truncated file must not leave a
-    // half-overwritten handle behind)
-    if (hd.flags != h->flags) {
+    // validate BEFORE touching device state: quirk mode, sharding and exact length (a truncated file must not
+    // leave a half-overwritten handle behind)
+    if (hd.flags != h->flags || hd.rank != h->sh.rank || hd.world != h->sh.world) {
         fclose(f);
-        set_last_error("cslam_ekf_load: checkpoint written with flags 0x%x, handle created with 0x%x", hd.flags, h->flags);
+        set_last_error("cslam_ekf_load: checkpoint written with flags 0x%x as rank %d of %d, handle has flags 0x%x, rank %d of %d",
+                       hd.flags, hd.rank, hd.world, h->flags, h->sh.rank, h->sh.world);
         return CSLAM_ERR_BAD_ARG;
     }
     {
-        const long long want = (long long)sizeof(hd) + 8LL * hd.n + 4LL * hd.n * ((long long)hd.n + 1);
+        const long long want = ckpt_bytes(h, hd.n);
         long long have = -1;
         if (fseek(f, 0, SEEK_END) == 0) have = ftell(f);
         if (have != want || fseek(f, (long)sizeof(hd), SEEK_SET) != 0) {
@@ -1956,23 +1978,35 @@ int cslam_ekf_load(cslam_ekf_t* h, const char* path) {
         L.np = L.infl_rows = 0;
         L.eps_mask = L.infl_eps_mask = 0;
         L.pass_pending_wait = false;
+        L.stable_busy = false;
     }
-    std::vector<double> x((size_t)n);
+    std::vector<double> x((size_t)std::max(3 * n, 1));
     ok = fread(x.data(), sizeof(double), n, f) == (size_t)n;
     cudaError_t e = cudaSuccess;
     if (ok) e = cudaMemcpy(h->X[h->cur], x.data(), n * sizeof(double), cudaMemcpyHostToDevice);
-    const int slab = std::max(1, (int)((size_t)(1 << 20) / std::max(n, 1)));
-    std::vector<double> rows((size_t)slab * n, 0.0);
-    for (int i0 = 0; ok && e == cudaSuccess && i0 < n; i0 += slab) {
-        const int nr = std::min(slab, n - i0);
+    if (ok && e == cudaSuccess) {
+        ok = fread(x.data(), sizeof(double), (size_t)3 * n, f) == (size_t)3 * n;
+        if (ok)
+            e = cudaMemcpy2D(h->R3, h->ld * sizeof(double), x.data(), (size_t)n * sizeof(double), (size_t)n * sizeof(double), 3,
+                             cudaMemcpyHostToDevice);
+    }
+    std::vector<double> rows((size_t)kShardRows * n, 0.0);
+    for (int i0 = 0; ok && e == cudaSuccess && i0 < n; i0 += kShardRows) {
+        if (!shard_owns(h->sh, i0)) continue;
+        const int nr = std::min(kShardRows, n - i0);
         for (int r = 0; ok && r < nr; r++) {
             const int i = i0 + r;
-            for (int j = 0; j < i; j++) rows[(size_t)r * n + j] = 0.0;  // below the diagonal: unauthoritative
+            for (int j = 0; j < n; j++) rows[(size_t)r * n + j] = 0.0;  // below the diagonal / rows 0..2: unauthoritative
+            if (i < 3) {
+                if (h->R3 == h->P)  // eager single-GPU handle: rows 0..2 ARE the first rows of P
+                    for (int j = i; j < n; j++) rows[(size_t)r * n + j] = x[(size_t)i * n + j];
+                continue;
+            }
             ok = fread(rows.data() + (size_t)r * n + i, sizeof(double), n - i, f) == (size_t)(n - i);
         }
         if (ok)
-            e = cudaMemcpy2D(h->P + (size_t)i0 * h->ld, h->ld * sizeof(double), rows.data(), (size_t)n * sizeof(double),
-                             (size_t)n * sizeof(double), nr, cudaMemcpyHostToDevice);
+            e = cudaMemcpy2D(h->P + shard_lrow(h->sh, i0) * h->ld, h->ld * sizeof(double), rows.data(),
+                             (size_t)n * sizeof(double), (size_t)n * sizeof(double), nr, cudaMemcpyHostToDevice);
     }
     fclose(f);
     if (e != cudaSuccess) {
@@ -1980,7 +2014,6 @@ int cslam_ekf_load(cslam_ekf_t* h, const char* path) {
         return CSLAM_ERR_CUDA;
     }
     CSLAM_REQUIRE(ok, CSLAM_ERR_BAD_ARG, "truncated checkpoint file");
-    if (h->R3 != h->P) CSLAM_CUDA(cudaMemcpy(h->R3, h->P, 3 * h->ld * sizeof(double), cudaMemcpyDeviceToDevice));
     h->n = n;
     h->diag_dirty = true;
     CSLAM_CUDA(cudaMemsetAsync(h->status, 0, sizeof(int), h->stream));
@@ -2005,6 +2038,7 @@ int cslam_ekf_reset(cslam_ekf_t* h, const double* X, int n, const double* P) {
         L.np = L.infl_rows = 0;
         L.eps_mask = L.infl_eps_mask = 0;
         L.pass_pending_wait = false;
+        L.stable_busy = false;
     }
     CSLAM_CUDA(cudaMemsetAsync(h->P, 0, (size_t)h->local_rows_cap * h->ld * sizeof(double), h->stream));
     if (h->R3 != h->P) CSLAM_CUDA(cudaMemsetAsync(h->R3, 0, 3 * h->ld * sizeof(double), h->stream));

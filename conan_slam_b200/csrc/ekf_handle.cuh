@@ -44,11 +44,12 @@ struct LazyState {
     int infl_rows = 0;           // rows of the OTHER bank that the pass in flight applies and `stable` lacks
     unsigned infl_eps_mask = 0;
     bool pass_pending_wait = false;  // a pass was launched and the chain stream has not waited for it yet
+    bool stable_busy = false;        // ... and that pass works IN PLACE on `stable` (no ping-pong twin, or a small pass)
     cudaStream_t pass_stream = nullptr;
     cudaEvent_t ev_chain = nullptr;  // "every reader of the array the next pass overwrites is done"
     cudaEvent_t ev_pass = nullptr;   // completion of the most recently launched pass
     int num_sms = 0;
-    int stages = 5;
+    int stages = 2;  // ring depth of the TMA pass (direct-store mode: 2 x 32 KB measured best on a B200)
     unsigned long long passes = 0;   // passes launched since create (diagnostics)
 };
 

@@ -168,7 +168,9 @@ int cslam_ekf_get_cov_gather(cslam_ekf_t* h, const int32_t* idx, int k, double* 
 int cslam_ekf_get_landmark_covs(cslam_ekf_t* h, int first_landmark, int count, double* out);
 /* Checkpoint / restore of X and the upper triangle of P (the reference keeps X, P in the driver and has
  * no persistence): header + X[n] + row i of P from the diagonal on, 4*n*(n+1) bytes of
- * covariance.  load() requires n <= the handle's capacity.  Single-GPU handles. */
+ * covariance.  load() requires n <= the handle's capacity, the same quirk flags and the same sharding; it
+ * validates the file (length, header) BEFORE it touches device state.  Sharded handles: every rank calls with
+ * the same path and writes / reads its own rows in <path>.r<rank>of<world>. */
 int cslam_ekf_save(cslam_ekf_t* h, const char* path);
 int cslam_ekf_load(cslam_ekf_t* h, const char* path);
 /* Load a state (tests / benchmarks / checkpoint restore): X has n entries, P is a dense

@@ -135,6 +135,15 @@ def ekf_checks():
         xs = [None] * world
         dist.all_gather_object(xs, g.X.tobytes())
         assert all(x == xs[0] for x in xs), "replicated X diverged across ranks"
+        # sharded checkpoint: every rank writes / reads its own rows (<path>.r<rank>of<world>)
+        path = f"/tmp/cslam_sharded_ckpt_{N}"
+        g.save(path)
+        nid2 = cd.nccl_unique_id(device=f"cuda:{local}")
+        g2 = cs.EKF(capacity_landmarks=N + 8, device=local, flags=flags, rank=rank, world=world, nccl_id=nid2)
+        g2.load(path)
+        assert g2.n == g.n and np.array_equal(g2.X, g.X)
+        assert np.array_equal(np.triu(g2.P), np.triu(g.P)), "sharded checkpoint round trip changed the covariance"
+        g2.close()
         g.close()
     print(f"rank {rank}: sharded EKF parity ok")
 

@@ -112,8 +112,10 @@ def test_one_pass_per_drive_cycle_and_inplace_mode_identical():
         assert passes - p0 == 4, passes - p0
         res.append((g.X, g.P))
         g.close()
-    assert np.array_equal(res[0][0], res[1][0])
-    assert np.array_equal(np.triu(res[0][1]), np.triu(res[1][1]))  # same kernel, same terms: bit-identical
+    # same terms, but the gains read the covariance through different sets of pending terms (ping-pong: snapshot of
+    # the array the running pass READS + its bank; in place: the updated array) -> equal up to rounding
+    assert helpers.rel_err(res[0][0], res[1][0]) < 1e-12
+    assert helpers.rel_err(np.triu(res[0][1]), np.triu(res[1][1])) < 1e-12
 
 
 def test_c2_full_covariance_parity():

@@ -16,8 +16,8 @@ namespace cslam {
 int make_cov_tensor_map(void* out_map64, double* P, size_t ld, size_t rows);
 int launch_cov_update_tma(const void* src_map, const void* dst_map, int n, const double* A, size_t lda, int r,
                           double diag_eps, Shard sh, const int* live, int nlive, int num_sms, int stages,
-                          cudaStream_t stream);
-extern int g_tma_dbg, g_tma_boxr, g_tma_dense;
+                          cudaStream_t stream, double* dst_ptr = nullptr, size_t dst_ld = 0, int dst_rows = 0);
+extern int g_tma_dbg, g_tma_boxr, g_tma_dense, g_tma_direct, g_tma_sub;
 }  // namespace cslam
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA %s at line %d\n", cudaGetErrorString(e), __LINE__); exit(1);} } while (0)
@@ -99,8 +99,8 @@ int main(int argc, char** argv) {
     k_init_panel<<<(unsigned)((16 * ld + 255) / 256), 256>>>(A, ld, n, 16);
     CK(cudaDeviceSynchronize());
     const double gb = 8.0 * n * ((double)n + 1.0) / 1e9 / sh.world;
-    printf("n=%d ld=%zu rows=%zu world=%d rank=%d SMs=%d boxr=%d dense=%d, algorithmic bytes per pass %.3f GB\n", n, ld, rows, sh.world,
-           sh.rank, sms, g_tma_boxr, g_tma_dense, gb);
+    printf("n=%d ld=%zu rows=%zu world=%d rank=%d SMs=%d boxr=%d dense=%d direct=%d sub=%d, algorithmic bytes per pass %.3f GB\n", n, ld, rows, sh.world,
+           sh.rank, sms, g_tma_boxr, g_tma_dense, g_tma_direct, g_tma_sub, gb);
     int bad = 0;
     for (int g = 2; g <= 8; g++) {
         k_init<<<gi, 256>>>(P1, ld, rows, n, sh);
@@ -108,7 +108,7 @@ int main(int argc, char** argv) {
         CK(cudaMemset(dres, 0, 16));
         run_ref_g(g, P1, ld, n, A, ld, sh);
         CK(cudaDeviceSynchronize());
-        if (launch_cov_update_tma(map, map, n, A, ld, 2 * g, 0.0, sh, nullptr, 0, sms, 5, 0) != 0) {
+        if (launch_cov_update_tma(map, map, n, A, ld, 2 * g, 0.0, sh, nullptr, 0, sms, 5, 0, P2, ld, (int)rows) != 0) {
             printf("launch: %s\n", cslam_last_error());
             return 1;
         }
@@ -128,10 +128,10 @@ int main(int argc, char** argv) {
     auto time_tma = [&](int g, int stages, int dbg, bool pp = false) {
         g_tma_dbg = dbg;
         float ms = 0.f;
-        launch_cov_update_tma(pp ? map1 : map, map, n, A, ld, 2 * g, 0.0, sh, nullptr, 0, sms, stages, 0);
+        launch_cov_update_tma(pp ? map1 : map, map, n, A, ld, 2 * g, 0.0, sh, nullptr, 0, sms, stages, 0, P2, ld, (int)rows);
         CK(cudaDeviceSynchronize());
         CK(cudaEventRecord(e0));
-        for (int i = 0; i < reps; i++) launch_cov_update_tma(pp ? map1 : map, map, n, A, ld, 2 * g, 0.0, sh, nullptr, 0, sms, stages, 0);
+        for (int i = 0; i < reps; i++) launch_cov_update_tma(pp ? map1 : map, map, n, A, ld, 2 * g, 0.0, sh, nullptr, 0, sms, stages, 0, P2, ld, (int)rows);
         CK(cudaEventRecord(e1));
         CK(cudaDeviceSynchronize());
         CK(cudaEventElapsedTime(&ms, e0, e1));
