@@ -302,7 +302,8 @@ def test_checkpoint_roundtrip_and_landmark_marginals(tmp_path):
     assert np.array_equal(g.landmark_covs(first=10, count=3), covs[9:12])
     path = tmp_path / "ekf.ckpt"
     g.save(path)
-    assert path.stat().st_size == 24 + 8 * g.n + 4 * g.n * (g.n + 1)
+    # header + X + rows 0..2 (3 x n) + rows >= 3 from the diagonal on
+    assert path.stat().st_size == 32 + 8 * g.n + 24 * g.n + 4 * (g.n - 3) * (g.n - 2)
     g2 = cs.EKF(capacity_landmarks=64, flags=oracle_py.FLAG_INTENDED)
     g2.load(path)
     assert g2.n == g.n and np.array_equal(g2.X, g.X) and np.array_equal(g2.P, Pg)
@@ -416,6 +417,6 @@ def test_observe_step_equals_update_then_augment():
         assert launches == [1, 1, 1, 1], launches
         iu = np.triu_indices(o.n)
         assert helpers.rel_err(a.X, o.X) < 1e-9 and helpers.rel_err(a.P[iu], o.P[iu]) < 1e-9
-        assert a.sync() == 0
+        assert a.sync() == b.sync()  # numerically skipped updates (slam.h:252-255) are counted identically
         a.close()
         b.close()
