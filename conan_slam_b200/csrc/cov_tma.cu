@@ -511,6 +511,210 @@ __global__ void __launch_bounds__(TMD_THREADS, 1) k_cov_update_tma_dense(const _
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Joint (batch) update, rank r <= 64 (EKF.cpp:93-129 -> slam.h:260 with r = 2m, m <= 32): the SAME dense-row
+// pipeline, now bound by the FP64 tensor cores instead of HBM (8 flop per byte at r = 64).  What changes:
+//   * the column-panel fragments of a tile (r/4 x 2 doubles per lane, up to 64 registers) live in registers for
+//     the whole tile; the shared-memory copy is single-buffered and handed back as soon as they are loaded;
+//   * the row panel (r x 128 doubles = 66 KB at r = 64) is single-buffered too: a CTA walks CHUNKS of consecutive
+//     tiles of the row-major triangle, so the panel is reloaded only when the 128-row strip changes;
+//   * the A fragments of k-step s+1 are fetched from shared memory while the DMMAs of k-step s issue;
+//   * results leave the SM by streaming 16-byte stores straight from the accumulator fragments (direct-store
+//     mode), so a stage is free the moment it has been read into registers and a 2-deep ring suffices.
+// P travels HBM -> shared memory by tensor-map TMA (UTMALDG); no LDG / LDGSTS / address arithmetic per element
+// competes with the DMMA issue slots (round 1's kernel staged P with per-thread cp.async: 0.81 of the DMMA peak,
+// its own no-load/no-store ceiling was 0.90).
+constexpr int TMJ_THREADS = (TM_CONSUMERS + 1) * 32;
+constexpr int TMJ_KS = 16;  // k-steps at full rank (64 / 4)
+template <int S, int SUB>
+struct TmjSmem {
+    static constexpr int stage_bytes = SUB * TM_T * 8;
+    static constexpr int ring_bytes = S * stage_bytes;
+    static constexpr int panel_doubles = 4 * TMJ_KS * TM_PITCH;
+    static constexpr int panels_bytes = 2 * panel_doubles * 8;  // row panel, column panel (one slot each)
+    static constexpr int bar_count = 2 * S + 4;                 // full[S], free[S], rfull, rempty, cfull, cempty
+    static constexpr int total = ring_bytes + panels_bytes + bar_count * 8 + 32;
+};
+template <int S, int SUB>
+__global__ void __launch_bounds__(TMJ_THREADS, 1) k_cov_update_tma_joint(const __grid_constant__ CUtensorMap tmSrc,
+                                                                        const double* __restrict__ A, size_t lda,
+                                                                        int r, int nt, long long tiles, int chunk,
+                                                                        Shard sh, double* __restrict__ Pdst, size_t ld,
+                                                                        int rows_cap) {
+    using L = TmjSmem<S, SUB>;
+    constexpr int RB = SUB / 8;
+    constexpr int STAGE = L::stage_bytes;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* ring = smem_raw;
+    double* rowp = reinterpret_cast<double*>(smem_raw + L::ring_bytes);
+    double* colp = rowp + L::panel_doubles;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L::ring_bytes + L::panels_bytes);
+    int4* tinfo = reinterpret_cast<int4*>(smem_raw + L::ring_bytes + L::panels_bytes + L::bar_count * 8);  // [2]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t bar0 = smem_u32(bars);
+    const uint32_t bar_full = bar0, bar_free = bar0 + 8 * S, bar_rfull = bar0 + 16 * S, bar_rempty = bar_rfull + 8,
+                   bar_cfull = bar_rfull + 16, bar_cempty = bar_rfull + 24;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_free + 8 * s, TM_CONSUMERS);
+        }
+        mbar_init(bar_rfull, 1);
+        mbar_init(bar_rempty, TM_CONSUMERS);
+        mbar_init(bar_cfull, 1);
+        mbar_init(bar_cempty, TM_CONSUMERS);
+        mbar_fence_init();
+    }
+    for (int idx = tid; idx < 2 * L::panel_doubles / 2; idx += TMJ_THREADS)
+        reinterpret_cast<double2*>(rowp)[idx] = make_double2(0.0, 0.0);  // rank padding rows stay zero
+    fence_proxy_async();
+    __syncthreads();
+    // this CTA's tiles: chunks b, b + grid, ... of `chunk` consecutive tiles of the rank's row-major triangle
+    const long long nchunks = (tiles + chunk - 1) / chunk;
+
+    if (warp == TM_CONSUMERS) {  // -------------------------------------------------- producer ----
+        if (lane != 0) return;
+        tmap_prefetch(&tmSrc);
+        const uint64_t pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
+        const uint32_t ring_u32 = smem_u32(ring), rp_u32 = smem_u32(rowp), cp_u32 = smem_u32(colp);
+        long long sub = 0, lt = 0, rgen = 0;
+        int st = 0, loaded_tr = -1;
+        uint32_t free_phase = 0;
+        for (long long c = blockIdx.x; c < nchunks; c += gridDim.x) {
+            const long long t0 = c * chunk, t1 = (t0 + chunk < tiles) ? t0 + chunk : tiles;
+            for (long long t = t0; t < t1; t++, lt++) {
+                int tr, tc;
+                shard_tile(t, nt, sh, tr, tc);
+                // is this the last tile that uses the row panel of strip tr?  (look one tile ahead in MY sequence)
+                long long tn = t + 1;
+                if (tn >= t1) tn = (c + gridDim.x < nchunks) ? (c + gridDim.x) * chunk : -1;
+                int ntr = -1, ntc = 0;
+                if (tn >= 0) shard_tile(tn, nt, sh, ntr, ntc);
+                const int i0 = tr * TM_T, j0 = tc * TM_T;
+                const int lrow0 = (int)shard_lrow(sh, i0);
+                const int ilen = min(TM_T, (int)lda - i0), jlen = min(TM_T, (int)lda - j0);
+                const bool new_row = tr != loaded_tr;
+                if (new_row) {
+                    if (rgen >= 1) mbar_wait(bar_rempty, (uint32_t)((rgen - 1) & 1));  // consumers left the old strip
+                    mbar_expect_tx(bar_rfull, (uint32_t)(r * ilen * 8));
+                    for (int k = 0; k < r; k++)
+                        bulk_g2s_hint(rp_u32 + 8 * TM_PITCH * k, A + (size_t)k * lda + i0, (uint32_t)ilen * 8, bar_rfull, pol_keep);
+                    loaded_tr = tr;
+                    rgen++;
+                }
+                if (lt >= 1) mbar_wait(bar_cempty, (uint32_t)((lt - 1) & 1));  // previous tile's fragments are in registers
+                tinfo[lt & 1] = make_int4(j0, lrow0, (new_row ? 1 : 0) | (ntr != tr ? 2 : 0), 0);
+                mbar_expect_tx(bar_cfull, (uint32_t)(r * jlen * 8));
+                for (int k = 0; k < r; k++)
+                    bulk_g2s_hint(cp_u32 + 8 * TM_PITCH * k, A + (size_t)k * lda + j0, (uint32_t)jlen * 8, bar_cfull, pol_keep);
+#pragma unroll 1
+                for (int s = 0; s < TM_T / SUB; s++) {
+                    if (sub >= S) {
+                        mbar_wait(bar_free + 8 * st, (free_phase >> st) & 1u);
+                        free_phase ^= 1u << st;
+                    }
+                    mbar_expect_tx(bar_full + 8 * st, STAGE);
+                    tma_load_2d(ring_u32 + st * STAGE, &tmSrc, j0, lrow0 + SUB * s, bar_full + 8 * st, pol_stream);
+                    st = st + 1 == S ? 0 : st + 1;
+                    sub++;
+                }
+            }
+        }
+        return;
+    }
+    // ---------------------------------------------------------------------------- consumers ----
+    const int g = lane >> 2, t = lane & 3, odd = g & 1;
+    const uint32_t offA = (uint32_t)(g * 1024 + (TM_BOXC * warp + 8 * odd + 2 * t) * 8);
+    const uint32_t offB = (uint32_t)(g * 1024 + (TM_BOXC * warp + 8 * (odd ^ 1) + 2 * t) * 8);
+    const int nks = (r + 3) / 4;
+    long long my_tiles = 0;
+    for (long long c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        const long long t0 = c * chunk;
+        my_tiles += ((t0 + chunk < tiles) ? t0 + chunk : tiles) - t0;
+    }
+    int st = 0;
+    uint32_t full_phase = 0;
+    long long rgen = 0;
+    const double* rp = rowp + g;
+    for (long long lt = 0; lt < my_tiles; lt++) {
+        mbar_wait(bar_cfull, (uint32_t)(lt & 1));
+        const int4 ti = tinfo[lt & 1];
+        double nb[TMJ_KS][2];
+        {
+            const double* cp = colp + TM_BOXC * warp + g;
+#pragma unroll
+            for (int ks = 0; ks < TMJ_KS; ks++)
+#pragma unroll
+                for (int cb = 0; cb < 2; cb++) nb[ks][cb] = ks < nks ? -cp[TM_PITCH * (4 * ks + t) + 8 * cb] : 0.0;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_cempty);
+        if (ti.z & 1) {  // new strip: its row panel
+            mbar_wait(bar_rfull, (uint32_t)(rgen & 1));
+            rgen++;
+        }
+#pragma unroll 1
+        for (int s = 0; s < TM_T / SUB; s++) {
+            mbar_wait(bar_full + 8 * st, (full_phase >> st) & 1u);
+            full_phase ^= 1u << st;
+            unsigned char* stage = ring + st * STAGE;
+            double2 acc[RB][2];
+#pragma unroll
+            for (int rb = 0; rb < RB; rb++) {
+                const double2 va = *reinterpret_cast<const double2*>(stage + rb * 8192 + offA);
+                const double2 vb = *reinterpret_cast<const double2*>(stage + rb * 8192 + offB);
+                acc[rb][0] = odd ? vb : va;
+                acc[rb][1] = odd ? va : vb;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_free + 8 * st);  // read into registers: the stage can be refilled
+            st = st + 1 == S ? 0 : st + 1;
+            double a0[RB], a1[RB];
+#pragma unroll
+            for (int rb = 0; rb < RB; rb++) a0[rb] = rp[TM_PITCH * t + SUB * s + 8 * rb];
+#pragma unroll
+            for (int ks = 0; ks < TMJ_KS; ks += 2) {
+                if (ks < nks) {
+                    if (ks + 1 < nks) {
+#pragma unroll
+                        for (int rb = 0; rb < RB; rb++) a1[rb] = rp[TM_PITCH * (4 * (ks + 1) + t) + SUB * s + 8 * rb];
+                    }
+#pragma unroll
+                    for (int rb = 0; rb < RB; rb++) {
+                        dmma884(acc[rb][0].x, acc[rb][0].y, a0[rb], nb[ks][0]);
+                        dmma884(acc[rb][1].x, acc[rb][1].y, a0[rb], nb[ks][1]);
+                    }
+                    if (ks + 1 < nks) {
+                        if (ks + 2 < nks) {
+#pragma unroll
+                            for (int rb = 0; rb < RB; rb++) a0[rb] = rp[TM_PITCH * (4 * (ks + 2) + t) + SUB * s + 8 * rb];
+                        }
+#pragma unroll
+                        for (int rb = 0; rb < RB; rb++) {
+                            dmma884(acc[rb][0].x, acc[rb][0].y, a1[rb], nb[ks + 1][0]);
+                            dmma884(acc[rb][1].x, acc[rb][1].y, a1[rb], nb[ks + 1][1]);
+                        }
+                    }
+                }
+            }
+            const int col0 = ti.x + TM_BOXC * warp + 2 * t;
+            double* prow = Pdst + (size_t)(ti.y + SUB * s + g) * ld + col0;
+#pragma unroll
+            for (int rb = 0; rb < RB; rb++) {
+                if (ti.y + SUB * s + 8 * rb + g < rows_cap) {
+                    if (col0 < (int)ld) __stcs(reinterpret_cast<double2*>(prow + (size_t)8 * rb * ld), acc[rb][0]);
+                    if (col0 + 8 < (int)ld) __stcs(reinterpret_cast<double2*>(prow + (size_t)8 * rb * ld + 8), acc[rb][1]);
+                }
+            }
+        }
+        if (ti.z & 2) {  // last tile of this strip in my sequence: the row panel may be replaced
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_rempty);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------
@@ -642,6 +846,33 @@ int launch_cov_update_tma(const void* src_map, const void* dst_map, int n, const
     }
 #undef TM_CASE
     return CSLAM_ERR_BAD_ARG;
+}
+
+// Joint update P -= sum_{k < r} A[k] A[k]^T, r <= 64, in place on the array behind src_map (dense-row tensor map).
+int launch_cov_update_tma_joint(const void* src_map, int n, const double* A, size_t lda, int r, Shard sh, int num_sms,
+                                double* P, size_t ld, int rows_cap, cudaStream_t stream) {
+    CSLAM_REQUIRE(r >= 1 && r <= 4 * TMJ_KS, CSLAM_ERR_BAD_ARG, "joint TMA pass: rank out of range (1..64)");
+    CSLAM_REQUIRE(g_tma_dense && g_tma_sub == 32, CSLAM_ERR_UNSUPPORTED, "joint TMA pass needs the dense 32-row tensor map");
+    CUtensorMap tm;
+    memcpy(&tm, src_map, sizeof(tm));
+    const int nt = (n + TM_T - 1) / TM_T;
+    const long long tiles = shard_tile_count(nt, sh);
+    if (tiles == 0) return CSLAM_OK;
+    const unsigned grid = (unsigned)std::min<long long>(num_sms, tiles);
+    static const int env_chunk = getenv("CSLAM_TMA_JOINT_CHUNK") ? atoi(getenv("CSLAM_TMA_JOINT_CHUNK")) : 0;
+    const int chunk = env_chunk > 0 ? env_chunk : (int)std::max<long long>(1, std::min<long long>(8, tiles / ((long long)grid * 12)));
+    using L = TmjSmem<2, 32>;
+    static bool attr[64] = {};
+    int dev = 0;
+    CSLAM_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr[dev]) {
+        CSLAM_CUDA(cudaFuncSetAttribute(k_cov_update_tma_joint<2, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total));
+        if (dev >= 0 && dev < 64) attr[dev] = true;
+    }
+    count_launch();
+    k_cov_update_tma_joint<2, 32><<<grid, TMJ_THREADS, L::total, stream>>>(tm, A, lda, r, nt, tiles, chunk, sh, P, ld, rows_cap);
+    CSLAM_CUDA(cudaGetLastError());
+    return CSLAM_OK;
 }
 
 }  // namespace cslam

@@ -1257,6 +1257,17 @@ static int create_common(cslam_ekf_t** out, int capacity_landmarks, int device, 
             if (make_cov_tensor_map(L.map[b], L.Pbuf[b], h->ld, (size_t)h->local_rows_cap) != CSLAM_OK)
                 return fail(CSLAM_ERR_CUDA);
         if (!L.pingpong) memcpy(L.map[1], L.map[0], sizeof(L.map[0]));
+        if (world > 1) {  // snapshot buffers + flags of the peer-memory column exchange (mapped by cslam_ekf_ipc_*)
+            const size_t xb = (size_t)2 * 2 * kSeqGroupLazyMax * h->lda * sizeof(double);
+            TRY(cudaMalloc(&L.xbuf, xb));
+            TRY(cudaMemsetAsync(L.xbuf, 0, xb, h->stream));
+            TRY(cudaMalloc(&L.sig, 8 * sizeof(unsigned long long)));
+            TRY(cudaMemsetAsync(L.sig, 0, 8 * sizeof(unsigned long long), h->stream));
+            TRY(cudaMalloc(&L.push_ticket, sizeof(unsigned)));
+            TRY(cudaMemsetAsync(L.push_ticket, 0, sizeof(unsigned), h->stream));
+            L.peer_xbuf[rank] = L.xbuf;
+            L.peer_sig[rank] = L.sig;
+        }
     }
     if (world > 1) {
         const NcclApi* api = nccl_api();
@@ -1306,6 +1317,15 @@ int cslam_ekf_destroy(cslam_ekf_t* h) {
     }
     if (h->lz.ev_chain) cudaEventDestroy(h->lz.ev_chain);
     if (h->lz.ev_pass) cudaEventDestroy(h->lz.ev_pass);
+    if (h->lz.peers_ready)
+        for (int q = 0; q < h->sh.world; q++)
+            if (q != h->sh.rank) {
+                cudaIpcCloseMemHandle(h->lz.peer_xbuf[q]);
+                cudaIpcCloseMemHandle(h->lz.peer_sig[q]);
+            }
+    cudaFree(h->lz.xbuf);
+    cudaFree(h->lz.sig);
+    cudaFree(h->lz.push_ticket);
     cudaFree(h->lz.Pbuf[1]);
     cudaFree(h->trace_dev);
     cudaFree(h->acc_dev);
@@ -1336,6 +1356,36 @@ int cslam_ekf_set_stream(cslam_ekf_t* h, void* cuda_stream) {
     if (h->own_stream) cudaStreamDestroy(h->stream);
     h->stream = static_cast<cudaStream_t>(cuda_stream);
     h->own_stream = false;
+    return CSLAM_OK;
+}
+
+// Peer-memory column exchange of sharded handles: 2 cudaIpcMemHandle_t (snapshot buffers, flags) per rank.
+int cslam_ekf_ipc_export(cslam_ekf_t* h, void* out128) {
+    CSLAM_NVTX_RANGE();
+    if (int rc = check_handle(h)) return rc;
+    CSLAM_REQUIRE(out128 != nullptr, CSLAM_ERR_BAD_ARG, "out is null");
+    CSLAM_REQUIRE(h->sh.world > 1 && h->lz.on && h->lz.xbuf, CSLAM_ERR_UNSUPPORTED, "not a sharded lazy handle");
+    cudaIpcMemHandle_t* hs = static_cast<cudaIpcMemHandle_t*>(out128);
+    CSLAM_CUDA(cudaIpcGetMemHandle(&hs[0], h->lz.xbuf));
+    CSLAM_CUDA(cudaIpcGetMemHandle(&hs[1], h->lz.sig));
+    return CSLAM_OK;
+}
+// all: world x 128 bytes in rank order.  Without this call a sharded handle exchanges its columns through NCCL.
+int cslam_ekf_ipc_import(cslam_ekf_t* h, const void* all, int world) {
+    CSLAM_NVTX_RANGE();
+    if (int rc = check_handle(h)) return rc;
+    CSLAM_REQUIRE(all != nullptr && world == h->sh.world && world <= 8, CSLAM_ERR_BAD_ARG, "bad argument");
+    CSLAM_REQUIRE(h->lz.on && h->lz.xbuf, CSLAM_ERR_UNSUPPORTED, "not a sharded lazy handle");
+    const cudaIpcMemHandle_t* hs = static_cast<const cudaIpcMemHandle_t*>(all);
+    for (int q = 0; q < world; q++) {
+        if (q == h->sh.rank) continue;
+        void *px = nullptr, *ps = nullptr;
+        CSLAM_CUDA(cudaIpcOpenMemHandle(&px, hs[2 * q], cudaIpcMemLazyEnablePeerAccess));
+        CSLAM_CUDA(cudaIpcOpenMemHandle(&ps, hs[2 * q + 1], cudaIpcMemLazyEnablePeerAccess));
+        h->lz.peer_xbuf[q] = static_cast<double*>(px);
+        h->lz.peer_sig[q] = static_cast<unsigned long long*>(ps);
+    }
+    h->lz.peers_ready = true;
     return CSLAM_OK;
 }
 
@@ -1607,13 +1657,14 @@ int cslam_ekf_update(cslam_ekf_t* h, const double* Z, const int32_t* idf, int m,
             cl.c[2 * k] = 3 + 2 * (idf[k] - 1);
             cl.c[2 * k + 1] = cl.c[2 * k] + 1;
         }
+        const double* snap = h->colbuf;
         if (h->lz.on) {
-            if (int rc = lazy_snapshot(h, cl, nullptr)) return rc;
+            if (int rc = lazy_snapshot(h, cl, nullptr, &snap)) return rc;
         } else {
             if (int rc = exchange_columns(h, cl)) return rc;
         }
         count_launch();
-        k_batch_pht<true><<<dim3((n + 127) / 128, m), 128, 0, h->stream>>>(h->P, h->R3, h->colbuf, h->ld, n, m,
+        k_batch_pht<true><<<dim3((n + 127) / 128, m), 128, 0, h->stream>>>(h->P, h->R3, snap, h->ld, n, m,
                                                                             h->small, h->PHT, h->lda);
     } else {
         count_launch();

