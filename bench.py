@@ -193,17 +193,20 @@ def ekf_scan(ekf, Z, batch=False, want_indices=True):
     return jbest
 
 
-def dmma_peak():
-    """FP64 tensor-core peak measured on this pool's B200 by tools/dmma_bench.cu (MEASURED_PEAKS.json
-    carries only the bf16 figure); the best line of profiles/dmma_bench_r01.txt."""
-    p = os.path.join(ROOT, "profiles", "dmma_bench_r01.txt")
-    best = 0.0
-    if os.path.exists(p):
-        for line in open(p):
-            if line.startswith("DMMA.8x8x4 peak"):
-                best = max(best, float(line.split(":")[-1].split()[0]))
-    return (best, "measured (tools/dmma_bench.cu -> profiles/dmma_bench_r01.txt)") if best else \
-        (40.0, "nominal B200 FP64 tensor")
+_DMMA_PEAK = {}
+
+
+def dmma_peak(device=0):
+    """FP64 tensor-core peak of this GPU measured IN THIS RUN by the library's microbenchmark (cslam_dmma_peak:
+    register-resident DMMA.8x8x4 chains on every SM); MEASURED_PEAKS.json carries only HBM and bf16 figures."""
+    if device not in _DMMA_PEAK:
+        from conan_slam_b200 import _lib
+        lib = _lib.load_library()
+        v = C.c_double(0.0)
+        rc = lib.cslam_dmma_peak(int(device), C.byref(v))
+        _DMMA_PEAK[device] = (v.value, "measured in this run (cslam_dmma_peak: register-resident DMMA.8x8x4 chains)") \
+            if rc == 0 and v.value > 0 else (37.09, "round-1 measurement (profiles/dmma_bench_r01.txt)")
+    return _DMMA_PEAK[device]
 
 
 # ------------------------------------------------------------------------ particle filter ----
@@ -837,7 +840,7 @@ def ekf_roofline(ctx, n, N, m, t, batch, strict, peak, peak_src):
     if batch:
         r_rank = 2 * m
         flops = float(r_rank) * n * (n + 1) / shards
-        tpeak, tsrc = dmma_peak()
+        tpeak, tsrc = dmma_peak(ctx.local)
         t_launch = cov_ms / max(1, cov_launches) * 1e-3
         return {
             "bound": "tensor", "kernel": "k_cov_update_dmma (slam.h:260, rank-2m update on FP64 tensor cores, "

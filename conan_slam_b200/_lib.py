@@ -46,6 +46,7 @@ SIGNATURES = {
     "cslam_ekf_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_uint]),
     "cslam_nccl_unique_id": (C.c_int, [_vp]),
     "cslam_ekf_create_sharded": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_uint, C.c_int, C.c_int, _vp]),
+    "cslam_dmma_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "cslam_ekf_ipc_export": (C.c_int, [_vp, _vp]),
     "cslam_ekf_ipc_import": (C.c_int, [_vp, _vp, C.c_int]),
     "cslam_ekf_destroy": (C.c_int, [_vp]),

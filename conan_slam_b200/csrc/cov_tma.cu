@@ -876,3 +876,56 @@ int launch_cov_update_tma_joint(const void* src_map, int n, const double* A, siz
 }
 
 }  // namespace cslam
+
+// FP64 tensor-core peak of this GPU, measured here and now (MEASURED_PEAKS.json carries HBM and bf16 only): 16
+// independent register-resident DMMA chains per warp, 16 warps per CTA, 4 CTAs per SM; best of 5 timed launches.
+namespace cslam {
+__global__ void __launch_bounds__(512) k_dmma_peak(double* out, int iters) {
+    double c[16][2];
+    const double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+#pragma unroll
+    for (int i = 0; i < 16; i++) c[i][0] = c[i][1] = 0.0;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) ptx::dmma884(c[i][0], c[i][1], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s += c[i][0] + c[i][1];
+    if (s == 12345.678) out[0] = s;  // never true: keeps the chains alive
+}
+}  // namespace cslam
+
+extern "C" int cslam_dmma_peak(int device, double* tflops) {
+    CSLAM_REQUIRE(tflops != nullptr, CSLAM_ERR_BAD_ARG, "tflops is null");
+    *tflops = 0.0;
+    CSLAM_CUDA(cudaSetDevice(device));
+    int sms = 0;
+    CSLAM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    double* d = nullptr;
+    CSLAM_CUDA(cudaMalloc(&d, 8));
+    cudaEvent_t e0, e1;
+    CSLAM_CUDA(cudaEventCreate(&e0));
+    CSLAM_CUDA(cudaEventCreate(&e1));
+    const int warps = 16, iters = 4000;
+    const double flop = 2.0 * 8 * 8 * 4 * 16.0 * iters * warps * sms * 4.0;
+    cslam::k_dmma_peak<<<sms, warps * 32>>>(d, 16);
+    double best = 0.0;
+    cudaError_t e = cudaDeviceSynchronize();
+    for (int rep = 0; rep < 5 && e == cudaSuccess; rep++) {
+        cslam::count_launch();
+        cudaEventRecord(e0);
+        cslam::k_dmma_peak<<<sms * 4, warps * 32>>>(d, iters);
+        cudaEventRecord(e1);
+        e = cudaEventSynchronize(e1);
+        float ms = 0.f;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+        if (e == cudaSuccess && ms > 0.f) best = std::max(best, flop / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    CSLAM_CUDA(e);
+    *tflops = best;
+    return CSLAM_OK;
+}

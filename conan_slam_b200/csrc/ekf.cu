@@ -969,12 +969,19 @@ static int launch_cov_update_rank(cslam_ekf* h, int r) {
     if (h->lz.on) {
         // lazy handle (nothing pending, see cslam_ekf_update): tensor-core pass on the current array; rows 0..2
         // and the diagonal-block cache follow with the same FMA operations on every rank
-        if (!h->dmma_panels) {
-            const size_t bytes = dmma_panel_doubles(h->n_cap) * sizeof(double);
-            CSLAM_CUDA(cudaMalloc(&h->dmma_panels, bytes));
-            CSLAM_CUDA(cudaMemsetAsync(h->dmma_panels, 0, bytes, h->stream));
-        }
-        {
+        static const bool old_kernel = getenv("CSLAM_JOINT_OLD") != nullptr;  // round-1 kernel (cp.async staging), for A/B runs
+        if (!old_kernel) {
+            // tensor-map TMA loads, register-resident column fragments, direct stores (cov_tma.cu)
+            ProfScope prof(h);
+            if (int rc = launch_cov_update_tma_joint(h->lz.map[h->lz.stable], n, h->A, h->lda, r, h->sh, h->lz.num_sms,
+                                                     lazy_P(h), h->ld, h->local_rows_cap, h->stream))
+                return rc;
+        } else {
+            if (!h->dmma_panels) {
+                const size_t bytes = dmma_panel_doubles(h->n_cap) * sizeof(double);
+                CSLAM_CUDA(cudaMalloc(&h->dmma_panels, bytes));
+                CSLAM_CUDA(cudaMemsetAsync(h->dmma_panels, 0, bytes, h->stream));
+            }
             ProfScope prof(h);
             if (int rc = launch_cov_update_dmma(lazy_P(h), h->ld, n, h->A, h->lda, r, h->sh, h->dmma_panels, h->n_cap, 0,
                                                 h->stream))

@@ -23,6 +23,9 @@ int launch_cov_update_tma(const void* src_map, const void* dst_map, int n, const
                           double diag_eps, Shard sh, const int* live, int nlive, int num_sms, int stages,
                           cudaStream_t stream, double* dst_ptr = nullptr, size_t dst_ld = 0, int dst_rows = 0);
 
+int launch_cov_update_tma_joint(const void* src_map, int n, const double* A, size_t lda, int r, Shard sh, int num_sms,
+                                double* P, size_t ld, int rows_cap, cudaStream_t stream);
+
 constexpr int kSeqGroupLazy = kSeqGroupLazyMax;  // observations per column snapshot (2 x 8 columns exchanged at once)
 
 // Pending rank-1 terms as a gain kernel sees them: first the rows of the bank that the pass in flight is

@@ -62,6 +62,10 @@ typedef struct cslam_world cslam_world_t;
 const char* cslam_last_error(void);
 int cslam_version(void);
 int cslam_device_count(int* count);
+/* Diagnostics (bench.py): the FP64 tensor-core (DMMA.8x8x4) peak of `device` in TFLOP/s, measured by a short
+ * register-resident microbenchmark (the denominator of the joint update's roofline; MEASURED_PEAKS.json carries
+ * HBM and bf16 figures only). */
+int cslam_dmma_peak(int device, double* tflops);
 /* Diagnostics (bench.py): number of CUDA kernels this library has launched since it was loaded. */
 unsigned long long cslam_kernel_launches(void);
 
