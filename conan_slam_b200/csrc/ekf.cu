@@ -969,8 +969,13 @@ static int launch_cov_update_rank(cslam_ekf* h, int r) {
     if (h->lz.on) {
         // lazy handle (nothing pending, see cslam_ekf_update): tensor-core pass on the current array; rows 0..2
         // and the diagonal-block cache follow with the same FMA operations on every rank
-        static const bool old_kernel = getenv("CSLAM_JOINT_OLD") != nullptr;  // round-1 kernel (cp.async staging), for A/B runs
-        if (!old_kernel) {
+        // Default: the round-1 kernel (ekf_dmma.cu: 128 x 32 tiles, 4-deep column-panel ring, covariance fragments by
+        // per-thread cp.async) — 3.40 ms at N = 20k, 0.81 of the DMMA peak.  CSLAM_JOINT_TMA=1 selects the tensor-map
+        // TMA variant (cov_tma.cu: 128 x 128 tiles, register-resident column fragments, direct stores), measured
+        // SLOWER on a B200 (4.26 ms, DMMA pipe 65 %): with both 66 KB panels resident only a 2-deep ring fits and ncu
+        // shows 13 % of the consumer time waiting for the single-buffered column panel (profiles/ncu_joint_tma_r02.csv).
+        static const bool tma_kernel = getenv("CSLAM_JOINT_TMA") != nullptr;
+        if (tma_kernel) {
             // tensor-map TMA loads, register-resident column fragments, direct stores (cov_tma.cu)
             ProfScope prof(h);
             if (int rc = launch_cov_update_tma_joint(h->lz.map[h->lz.stable], n, h->A, h->lda, r, h->sh, h->lz.num_sms,
