@@ -220,3 +220,22 @@ def test_checkpoint_roundtrip(tmp_path):
     other = cs.PF(num_particles=512, capacity_landmarks=9)
     with pytest.raises(Exception):
         other.load(path)  # particle count mismatch
+
+
+def test_resample_five_level_scan_hierarchy():
+    """More than 32^4 = 1,048,576 particles: the canonical scan needs a fifth level (round-1 advice: the host loop
+    read one past the end of its level table there).  Indices and neff against the oracle's stratifiedResample."""
+    import conan_slam_b200 as cs
+    npart = (1 << 20) + 96
+    rng = np.random.default_rng(77)
+    g = cs.PF(num_particles=npart, capacity_landmarks=1, flags=oracle_py.FLAG_INTENDED)
+    w = rng.uniform(0.0, 1.0, size=npart) ** 3 + 1e-12
+    u = rng.normal(size=npart) * 0.3
+    o = oracle_py.OraclePF(npart, oracle_py.FLAG_INTENDED)
+    g.weights = w
+    o.weights = w
+    kg, neff_g, did = g.resampleParticles(npart + 1, u, True)
+    ko, neff_o, did_o = o.resampleParticles(npart + 1, u, True)
+    assert did and did_o and np.array_equal(kg, ko)
+    assert neff_g == pytest.approx(neff_o, rel=1e-12)
+    g.close()
