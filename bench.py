@@ -602,11 +602,12 @@ def run_reference(args):
         "extrapolation": ("the value is EXTRAPOLATED: the reference's dense O(n^2)-per-update and O(N n^2)-per-scan "
                           "code is timed on a bounded smaller map and scaled by its own complexity (see "
                           "cpu_baseline.sample); a full-size step would take hours"),
-        "config": {"workload": f"EKF-SLAM {N} landmarks (state dim {n}), range-bearing observations, sequential "
-                               f"update: gate + gain + covariance, 4 observations per scan - the reference's dense "
-                               f"CPU algorithm", "landmarks": N, "state_dim": n, "obs_per_step": 4,
-                   "mode": "reference arithmetic (FP32)" if use_ref else "INTENDED (SURVEY Appendix A)",
-                   "l2": "n/a (CPU)", "parallelism": "single host thread (the reference has none)"},
+        # the SAME config object as our arm prints for this launch (the driver compares the two lines); what the
+        # reference arm actually ran is described in `reference_arm` and `cpu_baseline.sample`
+        "config": ekf_config(N, 4, args.gpus, args.gpus > 1 and args.multi == "sharded"),
+        "reference_arm": {"implementation": "the reference's own EKF.cpp / slam.h (oracle/_ref), dense CPU algorithm" if use_ref
+                          else "oracle port of the reference's dense algorithm",
+                          "arithmetic": "FP32 (as the reference)" if use_ref else "FP64", "host_threads": 1 if use_ref else threads},
         "cpu_baseline": base,
         "e2e": {"value": val, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -874,6 +875,28 @@ def ekf_roofline(ctx, n, N, m, t, batch, strict, peak, peak_src):
     }
 
 
+def ekf_config(N, m, world, sharded, batch=False, strict=False):
+    """The `config` object of an EKF line — shared by our arm and the reference arm (the driver compares them)."""
+    n = 3 + 2 * N
+    upd_kind = (f"batched JOINT update of {m} observations per scan (rank {2 * m}): gate + stacked gain + "
+                f"tensor-core covariance update" if batch else
+                f"sequential update: gate + gain + covariance, {m} observation{'s' if m > 1 else ''} per scan" +
+                (", one covariance pass per update (flush after every scan)" if strict else ""))
+    return {
+        "workload": (f"EKF-SLAM {N} landmarks (state dim {n}, FP64 P {8.0 * n * n / 1e9:.2f} GB), "
+                     f"range-bearing observations, {upd_kind}" +
+                     (f", covariance row-sharded over {world} GPUs" if sharded else
+                      (f", {world} independent filter replicas" if world > 1 else ""))),
+        "landmarks": N, "state_dim": n, "obs_per_step": m, "mode": "INTENDED (SURVEY Appendix A)",
+        "l2": f"inputs larger than L2 ({4.0 * n * n / 1e9 / (world if sharded else 1):.1f} GB of upper "
+              f"triangle streamed per GPU per covariance pass)",
+        "parallelism": ("row-sharded covariance (block-cyclic 128-row tiles), observed columns exchanged over NVLink "
+                        "peer memory inside the snapshot kernel, gains / gating overlapped with the covariance pass"
+                        if sharded else
+                        ("replicas only (one independent filter per GPU)" if world > 1 else "single GPU")),
+    }
+
+
 def ekf_result(ctx, eb, m, steps, warmup, batch=False, strict=False, with_e2e=True, with_parity=True):
     """One EKF workload on an existing EkfBench: parity check, device-timed loop, end-to-end loop -> result dict."""
     N, n = eb.N, eb.n
@@ -884,28 +907,12 @@ def ekf_result(ctx, eb, m, steps, warmup, batch=False, strict=False, with_e2e=Tr
         return None
     peak, peak_src = measured_peaks()
     value = t["updates"] / (t["ms"] * 1e-3)
-    r_rank = 2 * m
-    upd_kind = (f"batched JOINT update of {m} observations per scan (rank {r_rank}): gate + stacked gain + "
-                f"tensor-core covariance update" if batch else
-                f"sequential update: gate + gain + covariance, {m} observation{'s' if m > 1 else ''} per scan" +
-                (", one covariance pass per update (flush after every scan)" if strict else ""))
     sharded, world = ctx.sharded, ctx.world
     out = {
         "metric": "EKF updates/sec", "value": value, "unit": "updates/s", "n_gpus": world, "steps": steps,
         "warmup": warmup, "ms_per_step": t["ms"] / steps, "higher_is_better": True,
         "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {
-            "workload": (f"EKF-SLAM {N} landmarks (state dim {n}, FP64 P {8.0 * n * n / 1e9:.2f} GB), "
-                         f"range-bearing observations, {upd_kind}" +
-                         (f", covariance row-sharded over {world} GPUs" if sharded else
-                          (f", {world} independent filter replicas" if world > 1 else ""))),
-            "landmarks": N, "state_dim": n, "obs_per_step": m, "mode": "INTENDED (SURVEY Appendix A)",
-            "l2": f"inputs larger than L2 ({4.0 * n * n / 1e9 / (world if sharded else 1):.1f} GB of upper "
-                  f"triangle streamed per GPU per covariance pass)",
-            "parallelism": ("row-sharded covariance (block-cyclic 128-row tiles), NCCL all-reduce of the observed "
-                            "columns per scan, gains / gating overlapped with the covariance pass" if sharded else
-                            ("replicas only (one independent filter per GPU)" if world > 1 else "single GPU")),
-        },
+        "config": ekf_config(N, m, world, sharded, batch, strict),
         "clocks": t["clocks"],
         "gpu_launches": t["launches"],
         "covariance_passes": t["passes"],
