@@ -487,6 +487,7 @@ def pf_case(args, steps, warmup, spread="balanced", with_cpu=True, quiet=False):
     keep, neff_last, _ = cycle(want_keep=True)
     remote_frac = float(np.mean((keep // Pl) != rank))
     distinct = int(np.unique(keep).shape[0])
+    distinct_remote = int(np.unique(keep[(keep // Pl) != rank]).shape[0])  # what actually crosses NVLink (duplicates coalesce)
     if not quiet:
         log(f"[bench r{rank}] PF {spread}: neff={neff_last:.1f} of {P}, remote survivors {100 * remote_frac:.1f} %, "
             f"{distinct} distinct sources for {Pl} slots")
@@ -495,10 +496,11 @@ def pf_case(args, steps, warmup, spread="balanced", with_cpu=True, quiet=False):
         t = torch.tensor([ms, e2e_ms], device=f"cuda:{local}", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_ms = float(t[0]), float(t[1])
-        c = torch.tensor([launches, remote_frac], device=f"cuda:{local}", dtype=torch.float64)
+        c = torch.tensor([launches, remote_frac, distinct_remote], device=f"cuda:{local}", dtype=torch.float64)
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
         launches = int(c[0])
         remote_all = float(c[1]) / world
+        distinct_remote = int(c[2])
     pf.close()
     del xi, u, wmod
     torch.cuda.empty_cache()
@@ -533,7 +535,8 @@ def pf_case(args, steps, warmup, spread="balanced", with_cpu=True, quiet=False):
                      "whole_step_frac": bytes_step * Pl / (ms / steps * 1e-3) / 1e9 / peak},
         "valid": ok, "neff": neff_last, "remote_survivor_frac_rank0": remote_frac,
         "remote_survivor_frac_all_ranks": remote_all,
-        "nvlink_bytes_per_step_per_gpu": remote_all * Pl * bytes_particle / 2,
+        "remote_slots_per_step_all_gpus": remote_all * P,
+        "nvlink_bytes_per_step_all_gpus": distinct_remote * bytes_particle / 2,  # distinct remote sources x bytes read
         "distinct_sources_rank0": distinct,
     }
     if with_cpu and world == 1:
