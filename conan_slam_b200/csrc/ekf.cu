@@ -1254,6 +1254,11 @@ static int create_common(cslam_ekf_t** out, int capacity_landmarks, int device, 
         TRY(cudaEventCreateWithFlags(&L.ev_chain, cudaEventDisableTiming));
         TRY(cudaEventCreateWithFlags(&L.ev_pass, cudaEventDisableTiming));
         if (const char* e = getenv("CSLAM_TMA_STAGES")) L.stages = atoi(e);
+        if (const char* e = getenv("CSLAM_GAIN_FUSED")) L.fused_gains = atoi(e) != 0;
+        TRY(cudaMalloc(&L.R3alt, 3 * h->ld * sizeof(double)));
+        TRY(cudaMemsetAsync(L.R3alt, 0, 3 * h->ld * sizeof(double), h->stream));
+        TRY(cudaMalloc(&L.Dalt, 3 * (size_t)h->dcap * sizeof(double)));
+        TRY(cudaMemsetAsync(L.Dalt, 0, 3 * (size_t)h->dcap * sizeof(double), h->stream));
         // ping-pong pair: the pass of bank k streams array a -> array b while the gains of the following scans
         // read array a, so the chain never waits for a running pass.  Costs a second covariance array; taken
         // when it fits comfortably (CSLAM_PINGPONG=0/1 overrides).
@@ -1339,6 +1344,8 @@ int cslam_ekf_destroy(cslam_ekf_t* h) {
     cudaFree(h->lz.sig);
     cudaFree(h->lz.push_ticket);
     cudaFree(h->lz.Pbuf[1]);
+    cudaFree(h->lz.R3alt);
+    cudaFree(h->lz.Dalt);
     cudaFree(h->trace_dev);
     cudaFree(h->acc_dev);
     if (h->comm) {

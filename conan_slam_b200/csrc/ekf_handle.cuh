@@ -62,6 +62,11 @@ struct LazyState {
     void** d_peer_tab = nullptr;      // device copy: [0..7] xbuf pointers, [8..15] sig pointers
     unsigned long long epoch = 0;     // snapshots taken so far (same on every rank: SPMD)
     unsigned* push_ticket = nullptr;  // device: last-block ticket of the push kernel
+    // twins of R3 / D: the fused group-gain kernel (k_gain_group_lazy) writes the followed panels there while other
+    // blocks still read the old ones; the handle's R3 / D pointers are swapped after the launch
+    double* R3alt = nullptr;
+    double* Dalt = nullptr;
+    bool fused_gains = true;          // CSLAM_GAIN_FUSED=0: one gain kernel per observation + follow (regression tests)
 };
 constexpr int kSeqGroupLazyMax = 8;  // observations per snapshot group (2 columns each)
 

@@ -284,6 +284,245 @@ __global__ void __launch_bounds__(256) k_follow_lazy(double* __restrict__ R3, do
 }
 
 // ------------------------------------------------------------------------------------
+// One launch for a whole group of sequential landmark updates (EKF.cpp:457-479: singleUpdate re-linearises after
+// every observation) + what k_follow_lazy does + the wait for the peers' column pushes.
+//
+// The g updates of a group are sequentially dependent only through a SMALL system: update k needs the 5x5 block
+// of P_true at {0,1,2,f_k,f_k+1} and X there, i.e. the marginal over M = pose + the group's landmarks (3 + 2g <= 19
+// entries).  A row i of P_true restricted to the columns of M evolves under  P(i,:) -= W1_k(i) W1_k(:)^T  with
+// W1_k(i) a function of that row alone and of the small quantities (H_k, G_k, W1_k at the rows of M).  So every
+// block first replays the group on the |M| marginal rows (warp 0: lane a owns marginal row a, lane 0 factorises),
+// keeping H_k, G_k, V_k and W1_k(M) in shared memory, and then every thread takes its own row through the g
+// updates without any further synchronisation.  Each step performs exactly the operations k_gain_lazy /
+// k_follow_lazy perform, in the same order, so the results are bit-identical to the one-kernel-per-observation
+// chain (tests/test_ekf_lazy.py) — the launch count per scan drops from g + 2 to 1.
+// R3 / D are written to their twins (the marginal phase of other blocks still reads the old ones).
+struct ObsGroup {
+    double z[2 * kSeqGroupLazyMax];
+    int idf[kSeqGroupLazyMax];
+    int g;
+};
+
+template <int GM>
+struct GroupSmem {
+    int f[GM];                                // first state index of observation k's landmark, -1 = skipped
+    double Ac[2 * kLazyBank][3 + 2 * GM];      // pending terms (before the group) at the columns of M
+    double W[2 * GM][3 + 2 * GM];              // the group's own panel rows at the rows of M
+    GainSmall G[GM];
+    double Pc[5][5];
+    double X5[5];
+};
+
+template <int GM>
+struct GroupRow {
+    double pose[3];     // P_true(i, 0..2)
+    double col[2 * GM]; // P_true(i, f_k), P_true(i, f_k + 1)
+    double x;
+};
+
+template <int GM>
+__device__ __forceinline__ void group_row_load(GroupRow<GM>& r, int i, int g, const GroupSmem<GM>& sm,
+                                               const double* Xin, const double* __restrict__ R3,
+                                               const double* snap, size_t ld, size_t lda, const PendView& pv) {
+#pragma unroll
+    for (int b = 0; b < 3; b++) r.pose[b] = i <= b ? R3[(size_t)i * ld + b] : R3[(size_t)b * ld + i];
+#pragma unroll
+    for (int c = 0; c < 2 * GM; c++) r.col[c] = (c < 2 * g && sm.f[c >> 1] >= 0) ? __ldcg(snap + (size_t)c * lda + i) : 0.0;
+    r.x = Xin[i];
+    if (i < 3) return;  // rows 0..2 of the snapshot came from the always-current R3
+    const int nterm = pv.n0 + pv.n1;
+    for (int t = 0; t < nterm; t++) {
+        const double ai = pend_row(pv, lda, t)[i];
+        const bool eps = pend_eps(pv, t);
+#pragma unroll
+        for (int c = 0; c < 2 * GM; c++) {
+            if (c < 2 * g) {
+                r.col[c] = r.col[c] - ai * sm.Ac[t][3 + c];
+                if (eps && i == sm.f[c >> 1] + (c & 1) && sm.f[c >> 1] >= 0) r.col[c] += kFltMin;
+            }
+        }
+    }
+}
+// slam.h:257-259 for row i and observation k
+template <int GM>
+__device__ __forceinline__ void group_row_gain(GroupRow<GM>& r, int k, const GroupSmem<GM>& sm, double& w1_0,
+                                               double& w1_1) {
+    if (sm.f[k] < 0) {
+        w1_0 = 0.0;
+        w1_1 = 0.0;
+        return;
+    }
+    const GainSmall& g = sm.G[k];
+    double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+    for (int q = 0; q < GM; q++)
+        if (q == k) {
+            c0 = r.col[2 * q];
+            c1 = r.col[2 * q + 1];
+        }
+    double pht[2];
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+        pht[a] = (((r.pose[0] * g.H[a][0] + r.pose[1] * g.H[a][1]) + r.pose[2] * g.H[a][2]) + c0 * g.H[a][3]) + c1 * g.H[a][4];
+    w1_0 = pht[0] * g.G[0][0] + pht[1] * g.G[1][0];
+    w1_1 = pht[0] * g.G[0][1] + pht[1] * g.G[1][1];
+    const double w_0 = w1_0 * g.G[0][0] + w1_1 * g.G[0][1];
+    const double w_1 = w1_0 * g.G[1][0] + w1_1 * g.G[1][1];
+    r.x = r.x + (w_0 * g.V[0] + w_1 * g.V[1]);
+}
+// slam.h:260 restricted to row i and the columns of M: the two panel rows of observation k, in order
+template <int GM>
+__device__ __forceinline__ void group_row_sub(GroupRow<GM>& r, int k, int g, const GroupSmem<GM>& sm, double w1_0,
+                                              double w1_1) {
+    if (sm.f[k] < 0) return;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const double ai = h == 0 ? w1_0 : w1_1;
+        const double* w = sm.W[2 * k + h];
+#pragma unroll
+        for (int b = 0; b < 3; b++) r.pose[b] = r.pose[b] - ai * w[b];
+#pragma unroll
+        for (int c = 0; c < 2 * GM; c++)
+            if (c < 2 * g) r.col[c] = r.col[c] - ai * w[3 + c];
+    }
+}
+
+template <int GM>
+__global__ void __launch_bounds__(128, (GM > 4 ? 3 : 6)) k_gain_group_lazy(
+    const double* Xin, double* Xout, const double* __restrict__ R3, double* __restrict__ R3out,
+    const double* __restrict__ D, double* __restrict__ Dout, int dcap, int nf, const double* snap, size_t ld, size_t lda,
+    int n, ObsGroup og, double r00, double r10, double r01, double r11, unsigned flags, PendView pv, double* Aout,
+    int* __restrict__ status, const int* __restrict__ idf_dev, const unsigned long long* sig, int world,
+    unsigned long long epoch) {
+    __shared__ GroupSmem<GM> sm;
+    const int g = og.g;
+    const int tid = threadIdx.x;
+    // ---- phase 0: association indices, peers' pushes, pending terms at the columns of M
+    if (tid < g) {
+        const int j = idf_dev != nullptr ? idf_dev[tid] : og.idf[tid];
+        sm.f[tid] = j > 0 ? 3 + 2 * (j - 1) : -1;
+    }
+    if (sig != nullptr && tid >= 32 && tid < 32 + world) {  // warp 1: lane q waits for rank q's flag (bounded, ~4 s)
+        const volatile unsigned long long* s = sig + (tid - 32);
+        const long long t0 = clock64();
+        while (*s < epoch) {
+            if (clock64() - t0 > 8000000000LL) {
+                if (blockIdx.x == 0) atomicAdd(status, 1 << 20);
+                break;
+            }
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    const int d = 3 + 2 * g;
+    const int nterm = pv.n0 + pv.n1;
+    for (int idx = tid; idx < nterm * d; idx += blockDim.x) {
+        const int t = idx / d, b = idx % d;
+        double v = 0.0;
+        if (b < 3) {
+            v = pend_row(pv, lda, t)[b];
+        } else if (sm.f[(b - 3) >> 1] >= 0) {
+            v = pend_row(pv, lda, t)[sm.f[(b - 3) >> 1] + ((b - 3) & 1)];
+        }
+        sm.Ac[t][b] = v;
+    }
+    __syncthreads();
+    // ---- phase 1: the group replayed on the marginal rows (warp 0)
+    if (tid < 32) {
+        const int a = tid;
+        const bool act = a < d && (a < 3 || sm.f[(a - 3) >> 1] >= 0);
+        const int ia = a < 3 ? a : (act ? sm.f[(a - 3) >> 1] + ((a - 3) & 1) : 0);
+        GroupRow<GM> r;
+        if (act) group_row_load<GM>(r, ia, g, sm, Xin, R3, snap, ld, lda, pv);
+        for (int k = 0; k < g; k++) {
+            if (sm.f[k] >= 0) {  // warp-uniform
+                const int slot = a < 3 ? a : (a == 3 + 2 * k ? 3 : (a == 4 + 2 * k ? 4 : -1));
+                if (slot >= 0 && act) {
+                    double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+                    for (int q = 0; q < GM; q++)
+                        if (q == k) {
+                            c0 = r.col[2 * q];
+                            c1 = r.col[2 * q + 1];
+                        }
+                    sm.Pc[slot][0] = r.pose[0];
+                    sm.Pc[slot][1] = r.pose[1];
+                    sm.Pc[slot][2] = r.pose[2];
+                    sm.Pc[slot][3] = c0;
+                    sm.Pc[slot][4] = c1;
+                    sm.X5[slot] = r.x;
+                }
+                __syncwarp();
+                if (a == 0) {
+                    double Pc[5][5], X5[5];
+                    for (int p = 0; p < 5; p++) {
+                        X5[p] = sm.X5[p];
+                        for (int q = 0; q < 5; q++) Pc[p][q] = sm.Pc[p][q];
+                    }
+                    const double R[4] = {r00, r10, r01, r11};
+                    gain_prologue(X5, Pc, 3, og.z[2 * k], og.z[2 * k + 1], R, flags, sm.G[k]);
+                    if (!sm.G[k].ok && blockIdx.x == 0) atomicAdd(status, 1);
+                }
+                __syncwarp();
+            }
+            double w1_0 = 0.0, w1_1 = 0.0;
+            if (act) group_row_gain<GM>(r, k, sm, w1_0, w1_1);
+            if (a < d) {
+                sm.W[2 * k][a] = w1_0;
+                sm.W[2 * k + 1][a] = w1_1;
+            }
+            __syncwarp();
+            if (act) group_row_sub<GM>(r, k, g, sm, w1_0, w1_1);
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    // ---- phase 2: every thread takes its own row through the group; rows are shifted by one so that the two
+    // coordinates of a landmark (rows 3 + 2l, 4 + 2l) sit in one warp on lanes (even, odd)
+    const int i = blockIdx.x * blockDim.x + tid - 1;
+    const bool valid = i >= 0 && i < n;
+    GroupRow<GM> r;
+    if (valid) group_row_load<GM>(r, i, g, sm, Xin, R3, snap, ld, lda, pv);
+    const bool lm = valid && i >= 3 && ((i - 3) & 1) == 0 && (i - 3) / 2 < nf;
+    const int l = (i - 3) / 2;
+    double d00 = 0.0, d01 = 0.0, d11 = 0.0;
+    if (lm) {
+        d00 = D[l];
+        d01 = D[(size_t)dcap + l];
+        d11 = D[2 * (size_t)dcap + l];
+    }
+    for (int k = 0; k < g; k++) {
+        double w1_0 = 0.0, w1_1 = 0.0;
+        if (valid) {
+            group_row_gain<GM>(r, k, sm, w1_0, w1_1);
+            group_row_sub<GM>(r, k, g, sm, w1_0, w1_1);
+            Aout[(size_t)(2 * k) * lda + i] = w1_0;
+            Aout[(size_t)(2 * k + 1) * lda + i] = w1_1;
+        }
+        const double n0 = __shfl_down_sync(0xffffffffu, w1_0, 1);
+        const double n1 = __shfl_down_sync(0xffffffffu, w1_1, 1);
+        if (lm) {
+            d00 = d00 - w1_0 * w1_0;
+            d01 = d01 - w1_0 * n0;
+            d11 = d11 - n0 * n0;
+            d00 = d00 - w1_1 * w1_1;
+            d01 = d01 - w1_1 * n1;
+            d11 = d11 - n1 * n1;
+        }
+    }
+    if (valid) {
+        Xout[i] = r.x;
+        const int nrow = i < 3 ? i + 1 : 3;
+        for (int b = 0; b < nrow; b++) R3out[(size_t)b * ld + i] = r.pose[b];
+    }
+    if (lm) {
+        Dout[l] = d00;
+        Dout[(size_t)dcap + l] = d01;
+        Dout[2 * (size_t)dcap + l] = d11;
+    }
+}
+
+// ------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------
 static inline double* lazy_bank(cslam_ekf* h, int bank) { return h->A + (size_t)bank * kLazyBank * h->lda; }
@@ -401,9 +640,13 @@ static int allreduce_sum(cslam_ekf* h, double* buf, size_t count);
 
 // Column snapshot of `ncols` columns (host list or device indices) from the array the chain may read.
 // *snap receives the buffer the gains read ([ncols][lda]).
-static int lazy_snapshot(cslam_ekf* h, const ColList& cl, const int* idf_dev, const double** snap) {
+// *wait_fused (nullable): the caller's next kernel waits for the peers' flags itself (k_gain_group_lazy); set to
+// true when that wait is still owed.
+static int lazy_snapshot(cslam_ekf* h, const ColList& cl, const int* idf_dev, const double** snap,
+                         bool* wait_fused = nullptr) {
     if (int rc = lazy_acquire_read(h)) return rc;
     LazyState& L = h->lz;
+    if (wait_fused) *wait_fused = false;
     if (h->sh.world > 1 && L.peers_ready && cl.n <= 2 * kSeqGroupLazyMax) {
         // peer-memory exchange: push what this rank stores into every rank's buffer, then wait for every peer
         L.epoch++;
@@ -416,8 +659,12 @@ static int lazy_snapshot(cslam_ekf* h, const ColList& cl, const int* idf_dev, co
         count_launch();
         k_col_push<<<dim3((h->n + 255) / 256, cl.n), 256, 0, h->stream>>>(lazy_P(h), h->R3, h->ld, h->n, cl, h->lda, buf_off,
                                                                           h->sh, idf_dev, pt, L.epoch, L.push_ticket);
-        count_launch();
-        k_wait_peers<<<1, 32, 0, h->stream>>>(L.sig, h->sh.world, L.epoch, h->status);
+        if (wait_fused) {
+            *wait_fused = true;
+        } else {
+            count_launch();
+            k_wait_peers<<<1, 32, 0, h->stream>>>(L.sig, h->sh.world, L.epoch, h->status);
+        }
         CSLAM_CUDA(cudaGetLastError());
         *snap = L.xbuf + buf_off;
         return CSLAM_OK;
@@ -450,9 +697,50 @@ static int lazy_sequential(cslam_ekf* h, const double* Z, const int32_t* idf_hos
             cl.c[2 * k + 1] = cl.c[2 * k] + 1;
         }
         const double* snap = nullptr;
-        if (int rc = lazy_snapshot(h, cl, idf_dev ? idf_dev + base : nullptr, &snap)) return rc;
+        bool wait_fused = false;
+        if (int rc = lazy_snapshot(h, cl, idf_dev ? idf_dev + base : nullptr, &snap, L.fused_gains ? &wait_fused : nullptr))
+            return rc;
         const int np0 = L.np;
         double* bank = lazy_bank(h, L.bank);
+        if (L.fused_gains) {  // the whole group, the R3 / D follow and the wait for the peers in one launch
+            PendView pv;
+            pv.A0 = lazy_bank(h, L.bank ^ 1);
+            pv.n0 = L.infl_rows;
+            pv.eps0 = L.infl_eps_mask;
+            pv.A1 = bank;
+            pv.n1 = np0;
+            pv.eps1 = L.eps_mask;
+            pv.r3_from = L.infl_rows + np0;
+            ObsGroup og;
+            og.g = g;
+            for (int k = 0; k < kSeqGroupLazyMax; k++) {
+                og.z[2 * k] = k < g ? Z[2 * (base + k)] : 0.0;
+                og.z[2 * k + 1] = k < g ? Z[2 * (base + k) + 1] : 0.0;
+                og.idf[k] = (k < g && idf_host) ? idf_host[base + k] : 0;
+            }
+            const unsigned blocks = (unsigned)((n + 1 + 127) / 128);
+            const int nf = (n - 3) / 2;
+            count_launch();
+#define CSLAM_GROUP(GM)                                                                                               \
+    k_gain_group_lazy<GM><<<blocks, 128, 0, h->stream>>>(                                                              \
+        h->X[h->cur], h->X[h->cur ^ 1], h->R3, L.R3alt, h->D, L.Dalt, h->dcap, nf, snap, h->ld, h->lda, n, og, R[0], R[1], \
+        R[2], R[3], h->flags, pv, bank + (size_t)np0 * h->lda, h->status, idf_dev ? idf_dev + base : nullptr,          \
+        wait_fused ? L.sig : nullptr, h->sh.world, L.epoch)
+            if (g <= 1) CSLAM_GROUP(1);
+            else if (g <= 2) CSLAM_GROUP(2);
+            else if (g <= 4) CSLAM_GROUP(4);
+            else CSLAM_GROUP(8);
+#undef CSLAM_GROUP
+            CSLAM_CUDA(cudaGetLastError());
+            h->cur ^= 1;
+            std::swap(h->R3, L.R3alt);
+            std::swap(h->D, L.Dalt);
+            L.np = np0 + 2 * g;
+            base += g;
+            if (L.np == kLazyBank)
+                if (int rc = lazy_flush(h)) return rc;
+            continue;
+        }
         for (int k = 0; k < g; k++) {
             const int i = base + k;
             PendView pv;

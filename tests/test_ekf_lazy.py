@@ -238,3 +238,39 @@ def test_lazy_checkpoint_roundtrip(tmp_path):
     assert np.array_equal(h.X, Xs)
     for f in (g, h, h2):
         f.close()
+
+
+def test_fused_group_gains_bit_identical_to_one_kernel_per_observation():
+    """k_gain_group_lazy (the whole scan's gains + the R3 / D follow in one launch, group replayed on the small
+    marginal first) performs the operations of the per-observation chain in the same order: identical bits.
+    Covers groups of 1, 2, 3 (padded template), 4 and 8 observations, a landmark observed twice in one scan, the
+    fused gate+update scan, heading terms pending in the bank and a pass in flight."""
+    import conan_slam_b200 as cs
+    N = 1500
+    X, P, lm = helpers.synthetic_map(N, 21, decorrelate=1)
+    near = np.argsort(np.hypot(lm[0] - X[0], lm[1] - X[1]))[:40]
+    res = []
+    for fused in (1, 0):
+        rng = np.random.default_rng(5)
+        with _env(CSLAM_GAIN_FUSED=fused):
+            g = cs.EKF(capacity_landmarks=N, device=0, flags=cs.FLAG_INTENDED)
+        g.reset(X, P)
+        for m in (1, 2, 3, 4, 8, 4, 4, 8):
+            g.controlSteps(np.zeros(3), np.full(3, 0.01), np.full(3, X[2] + 1e-4), True, helpers.QE, 73.0, 0.01,
+                           want_trace=False)
+            ids = (rng.choice(near, size=m, replace=False) + 1).astype(np.int32)
+            if m == 4:
+                ids[3] = ids[1]  # the same landmark twice in one scan (nearest-neighbour association allows it)
+            Z = helpers.observe(X, lm, ids, rng)
+            g.update(Z, helpers.RE, ids, False)
+        ids = (rng.choice(near, size=4, replace=False) + 1).astype(np.int32)
+        jb, _ = g.scan(helpers.observe(X, lm, ids, rng), helpers.RE, GATE1, GATE2)
+        assert np.array_equal(jb, ids)
+        skipped = g.sync()
+        idx = np.concatenate([np.arange(3), 3 + 2 * np.repeat(near, 2) + np.tile([0, 1], near.size)])
+        res.append((g.X.copy(), g.cov_gather(idx), g.landmark_covs(), skipped, g.pass_count()))
+    a, b = res
+    assert a[3] == b[3] and a[4] == b[4]
+    assert np.array_equal(a[0], b[0])
+    assert np.array_equal(a[1], b[1])
+    assert np.array_equal(a[2], b[2])
