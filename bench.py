@@ -741,6 +741,38 @@ class EkfBench:
         except Exception as e:  # pragma: no cover - reported, never fatal for the timing
             return {"ok": False, "error": f"{type(e).__name__}: {e}"}
 
+    # ---- the per-scan chain (gate -> column snapshot -> gains) on its own stream, timed scan by scan ----
+    def chain_probe(self, m, reps=6):
+        """CUDA events on the chain stream around single scans.  From a flushed state: scan A and B run with no
+        covariance pass in flight (B's 16th pending row launches a pass on the pass stream, which the chain does not
+        wait for); scan C runs while that pass streams the covariance next to it.  The covariance pass hides behind
+        the chain or the chain behind the pass: per scan the filter costs max(chain, pass share)."""
+        ctx, ekf, torch = self.ctx, self.ekf, self.ctx.torch
+        if m != 4:
+            return None
+        scans = self.scans(m)
+        res = {"idle": [], "beside_pass": []}
+        with torch.cuda.stream(self.stream):
+            for r in range(reps):
+                ekf.flush()
+                ekf.sync()
+                ctx.barrier()
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+                for k in range(3):
+                    ev[k].record(self.stream)
+                    ekf_scan(ekf, scans[(3 * r + k) % len(scans)][0], False, want_indices=False)
+                ev[3].record(self.stream)
+                ekf.flush()
+                ekf.sync()
+                d = [ev[k].elapsed_time(ev[k + 1]) for k in range(3)]
+                if r > 0:
+                    res["idle"].append(d[0])
+                    res["beside_pass"].append(d[2])
+        med = {k: float(np.median(v)) for k, v in res.items()}
+        med = dict(zip(med.keys(), ctx.allmax(*med.values())))
+        return {"ms_per_scan_chain_idle": med["idle"], "ms_per_scan_chain_beside_pass": med["beside_pass"],
+                "note": "gate + column snapshot (peer push when sharded) + gains of one 4-observation scan, max over ranks"}
+
     # ---- device-timed throughput (state resident in HBM) + live kernel timing ----
     def timed(self, m, steps, warmup, batch=False, strict=False):
         ctx, ekf, torch = self.ctx, self.ekf, self.ctx.torch
@@ -1025,6 +1057,10 @@ def main():
     eb = EkfBench(ctx, N, max(8, args.steps + args.warmup))
     out = ekf_result(ctx, eb, m, args.steps, args.warmup, batch=args.batch, strict=args.strict)
     extras = {}
+    if not args.batch and not args.strict:
+        cp = guarded("chain_probe", lambda: eb.chain_probe(m))
+        if ctx.rank == 0 and cp is not None:
+            out["chain_probe"] = cp
     if ctx.world == 1 and not args.batch:
         d = guarded("drive_cycle", lambda: eb.drive(m))
         if ctx.rank == 0:

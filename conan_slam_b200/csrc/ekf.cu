@@ -1257,6 +1257,8 @@ static int create_common(cslam_ekf_t** out, int capacity_landmarks, int device, 
         if (const char* e = getenv("CSLAM_GAIN_FUSED")) L.fused_gains = atoi(e) != 0;
         TRY(cudaMalloc(&L.R3alt, 3 * h->ld * sizeof(double)));
         TRY(cudaMemsetAsync(L.R3alt, 0, 3 * h->ld * sizeof(double), h->stream));
+        TRY(cudaMalloc(&L.hdr, sizeof(GroupHeader)));
+        TRY(cudaMemsetAsync(L.hdr, 0, sizeof(GroupHeader), h->stream));
         TRY(cudaMalloc(&L.Dalt, 3 * (size_t)h->dcap * sizeof(double)));
         TRY(cudaMemsetAsync(L.Dalt, 0, 3 * (size_t)h->dcap * sizeof(double), h->stream));
         // ping-pong pair: the pass of bank k streams array a -> array b while the gains of the following scans
@@ -1346,6 +1348,7 @@ int cslam_ekf_destroy(cslam_ekf_t* h) {
     cudaFree(h->lz.Pbuf[1]);
     cudaFree(h->lz.R3alt);
     cudaFree(h->lz.Dalt);
+    cudaFree(h->lz.hdr);
     cudaFree(h->trace_dev);
     cudaFree(h->acc_dev);
     if (h->comm) {

@@ -31,6 +31,11 @@ struct BatchSmall {  // device-resident scratch of the joint update (EKF.cpp:93-
 // pending terms themselves.  The pass runs on its own stream and overlaps the gate / gain chain of the
 // following scans; with a ping-pong pair of arrays the chain never waits for a pass that is still running.
 constexpr int kLazyBank = 16;  // panel rows per bank = rank of one pass (cov_tma.cu: KS <= 4)
+constexpr int kSeqGroupLazyMax = 8;  // observations per snapshot group (2 columns each)
+struct GroupHeader {  // written by the snapshot kernel, read by k_gain_group_lazy (ekf_lazy.cuh)
+    int f[kSeqGroupLazyMax];                              // first state index of observation k, -1 = none
+    double Ac[2 * kLazyBank][3 + 2 * kSeqGroupLazyMax];   // pending term t at column b of the group's marginal
+};
 struct LazyState {
     bool on = false;
     bool pingpong = false;
@@ -66,9 +71,9 @@ struct LazyState {
     // blocks still read the old ones; the handle's R3 / D pointers are swapped after the launch
     double* R3alt = nullptr;
     double* Dalt = nullptr;
+    GroupHeader* hdr = nullptr;
     bool fused_gains = true;          // CSLAM_GAIN_FUSED=0: one gain kernel per observation + follow (regression tests)
 };
-constexpr int kSeqGroupLazyMax = 8;  // observations per snapshot group (2 columns each)
 
 struct GateScratch {
     double* part_nd = nullptr;   // [blocks][m]

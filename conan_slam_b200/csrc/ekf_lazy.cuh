@@ -46,15 +46,49 @@ __device__ __forceinline__ bool pend_eps(const PendView& pv, int t) {
     return t < pv.n0 ? ((pv.eps0 >> t) & 1u) != 0 : ((pv.eps1 >> (t - pv.n0)) & 1u) != 0;
 }
 
+// What a whole group of sequential updates needs of the pending terms BEFORE it reads a single row: the pending
+// panel rows at the columns of the group's marginal M = {0, 1, 2, f_0, f_0 + 1, ...}.  Block (0, 0) of the
+// snapshot kernel gathers them next to its own work, so the group-gain kernel starts with ONE fixed-address read
+// instead of "association index -> column -> pending rows" (two dependent round trips to a loaded memory system).
+// (struct GroupHeader: ekf_handle.cuh)
+__device__ __forceinline__ void write_group_header(GroupHeader* __restrict__ hdr, const PendView& pv, size_t lda,
+                                                   const ColList& cl, const int* __restrict__ idf_dev) {
+    const int g = cl.n >> 1, d = 3 + 2 * g, nterm = pv.n0 + pv.n1;
+    for (int idx = threadIdx.x; idx < nterm * d + g; idx += blockDim.x) {
+        if (idx >= nterm * d) {
+            const int k = idx - nterm * d;
+            int c = cl.c[2 * k];
+            if (idf_dev != nullptr) {
+                const int j = idf_dev[k];
+                c = j > 0 ? 3 + 2 * (j - 1) : -1;
+            }
+            hdr->f[k] = c;
+            continue;
+        }
+        const int t = idx / d, b = idx % d;
+        int c = b;
+        if (b >= 3) {
+            c = cl.c[b - 3];
+            if (idf_dev != nullptr) {
+                const int j = idf_dev[(b - 3) >> 1];
+                c = j > 0 ? 3 + 2 * (j - 1) + ((b - 3) & 1) : -1;
+            }
+        }
+        hdr->Ac[t][b] = c >= 0 ? pend_row(pv, lda, t)[c] : 0.0;
+    }
+}
+
 // Column snapshot: colbuf[k][i] = P_dev(i, c_k) for the listed columns (symmetric read of the upper triangle;
 // rows 0..2 come from the always-current R3).  Sharded: every rank contributes what it stores, zeros
 // elsewhere, and an all-reduce completes the columns (x + 0 is exact).  idf_dev (nullable): fused scan —
 // column k belongs to observation k/2 whose 1-based landmark index sits in device memory (0 = none).
 __global__ void __launch_bounds__(256) k_col_pack_lazy(const double* __restrict__ P, const double* __restrict__ R3,
                                                        size_t ld, int n, ColList cl, double* __restrict__ colbuf,
-                                                       size_t lda, Shard sh, const int* __restrict__ idf_dev) {
+                                                       size_t lda, Shard sh, const int* __restrict__ idf_dev,
+                                                       GroupHeader* __restrict__ hdr, PendView pv) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int k = blockIdx.y;
+    if (hdr != nullptr && blockIdx.x == 0 && blockIdx.y == 0) write_group_header(hdr, pv, lda, cl, idf_dev);
     if (i >= n) return;
     int c = cl.c[k];
     if (idf_dev != nullptr) {
@@ -85,9 +119,11 @@ struct PeerTab {
 __global__ void __launch_bounds__(256) k_col_push(const double* __restrict__ P, const double* __restrict__ R3, size_t ld,
                                                   int n, ColList cl, size_t lda, size_t buf_off, Shard sh,
                                                   const int* __restrict__ idf_dev, PeerTab pt,
-                                                  unsigned long long epoch, unsigned* __restrict__ ticket) {
+                                                  unsigned long long epoch, unsigned* __restrict__ ticket,
+                                                  GroupHeader* __restrict__ hdr, PendView pv) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int k = blockIdx.y;
+    if (hdr != nullptr && blockIdx.x == 0 && blockIdx.y == 0) write_group_header(hdr, pv, lda, cl, idf_dev);
     if (i < n) {
         int c = cl.c[k];
         if (idf_dev != nullptr) {
@@ -387,22 +423,27 @@ __device__ __forceinline__ void group_row_sub(GroupRow<GM>& r, int k, int g, con
     }
 }
 
+// 9 row warps + 1: at n = 40 003 the grid is 139 blocks <= 148 SMs (one wave), and 320 threads x 88 registers fit on
+// an SM NEXT TO the persistent covariance pass (352 threads x 104 registers for a 16-row bank) — a block that had
+// to wait for the pass to leave would stall the chain for the rest of the pass.
+constexpr int kGroupRowThreads = 352;                    // warps 1..11: one state row each
+constexpr int kGroupThreads = 32 + kGroupRowThreads;     // warp 0 replays the group on the marginal
 template <int GM>
-__global__ void __launch_bounds__(128, (GM > 4 ? 3 : 6)) k_gain_group_lazy(
+__global__ void __maxnreg__(64) k_gain_group_lazy(
     const double* Xin, double* Xout, const double* __restrict__ R3, double* __restrict__ R3out,
     const double* __restrict__ D, double* __restrict__ Dout, int dcap, int nf, const double* snap, size_t ld, size_t lda,
     int n, ObsGroup og, double r00, double r10, double r01, double r11, unsigned flags, PendView pv, double* Aout,
-    int* __restrict__ status, const int* __restrict__ idf_dev, const unsigned long long* sig, int world,
+    int* __restrict__ status, const GroupHeader* __restrict__ hdr, const unsigned long long* sig, int world,
     unsigned long long epoch) {
     __shared__ GroupSmem<GM> sm;
     const int g = og.g;
     const int tid = threadIdx.x;
-    // ---- phase 0: association indices, peers' pushes, pending terms at the columns of M
-    if (tid < g) {
-        const int j = idf_dev != nullptr ? idf_dev[tid] : og.idf[tid];
-        sm.f[tid] = j > 0 ? 3 + 2 * (j - 1) : -1;
-    }
-    if (sig != nullptr && tid >= 32 && tid < 32 + world) {  // warp 1: lane q waits for rank q's flag (bounded, ~4 s)
+    const int d = 3 + 2 * g;
+    const int nterm = pv.n0 + pv.n1;
+    // ---- phase 0: the header the snapshot kernel left (columns of M, pending terms there); peers' pushes
+    if (tid < g) sm.f[tid] = hdr->f[tid];
+    for (int idx = tid; idx < nterm * d; idx += blockDim.x) sm.Ac[idx / d][idx % d] = hdr->Ac[idx / d][idx % d];
+    if (sig != nullptr && tid >= 32 && tid < 32 + world) {  // lane q of warp 1 waits for rank q's flag (bounded, ~4 s)
         const volatile unsigned long long* s = sig + (tid - 32);
         const long long t0 = clock64();
         while (*s < epoch) {
@@ -414,25 +455,16 @@ __global__ void __launch_bounds__(128, (GM > 4 ? 3 : 6)) k_gain_group_lazy(
         __threadfence_system();
     }
     __syncthreads();
-    const int d = 3 + 2 * g;
-    const int nterm = pv.n0 + pv.n1;
-    for (int idx = tid; idx < nterm * d; idx += blockDim.x) {
-        const int t = idx / d, b = idx % d;
-        double v = 0.0;
-        if (b < 3) {
-            v = pend_row(pv, lda, t)[b];
-        } else if (sm.f[(b - 3) >> 1] >= 0) {
-            v = pend_row(pv, lda, t)[sm.f[(b - 3) >> 1] + ((b - 3) & 1)];
-        }
-        sm.Ac[t][b] = v;
-    }
-    __syncthreads();
-    // ---- phase 1: the group replayed on the marginal rows (warp 0)
+    // rows are shifted by one so that the two coordinates of a landmark (rows 3 + 2l, 4 + 2l) sit in one warp on
+    // lanes (even, odd); the row threads issue their loads BEFORE they wait for the marginal replay
+    const int i = blockIdx.x * kGroupRowThreads + (tid - 32) - 1;
+    const bool valid = tid >= 32 && i >= 0 && i < n;
+    GroupRow<GM> r;
     if (tid < 32) {
+        // ---- phase 1: the group replayed on the marginal rows (lane a owns row a of M, lane 0 factorises)
         const int a = tid;
         const bool act = a < d && (a < 3 || sm.f[(a - 3) >> 1] >= 0);
         const int ia = a < 3 ? a : (act ? sm.f[(a - 3) >> 1] + ((a - 3) & 1) : 0);
-        GroupRow<GM> r;
         if (act) group_row_load<GM>(r, ia, g, sm, Xin, R3, snap, ld, lda, pv);
         for (int k = 0; k < g; k++) {
             if (sm.f[k] >= 0) {  // warp-uniform
@@ -475,14 +507,9 @@ __global__ void __launch_bounds__(128, (GM > 4 ? 3 : 6)) k_gain_group_lazy(
             if (act) group_row_sub<GM>(r, k, g, sm, w1_0, w1_1);
             __syncwarp();
         }
+    } else if (valid) {
+        group_row_load<GM>(r, i, g, sm, Xin, R3, snap, ld, lda, pv);
     }
-    __syncthreads();
-    // ---- phase 2: every thread takes its own row through the group; rows are shifted by one so that the two
-    // coordinates of a landmark (rows 3 + 2l, 4 + 2l) sit in one warp on lanes (even, odd)
-    const int i = blockIdx.x * blockDim.x + tid - 1;
-    const bool valid = i >= 0 && i < n;
-    GroupRow<GM> r;
-    if (valid) group_row_load<GM>(r, i, g, sm, Xin, R3, snap, ld, lda, pv);
     const bool lm = valid && i >= 3 && ((i - 3) & 1) == 0 && (i - 3) / 2 < nf;
     const int l = (i - 3) / 2;
     double d00 = 0.0, d01 = 0.0, d11 = 0.0;
@@ -491,6 +518,9 @@ __global__ void __launch_bounds__(128, (GM > 4 ? 3 : 6)) k_gain_group_lazy(
         d01 = D[(size_t)dcap + l];
         d11 = D[2 * (size_t)dcap + l];
     }
+    __syncthreads();
+    if (tid < 32) return;
+    // ---- phase 2: every row thread takes its own row through the group
     for (int k = 0; k < g; k++) {
         double w1_0 = 0.0, w1_1 = 0.0;
         if (valid) {
@@ -643,10 +673,13 @@ static int allreduce_sum(cslam_ekf* h, double* buf, size_t count);
 // *wait_fused (nullable): the caller's next kernel waits for the peers' flags itself (k_gain_group_lazy); set to
 // true when that wait is still owed.
 static int lazy_snapshot(cslam_ekf* h, const ColList& cl, const int* idf_dev, const double** snap,
-                         bool* wait_fused = nullptr) {
+                         bool* wait_fused = nullptr, const PendView* pvp = nullptr) {
     if (int rc = lazy_acquire_read(h)) return rc;
     LazyState& L = h->lz;
     if (wait_fused) *wait_fused = false;
+    GroupHeader* hdr = pvp ? L.hdr : nullptr;  // the fused group-gain kernel's header, gathered by block (0, 0)
+    PendView pv{};
+    if (pvp) pv = *pvp;
     if (h->sh.world > 1 && L.peers_ready && cl.n <= 2 * kSeqGroupLazyMax) {
         // peer-memory exchange: push what this rank stores into every rank's buffer, then wait for every peer
         L.epoch++;
@@ -658,7 +691,7 @@ static int lazy_snapshot(cslam_ekf* h, const ColList& cl, const int* idf_dev, co
         }
         count_launch();
         k_col_push<<<dim3((h->n + 255) / 256, cl.n), 256, 0, h->stream>>>(lazy_P(h), h->R3, h->ld, h->n, cl, h->lda, buf_off,
-                                                                          h->sh, idf_dev, pt, L.epoch, L.push_ticket);
+                                                                          h->sh, idf_dev, pt, L.epoch, L.push_ticket, hdr, pv);
         if (wait_fused) {
             *wait_fused = true;
         } else {
@@ -672,7 +705,7 @@ static int lazy_snapshot(cslam_ekf* h, const ColList& cl, const int* idf_dev, co
     *snap = h->colbuf;
     count_launch();
     k_col_pack_lazy<<<dim3((h->n + 255) / 256, cl.n), 256, 0, h->stream>>>(lazy_P(h), h->R3, h->ld, h->n, cl, h->colbuf,
-                                                                           h->lda, h->sh, idf_dev);
+                                                                           h->lda, h->sh, idf_dev, hdr, pv);
     CSLAM_CUDA(cudaGetLastError());
     if (h->sh.world > 1) return allreduce_sum(h, h->colbuf, (size_t)cl.n * h->lda);
     return CSLAM_OK;
@@ -698,19 +731,22 @@ static int lazy_sequential(cslam_ekf* h, const double* Z, const int32_t* idf_hos
         }
         const double* snap = nullptr;
         bool wait_fused = false;
-        if (int rc = lazy_snapshot(h, cl, idf_dev ? idf_dev + base : nullptr, &snap, L.fused_gains ? &wait_fused : nullptr))
-            return rc;
+        if (int rc = lazy_acquire_read(h)) return rc;  // in-place mode: the pass in flight first (changes the pending view)
         const int np0 = L.np;
         double* bank = lazy_bank(h, L.bank);
+        PendView pvg;  // pending terms as they stand before the group
+        pvg.A0 = lazy_bank(h, L.bank ^ 1);
+        pvg.n0 = L.infl_rows;
+        pvg.eps0 = L.infl_eps_mask;
+        pvg.A1 = bank;
+        pvg.n1 = np0;
+        pvg.eps1 = L.eps_mask;
+        pvg.r3_from = L.infl_rows + np0;
+        if (int rc = lazy_snapshot(h, cl, idf_dev ? idf_dev + base : nullptr, &snap, L.fused_gains ? &wait_fused : nullptr,
+                                   L.fused_gains ? &pvg : nullptr))
+            return rc;
         if (L.fused_gains) {  // the whole group, the R3 / D follow and the wait for the peers in one launch
-            PendView pv;
-            pv.A0 = lazy_bank(h, L.bank ^ 1);
-            pv.n0 = L.infl_rows;
-            pv.eps0 = L.infl_eps_mask;
-            pv.A1 = bank;
-            pv.n1 = np0;
-            pv.eps1 = L.eps_mask;
-            pv.r3_from = L.infl_rows + np0;
+            const PendView& pv = pvg;
             ObsGroup og;
             og.g = g;
             for (int k = 0; k < kSeqGroupLazyMax; k++) {
@@ -718,13 +754,13 @@ static int lazy_sequential(cslam_ekf* h, const double* Z, const int32_t* idf_hos
                 og.z[2 * k + 1] = k < g ? Z[2 * (base + k) + 1] : 0.0;
                 og.idf[k] = (k < g && idf_host) ? idf_host[base + k] : 0;
             }
-            const unsigned blocks = (unsigned)((n + 1 + 127) / 128);
+            const unsigned blocks = (unsigned)((n + 1 + kGroupRowThreads - 1) / kGroupRowThreads);
             const int nf = (n - 3) / 2;
             count_launch();
 #define CSLAM_GROUP(GM)                                                                                               \
-    k_gain_group_lazy<GM><<<blocks, 128, 0, h->stream>>>(                                                              \
+    k_gain_group_lazy<GM><<<blocks, kGroupThreads, 0, h->stream>>>(                                                              \
         h->X[h->cur], h->X[h->cur ^ 1], h->R3, L.R3alt, h->D, L.Dalt, h->dcap, nf, snap, h->ld, h->lda, n, og, R[0], R[1], \
-        R[2], R[3], h->flags, pv, bank + (size_t)np0 * h->lda, h->status, idf_dev ? idf_dev + base : nullptr,          \
+        R[2], R[3], h->flags, pv, bank + (size_t)np0 * h->lda, h->status, L.hdr,                                       \
         wait_fused ? L.sig : nullptr, h->sh.world, L.epoch)
             if (g <= 1) CSLAM_GROUP(1);
             else if (g <= 2) CSLAM_GROUP(2);
