@@ -742,7 +742,7 @@ class EkfBench:
             return {"ok": False, "error": f"{type(e).__name__}: {e}"}
 
     # ---- the per-scan chain (gate -> column snapshot -> gains) on its own stream, timed scan by scan ----
-    def chain_probe(self, m, reps=6):
+    def chain_probe(self, m, reps=12):
         """CUDA events on the chain stream around single scans.  From a flushed state: scan A and B run with no
         covariance pass in flight (B's 16th pending row launches a pass on the pass stream, which the chain does not
         wait for); scan C runs while that pass streams the covariance next to it.  The covariance pass hides behind
@@ -770,7 +770,10 @@ class EkfBench:
                     res["beside_pass"].append(d[2])
         med = {k: float(np.median(v)) for k, v in res.items()}
         med = dict(zip(med.keys(), ctx.allmax(*med.values())))
+        lo = {k: float(np.min(v)) for k, v in res.items()}
+        lo = dict(zip(lo.keys(), ctx.allmax(*lo.values())))
         return {"ms_per_scan_chain_idle": med["idle"], "ms_per_scan_chain_beside_pass": med["beside_pass"],
+                "min_idle": lo["idle"], "min_beside_pass": lo["beside_pass"], "reps": reps - 1,
                 "note": "gate + column snapshot (peer push when sharded) + gains of one 4-observation scan, max over ranks"}
 
     # ---- device-timed throughput (state resident in HBM) + live kernel timing ----

@@ -824,7 +824,7 @@ __global__ void __launch_bounds__(1024) k_observe_step_small(const double* Xin, 
 int launch_gate(const double* X, const double* P, const double* R3, const double* D, int dcap, size_t ld, int nf,
                 const double* Z, int m, const double R[4], double gate1, double gate2, double* part_nd,
                 double* part_out, int* part_j, unsigned* ticket, int* jbest, double* nbest, double* outer,
-                unsigned long long* assoc_count, cudaStream_t stream);
+                unsigned long long* assoc_count, cudaStream_t stream, int final_stage = 1, int* nblocks_out = nullptr);
 
 // ------------------------------------------------------------------------ accessors ----
 // sharded: every rank fills the entries it stores (zeros elsewhere) and the block is all-reduced.
@@ -857,6 +857,10 @@ int launch_cov_update_dmma(double* P, size_t ld, int n, const double* A, size_t 
 
 }  // namespace cslam
 #include "ekf_lazy.cuh"
+
+extern "C" {
+static void apply_l2_window(cslam_ekf* h);
+}
 namespace cslam {
 
 // ------------------------------------------------------------------------------------
@@ -1255,6 +1259,11 @@ static int create_common(cslam_ekf_t** out, int capacity_landmarks, int device, 
         TRY(cudaEventCreateWithFlags(&L.ev_pass, cudaEventDisableTiming));
         if (const char* e = getenv("CSLAM_TMA_STAGES")) L.stages = atoi(e);
         if (const char* e = getenv("CSLAM_GAIN_FUSED")) L.fused_gains = atoi(e) != 0;
+        if (const char* e = getenv("CSLAM_GATE_DEFER")) L.defer_gate_merge = atoi(e) != 0;
+        if (getenv("CSLAM_KTRACE")) {
+            TRY(cudaMalloc(&L.ktrace, (size_t)8 * LazyState::kTraceCap * sizeof(unsigned long long)));
+            TRY(cudaMemsetAsync(L.ktrace, 0, (size_t)8 * LazyState::kTraceCap * sizeof(unsigned long long), h->stream));
+        }
         TRY(cudaMalloc(&L.R3alt, 3 * h->ld * sizeof(double)));
         TRY(cudaMemsetAsync(L.R3alt, 0, 3 * h->ld * sizeof(double), h->stream));
         TRY(cudaMalloc(&L.hdr, sizeof(GroupHeader)));
@@ -1278,8 +1287,11 @@ static int create_common(cslam_ekf_t** out, int capacity_landmarks, int device, 
         if (!L.pingpong) memcpy(L.map[1], L.map[0], sizeof(L.map[0]));
         if (world > 1) {  // snapshot buffers + flags of the peer-memory column exchange (mapped by cslam_ekf_ipc_*)
             const size_t xb = (size_t)2 * 2 * kSeqGroupLazyMax * h->lda * sizeof(double);
-            TRY(cudaMalloc(&L.xbuf, xb));
-            TRY(cudaMemsetAsync(L.xbuf, 0, xb, h->stream));
+            // ... followed by the flagged-cell copy of the same buffers (16-byte cells, k_col_push_ll): one allocation,
+            // one IPC handle
+            L.xll_off = xb;
+            TRY(cudaMalloc(&L.xbuf, 3 * xb));
+            TRY(cudaMemsetAsync(L.xbuf, 0, 3 * xb, h->stream));
             TRY(cudaMalloc(&L.sig, 8 * sizeof(unsigned long long)));
             TRY(cudaMemsetAsync(L.sig, 0, 8 * sizeof(unsigned long long), h->stream));
             TRY(cudaMalloc(&L.push_ticket, sizeof(unsigned)));
@@ -1301,6 +1313,7 @@ static int create_common(cslam_ekf_t** out, int capacity_landmarks, int device, 
     }
     TRY(cudaStreamSynchronize(h->stream));
 #undef TRY
+    apply_l2_window(h);
     *out = h;
     return CSLAM_OK;
 }
@@ -1349,6 +1362,20 @@ int cslam_ekf_destroy(cslam_ekf_t* h) {
     cudaFree(h->lz.R3alt);
     cudaFree(h->lz.Dalt);
     cudaFree(h->lz.hdr);
+    if (h->lz.ktrace) {  // diagnostics: dump the kernel timestamps
+        const char* path = getenv("CSLAM_KTRACE");
+        const int cnt = std::min(h->lz.kslot, LazyState::kTraceCap);
+        std::vector<unsigned long long> t((size_t)8 * cnt);
+        if (path && cnt > 0 &&
+            cudaMemcpy(t.data(), h->lz.ktrace, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            const std::string file = std::string(path) + ".r" + std::to_string(h->sh.rank);
+            if (FILE* f = fopen(file.c_str(), "ab")) {
+                fwrite(t.data(), sizeof(unsigned long long), t.size(), f);
+                fclose(f);
+            }
+        }
+        cudaFree(h->lz.ktrace);
+    }
     cudaFree(h->trace_dev);
     cudaFree(h->acc_dev);
     if (h->comm) {
@@ -1371,6 +1398,34 @@ int cslam_ekf_destroy(cslam_ekf_t* h) {
     return CSLAM_OK;
 }
 
+// Deferred-pass handles: the per-scan chain re-reads the two banks of pending panel rows (up to 32 rows x n) for
+// every scan while the covariance pass streams the whole covariance through L2 next to it.  An access-policy window
+// on the chain stream keeps the banks resident in L2 (persisting lines), so that those reads do not queue up behind
+// the pass's HBM traffic.  CSLAM_L2_PERSIST=0 turns it off.
+static void apply_l2_window(cslam_ekf* h) {
+    if (!h->lz.on) return;
+    if (const char* e = getenv("CSLAM_L2_PERSIST"))
+        if (atoi(e) == 0) return;
+    int max_persist = 0, max_window = 0;
+    if (cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, h->device) != cudaSuccess ||
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, h->device) != cudaSuccess ||
+        max_persist <= 0 || max_window <= 0) {
+        cudaGetLastError();
+        return;
+    }
+    const size_t want = (size_t)2 * kLazyBank * h->lda * sizeof(double);
+    const size_t bytes = std::min(want, std::min((size_t)max_window, (size_t)max_persist));
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min((size_t)max_persist, bytes + (bytes >> 2)));
+    cudaStreamAttrValue v;
+    memset(&v, 0, sizeof(v));
+    v.accessPolicyWindow.base_ptr = h->A;
+    v.accessPolicyWindow.num_bytes = bytes;
+    v.accessPolicyWindow.hitRatio = 1.0f;
+    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    v.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    if (cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();
+}
+
 int cslam_ekf_set_stream(cslam_ekf_t* h, void* cuda_stream) {
     CSLAM_NVTX_RANGE();
     if (int rc = check_handle(h)) return rc;
@@ -1378,6 +1433,7 @@ int cslam_ekf_set_stream(cslam_ekf_t* h, void* cuda_stream) {
     if (h->own_stream) cudaStreamDestroy(h->stream);
     h->stream = static_cast<cudaStream_t>(cuda_stream);
     h->own_stream = false;
+    apply_l2_window(h);
     return CSLAM_OK;
 }
 
@@ -1758,23 +1814,48 @@ int cslam_ekf_scan(cslam_ekf_t* h, const double* Z, int m, const double R[4], do
     CSLAM_REQUIRE(Z && R, CSLAM_ERR_BAD_ARG, "null argument");
     const int n = h->n, nf = (n - 3) / 2;
     if (int rc = refresh_diag_cache(h)) return rc;
-    // dataAssociate at the pre-update state for the whole scan (test/main.cpp:193), indices stay in d_jbest
+    // dataAssociate at the pre-update state for the whole scan (test/main.cpp:193), indices stay in d_jbest.
+    // Deferred-pass handles: the gate kernel stops at its per-block candidates and the snapshot kernel of the
+    // first update group merges them (gate_parts.cuh) — no ticket / last-block stage on the per-scan chain.
+    const bool merge_later = h->lz.on && h->lz.fused_gains && h->lz.defer_gate_merge && nf > 0;
+    int gate_blocks = 0;
     if (int rc = launch_gate(h->X[h->cur], h->P, h->R3, (h->sh.world > 1 || h->lz.on) ? h->D : nullptr, h->dcap, h->ld, nf, Z, m, R,
                              gate1, gate2,
                              h->gate.part_nd, h->gate.part_out, h->gate.part_j, h->ticket + 1, h->gate.d_jbest,
-                             h->gate.d_nbest, h->gate.d_outer, h->assoc_count, h->stream))
+                             h->gate.d_nbest, h->gate.d_outer, h->assoc_count, h->stream, merge_later ? 0 : 1, &gate_blocks))
         return rc;
-    if (jbest || is_new) {  // optional read-back, queued behind the gate only: overlaps the updates
+    auto queue_readback = [&]() -> int {  // optional read-back, queued behind the association only: overlaps the updates
+        if (!(jbest || is_new)) return CSLAM_OK;
         char* pin = static_cast<char*>(h->pinned);
         CSLAM_CUDA(cudaMemcpyAsync(pin, h->gate.d_jbest, m * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CSLAM_CUDA(cudaMemcpyAsync(pin + 2048, h->gate.d_outer, m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         CSLAM_CUDA(cudaEventRecord(h->scan_ev, h->stream));
-    }
+        return CSLAM_OK;
+    };
+    if (!merge_later)
+        if (int rc = queue_readback()) return rc;
     // singleUpdate (EKF.cpp:457-479): re-linearised per observation, in observation order
     if (nf > 0) {
-        if (int rc = h->lz.on ? lazy_sequential(h, Z, nullptr, h->gate.d_jbest, m, R)
-                              : sequential_updates(h, Z, nullptr, h->gate.d_jbest, m, R))
+        if (h->lz.on) {
+            GateParts gp;
+            if (merge_later) {
+                gp.nd = h->gate.part_nd;
+                gp.out = h->gate.part_out;
+                gp.j = h->gate.part_j;
+                gp.nblocks = gate_blocks;
+                gp.m = m;
+                gp.jbest = h->gate.d_jbest;
+                gp.nbest = h->gate.d_nbest;
+                gp.outer = h->gate.d_outer;
+                gp.assoc_count = h->assoc_count;
+            }
+            std::function<int()> rb = queue_readback;
+            if (int rc = lazy_sequential(h, Z, nullptr, h->gate.d_jbest, m, R, merge_later ? &gp : nullptr,
+                                         merge_later ? &rb : nullptr))
+                return rc;
+        } else if (int rc = sequential_updates(h, Z, nullptr, h->gate.d_jbest, m, R)) {
             return rc;
+        }
     }
     if (jbest || is_new) {
         CSLAM_CUDA(cudaEventSynchronize(h->scan_ev));

@@ -61,6 +61,7 @@ struct LazyState {
     // mapped), then raises a flag on every peer; a one-warp kernel waits for all flags before the gains read.
     bool peers_ready = false;
     double* xbuf = nullptr;           // [2][2 * kSeqGroupLazyMax][lda]: snapshot buffers (double-buffered by epoch parity)
+    size_t xll_off = 0;               // byte offset of the flagged-cell buffers ([2][2 * kSeqGroupLazyMax][lda] x 16 B) in xbuf's allocation
     unsigned long long* sig = nullptr;  // [8]: sig[q] = last epoch rank q has finished pushing to this rank
     double* peer_xbuf[8] = {};        // IPC mappings (self = own pointers)
     unsigned long long* peer_sig[8] = {};
@@ -72,6 +73,12 @@ struct LazyState {
     double* R3alt = nullptr;
     double* Dalt = nullptr;
     GroupHeader* hdr = nullptr;
+    // CSLAM_KTRACE=<file>: device timestamps (globaltimer) of the snapshot and group-gain kernels, 4 per group:
+    // [snapshot first block in, snapshot last block out, group first block in, group last block out]; dumped at destroy
+    unsigned long long* ktrace = nullptr;
+    int kslot = 0;
+    static constexpr int kTraceCap = 8192;
+    bool defer_gate_merge = false;    // CSLAM_GATE_DEFER=1: the snapshot kernel merges the gate candidates (measured slower beside a pass: 0.128 vs 0.108 ms per scan)
     bool fused_gains = true;          // CSLAM_GAIN_FUSED=0: one gain kernel per observation + follow (regression tests)
 };
 

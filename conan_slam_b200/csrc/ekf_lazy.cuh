@@ -10,10 +10,12 @@
 // 2x2 diagonal blocks (kept current eagerly).  Nothing else of P is ever read between passes.
 #pragma once
 #include <algorithm>
+#include <functional>
 
 #include "common.cuh"
 #include "cov_update.cuh"
 #include "ekf_handle.cuh"
+#include "gate_parts.cuh"
 
 namespace cslam {
 
@@ -30,6 +32,18 @@ constexpr int kSeqGroupLazy = kSeqGroupLazyMax;  // observations per column snap
 
 // Pending rank-1 terms as a gain kernel sees them: first the rows of the bank that the pass in flight is
 // applying (the column snapshot was taken from the array that pass READS), then the rows of the current bank.
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void ktrace_in(unsigned long long* tr) {
+    if (tr != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) tr[0] = globaltimer_ns();
+}
+__device__ __forceinline__ void ktrace_out(unsigned long long* tr) {
+    if (tr != nullptr && threadIdx.x == 0) atomicMax(tr + 1, globaltimer_ns());
+}
+
 struct PendView {
     const double* A0;
     int n0;
@@ -51,30 +65,50 @@ __device__ __forceinline__ bool pend_eps(const PendView& pv, int t) {
 // snapshot kernel gathers them next to its own work, so the group-gain kernel starts with ONE fixed-address read
 // instead of "association index -> column -> pending rows" (two dependent round trips to a loaded memory system).
 // (struct GroupHeader: ekf_handle.cuh)
+// Fused scan, first snapshot of a scan: the gate kernel left per-block candidates (gate_parts.cuh).  Warp 0 of every
+// block merges those of the observation its column belongs to; block (0, 0) merges all of them, publishes the
+// scan's results (d_jbest / nbest / outer, running association count) and returns with s_j[k] = index of
+// observation k for the header.  Returns the 1-based landmark index of observation `obs` (0 = none).
+__device__ __forceinline__ int snapshot_associate(const GateParts& gp, int obs, bool lead_block, int* s_j) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (lead_block) {
+        for (int i = warp; i < gp.m; i += nw) {
+            const Cand c = gate_final_merge(gp.nd, gp.out, gp.j, gp.nblocks, i, lane);
+            if (lane == 0) {
+                const int j = (c.j == 0x7fffffff) ? 0 : c.j;
+                s_j[i] = j;
+                gp.jbest[i] = j;
+                gp.nbest[i] = c.nd;
+                gp.outer[i] = c.out;
+                if (gp.assoc_count != nullptr && j != 0) atomicAdd(gp.assoc_count, 1ULL);
+            }
+        }
+    } else if (warp == 0) {
+        const Cand c = gate_final_merge(gp.nd, gp.out, gp.j, gp.nblocks, obs, lane);
+        if (lane == 0) s_j[obs] = (c.j == 0x7fffffff) ? 0 : c.j;
+    }
+    __syncthreads();
+    return s_j[obs];
+}
+
 __device__ __forceinline__ void write_group_header(GroupHeader* __restrict__ hdr, const PendView& pv, size_t lda,
-                                                   const ColList& cl, const int* __restrict__ idf_dev) {
+                                                   const ColList& cl, const int* idf_dev) {
     const int g = cl.n >> 1, d = 3 + 2 * g, nterm = pv.n0 + pv.n1;
-    for (int idx = threadIdx.x; idx < nterm * d + g; idx += blockDim.x) {
-        if (idx >= nterm * d) {
-            const int k = idx - nterm * d;
-            int c = cl.c[2 * k];
-            if (idf_dev != nullptr) {
-                const int j = idf_dev[k];
-                c = j > 0 ? 3 + 2 * (j - 1) : -1;
-            }
-            hdr->f[k] = c;
-            continue;
+    __shared__ int s_f[kSeqGroupLazyMax];  // columns first (one read of the association indices), pending rows after
+    if (threadIdx.x < g) {
+        int c = cl.c[2 * threadIdx.x];
+        if (idf_dev != nullptr) {
+            const int j = idf_dev[threadIdx.x];
+            c = j > 0 ? 3 + 2 * (j - 1) : -1;
         }
+        s_f[threadIdx.x] = c;
+        hdr->f[threadIdx.x] = c;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nterm * d; idx += blockDim.x) {
         const int t = idx / d, b = idx % d;
-        int c = b;
-        if (b >= 3) {
-            c = cl.c[b - 3];
-            if (idf_dev != nullptr) {
-                const int j = idf_dev[(b - 3) >> 1];
-                c = j > 0 ? 3 + 2 * (j - 1) + ((b - 3) & 1) : -1;
-            }
-        }
-        hdr->Ac[t][b] = c >= 0 ? pend_row(pv, lda, t)[c] : 0.0;
+        const int c = b < 3 ? b : (s_f[(b - 3) >> 1] >= 0 ? s_f[(b - 3) >> 1] + ((b - 3) & 1) : -1);
+        hdr->Ac[t][b] = c >= 0 ? __ldcg(pend_row(pv, lda, t) + c) : 0.0;
     }
 }
 
@@ -84,15 +118,28 @@ __device__ __forceinline__ void write_group_header(GroupHeader* __restrict__ hdr
 // column k belongs to observation k/2 whose 1-based landmark index sits in device memory (0 = none).
 __global__ void __launch_bounds__(256) k_col_pack_lazy(const double* __restrict__ P, const double* __restrict__ R3,
                                                        size_t ld, int n, ColList cl, double* __restrict__ colbuf,
-                                                       size_t lda, Shard sh, const int* __restrict__ idf_dev,
-                                                       GroupHeader* __restrict__ hdr, PendView pv) {
+                                                       size_t lda, Shard sh, const int* idf_dev,
+                                                       GroupHeader* __restrict__ hdr, PendView pv, GateParts gp,
+                                                       unsigned long long* tr) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int k = blockIdx.y;
-    if (hdr != nullptr && blockIdx.x == 0 && blockIdx.y == 0) write_group_header(hdr, pv, lda, cl, idf_dev);
+    ktrace_in(tr);
+    __shared__ int s_j[CSLAM_MAX_OBS];
+    const bool lead = blockIdx.x == 0 && blockIdx.y == 0;
+    int jmine = -1;
+    if (gp.nd != nullptr) {
+        jmine = snapshot_associate(gp, k >> 1, lead, s_j);
+        idf_dev = s_j;  // (shared memory: generic pointer)
+    }
+    if (hdr != nullptr && lead) write_group_header(hdr, pv, lda, cl, idf_dev);
+    if (tr != nullptr) {  // diagnostics only: every block reports when it is done
+        __syncthreads();
+        ktrace_out(tr);
+    }
     if (i >= n) return;
     int c = cl.c[k];
     if (idf_dev != nullptr) {
-        const int j = idf_dev[k >> 1];
+        const int j = jmine >= 0 ? jmine : idf_dev[k >> 1];
         c = j > 0 ? 3 + 2 * (j - 1) + (k & 1) : -1;
     }
     double v = 0.0;
@@ -120,14 +167,23 @@ __global__ void __launch_bounds__(256) k_col_push(const double* __restrict__ P, 
                                                   int n, ColList cl, size_t lda, size_t buf_off, Shard sh,
                                                   const int* __restrict__ idf_dev, PeerTab pt,
                                                   unsigned long long epoch, unsigned* __restrict__ ticket,
-                                                  GroupHeader* __restrict__ hdr, PendView pv) {
+                                                  GroupHeader* __restrict__ hdr, PendView pv, GateParts gp,
+                                                  unsigned long long* tr) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int k = blockIdx.y;
-    if (hdr != nullptr && blockIdx.x == 0 && blockIdx.y == 0) write_group_header(hdr, pv, lda, cl, idf_dev);
+    ktrace_in(tr);
+    __shared__ int s_j[CSLAM_MAX_OBS];
+    const bool lead = blockIdx.x == 0 && blockIdx.y == 0;
+    int jmine = -1;
+    if (gp.nd != nullptr) {
+        jmine = snapshot_associate(gp, k >> 1, lead, s_j);
+        idf_dev = s_j;
+    }
+    if (hdr != nullptr && lead) write_group_header(hdr, pv, lda, cl, idf_dev);
     if (i < n) {
         int c = cl.c[k];
         if (idf_dev != nullptr) {
-            const int j = idf_dev[k >> 1];
+            const int j = jmine >= 0 ? jmine : idf_dev[k >> 1];
             c = j > 0 ? 3 + 2 * (j - 1) + (k & 1) : -1;
         }
         bool mine = false;
@@ -150,11 +206,16 @@ __global__ void __launch_bounds__(256) k_col_push(const double* __restrict__ P, 
         }
     }
     // last block: every block's stores are performed system-wide (fence.sys + ticket), then raise the flags
+    // (bar.sync orders the block's stores before thread 0's fence; the fence is cumulative — the pattern of a
+    // cooperative-groups grid barrier: one system-scope fence per block, not one per thread)
     __shared__ bool is_last;
-    __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0) is_last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1;
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        is_last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1;
+    }
     __syncthreads();
+    ktrace_out(tr);
     if (!is_last) return;
     __threadfence_system();
     if (threadIdx.x < sh.world) {
@@ -163,6 +224,82 @@ __global__ void __launch_bounds__(256) k_col_push(const double* __restrict__ P, 
     }
     if (threadIdx.x == 0) *ticket = 0;
 }
+// The same exchange without any fence or flag (what the fused group-gain kernel reads): every entry travels as a
+// 16-byte cell {low word, epoch, high word, epoch}.  Each 8-byte half carries its own epoch tag, so a reader that
+// sees both tags equal to the epoch it waits for has the value, however the store was split on its way (the
+// "LL" protocol of NCCL, with a 64-bit payload).  The sender neither fences nor signals — under a covariance pass
+// that saturates the memory system a system-scope fence costs tens of microseconds — and the receiver's row threads
+// poll exactly the cells they need.  Cells are reused two snapshots later (epoch parity); a rank can only be one
+// snapshot ahead of its peers because its next gains need their pushes.
+struct PeerLL {
+    uint4* x[8];
+};
+__global__ void __launch_bounds__(256) k_col_push_ll(const double* __restrict__ P, const double* __restrict__ R3,
+                                                     size_t ld, int n, ColList cl, size_t lda, size_t cell_off, Shard sh,
+                                                     const int* idf_dev, PeerLL pt, unsigned epoch,
+                                                     GroupHeader* __restrict__ hdr, PendView pv, GateParts gp,
+                                                     unsigned long long* tr) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;
+    ktrace_in(tr);
+    __shared__ int s_j[CSLAM_MAX_OBS];
+    const bool lead = blockIdx.x == 0 && blockIdx.y == 0;
+    int jmine = -1;
+    if (gp.nd != nullptr) {
+        jmine = snapshot_associate(gp, k >> 1, lead, s_j);
+        idf_dev = s_j;
+    }
+    if (hdr != nullptr && lead) write_group_header(hdr, pv, lda, cl, idf_dev);
+    if (i < n) {
+        int c = cl.c[k];
+        if (idf_dev != nullptr) {
+            const int j = jmine >= 0 ? jmine : idf_dev[k >> 1];
+            c = j > 0 ? 3 + 2 * (j - 1) + (k & 1) : -1;
+        }
+        bool mine = false;
+        double v = 0.0;
+        if (c < 0) {  // observation without a landmark: nobody reads the column
+        } else if (i < 3) {
+            mine = sh.rank == 0;
+            if (mine) v = R3[(size_t)i * ld + c];
+        } else if (i <= c) {
+            mine = shard_owns(sh, i);
+            if (mine) v = P[shard_lrow(sh, i) * ld + c];
+        } else {
+            mine = shard_owns(sh, c);
+            if (mine) v = P[shard_lrow(sh, c) * ld + i];
+        }
+        if (mine) {
+            const uint4 cell = make_uint4((unsigned)__double2loint(v), epoch, (unsigned)__double2hiint(v), epoch);
+            const size_t off = cell_off + (size_t)k * lda + i;
+            for (int p = 0; p < sh.world; p++) pt.x[p][off] = cell;
+        }
+    }
+    if (tr != nullptr) {
+        __syncthreads();
+        ktrace_out(tr);
+    }
+}
+__device__ __forceinline__ uint4 ll_load(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+// Bounded wait (~4 s) for one cell; a peer that never delivers is counted in `status` instead of hanging the GPU.
+__device__ __forceinline__ double ll_wait(const uint4* p, uint4 v, unsigned epoch, int* status) {
+    if (v.y != epoch || v.w != epoch) {
+        const long long t0 = clock64();
+        do {
+            v = ll_load(p);
+            if (clock64() - t0 > 8000000000LL) {
+                atomicAdd(status, 1 << 20);
+                break;
+            }
+        } while (v.y != epoch || v.w != epoch);
+    }
+    return __hiloint2double((int)v.z, (int)v.x);
+}
+
 // One warp: lane q waits until rank q has published `epoch` here.  A bounded wait: if a peer never arrives (a
 // crashed rank) the kernel gives up after ~4 s and counts an error instead of hanging the GPU.
 __global__ void k_wait_peers(const unsigned long long* sig, int world, unsigned long long epoch, int* __restrict__ status) {
@@ -356,25 +493,50 @@ struct GroupRow {
     double x;
 };
 
-template <int GM>
+template <int GM, bool LL>
 __device__ __forceinline__ void group_row_load(GroupRow<GM>& r, int i, int g, const GroupSmem<GM>& sm,
                                                const double* Xin, const double* __restrict__ R3,
-                                               const double* snap, size_t ld, size_t lda, const PendView& pv) {
+                                               const double* snap, size_t ld, size_t lda, const PendView& pv,
+                                               unsigned epoch, int* status) {
 #pragma unroll
     for (int b = 0; b < 3; b++) r.pose[b] = i <= b ? R3[(size_t)i * ld + b] : R3[(size_t)b * ld + i];
+    if constexpr (LL) {  // flagged cells pushed by the peers: all loads first, then wait for the stragglers
+        const uint4* cells = reinterpret_cast<const uint4*>(snap);
+        uint4 v[2 * GM];
 #pragma unroll
-    for (int c = 0; c < 2 * GM; c++) r.col[c] = (c < 2 * g && sm.f[c >> 1] >= 0) ? __ldcg(snap + (size_t)c * lda + i) : 0.0;
+        for (int c = 0; c < 2 * GM; c++)
+            if (c < 2 * g && sm.f[c >> 1] >= 0) v[c] = ll_load(cells + (size_t)c * lda + i);
+#pragma unroll
+        for (int c = 0; c < 2 * GM; c++)
+            r.col[c] = (c < 2 * g && sm.f[c >> 1] >= 0) ? ll_wait(cells + (size_t)c * lda + i, v[c], epoch, status) : 0.0;
+    } else {
+#pragma unroll
+        for (int c = 0; c < 2 * GM; c++)
+            r.col[c] = (c < 2 * g && sm.f[c >> 1] >= 0) ? __ldcg(snap + (size_t)c * lda + i) : 0.0;
+    }
     r.x = Xin[i];
     if (i < 3) return;  // rows 0..2 of the snapshot came from the always-current R3
+    // pending terms in batches of 8: the loads of a batch are issued together (one round trip to a memory system
+    // that the covariance pass keeps saturated — one-by-one they cost a full loaded latency each), the operations
+    // stay in term order
     const int nterm = pv.n0 + pv.n1;
-    for (int t = 0; t < nterm; t++) {
-        const double ai = pend_row(pv, lda, t)[i];
-        const bool eps = pend_eps(pv, t);
+    for (int t0 = 0; t0 < nterm; t0 += 8) {
+        double a[8];
 #pragma unroll
-        for (int c = 0; c < 2 * GM; c++) {
-            if (c < 2 * g) {
-                r.col[c] = r.col[c] - ai * sm.Ac[t][3 + c];
-                if (eps && i == sm.f[c >> 1] + (c & 1) && sm.f[c >> 1] >= 0) r.col[c] += kFltMin;
+        for (int q = 0; q < 8; q++) a[q] = t0 + q < nterm ? __ldcg(pend_row(pv, lda, t0 + q) + i) : 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const int t = t0 + q;
+            if (t < nterm) {
+                const double ai = a[q];
+                const bool eps = pend_eps(pv, t);
+#pragma unroll
+                for (int c = 0; c < 2 * GM; c++) {
+                    if (c < 2 * g) {
+                        r.col[c] = r.col[c] - ai * sm.Ac[t][3 + c];
+                        if (eps && i == sm.f[c >> 1] + (c & 1) && sm.f[c >> 1] >= 0) r.col[c] += kFltMin;
+                    }
+                }
             }
         }
     }
@@ -428,33 +590,23 @@ __device__ __forceinline__ void group_row_sub(GroupRow<GM>& r, int k, int g, con
 // to wait for the pass to leave would stall the chain for the rest of the pass.
 constexpr int kGroupRowThreads = 352;                    // warps 1..11: one state row each
 constexpr int kGroupThreads = 32 + kGroupRowThreads;     // warp 0 replays the group on the marginal
-template <int GM>
+template <int GM, bool LL>
 __global__ void __maxnreg__(64) k_gain_group_lazy(
     const double* Xin, double* Xout, const double* __restrict__ R3, double* __restrict__ R3out,
     const double* __restrict__ D, double* __restrict__ Dout, int dcap, int nf, const double* snap, size_t ld, size_t lda,
     int n, ObsGroup og, double r00, double r10, double r01, double r11, unsigned flags, PendView pv, double* Aout,
-    int* __restrict__ status, const GroupHeader* __restrict__ hdr, const unsigned long long* sig, int world,
-    unsigned long long epoch) {
+    int* __restrict__ status, const GroupHeader* __restrict__ hdr, unsigned epoch, unsigned long long* tr) {
     __shared__ GroupSmem<GM> sm;
+    ktrace_in(tr != nullptr ? tr + 2 : nullptr);
     const int g = og.g;
     const int tid = threadIdx.x;
     const int d = 3 + 2 * g;
     const int nterm = pv.n0 + pv.n1;
-    // ---- phase 0: the header the snapshot kernel left (columns of M, pending terms there); peers' pushes
+    // ---- phase 0: the header the snapshot kernel left (columns of M, pending terms there)
     if (tid < g) sm.f[tid] = hdr->f[tid];
     for (int idx = tid; idx < nterm * d; idx += blockDim.x) sm.Ac[idx / d][idx % d] = hdr->Ac[idx / d][idx % d];
-    if (sig != nullptr && tid >= 32 && tid < 32 + world) {  // lane q of warp 1 waits for rank q's flag (bounded, ~4 s)
-        const volatile unsigned long long* s = sig + (tid - 32);
-        const long long t0 = clock64();
-        while (*s < epoch) {
-            if (clock64() - t0 > 8000000000LL) {
-                if (blockIdx.x == 0) atomicAdd(status, 1 << 20);
-                break;
-            }
-        }
-        __threadfence_system();
-    }
     __syncthreads();
+    if (tr != nullptr && blockIdx.x == 0 && tid == 0) tr[4] = globaltimer_ns();  // header + peers' flags in
     // rows are shifted by one so that the two coordinates of a landmark (rows 3 + 2l, 4 + 2l) sit in one warp on
     // lanes (even, odd); the row threads issue their loads BEFORE they wait for the marginal replay
     const int i = blockIdx.x * kGroupRowThreads + (tid - 32) - 1;
@@ -465,7 +617,7 @@ __global__ void __maxnreg__(64) k_gain_group_lazy(
         const int a = tid;
         const bool act = a < d && (a < 3 || sm.f[(a - 3) >> 1] >= 0);
         const int ia = a < 3 ? a : (act ? sm.f[(a - 3) >> 1] + ((a - 3) & 1) : 0);
-        if (act) group_row_load<GM>(r, ia, g, sm, Xin, R3, snap, ld, lda, pv);
+        if (act) group_row_load<GM, LL>(r, ia, g, sm, Xin, R3, snap, ld, lda, pv, epoch, status);
         for (int k = 0; k < g; k++) {
             if (sm.f[k] >= 0) {  // warp-uniform
                 const int slot = a < 3 ? a : (a == 3 + 2 * k ? 3 : (a == 4 + 2 * k ? 4 : -1));
@@ -508,7 +660,7 @@ __global__ void __maxnreg__(64) k_gain_group_lazy(
             __syncwarp();
         }
     } else if (valid) {
-        group_row_load<GM>(r, i, g, sm, Xin, R3, snap, ld, lda, pv);
+        group_row_load<GM, LL>(r, i, g, sm, Xin, R3, snap, ld, lda, pv, epoch, status);
     }
     const bool lm = valid && i >= 3 && ((i - 3) & 1) == 0 && (i - 3) / 2 < nf;
     const int l = (i - 3) / 2;
@@ -518,7 +670,9 @@ __global__ void __maxnreg__(64) k_gain_group_lazy(
         d01 = D[(size_t)dcap + l];
         d11 = D[2 * (size_t)dcap + l];
     }
+    if (tr != nullptr && blockIdx.x == 0 && tid == 0) tr[5] = globaltimer_ns();  // marginal replay done
     __syncthreads();
+    if (tr != nullptr && blockIdx.x == 0 && tid == 32) tr[6] = globaltimer_ns();  // row loads landed too
     if (tid < 32) return;
     // ---- phase 2: every row thread takes its own row through the group
     for (int k = 0; k < g; k++) {
@@ -550,6 +704,7 @@ __global__ void __maxnreg__(64) k_gain_group_lazy(
         Dout[(size_t)dcap + l] = d01;
         Dout[2 * (size_t)dcap + l] = d11;
     }
+    if (tr != nullptr && tid == 32) atomicMax(tr + 3, globaltimer_ns());
 }
 
 // ------------------------------------------------------------------------------------
@@ -670,19 +825,37 @@ static int allreduce_sum(cslam_ekf* h, double* buf, size_t count);
 
 // Column snapshot of `ncols` columns (host list or device indices) from the array the chain may read.
 // *snap receives the buffer the gains read ([ncols][lda]).
-// *wait_fused (nullable): the caller's next kernel waits for the peers' flags itself (k_gain_group_lazy); set to
-// true when that wait is still owed.
+// *wait_fused (nullable): the caller's next kernel (k_gain_group_lazy) can wait for the peers' data itself; set to
+// true when *snap points to flagged cells (k_col_push_ll) that it has to poll.
 static int lazy_snapshot(cslam_ekf* h, const ColList& cl, const int* idf_dev, const double** snap,
-                         bool* wait_fused = nullptr, const PendView* pvp = nullptr) {
+                         bool* wait_fused = nullptr, const PendView* pvp = nullptr, const GateParts* gpp = nullptr) {
     if (int rc = lazy_acquire_read(h)) return rc;
     LazyState& L = h->lz;
     if (wait_fused) *wait_fused = false;
     GroupHeader* hdr = pvp ? L.hdr : nullptr;  // the fused group-gain kernel's header, gathered by block (0, 0)
     PendView pv{};
     if (pvp) pv = *pvp;
+    GateParts gp;
+    if (gpp) gp = *gpp;
+    unsigned long long* tr = (pvp && L.ktrace) ? L.ktrace + 8 * (size_t)(L.kslot % LazyState::kTraceCap) : nullptr;
     if (h->sh.world > 1 && L.peers_ready && cl.n <= 2 * kSeqGroupLazyMax) {
-        // peer-memory exchange: push what this rank stores into every rank's buffer, then wait for every peer
+        // peer-memory exchange: push what this rank stores into every rank's buffer
         L.epoch++;
+        if (wait_fused) {  // flagged cells, no fence / flag / wait kernel: the reader polls the cells it needs
+            const size_t cell_off = (size_t)(L.epoch & 1) * 2 * kSeqGroupLazyMax * h->lda;
+            PeerLL pl;
+            for (int q = 0; q < 8; q++)
+                pl.x[q] = L.peer_xbuf[q] ? reinterpret_cast<uint4*>(reinterpret_cast<char*>(L.peer_xbuf[q]) + L.xll_off) : nullptr;
+            count_launch();
+            k_col_push_ll<<<dim3((h->n + 255) / 256, cl.n), 256, 0, h->stream>>>(lazy_P(h), h->R3, h->ld, h->n, cl, h->lda,
+                                                                                 cell_off, h->sh, idf_dev, pl,
+                                                                                 (unsigned)L.epoch, hdr, pv, gp, tr);
+            CSLAM_CUDA(cudaGetLastError());
+            *wait_fused = true;
+            *snap = reinterpret_cast<const double*>(reinterpret_cast<const uint4*>(reinterpret_cast<char*>(L.xbuf) + L.xll_off) +
+                                                    cell_off);
+            return CSLAM_OK;
+        }
         const size_t buf_off = (size_t)(L.epoch & 1) * 2 * kSeqGroupLazyMax * h->lda;
         PeerTab pt;
         for (int q = 0; q < 8; q++) {
@@ -691,13 +864,9 @@ static int lazy_snapshot(cslam_ekf* h, const ColList& cl, const int* idf_dev, co
         }
         count_launch();
         k_col_push<<<dim3((h->n + 255) / 256, cl.n), 256, 0, h->stream>>>(lazy_P(h), h->R3, h->ld, h->n, cl, h->lda, buf_off,
-                                                                          h->sh, idf_dev, pt, L.epoch, L.push_ticket, hdr, pv);
-        if (wait_fused) {
-            *wait_fused = true;
-        } else {
-            count_launch();
-            k_wait_peers<<<1, 32, 0, h->stream>>>(L.sig, h->sh.world, L.epoch, h->status);
-        }
+                                                                          h->sh, idf_dev, pt, L.epoch, L.push_ticket, hdr, pv, gp, tr);
+        count_launch();
+        k_wait_peers<<<1, 32, 0, h->stream>>>(L.sig, h->sh.world, L.epoch, h->status);
         CSLAM_CUDA(cudaGetLastError());
         *snap = L.xbuf + buf_off;
         return CSLAM_OK;
@@ -705,7 +874,7 @@ static int lazy_snapshot(cslam_ekf* h, const ColList& cl, const int* idf_dev, co
     *snap = h->colbuf;
     count_launch();
     k_col_pack_lazy<<<dim3((h->n + 255) / 256, cl.n), 256, 0, h->stream>>>(lazy_P(h), h->R3, h->ld, h->n, cl, h->colbuf,
-                                                                           h->lda, h->sh, idf_dev, hdr, pv);
+                                                                           h->lda, h->sh, idf_dev, hdr, pv, gp, tr);
     CSLAM_CUDA(cudaGetLastError());
     if (h->sh.world > 1) return allreduce_sum(h, h->colbuf, (size_t)cl.n * h->lda);
     return CSLAM_OK;
@@ -714,8 +883,11 @@ static int lazy_snapshot(cslam_ekf* h, const ColList& cl, const int* idf_dev, co
 // singleUpdate (EKF.cpp:457-479) in lazy mode: per group of observations one column snapshot, per
 // observation one gain kernel (re-linearised at the X the previous observation produced), then R3 / D
 // follow; the 2g panel rows join the pending bank and a pass is launched whenever a bank is full.
+// gate_parts (fused scan): the first snapshot merges the gate kernel's candidates; after_assoc queues the
+// optional index read-back right behind that kernel.
 static int lazy_sequential(cslam_ekf* h, const double* Z, const int32_t* idf_host, const int* idf_dev, int m,
-                           const double R[4]) {
+                           const double R[4], const GateParts* gate_parts = nullptr,
+                           const std::function<int()>* after_assoc = nullptr) {
     LazyState& L = h->lz;
     const int n = h->n;
     int base = 0;
@@ -743,8 +915,10 @@ static int lazy_sequential(cslam_ekf* h, const double* Z, const int32_t* idf_hos
         pvg.eps1 = L.eps_mask;
         pvg.r3_from = L.infl_rows + np0;
         if (int rc = lazy_snapshot(h, cl, idf_dev ? idf_dev + base : nullptr, &snap, L.fused_gains ? &wait_fused : nullptr,
-                                   L.fused_gains ? &pvg : nullptr))
+                                   L.fused_gains ? &pvg : nullptr, base == 0 ? gate_parts : nullptr))
             return rc;
+        if (base == 0 && after_assoc)
+            if (int rc = (*after_assoc)()) return rc;
         if (L.fused_gains) {  // the whole group, the R3 / D follow and the wait for the peers in one launch
             const PendView& pv = pvg;
             ObsGroup og;
@@ -757,15 +931,23 @@ static int lazy_sequential(cslam_ekf* h, const double* Z, const int32_t* idf_hos
             const unsigned blocks = (unsigned)((n + 1 + kGroupRowThreads - 1) / kGroupRowThreads);
             const int nf = (n - 3) / 2;
             count_launch();
-#define CSLAM_GROUP(GM)                                                                                               \
-    k_gain_group_lazy<GM><<<blocks, kGroupThreads, 0, h->stream>>>(                                                              \
+#define CSLAM_GROUP(GM, LL)                                                                                            \
+    k_gain_group_lazy<GM, LL><<<blocks, kGroupThreads, 0, h->stream>>>(                                                 \
         h->X[h->cur], h->X[h->cur ^ 1], h->R3, L.R3alt, h->D, L.Dalt, h->dcap, nf, snap, h->ld, h->lda, n, og, R[0], R[1], \
-        R[2], R[3], h->flags, pv, bank + (size_t)np0 * h->lda, h->status, L.hdr,                                       \
-        wait_fused ? L.sig : nullptr, h->sh.world, L.epoch)
-            if (g <= 1) CSLAM_GROUP(1);
-            else if (g <= 2) CSLAM_GROUP(2);
-            else if (g <= 4) CSLAM_GROUP(4);
-            else CSLAM_GROUP(8);
+        R[2], R[3], h->flags, pv, bank + (size_t)np0 * h->lda, h->status, L.hdr, (unsigned)L.epoch,                     \
+        L.ktrace ? L.ktrace + 8 * (size_t)(L.kslot++ % LazyState::kTraceCap) : nullptr)
+#define CSLAM_GROUP2(GM)               \
+    do {                               \
+        if (wait_fused)                \
+            CSLAM_GROUP(GM, true);     \
+        else                           \
+            CSLAM_GROUP(GM, false);    \
+    } while (0)
+            if (g <= 1) CSLAM_GROUP2(1);
+            else if (g <= 2) CSLAM_GROUP2(2);
+            else if (g <= 4) CSLAM_GROUP2(4);
+            else CSLAM_GROUP2(8);
+#undef CSLAM_GROUP2
 #undef CSLAM_GROUP
             CSLAM_CUDA(cudaGetLastError());
             h->cur ^= 1;

@@ -3,6 +3,7 @@
 // same IEEE operation, in the same order, as in oracle/slam_oracle.hpp
 // (ekf_compute_association_sparse + PartialPivLU) — association indices must match exactly.
 #include "common.cuh"
+#include "gate_parts.cuh"
 
 namespace cslam {
 
@@ -22,19 +23,6 @@ struct GatePack {
     double gate1, gate2;
 };
 
-struct Cand {
-    double nd;
-    double out;
-    int j;
-};
-__device__ __forceinline__ void cand_merge(Cand& a, double nd, int j, double out) {
-    if (nd < a.nd || (nd == a.nd && j < a.j)) {
-        a.nd = nd;
-        a.j = j;
-    }
-    if (out < a.out) a.out = out;
-}
-
 // R3 = rows 0..2 of P (P itself on one GPU); D = replicated cache of the diagonal blocks
 // ([3][dcap], sharded handles) or nullptr (read them from P).
 constexpr int kGateThreads = 128;  // 4 warps: twice the CTAs of a 256-thread block (20k landmarks -> 157 CTAs >= 148 SMs)
@@ -44,7 +32,7 @@ __global__ void __launch_bounds__(kGateThreads) k_gate(const double* __restrict_
                                               double* __restrict__ part_out, int* __restrict__ part_j,
                                               unsigned* __restrict__ ticket, int* __restrict__ jbest,
                                               double* __restrict__ nbest, double* __restrict__ outer,
-                                              unsigned long long* __restrict__ assoc_count) {
+                                              unsigned long long* __restrict__ assoc_count, int final_stage) {
     constexpr int NW = kGateThreads / 32;
     __shared__ double s_nd[NW][CSLAM_MAX_OBS];
     __shared__ double s_out[NW][CSLAM_MAX_OBS];
@@ -157,6 +145,7 @@ __global__ void __launch_bounds__(kGateThreads) k_gate(const double* __restrict_
         part_out[(size_t)blockIdx.x * CSLAM_MAX_OBS + i] = c.out;
         part_j[(size_t)blockIdx.x * CSLAM_MAX_OBS + i] = c.j;
     }
+    if (!final_stage) return;  // the next kernel of the stream merges the candidates (gate_parts.cuh)
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
@@ -166,18 +155,7 @@ __global__ void __launch_bounds__(kGateThreads) k_gate(const double* __restrict_
     // final stage: one warp per observation, lanes stride over the per-block candidates, then the same
     // lexicographic (nd, j) merge across the warp — the order of merges does not change the result
     for (int i = warp; i < gp.m; i += NW) {
-        Cand c{inf, inf, 0x7fffffff};
-        for (unsigned b = lane; b < gridDim.x; b += 32)
-            cand_merge(c, ((volatile double*)part_nd)[(size_t)b * CSLAM_MAX_OBS + i],
-                       ((volatile int*)part_j)[(size_t)b * CSLAM_MAX_OBS + i],
-                       ((volatile double*)part_out)[(size_t)b * CSLAM_MAX_OBS + i]);
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const double ond = __shfl_xor_sync(0xffffffffu, c.nd, off);
-            const double oout = __shfl_xor_sync(0xffffffffu, c.out, off);
-            const int oj = __shfl_xor_sync(0xffffffffu, c.j, off);
-            cand_merge(c, ond, oj, oout);
-        }
+        const Cand c = gate_final_merge(part_nd, part_out, part_j, (int)gridDim.x, i, lane);
         if (lane == 0) {
             jbest[i] = (c.j == 0x7fffffff) ? 0 : c.j;
             nbest[i] = c.nd;
@@ -194,7 +172,7 @@ __global__ void __launch_bounds__(kGateThreads) k_gate(const double* __restrict_
 int launch_gate(const double* X, const double* P, const double* R3, const double* D, int dcap, size_t ld, int nf,
                 const double* Z, int m, const double R[4], double gate1, double gate2, double* part_nd,
                 double* part_out, int* part_j, unsigned* ticket, int* jbest, double* nbest, double* outer,
-                unsigned long long* assoc_count, cudaStream_t stream) {
+                unsigned long long* assoc_count, cudaStream_t stream, int final_stage, int* nblocks_out) {
     GatePack gp;
     memset(&gp, 0, sizeof(gp));
     memcpy(gp.z, Z, sizeof(double) * 2 * m);
@@ -205,8 +183,9 @@ int launch_gate(const double* X, const double* P, const double* R3, const double
     const int blocks = nf > 0 ? (nf + kGateThreads - 1) / kGateThreads : 1;
     count_launch();
     k_gate<<<blocks, kGateThreads, 0, stream>>>(X, P, R3, D, dcap, ld, nf, gp, part_nd, part_out, part_j, ticket, jbest, nbest,
-                                                outer, assoc_count);
+                                                outer, assoc_count, final_stage);
     CSLAM_CUDA(cudaGetLastError());
+    if (nblocks_out) *nblocks_out = blocks;
     return CSLAM_OK;
 }
 
