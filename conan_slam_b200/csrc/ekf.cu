@@ -857,10 +857,6 @@ int launch_cov_update_dmma(double* P, size_t ld, int n, const double* A, size_t 
 
 }  // namespace cslam
 #include "ekf_lazy.cuh"
-
-extern "C" {
-static void apply_l2_window(cslam_ekf* h);
-}
 namespace cslam {
 
 // ------------------------------------------------------------------------------------
@@ -1313,7 +1309,6 @@ static int create_common(cslam_ekf_t** out, int capacity_landmarks, int device, 
     }
     TRY(cudaStreamSynchronize(h->stream));
 #undef TRY
-    apply_l2_window(h);
     *out = h;
     return CSLAM_OK;
 }
@@ -1398,34 +1393,6 @@ int cslam_ekf_destroy(cslam_ekf_t* h) {
     return CSLAM_OK;
 }
 
-// Deferred-pass handles: the per-scan chain re-reads the two banks of pending panel rows (up to 32 rows x n) for
-// every scan while the covariance pass streams the whole covariance through L2 next to it.  An access-policy window
-// on the chain stream keeps the banks resident in L2 (persisting lines), so that those reads do not queue up behind
-// the pass's HBM traffic.  CSLAM_L2_PERSIST=0 turns it off.
-static void apply_l2_window(cslam_ekf* h) {
-    if (!h->lz.on) return;
-    if (const char* e = getenv("CSLAM_L2_PERSIST"))
-        if (atoi(e) == 0) return;
-    int max_persist = 0, max_window = 0;
-    if (cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, h->device) != cudaSuccess ||
-        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, h->device) != cudaSuccess ||
-        max_persist <= 0 || max_window <= 0) {
-        cudaGetLastError();
-        return;
-    }
-    const size_t want = (size_t)2 * kLazyBank * h->lda * sizeof(double);
-    const size_t bytes = std::min(want, std::min((size_t)max_window, (size_t)max_persist));
-    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min((size_t)max_persist, bytes + (bytes >> 2)));
-    cudaStreamAttrValue v;
-    memset(&v, 0, sizeof(v));
-    v.accessPolicyWindow.base_ptr = h->A;
-    v.accessPolicyWindow.num_bytes = bytes;
-    v.accessPolicyWindow.hitRatio = 1.0f;
-    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    v.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
-    if (cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();
-}
-
 int cslam_ekf_set_stream(cslam_ekf_t* h, void* cuda_stream) {
     CSLAM_NVTX_RANGE();
     if (int rc = check_handle(h)) return rc;
@@ -1433,7 +1400,6 @@ int cslam_ekf_set_stream(cslam_ekf_t* h, void* cuda_stream) {
     if (h->own_stream) cudaStreamDestroy(h->stream);
     h->stream = static_cast<cudaStream_t>(cuda_stream);
     h->own_stream = false;
-    apply_l2_window(h);
     return CSLAM_OK;
 }
 

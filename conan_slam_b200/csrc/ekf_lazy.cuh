@@ -44,6 +44,12 @@ __device__ __forceinline__ void ktrace_out(unsigned long long* tr) {
     if (tr != nullptr && threadIdx.x == 0) atomicMax(tr + 1, globaltimer_ns());
 }
 
+// c - a * b with one rounding.  The chain's small kernels run beside a covariance pass that keeps the FP64 pipe
+// busy with DMMAs: every instruction saved there is latency saved, and nothing requires the two-rounding form here
+// (the pass itself accumulates fused).  Used by EVERY kernel that brings an entry up to date with pending terms, so
+// that the fused group kernel, the one-kernel-per-observation chain and the follow kernel stay bit-identical.
+__device__ __forceinline__ double nfma(double a, double b, double c) { return __fma_rn(-a, b, c); }
+
 struct PendView {
     const double* A0;
     int n0;
@@ -356,7 +362,7 @@ __global__ void __launch_bounds__(256) k_gain_lazy(const double* Xin, double* Xo
             t0 = 0;
         }
         for (int t = t0; t < nterm; t++) {
-            v = v - sAc[t][lo] * sAc[t][hi];
+            v = nfma(sAc[t][lo], sAc[t][hi], v);
             if (lo == hi && pend_eps(pv, t)) v += kFltMin;
         }
         sPc[a][b] = v;
@@ -380,8 +386,8 @@ __global__ void __launch_bounds__(256) k_gain_lazy(const double* Xin, double* Xo
         // the snapshot columns lack every pending term (rows 0..2 of them came from R3: only the group's own)
         for (int t = (i < 3 ? pv.r3_from : 0); t < pv.r3_from; t++) {
             const double ai = pend_row(pv, lda, t)[i];
-            pc[3] = pc[3] - ai * sAc[t][3];
-            pc[4] = pc[4] - ai * sAc[t][4];
+            pc[3] = nfma(ai, sAc[t][3], pc[3]);
+            pc[4] = nfma(ai, sAc[t][4], pc[4]);
             if (pend_eps(pv, t)) {
                 if (i == f) pc[3] += kFltMin;
                 if (i == f + 1) pc[4] += kFltMin;
@@ -390,7 +396,7 @@ __global__ void __launch_bounds__(256) k_gain_lazy(const double* Xin, double* Xo
         for (int t = pv.r3_from; t < nterm; t++) {
             const double ai = pend_row(pv, lda, t)[i];
 #pragma unroll
-            for (int b = 0; b < 5; b++) pc[b] = pc[b] - ai * sAc[t][b];
+            for (int b = 0; b < 5; b++) pc[b] = nfma(ai, sAc[t][b], pc[b]);
             if (pend_eps(pv, t)) {
                 if (i < 3) pc[i] += kFltMin;
                 if (i == f) pc[3] += kFltMin;
@@ -434,14 +440,14 @@ __global__ void __launch_bounds__(256) k_follow_lazy(double* __restrict__ R3, do
         const double aj = a[j];
         const bool eps = (epsm >> q) & 1ULL;
         for (int i = 0; i < nrow; i++) {
-            o[i] = o[i] - a[i] * aj;
+            o[i] = nfma(aj, a[i], o[i]);
             if (eps && i == j) o[i] += kFltMin;
         }
         if (lm) {
             const double aj1 = a[j + 1];
-            d00 = d00 - aj * aj;
-            d01 = d01 - aj * aj1;
-            d11 = d11 - aj1 * aj1;
+            d00 = nfma(aj, aj, d00);
+            d01 = nfma(aj, aj1, d01);
+            d11 = nfma(aj1, aj1, d11);
             if (eps) {
                 d00 += kFltMin;
                 d11 += kFltMin;
@@ -533,7 +539,7 @@ __device__ __forceinline__ void group_row_load(GroupRow<GM>& r, int i, int g, co
 #pragma unroll
                 for (int c = 0; c < 2 * GM; c++) {
                     if (c < 2 * g) {
-                        r.col[c] = r.col[c] - ai * sm.Ac[t][3 + c];
+                        r.col[c] = nfma(ai, sm.Ac[t][3 + c], r.col[c]);
                         if (eps && i == sm.f[c >> 1] + (c & 1) && sm.f[c >> 1] >= 0) r.col[c] += kFltMin;
                     }
                 }
@@ -578,10 +584,10 @@ __device__ __forceinline__ void group_row_sub(GroupRow<GM>& r, int k, int g, con
         const double ai = h == 0 ? w1_0 : w1_1;
         const double* w = sm.W[2 * k + h];
 #pragma unroll
-        for (int b = 0; b < 3; b++) r.pose[b] = r.pose[b] - ai * w[b];
+        for (int b = 0; b < 3; b++) r.pose[b] = nfma(ai, w[b], r.pose[b]);
 #pragma unroll
         for (int c = 0; c < 2 * GM; c++)
-            if (c < 2 * g) r.col[c] = r.col[c] - ai * w[3 + c];
+            if (c < 2 * g) r.col[c] = nfma(ai, w[3 + c], r.col[c]);
     }
 }
 
@@ -656,9 +662,15 @@ __global__ void __maxnreg__(64) k_gain_group_lazy(
                 sm.W[2 * k + 1][a] = w1_1;
             }
             __syncwarp();
+            // observation k is settled (H, G, V, W1 at the rows of M): release the row warps for it and go on with
+            // k + 1 while they work — named barrier 1 + k, this warp arrives, the row warps wait
+            __threadfence_block();
+            asm volatile("barrier.arrive %0, %1;" ::"r"(1 + k), "r"(kGroupThreads) : "memory");
             if (act) group_row_sub<GM>(r, k, g, sm, w1_0, w1_1);
             __syncwarp();
         }
+        if (tr != nullptr && blockIdx.x == 0 && tid == 0) tr[5] = globaltimer_ns();  // marginal replay done
+        return;
     } else if (valid) {
         group_row_load<GM, LL>(r, i, g, sm, Xin, R3, snap, ld, lda, pv, epoch, status);
     }
@@ -670,12 +682,10 @@ __global__ void __maxnreg__(64) k_gain_group_lazy(
         d01 = D[(size_t)dcap + l];
         d11 = D[2 * (size_t)dcap + l];
     }
-    if (tr != nullptr && blockIdx.x == 0 && tid == 0) tr[5] = globaltimer_ns();  // marginal replay done
-    __syncthreads();
-    if (tr != nullptr && blockIdx.x == 0 && tid == 32) tr[6] = globaltimer_ns();  // row loads landed too
-    if (tid < 32) return;
-    // ---- phase 2: every row thread takes its own row through the group
+    if (tr != nullptr && blockIdx.x == 0 && tid == 32) tr[6] = globaltimer_ns();  // row loads landed
+    // ---- phase 2: every row thread takes its own row through the group, observation k as soon as warp 0 settled it
     for (int k = 0; k < g; k++) {
+        asm volatile("barrier.sync %0, %1;" ::"r"(1 + k), "r"(kGroupThreads) : "memory");
         double w1_0 = 0.0, w1_1 = 0.0;
         if (valid) {
             group_row_gain<GM>(r, k, sm, w1_0, w1_1);
@@ -686,12 +696,12 @@ __global__ void __maxnreg__(64) k_gain_group_lazy(
         const double n0 = __shfl_down_sync(0xffffffffu, w1_0, 1);
         const double n1 = __shfl_down_sync(0xffffffffu, w1_1, 1);
         if (lm) {
-            d00 = d00 - w1_0 * w1_0;
-            d01 = d01 - w1_0 * n0;
-            d11 = d11 - n0 * n0;
-            d00 = d00 - w1_1 * w1_1;
-            d01 = d01 - w1_1 * n1;
-            d11 = d11 - n1 * n1;
+            d00 = nfma(w1_0, w1_0, d00);
+            d01 = nfma(w1_0, n0, d01);
+            d11 = nfma(n0, n0, d11);
+            d00 = nfma(w1_1, w1_1, d00);
+            d01 = nfma(w1_1, n1, d01);
+            d11 = nfma(n1, n1, d11);
         }
     }
     if (valid) {
