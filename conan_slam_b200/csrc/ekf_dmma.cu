@@ -295,10 +295,16 @@ int launch_cov_update_dmma(double* P, size_t ld, int n, const double* A, size_t 
     if (strips == 0) return CSLAM_OK;
     const dim3 grid((nbc + chunk - 1) / chunk, strips);
     count_launch();
+    int dev = 0;
+    CSLAM_CUDA(cudaGetDevice(&dev));
 #define DM_LAUNCH(FULL)                                                                                        \
     do {                                                                                                       \
-        CSLAM_CUDA(cudaFuncSetAttribute(k_cov_update_dmma<FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                        DM_SMEM));                                                             \
+        static bool attr_set[64] = {}; /* per device: the attribute is set once, not per call */               \
+        if (dev < 0 || dev >= 64 || !attr_set[dev]) {                                                          \
+            CSLAM_CUDA(cudaFuncSetAttribute(k_cov_update_dmma<FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                            DM_SMEM));                                                         \
+            if (dev >= 0 && dev < 64) attr_set[dev] = true;                                                    \
+        }                                                                                                      \
         k_cov_update_dmma<FULL><<<grid, DM_THREADS, DM_SMEM, stream>>>(P, ld, n, Ar, Ac, rp, nbc, chunk, sh,   \
                                                                        g_dmma_dbg);                            \
     } while (0)
