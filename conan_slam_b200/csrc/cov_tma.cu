@@ -320,6 +320,7 @@ __global__ void __launch_bounds__(TMD_THREADS, 1) k_cov_update_tma_dense(const _
     const uint32_t bar0 = smem_u32(bars);
     const uint32_t bar_full = bar0, bar_done = bar0 + 8 * S, bar_free = bar0 + 16 * S, bar_pfull = bar0 + 24 * S,
                    bar_pempty = bar_pfull + 16, bar_cfull = bar_pfull + 32, bar_cempty = bar_pfull + 40;
+    const uint32_t skew = (uint32_t)dbg & 0x40000000u;  // zero at run time, unknown to the assembler (mbar_arrive_after)
     auto rowp = [&](int slot) { return panels + (size_t)slot * L::panel_doubles; };
     double* colp = panels + 2 * (size_t)L::panel_doubles;
     if (tid == 0) {
@@ -438,8 +439,13 @@ __global__ void __launch_bounds__(TMD_THREADS, 1) k_cov_update_tma_dense(const _
 #pragma unroll
                 for (int cb = 0; cb < 2; cb++) nb[ks][cb] = -cp[TM_PITCH * (4 * ks + t) + 8 * cb];
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_cempty);
+        {  // hand the buffer back once these loads have landed (see the note at the stage release below)
+            uint32_t dep = 0;
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++) dep |= hi32(nb[ks][0]) | hi32(nb[ks][1]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive_after(bar_cempty, skew, dep);
+        }
         mbar_wait(bar_pfull + 8 * slot, (uint32_t)((lt >> 1) & 1));
         const int4 ti = tinfo[slot];
         const double* rp = rowp(slot) + g;
@@ -449,16 +455,25 @@ __global__ void __launch_bounds__(TMD_THREADS, 1) k_cov_update_tma_dense(const _
             full_phase ^= 1u << st;
             unsigned char* stage = ring + st * STAGE;
             double2 acc[RB][2];
+            uint32_t dep = 0;
 #pragma unroll
             for (int rb = 0; rb < RB; rb++) {
                 const double2 va = *reinterpret_cast<const double2*>(stage + rb * 8192 + offA);
                 const double2 vb = *reinterpret_cast<const double2*>(stage + rb * 8192 + offB);
                 acc[rb][0] = odd ? vb : va;
                 acc[rb][1] = odd ? va : vb;
+                dep |= hi32(va.x) | hi32(vb.x);
             }
-            if (Pdst != nullptr) {  // direct-store mode: the stage has been read, hand it back at once
+            // Direct-store mode hands the stage back as soon as it has been read — i.e. once the loads above have
+            // LANDED: an arrive merely placed behind them is issued while they may still sit in the load/store
+            // queue (behind this warp's streaming global stores of the previous sub-tile, which stall when HBM is
+            // saturated); the producer then refills the stage and the queued loads read the NEXT sub-tile's first
+            // rows.  Seen as 4-16 wrong elements in the first rows of a sub-tile once in ~10 passes with rings of
+            // 3-5 stages (tools/cov_tma_bench.cu, TMA_DET=<rounds>); mbar_arrive_after carries a register
+            // dependency on every load.
+            if (Pdst != nullptr) {
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_free + 8 * st);
+                if (lane == 0) mbar_arrive_after(bar_free + 8 * st, skew, dep);
             }
 #pragma unroll
             for (int ks = 0; ks < KS; ks++) {
@@ -648,8 +663,7 @@ __global__ void __launch_bounds__(TMJ_THREADS, 1) k_cov_update_tma_joint(const _
 #pragma unroll
                 for (int cb = 0; cb < 2; cb++) nb[ks][cb] = ks < nks ? -cp[TM_PITCH * (4 * ks + t) + 8 * cb] : 0.0;
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_cempty);
+        // (column-panel buffer released after the first sub-tile's DMMAs, see k_cov_update_tma_dense)
         if (ti.z & 1) {  // new strip: its row panel
             mbar_wait(bar_rfull, (uint32_t)(rgen & 1));
             rgen++;
@@ -667,8 +681,7 @@ __global__ void __launch_bounds__(TMJ_THREADS, 1) k_cov_update_tma_joint(const _
                 acc[rb][0] = odd ? vb : va;
                 acc[rb][1] = odd ? va : vb;
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_free + 8 * st);  // read into registers: the stage can be refilled
+            const int st_read = st;
             st = st + 1 == S ? 0 : st + 1;
             double a0[RB], a1[RB];
 #pragma unroll
@@ -697,6 +710,13 @@ __global__ void __launch_bounds__(TMJ_THREADS, 1) k_cov_update_tma_joint(const _
                         }
                     }
                 }
+            }
+            // the stage / column panel go back once the DMMAs have consumed what was loaded from them
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_free + 8 * st_read);
+            if (s == 0) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_cempty);
             }
             const int col0 = ti.x + TM_BOXC * warp + 2 * t;
             double* prow = Pdst + (size_t)(ti.y + SUB * s + g) * ld + col0;

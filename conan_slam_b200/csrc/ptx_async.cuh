@@ -23,6 +23,21 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// Arrive that cannot be issued before `dep` — a word derived from registers that shared-memory loads fill — is
+// available: used to hand a buffer back to its producer right after reading it.  A plain arrive placed behind the
+// loads is issued while they may still wait in the load/store queue (e.g. behind streaming global stores that
+// stall on a saturated HBM), the producer refills the buffer and the queued loads read the new contents.  The
+// barrier address is selected between `bar` and `bar + skew` by a predicate computed from `dep`; `skew` must be a
+// value the assembler cannot know (derived from a kernel argument) that is ZERO at run time, so both choices are
+// the same barrier: a true register dependency at no semantic cost.
+__device__ __forceinline__ void mbar_arrive_after(uint32_t bar, uint32_t skew, uint32_t dep) {
+    asm volatile(
+        "{\n .reg .pred p;\n .reg .b32 a;\n setp.eq.u32 p, %1, 0x7ff8dead;\n add.u32 a, %0, %2;\n selp.b32 a, a, %0, p;\n"
+        " mbarrier.arrive.shared::cta.b64 _, [a];\n}\n" ::"r"(bar),
+        "r"(dep), "r"(skew)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t hi32(double x) { return (uint32_t)__double2hiint(x); }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     do {

@@ -37,6 +37,7 @@ __global__ void k_init_panel(double* A, size_t lda, int n, int rows) {
     const int k = (int)(idx / lda), i = (int)(idx % lda);
     A[idx] = i < n ? 0.05 * sin(0.013 * i * (k + 1) + 0.7 * k) + 0.01 * cos(0.001 * i) : 0.0;
 }
+__device__ unsigned long long* g_where = nullptr;
 __global__ void k_compare(const double* P1, const double* P2, size_t ld, size_t rows, int n, Shard sh,
                           unsigned long long* out) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -50,7 +51,17 @@ __global__ void k_compare(const double* P1, const double* P2, size_t ld, size_t 
     double rel = fabs(a - b) / fmax(fabs(a), 1e-2);
     if (!(rel == rel)) rel = 1e300;
     atomicMax(out, (unsigned long long)__double_as_longlong(rel));
-    if (a != b) atomicAdd(out + 1, 1ULL);
+    if (a != b) {
+        const unsigned long long k = atomicAdd(out + 1, 1ULL);
+        if (rel > 1e-9 && g_where != nullptr) {  // where the gross mismatches are (first 32)
+            const unsigned long long q = atomicAdd(g_where, 1ULL);
+            if (q < 32) {
+                g_where[1 + 2 * q] = (unsigned long long)i;
+                g_where[2 + 2 * q] = (unsigned long long)j;
+            }
+        }
+        (void)k;
+    }
 }
 
 template <int M>
@@ -101,6 +112,58 @@ int main(int argc, char** argv) {
     const double gb = 8.0 * n * ((double)n + 1.0) / 1e9 / sh.world;
     printf("n=%d ld=%zu rows=%zu world=%d rank=%d SMs=%d boxr=%d dense=%d direct=%d sub=%d, algorithmic bytes per pass %.3f GB\n", n, ld, rows, sh.world,
            sh.rank, sms, g_tma_boxr, g_tma_dense, g_tma_direct, g_tma_sub, gb);
+    if (getenv("TMA_DET")) {  // run-to-run determinism of each kernel on its own: the same pass twice, bitwise compare
+        const int rounds = atoi(getenv("TMA_DET"));
+        double* P3 = nullptr;
+        CK(cudaMalloc(&P3, ld * rows * sizeof(double)));
+        unsigned char map3[128];
+        if (make_cov_tensor_map(map3, P3, ld, rows) != 0) return 1;
+        unsigned long long* dwhere = nullptr;
+        CK(cudaMalloc(&dwhere, 65 * 8));
+        CK(cudaMemcpyToSymbol(g_where, &dwhere, sizeof(dwhere)));
+        const char* names[] = {"FMA pass", "TMA in place S=5", "TMA in place S=2", "TMA in place S=3", "TMA in place S=4",
+                               "TMA out of place S=5", "TMA out of place S=2"};
+        for (int it = 0; it < rounds; it++)
+            for (int which = 0; which < 7; which++)
+                for (int g = 2; g <= 8; g += 2) {
+                    k_init<<<gi, 256>>>(P1, ld, rows, n, sh);
+                    k_init<<<gi, 256>>>(P2, ld, rows, n, sh);
+                    CK(cudaMemset(dres, 0, 16));
+                    CK(cudaMemset(dwhere, 0, 65 * 8));
+                    const double *ra = P1, *rb = P2;
+                    if (which == 0) {
+                        run_ref_g(g, P1, ld, n, A, ld, sh);
+                        run_ref_g(g, P2, ld, n, A, ld, sh);
+                    } else if (which <= 4) {
+                        const int stages = which == 1 ? 5 : which == 2 ? 2 : which == 3 ? 3 : 4;
+                        launch_cov_update_tma(map1, map1, n, A, ld, 2 * g, 0.0, sh, nullptr, 0, sms, stages, 0, P1, ld, (int)rows);
+                        launch_cov_update_tma(map, map, n, A, ld, 2 * g, 0.0, sh, nullptr, 0, sms, stages, 0, P2, ld, (int)rows);
+                    } else {
+                        const int stages = which == 5 ? 5 : 2;
+                        launch_cov_update_tma(map1, map, n, A, ld, 2 * g, 0.0, sh, nullptr, 0, sms, stages, 0, P2, ld, (int)rows);
+                        launch_cov_update_tma(map1, map3, n, A, ld, 2 * g, 0.0, sh, nullptr, 0, sms, stages, 0, P3, ld, (int)rows);
+                        ra = P2;
+                        rb = P3;
+                    }
+                    CK(cudaDeviceSynchronize());
+                    k_compare<<<gi, 256>>>(ra, rb, ld, rows, n, sh, dres);
+                    unsigned long long res[2];
+                    CK(cudaMemcpy(res, dres, 16, cudaMemcpyDeviceToHost));
+                    double rel;
+                    memcpy(&rel, &res[0], 8);
+                    if (res[1] != 0) {
+                        printf("round %d %s g=%d: %llu elements differ between two runs (max rel %.3e)\n", it, names[which], g,
+                               res[1], rel);
+                        unsigned long long w[65];
+                        CK(cudaMemcpy(w, dwhere, sizeof(w), cudaMemcpyDeviceToHost));
+                        for (unsigned long long q = 0; q < w[0] && q < 32; q++)
+                            printf("   (%llu,%llu) tile (%llu,%llu) in-tile (%llu,%llu)\n", w[1 + 2 * q], w[2 + 2 * q], w[1 + 2 * q] / 128,
+                                   w[2 + 2 * q] / 128, w[1 + 2 * q] % 128, w[2 + 2 * q] % 128);
+                    }
+                }
+        printf("determinism check done (%d rounds x 7 variants x 4 ranks)\n", rounds);
+        return 0;
+    }
     int bad = 0;
     for (int g = 2; g <= 8; g++) {
         k_init<<<gi, 256>>>(P1, ld, rows, n, sh);
@@ -138,6 +201,38 @@ int main(int argc, char** argv) {
         g_tma_dbg = 0;
         return ms / reps;
     };
+    if (getenv("TMA_ISO")) {  // one pass at a time against back-to-back passes, same direction and alternating (ping-pong)
+        const int g = 8, stages = 2;
+        auto one = [&](bool fwd) {
+            return fwd ? launch_cov_update_tma(map1, map, n, A, ld, 2 * g, 0.0, sh, nullptr, 0, sms, stages, 0, P2, ld, (int)rows)
+                       : launch_cov_update_tma(map, map1, n, A, ld, 2 * g, 0.0, sh, nullptr, 0, sms, stages, 0, P1, ld, (int)rows);
+        };
+        for (int mode = 0; mode < 3; mode++) {
+            float tot = 0.f, ms = 0.f;
+            one(true);
+            CK(cudaDeviceSynchronize());
+            if (mode == 0) {  // isolated: synchronise around every launch
+                for (int i = 0; i < reps; i++) {
+                    CK(cudaEventRecord(e0));
+                    one(true);
+                    CK(cudaEventRecord(e1));
+                    CK(cudaDeviceSynchronize());
+                    CK(cudaEventElapsedTime(&ms, e0, e1));
+                    tot += ms;
+                }
+            } else {
+                CK(cudaEventRecord(e0));
+                for (int i = 0; i < reps; i++) one(mode == 1 ? true : (i & 1) == 0);
+                CK(cudaEventRecord(e1));
+                CK(cudaDeviceSynchronize());
+                CK(cudaEventElapsedTime(&tot, e0, e1));
+            }
+            printf("n=%d rank 16, 2 stages: %s: %8.4f ms per pass, %7.1f GB/s\n", n,
+                   mode == 0 ? "one at a time (sync between)" : mode == 1 ? "back to back, P1 -> P2 every time" : "back to back, ping-pong",
+                   tot / reps, gb / (tot / reps * 1e-3));
+        }
+        return 0;
+    }
     for (int g = 2; g <= 8; g++) {
         float ms_ref = 0.f;
         run_ref_g(g, P1, ld, n, A, ld, sh);
