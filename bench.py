@@ -667,7 +667,8 @@ class EkfBench:
     def __init__(self, ctx, N, nscans):
         cs, torch = ctx.cs, ctx.torch
         self.ctx, self.N, self.n = ctx, N, 3 + 2 * N
-        self.stream = torch.cuda.Stream(device=ctx.local)
+        # high priority: the per-scan chain must be dispatched ahead of the pending CTAs of a running covariance pass
+        self.stream = torch.cuda.Stream(device=ctx.local, priority=-1)
         t0 = time.time()
         if ctx.sharded:
             from conan_slam_b200 import dist as cdist
@@ -742,39 +743,54 @@ class EkfBench:
             return {"ok": False, "error": f"{type(e).__name__}: {e}"}
 
     # ---- the per-scan chain (gate -> column snapshot -> gains) on its own stream, timed scan by scan ----
-    def chain_probe(self, m, reps=12):
-        """CUDA events on the chain stream around single scans.  From a flushed state: scan A and B run with no
-        covariance pass in flight (B's 16th pending row launches a pass on the pass stream, which the chain does not
-        wait for); scan C runs while that pass streams the covariance next to it.  The covariance pass hides behind
-        the chain or the chain behind the pass: per scan the filter costs max(chain, pass share)."""
+    def chain_probe(self, m, reps=8):
+        """CUDA events on the chain stream around single scans.  From a flushed state the scans that fill the first
+        bank run with no covariance pass in flight (the last one launches the pass on the pass stream, which the
+        chain does not wait for); the scan after it runs while that pass works on the covariance next to it.  The
+        pass hides behind the chain or the chain behind the pass: per scan the filter costs max(chain, pass share)."""
         ctx, ekf, torch = self.ctx, self.ekf, self.ctx.torch
         if m != 4:
             return None
         scans = self.scans(m)
         res = {"idle": [], "beside_pass": []}
+        per_bank = None
         with torch.cuda.stream(self.stream):
             for r in range(reps):
                 ekf.flush()
                 ekf.sync()
                 ctx.barrier()
-                ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-                for k in range(3):
-                    ev[k].record(self.stream)
-                    ekf_scan(ekf, scans[(3 * r + k) % len(scans)][0], False, want_indices=False)
-                ev[3].record(self.stream)
+                p0 = ekf.pass_count()[0]
+                ev = [torch.cuda.Event(enable_timing=True)]
+                ev[0].record(self.stream)
+                launched_at = None
+                for k in range(20):
+                    ekf_scan(ekf, scans[(5 * r + k) % len(scans)][0], False, want_indices=False)
+                    ev.append(torch.cuda.Event(enable_timing=True))
+                    ev[-1].record(self.stream)
+                    if launched_at is None and ekf.pass_count()[0] > p0:
+                        launched_at = k
+                    elif launched_at is not None:
+                        break
                 ekf.flush()
                 ekf.sync()
-                d = [ev[k].elapsed_time(ev[k + 1]) for k in range(3)]
+                if launched_at is None:
+                    continue
+                per_bank = launched_at + 1
                 if r > 0:
-                    res["idle"].append(d[0])
-                    res["beside_pass"].append(d[2])
+                    res["idle"].append(ev[0].elapsed_time(ev[1]))
+                    res["beside_pass"].append(ev[launched_at + 1].elapsed_time(ev[launched_at + 2]))
+        if not res["idle"]:
+            return None
         med = {k: float(np.median(v)) for k, v in res.items()}
         med = dict(zip(med.keys(), ctx.allmax(*med.values())))
         lo = {k: float(np.min(v)) for k, v in res.items()}
         lo = dict(zip(lo.keys(), ctx.allmax(*lo.values())))
         return {"ms_per_scan_chain_idle": med["idle"], "ms_per_scan_chain_beside_pass": med["beside_pass"],
-                "min_idle": lo["idle"], "min_beside_pass": lo["beside_pass"], "reps": reps - 1,
-                "note": "gate + column snapshot (peer push when sharded) + gains of one 4-observation scan, max over ranks"}
+                "min_idle": lo["idle"], "min_beside_pass": lo["beside_pass"], "reps": len(res["idle"]),
+                "scans_per_bank": per_bank,
+                "note": "gate + column snapshot (peer push when sharded) + gains of one 4-observation scan, max over ranks; "
+                        "idle: first scan after a flush; beside_pass: first scan after a full bank launched its pass "
+                        "(it also carries the most pending terms)"}
 
     # ---- device-timed throughput (state resident in HBM) + live kernel timing ----
     def timed(self, m, steps, warmup, batch=False, strict=False):
@@ -896,7 +912,26 @@ def ekf_roofline(ctx, n, N, m, t, batch, strict, peak, peak_src):
     per_pass = upd_local / max(1, cov_launches)
     alg_update_bytes = (8.0 * n * (n + 1)) / shards + 112.0 * n  # cov R+W + 5 P columns + X + gating
     lazy = n >= 2048 or ctx.world > 1
-    kname = "k_cov_update_tma_dense" if lazy else "k_cov_update_multi"
+    if lazy and per_pass > 8.5:
+        # banks of more than 16 panel rows go through the FP64 tensor-core kernel (ekf_dmma.cu, out of place): the
+        # pass is bound by the DMMA pipe, not by HBM — report it against the in-run DMMA peak, HBM figures beside it
+        r_rank = 2.0 * per_pass
+        flops = r_rank * n * (n + 1) / shards
+        tpeak, tsrc = dmma_peak(ctx.local)
+        t_launch = cov_ms / max(1, cov_launches) * 1e-3
+        return {
+            "bound": "tensor",
+            "kernel": "k_cov_update_dmma (slam.h:260 for every pending update of a bank — up to 64 panel rows = 32 sequential "
+                      "landmark updates per launch — rank-r term on the FP64 tensor cores (DMMA.8x8x4), the covariance read "
+                      "from one array and written to its twin once per bank) incl. its panel-tiling kernel",
+            "updates_per_launch": per_pass, "panel_rows_per_update": 2,
+            "achieved": flops / t_launch / 1e12, "peak": tpeak, "unit": "TFLOP/s",
+            "frac": (flops / t_launch / 1e12) / tpeak, "peak_source": tsrc,
+            "traffic": ncu_traffic("k_cov_update_dmma", n) if ctx.world == 1 else None,
+            "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": 8.0 * n * (n + 1) / shards,
+            "hbm_gbs_same_launch": ach, "hbm_frac_same_launch": ach / peak if peak else 0.0,
+            "per": "GPU", "launches_timed": cov_launches, "avg_launch_ms": cov_ms / max(1, cov_launches),
+        }
     return {
         "bound": "hbm",
         "kernel": (f"{kname} (slam.h:260 for every pending update — up to 16 panel rows = 8 sequential landmark updates "
@@ -1023,8 +1058,8 @@ def guarded(name, fn):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--landmarks", type=int, default=20000)
     ap.add_argument("--obs", type=int, default=None, help="observations per scan (default 4; 32 with --batch)")
@@ -1073,7 +1108,7 @@ def main():
         if ctx.world == 1:
             extras["c3_obs1"] = guarded("c3_obs1", lambda: ekf_result(ctx, eb, 1, 12, 3, strict=True, with_parity=False))
             extras["c3_batch"] = guarded("c3_batch", lambda: ekf_result(ctx, eb, 32, 6, 3, batch=True))
-            extras["c3_obs8"] = guarded("c3_obs8", lambda: ekf_result(ctx, eb, 8, 10, 3, with_parity=False, with_e2e=False))
+            extras["c3_obs8"] = guarded("c3_obs8", lambda: ekf_result(ctx, eb, 8, 24, 4, with_parity=False, with_e2e=False))
     eb.close()
     if extras_on:
         if ctx.world == 1:
@@ -1087,8 +1122,8 @@ def main():
                 extras["c1_loop"] = guarded("c1_loop", c1_loop)
         if ctx.world >= 2:
             def c5():
-                e5 = EkfBench(ctx, 60000, 16)
-                r = ekf_result(ctx, e5, 4, 8, 3)
+                e5 = EkfBench(ctx, 60000, 40)
+                r = ekf_result(ctx, e5, 4, 32, 4)
                 e5.close()
                 return r
             free_gb = ctx.torch.cuda.mem_get_info()[0] / 1e9

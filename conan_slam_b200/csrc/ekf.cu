@@ -853,7 +853,8 @@ __global__ void k_scatter_upper(double* __restrict__ P, double* __restrict__ R3,
 // defined in ekf_dmma.cu: tensor-core (FP64 DMMA) rank-r update for large maps
 size_t dmma_panel_doubles(int n_cap);
 int launch_cov_update_dmma(double* P, size_t ld, int n, const double* A, size_t lda, int r, Shard sh,
-                           double* panels, int n_cap, int chunk, cudaStream_t stream);
+                           double* panels, int n_cap, int chunk, cudaStream_t stream, double* Pdst = nullptr,
+                           double diag_eps = 0.0);
 
 }  // namespace cslam
 #include "ekf_lazy.cuh"
@@ -1202,13 +1203,27 @@ static int create_common(cslam_ekf_t** out, int capacity_landmarks, int device, 
             return fail(CSLAM_ERR_CUDA);                                                     \
         }                                                                                    \
     } while (0)
-    TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    {
+        // The handle's own stream gets the HIGHEST priority: on a deferred-pass handle the small kernels of the
+        // per-scan chain must be dispatched into the resources a running covariance pass leaves free, ahead of that
+        // pass's own pending CTAs (equal priorities are served in launch order: the chain would wait for the whole
+        // grid of the tensor-core pass to be dispatched).  A caller stream (cslam_ekf_set_stream) should be created
+        // with a higher priority than the default for the same reason; the pass stream has the lowest.
+        int least = 0, greatest = 0;
+        TRY(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        TRY(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, greatest));
+    }
     TRY(cudaEventCreateWithFlags(&h->scan_ev, cudaEventDisableTiming));
     h->own_stream = true;
     TRY(cudaMalloc(&h->X[0], h->ld * sizeof(double)));
     TRY(cudaMalloc(&h->X[1], h->ld * sizeof(double)));
     TRY(cudaMalloc(&h->P, pbytes));
-    TRY(cudaMalloc(&h->A, (size_t)kMaxRank * h->lda * sizeof(double)));
+    {  // deferred covariance passes (ekf_lazy.cuh): large and sharded maps; CSLAM_LAZY=0/1 overrides
+        const char* e = getenv("CSLAM_LAZY");
+        h->lz.on = e ? atoi(e) != 0 : (h->n_cap >= 2048 || world > 1);
+    }
+    const size_t a_rows = h->lz.on ? (size_t)std::max(kMaxRank, 2 * kLazyBankMax) : (size_t)kMaxRank;  // two banks when lazy
+    TRY(cudaMalloc(&h->A, a_rows * h->lda * sizeof(double)));
     TRY(cudaMalloc(&h->PHT, (size_t)kMaxRank * h->lda * sizeof(double)));
     TRY(cudaMalloc(&h->small, sizeof(BatchSmall)));
     TRY(cudaMalloc(&h->status, sizeof(int)));
@@ -1227,15 +1242,11 @@ static int create_common(cslam_ekf_t** out, int capacity_landmarks, int device, 
     TRY(cudaMemsetAsync(h->X[0], 0, h->ld * sizeof(double), h->stream));
     TRY(cudaMemsetAsync(h->X[1], 0, h->ld * sizeof(double), h->stream));
     TRY(cudaMemsetAsync(h->P, 0, pbytes, h->stream));
-    TRY(cudaMemsetAsync(h->A, 0, (size_t)kMaxRank * h->lda * sizeof(double), h->stream));
+    TRY(cudaMemsetAsync(h->A, 0, a_rows * h->lda * sizeof(double), h->stream));
     TRY(cudaMemsetAsync(h->PHT, 0, (size_t)kMaxRank * h->lda * sizeof(double), h->stream));
     TRY(cudaMemsetAsync(h->status, 0, sizeof(int), h->stream));
     TRY(cudaMemsetAsync(h->ticket, 0, 4 * sizeof(unsigned), h->stream));
     h->R3 = h->P;  // one GPU, or rank 0 of a sharded handle: rows 0..2 are the first rows of P
-    {  // deferred covariance passes (ekf_lazy.cuh): large and sharded maps; CSLAM_LAZY=0/1 overrides
-        const char* e = getenv("CSLAM_LAZY");
-        h->lz.on = e ? atoi(e) != 0 : (h->n_cap >= 2048 || world > 1);
-    }
     if (world > 1 || h->lz.on) {
         if (rank != 0 || h->lz.on) {  // lazy handles keep rows 0..2 in their own panel on EVERY rank
             TRY(cudaMalloc(&h->R3, 3 * h->ld * sizeof(double)));
@@ -1250,7 +1261,11 @@ static int create_common(cslam_ekf_t** out, int capacity_landmarks, int device, 
         LazyState& L = h->lz;
         L.Pbuf[0] = h->P;
         TRY(cudaDeviceGetAttribute(&L.num_sms, cudaDevAttrMultiProcessorCount, device));
-        TRY(cudaStreamCreateWithFlags(&L.pass_stream, cudaStreamNonBlocking));
+        {
+            int least = 0, greatest = 0;
+            TRY(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+            TRY(cudaStreamCreateWithPriority(&L.pass_stream, cudaStreamNonBlocking, least));
+        }
         TRY(cudaEventCreateWithFlags(&L.ev_chain, cudaEventDisableTiming));
         TRY(cudaEventCreateWithFlags(&L.ev_pass, cudaEventDisableTiming));
         if (const char* e = getenv("CSLAM_TMA_STAGES")) L.stages = atoi(e);
@@ -1281,6 +1296,20 @@ static int create_common(cslam_ekf_t** out, int capacity_landmarks, int device, 
             if (make_cov_tensor_map(L.map[b], L.Pbuf[b], h->ld, (size_t)h->local_rows_cap) != CSLAM_OK)
                 return fail(CSLAM_ERR_CUDA);
         if (!L.pingpong) memcpy(L.map[1], L.map[0], sizeof(L.map[0]));
+        // Bank size: 64 rows (32 sequential updates per read + write of the covariance, tensor-core pass) where the
+        // pass still is the longer side of a scan — one or two GPUs; 32 rows from four GPUs on, where the per-scan
+        // chain (whose cost grows with the number of pending terms) would otherwise become the limit.  In place
+        // (no ping-pong twin) the chain waits for every pass, so the bank that keeps the TMA pass is used.
+        L.bank_rows = !L.pingpong ? kLazyBankTma : (world <= 2 ? 64 : 32);
+        if (const char* eb = getenv("CSLAM_LAZY_BANK")) {
+            const int v = atoi(eb);
+            if (v >= 2 && v <= kLazyBankMax && (v % 2) == 0) L.bank_rows = v;
+        }
+        if (L.bank_rows > kLazyBankTma) {
+            const size_t bytes = dmma_panel_doubles(h->n_cap) * sizeof(double);
+            TRY(cudaMalloc(&L.pass_panels, bytes));
+            TRY(cudaMemsetAsync(L.pass_panels, 0, bytes, h->stream));
+        }
         if (world > 1) {  // snapshot buffers + flags of the peer-memory column exchange (mapped by cslam_ekf_ipc_*)
             const size_t xb = (size_t)2 * 2 * kSeqGroupLazyMax * h->lda * sizeof(double);
             // ... followed by the flagged-cell copy of the same buffers (16-byte cells, k_col_push_ll): one allocation,
@@ -1356,6 +1385,7 @@ int cslam_ekf_destroy(cslam_ekf_t* h) {
     cudaFree(h->lz.Pbuf[1]);
     cudaFree(h->lz.R3alt);
     cudaFree(h->lz.Dalt);
+    cudaFree(h->lz.pass_panels);
     cudaFree(h->lz.hdr);
     if (h->lz.ktrace) {  // diagnostics: dump the kernel timestamps
         const char* path = getenv("CSLAM_KTRACE");

@@ -128,10 +128,14 @@ __device__ __forceinline__ void dmma_ksteps(double (&f)[4][2][2], const double* 
 }
 
 template <bool FULL>
-__global__ void __launch_bounds__(DM_THREADS, 1) k_cov_update_dmma(double* __restrict__ P, size_t ld, int n,
+__global__ void __launch_bounds__(DM_THREADS, 1) k_cov_update_dmma(double* P, size_t ld, int n,
                                                                    const double* __restrict__ Ar,
                                                                    const double* __restrict__ Ac, int rp, int nbc,
-                                                                   int chunk, Shard sh, int dbg) {
+                                                                   int chunk, Shard sh, int dbg, ptrdiff_t dshift,
+                                                                   double diag_eps) {
+    // dshift: distance (in doubles) from the array that is READ (P) to the array that is WRITTEN — 0 in place, the
+    // ping-pong twin for the deferred passes of ekf_lazy.cuh.  diag_eps: added to every diagonal element (the
+    // heading terms of a bank, slam.h:719).
 #ifndef CSLAM_DMMA_ABLATION
     dbg = 0;  // the load/store ablation of tools/dmma_bench.cu is compiled out of the library
 #endif
@@ -257,9 +261,14 @@ __global__ void __launch_bounds__(DM_THREADS, 1) k_cov_update_dmma(double* __res
                     for (int bj = 0; bj < 2; bj++) {
                         const int j = jw + bj * 8 + 2 * lc;
                         // pairs straddling the diagonal (j + 1 == i) rewrite one unauthoritative lower element
-                        if (kind == 1 || (i < n && j < n && j + 1 >= i))
-                            __stcs(reinterpret_cast<double2*>(prow[bi] + jw + bj * 8),
-                                   make_double2(f[bi][bj][0], f[bi][bj][1]));
+                        if (kind == 1 || (i < n && j < n && j + 1 >= i)) {
+                            double v0 = f[bi][bj][0], v1 = f[bi][bj][1];
+                            if (kind == 2 && diag_eps != 0.0) {
+                                if (i == j) v0 += diag_eps;
+                                if (i == j + 1) v1 += diag_eps;
+                            }
+                            __stcs(reinterpret_cast<double2*>(prow[bi] + jw + bj * 8 + dshift), make_double2(v0, v1));
+                        }
                     }
                 }
             }
@@ -279,7 +288,8 @@ size_t dmma_panel_doubles(int n_cap) {
 int g_dmma_dbg = 0;  // development knob of tools/dmma_bench.cu (1: skip P loads, 2: skip P stores)
 
 int launch_cov_update_dmma(double* P, size_t ld, int n, const double* A, size_t lda, int r, Shard sh,
-                           double* panels, int n_cap, int chunk, cudaStream_t stream) {
+                           double* panels, int n_cap, int chunk, cudaStream_t stream, double* Pdst = nullptr,
+                           double diag_eps = 0.0) {
     const int rp = (r + 3) / 4 * 4;
     const int ntr = (n + DM_TM - 1) / DM_TM;
     const int nbc = (n + DM_TN - 1) / DM_TN;
@@ -294,6 +304,7 @@ int launch_cov_update_dmma(double* P, size_t ld, int n, const double* A, size_t 
     for (int tr = sh.rank; tr < ntr; tr += sh.world) strips++;
     if (strips == 0) return CSLAM_OK;
     const dim3 grid((nbc + chunk - 1) / chunk, strips);
+    const ptrdiff_t dshift = Pdst != nullptr ? Pdst - P : 0;
     count_launch();
     int dev = 0;
     CSLAM_CUDA(cudaGetDevice(&dev));
@@ -306,7 +317,7 @@ int launch_cov_update_dmma(double* P, size_t ld, int n, const double* A, size_t 
             if (dev >= 0 && dev < 64) attr_set[dev] = true;                                                    \
         }                                                                                                      \
         k_cov_update_dmma<FULL><<<grid, DM_THREADS, DM_SMEM, stream>>>(P, ld, n, Ar, Ac, rp, nbc, chunk, sh,   \
-                                                                       g_dmma_dbg);                            \
+                                                                       g_dmma_dbg, dshift, diag_eps);          \
     } while (0)
     if (rp == DM_K) DM_LAUNCH(true); else DM_LAUNCH(false);
 #undef DM_LAUNCH

@@ -30,11 +30,17 @@ struct BatchSmall {  // device-resident scratch of the joint update (EKF.cpp:93-
 // Gains read the few entries of P they need from a column snapshot and bring them up to date with the
 // pending terms themselves.  The pass runs on its own stream and overlaps the gate / gain chain of the
 // following scans; with a ping-pong pair of arrays the chain never waits for a pass that is still running.
-constexpr int kLazyBank = 16;  // panel rows per bank = rank of one pass (cov_tma.cu: KS <= 4)
+// Panel rows per bank = rank of one pass.  Up to 16 rows go through the TMA streaming pass (cov_tma.cu, HBM-bound,
+// its time does not depend on the rank); a bank of up to 64 rows through the FP64 tensor-core kernel of the joint
+// update (ekf_dmma.cu, out of place into the ping-pong twin): 3.4 ms for 32 sequential updates at N = 20 000 against
+// 2.1 ms for 8 — the covariance is read and written once per 32 updates instead of once per 8.  LazyState::bank_rows
+// is the size in use (CSLAM_LAZY_BANK overrides); kLazyBankMax sizes the buffers.
+constexpr int kLazyBankMax = 64;
+constexpr int kLazyBankTma = 16;
 constexpr int kSeqGroupLazyMax = 8;  // observations per snapshot group (2 columns each)
 struct GroupHeader {  // written by the snapshot kernel, read by k_gain_group_lazy (ekf_lazy.cuh)
     int f[kSeqGroupLazyMax];                              // first state index of observation k, -1 = none
-    double Ac[2 * kLazyBank][3 + 2 * kSeqGroupLazyMax];   // pending term t at column b of the group's marginal
+    double Ac[2 * kLazyBankMax][3 + 2 * kSeqGroupLazyMax];   // pending term t at column b of the group's marginal
 };
 struct LazyState {
     bool on = false;
@@ -43,11 +49,13 @@ struct LazyState {
     unsigned char map[2][128];             // tensor maps of Pbuf[0 / 1] (64 bytes used, copied by value per launch)
     int stable = 0;   // array the chain stream may read: never written by a pass in flight when pingpong
     int newest = 0;   // array that holds the newest state once every launched pass has completed
-    int bank = 0;     // bank that receives new panel rows: rows [bank * kLazyBank, +kLazyBank) of h->A
+    int bank_rows = kLazyBankTma;  // rows per bank in use (<= kLazyBankMax)
+    int bank = 0;     // bank that receives new panel rows: rows [bank * kLazyBankMax, +bank_rows) of h->A
     int np = 0;       // rows pending in `bank`
-    unsigned eps_mask = 0;       // bit k: pending row k is a heading term (diagonal += FLT_MIN, slam.h:719)
+    unsigned long long eps_mask = 0;  // bit k: pending row k is a heading term (diagonal += FLT_MIN, slam.h:719)
     int infl_rows = 0;           // rows of the OTHER bank that the pass in flight applies and `stable` lacks
-    unsigned infl_eps_mask = 0;
+    unsigned long long infl_eps_mask = 0;
+    double* pass_panels = nullptr;    // pre-tiled panel copy for the tensor-core pass (ekf_dmma.cu), pass stream only
     bool pass_pending_wait = false;  // a pass was launched and the chain stream has not waited for it yet
     bool stable_busy = false;        // ... and that pass works IN PLACE on `stable` (no ping-pong twin, or a small pass)
     cudaStream_t pass_stream = nullptr;

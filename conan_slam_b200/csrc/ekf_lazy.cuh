@@ -53,17 +53,17 @@ __device__ __forceinline__ double nfma(double a, double b, double c) { return __
 struct PendView {
     const double* A0;
     int n0;
-    unsigned eps0;
+    unsigned long long eps0;
     const double* A1;
     int n1;
-    unsigned eps1;
+    unsigned long long eps1;
     int r3_from;  // rows 0..2 are current up to the start of the running group: they lack terms >= r3_from only
 };
 __device__ __forceinline__ const double* pend_row(const PendView& pv, size_t lda, int t) {
     return t < pv.n0 ? pv.A0 + (size_t)t * lda : pv.A1 + (size_t)(t - pv.n0) * lda;
 }
 __device__ __forceinline__ bool pend_eps(const PendView& pv, int t) {
-    return t < pv.n0 ? ((pv.eps0 >> t) & 1u) != 0 : ((pv.eps1 >> (t - pv.n0)) & 1u) != 0;
+    return t < pv.n0 ? ((pv.eps0 >> t) & 1ull) != 0 : ((pv.eps1 >> (t - pv.n0)) & 1ull) != 0;
 }
 
 // What a whole group of sequential updates needs of the pending terms BEFORE it reads a single row: the pending
@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(256) k_gain_lazy(const double* Xin, double* Xo
                                                    int* __restrict__ status, const int* __restrict__ idf_dev) {
     __shared__ GainSmall g;
     __shared__ double sPc[5][5];
-    __shared__ double sAc[2 * kLazyBank][5];  // a_t[c] for the five columns c in {0, 1, 2, f, f+1}
+    __shared__ double sAc[2 * kLazyBankMax][5];  // a_t[c] for the five columns c in {0, 1, 2, f, f+1}
     if (idf_dev != nullptr) idf = *idf_dev;
     const int i0 = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
     if (idf == 0) {  // no landmark passed the gate: X is carried over, zero panel rows are a no-op update
@@ -485,7 +485,7 @@ struct ObsGroup {
 template <int GM>
 struct GroupSmem {
     int f[GM];                                // first state index of observation k's landmark, -1 = skipped
-    double Ac[2 * kLazyBank][3 + 2 * GM];      // pending terms (before the group) at the columns of M
+    double Ac[2 * kLazyBankMax][3 + 2 * GM];      // pending terms (before the group) at the columns of M
     double W[2 * GM][3 + 2 * GM];              // the group's own panel rows at the rows of M
     GainSmall G[GM];
     double Pc[5][5];
@@ -720,7 +720,7 @@ __global__ void __maxnreg__(64) k_gain_group_lazy(
 // ------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------
-static inline double* lazy_bank(cslam_ekf* h, int bank) { return h->A + (size_t)bank * kLazyBank * h->lda; }
+static inline double* lazy_bank(cslam_ekf* h, int bank) { return h->A + (size_t)bank * kLazyBankMax * h->lda; }
 static inline double* lazy_P(cslam_ekf* h) { return h->lz.on ? h->lz.Pbuf[h->lz.stable] : h->P; }
 
 // Launch one pass for the rows pending in the current bank (if any).  Chain stream: waits for the pass BEFORE
@@ -736,7 +736,7 @@ static int lazy_flush(cslam_ekf* h) {
     // off from rank 4 on) — it works in place, so the chain must wait for it before it reads the array again.
     const bool small = L.np <= 2;
     const int src = L.newest, dst = (L.pingpong && !small) ? (L.newest ^ 1) : L.newest;
-    const double eps = (double)__builtin_popcount(L.eps_mask) * kFltMin;
+    const double eps = (double)__builtin_popcountll(L.eps_mask) * kFltMin;
     {
         ProfScope prof(h, L.pass_stream);
         if (small) {
@@ -752,10 +752,16 @@ static int lazy_flush(cslam_ekf* h) {
                         L.Pbuf[src], h->ld, h->n, lazy_bank(h, L.bank), h->lda, nt, eps, h->sh, nullptr);
                 CSLAM_CUDA(cudaGetLastError());
             }
-        } else if (int rc = launch_cov_update_tma(L.map[src], L.map[dst], h->n, lazy_bank(h, L.bank), h->lda, L.np, eps,
-                                                  h->sh, nullptr, 0, L.num_sms, L.stages, L.pass_stream, L.Pbuf[dst], h->ld,
-                                                  h->local_rows_cap)) {
-            return rc;
+        } else if (L.np <= kLazyBankTma) {
+            if (int rc = launch_cov_update_tma(L.map[src], L.map[dst], h->n, lazy_bank(h, L.bank), h->lda, L.np, eps, h->sh,
+                                               nullptr, 0, L.num_sms, L.stages, L.pass_stream, L.Pbuf[dst], h->ld,
+                                               h->local_rows_cap))
+                return rc;
+        } else {
+            // more than 16 rows: the FP64 tensor-core kernel of the joint update, reading `src` and writing `dst`
+            if (int rc = launch_cov_update_dmma(L.Pbuf[src], h->ld, h->n, lazy_bank(h, L.bank), h->lda, L.np, h->sh,
+                                                L.pass_panels, h->n_cap, 0, L.pass_stream, L.Pbuf[dst], eps))
+                return rc;
         }
     }
     if (L.pass_pending_wait) CSLAM_CUDA(cudaStreamWaitEvent(h->stream, L.ev_pass, 0));  // the previous pass
@@ -814,7 +820,7 @@ static int lazy_follow(cslam_ekf* h, const double* rows, int cnt, unsigned long 
 // EKF.cpp:328-352 in lazy mode: the gain needs only rows 0..2; the rank-1 term joins the pending bank.
 static int lazy_heading(cslam_ekf* h, double phi) {
     LazyState& L = h->lz;
-    if (L.np + 1 > kLazyBank)
+    if (L.np + 1 > L.bank_rows)
         if (int rc = lazy_flush(h)) return rc;
     const int n = h->n;
     const double sigma = 0.01F * kPi / 180.0F;  // EKF.cpp:337
@@ -825,9 +831,9 @@ static int lazy_heading(cslam_ekf* h, double phi) {
     CSLAM_CUDA(cudaGetLastError());
     h->cur ^= 1;
     if (int rc = lazy_follow(h, row, 1, 1ULL)) return rc;
-    L.eps_mask |= 1u << L.np;
+    L.eps_mask |= 1ull << L.np;
     L.np += 1;
-    if (L.np == kLazyBank) return lazy_flush(h);
+    if (L.np == L.bank_rows) return lazy_flush(h);
     return CSLAM_OK;
 }
 
@@ -902,9 +908,9 @@ static int lazy_sequential(cslam_ekf* h, const double* Z, const int32_t* idf_hos
     const int n = h->n;
     int base = 0;
     while (base < m) {
-        if (kLazyBank - L.np < 2)
+        if (L.bank_rows - L.np < 2)
             if (int rc = lazy_flush(h)) return rc;
-        const int g = std::min({m - base, (kLazyBank - L.np) / 2, kSeqGroupLazy});
+        const int g = std::min({m - base, (L.bank_rows - L.np) / 2, kSeqGroupLazy});
         ColList cl;
         cl.n = 2 * g;
         for (int k = 0; k < g; k++) {
@@ -965,7 +971,7 @@ static int lazy_sequential(cslam_ekf* h, const double* Z, const int32_t* idf_hos
             std::swap(h->D, L.Dalt);
             L.np = np0 + 2 * g;
             base += g;
-            if (L.np == kLazyBank)
+            if (L.np == L.bank_rows)
                 if (int rc = lazy_flush(h)) return rc;
             continue;
         }
@@ -990,7 +996,7 @@ static int lazy_sequential(cslam_ekf* h, const double* Z, const int32_t* idf_hos
         if (int rc = lazy_follow(h, bank + (size_t)np0 * h->lda, 2 * g, 0ULL)) return rc;
         L.np = np0 + 2 * g;
         base += g;
-        if (L.np == kLazyBank)
+        if (L.np == L.bank_rows)
             if (int rc = lazy_flush(h)) return rc;
     }
     return CSLAM_OK;
