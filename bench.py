@@ -884,7 +884,8 @@ class EkfBench:
                 "ms_per_cycle": d0.elapsed_time(d1) / cycles,
                 "covariance_passes_per_cycle": (ekf.pass_count()[0] - p0) / cycles,
                 "round1_ms_per_cycle": {"stepwise (7 passes)": 14.4, "merged heading passes (2 passes)": 4.6},
-                "note": "heading and landmark updates are deferred rank-1 terms: one pass per 16 of them"}
+                "note": "heading and landmark updates are deferred rank-1 terms: one covariance pass per bank of up to 64 of them "
+                        "(14 per cycle), the flush at the end of the timed cycles included"}
 
 
 def ekf_roofline(ctx, n, N, m, t, batch, strict, peak, peak_src):
@@ -936,10 +937,12 @@ def ekf_roofline(ctx, n, N, m, t, batch, strict, peak, peak_src):
         "bound": "hbm",
         "kernel": (f"{kname} (slam.h:260 for every pending update — up to 16 panel rows = 8 sequential landmark updates "
                    f"per launch — in ONE tensor-map TMA read + write of the upper triangle, rank-r term on the FP64 "
-                   f"tensor cores)" if lazy else f"{kname} (slam.h:260, upper-triangle update)"),
+                   f"tensor cores)" if kname == "k_cov_update_tma_dense" else
+                   f"{kname} (slam.h:260, upper-triangle update, FMA streaming kernel)"),
         "updates_per_launch": per_pass, "panel_rows_per_update": 2,
         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak if peak else 0.0,
-        "peak_source": peak_src, "traffic": ncu_traffic(kname, n) if ctx.world == 1 else None,
+        "peak_source": peak_src,
+        "traffic": ncu_traffic("k_cov_update<2,128>" if kname == "k_cov_update" else kname, n) if ctx.world == 1 else None,
         "algorithmic_bytes_per_launch": 8.0 * n * (n + 1) / shards, "per": "GPU",
         "launches_timed": cov_launches, "avg_launch_ms": cov_ms / max(1, cov_launches),
         "whole_update_frac": (alg_update_bytes * upd_local / (t["ms"] * 1e-3) / 1e9) / peak if peak else 0.0,
