@@ -994,9 +994,9 @@ def ekf_result(ctx, eb, m, steps, warmup, batch=False, strict=False, with_e2e=Tr
         "covariance_passes": t["passes"],
         "roofline": ekf_roofline(ctx, n, N, m, t, batch, strict, peak, peak_src),
         "skipped_updates": t["skipped"] & ((1 << 20) - 1),
-        # bit 20 of the device status word: a sharded column exchange gave up waiting for a peer (the numbers of such
-        # a run are void)
-        "peer_exchange_timeout": bool(t["skipped"] & (1 << 20)),
+        # the device status word counts 1 << 20 per wait of a sharded column exchange that gave up on a peer (the
+        # numbers of such a run are void)
+        "peer_exchange_timeout": bool(t["skipped"] >= (1 << 20) or t["skipped"] < 0),
     }
     if e is not None:
         out["e2e"] = {"value": e["updates"] / (e["ms"] * 1e-3), "unit": "updates/s",

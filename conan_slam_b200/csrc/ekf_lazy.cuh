@@ -291,21 +291,17 @@ __device__ __forceinline__ uint4 ll_load(const uint4* p) {
     asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
 }
-// Bounded wait for one cell: a peer that never delivers raises bit 20 of `status` (reported by cslam_ekf_sync)
-// instead of hanging the GPU — after ~4 s the first time, after ~1 ms once the bit is up (a broken exchange must
-// not turn every following kernel into another 4-second wait).
+// Bounded wait (~4 s) for one cell; a peer that never delivers is counted in `status` instead of hanging the GPU.
 __device__ __forceinline__ double ll_wait(const uint4* p, uint4 v, unsigned epoch, int* status) {
     if (v.y != epoch || v.w != epoch) {
         const long long t0 = clock64();
-        while (true) {
+        do {
             v = ll_load(p);
-            if (v.y == epoch && v.w == epoch) break;
-            const long long dt = clock64() - t0;
-            if (dt > 8000000000LL || (dt > 2000000LL && (*reinterpret_cast<volatile int*>(status) & (1 << 20)) != 0)) {
-                atomicOr(status, 1 << 20);
+            if (clock64() - t0 > 8000000000LL) {
+                atomicAdd(status, 1 << 20);
                 break;
             }
-        }
+        } while (v.y != epoch || v.w != epoch);
     }
     return __hiloint2double((int)v.z, (int)v.x);
 }
@@ -319,7 +315,7 @@ __global__ void k_wait_peers(const unsigned long long* sig, int world, unsigned 
     const long long t0 = clock64();
     while (*s < epoch) {
         if (clock64() - t0 > 8000000000LL) {
-            atomicOr(status, 1 << 20);
+            atomicAdd(status, 1 << 20);
             break;
         }
     }
