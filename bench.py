@@ -933,6 +933,10 @@ def ekf_roofline(ctx, n, N, m, t, batch, strict, peak, peak_src):
             "hbm_gbs_same_launch": ach, "hbm_frac_same_launch": ach / peak if peak else 0.0,
             "per": "GPU", "launches_timed": cov_launches, "avg_launch_ms": cov_ms / max(1, cov_launches),
         }
+    if lazy and per_pass <= 1.01:
+        kname = "k_cov_update"  # one- and two-row passes: the FMA streaming kernel, in place (ekf_lazy.cuh: lazy_flush)
+    else:
+        kname = "k_cov_update_tma_dense" if lazy else "k_cov_update_multi"
     return {
         "bound": "hbm",
         "kernel": (f"{kname} (slam.h:260 for every pending update — up to 16 panel rows = 8 sequential landmark updates "
