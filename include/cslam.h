@@ -88,19 +88,23 @@ int cslam_ekf_create_sharded(cslam_ekf_t** out, int capacity_landmarks, int devi
                              int world, const void* nccl_unique_id);
 /* Sharded handles exchange the observed columns of P once per scan.  After export on every rank / exchange on the
  * host / import (2 x 64-byte CUDA-IPC handles per rank, as for the particle filter), that exchange is fused into the
- * snapshot kernel: every rank writes the entries it stores straight into every peer's buffer over NVLink and raises
- * a flag — no collective on the critical path.  Without it the columns travel by one NCCL all-reduce. */
+ * snapshot kernel: every rank writes the entries it stores straight into every peer's buffer over NVLink as flagged
+ * 16-byte cells (the reader polls the cells it needs) — no collective, fence or flag on the critical path.  Without it the columns travel by one NCCL all-reduce. */
 int cslam_ekf_ipc_export(cslam_ekf_t* h, void* out128);
 int cslam_ekf_ipc_import(cslam_ekf_t* h, const void* all_ranks_128_each, int world);
 int cslam_ekf_destroy(cslam_ekf_t* h);
-/* Run this handle's kernels on a caller-provided cudaStream_t (e.g. a torch stream). */
+/* Run this handle's kernels on a caller-provided cudaStream_t (e.g. a torch stream).  On a deferred-pass handle
+ * (below) give that stream a priority above the default (cudaStreamCreateWithPriority): the small kernels of a scan
+ * are then dispatched beside the running covariance pass instead of behind its grid.  The handle's own stream has it. */
 int cslam_ekf_set_stream(cslam_ekf_t* h, void* cuda_stream);
 /* Wait for the stream; *skipped_updates (nullable) = updates skipped as non-SPD since create/reset. */
 int cslam_ekf_sync(cslam_ekf_t* h, int* skipped_updates);
 /* Large (capacity >= 1023 landmarks) and sharded handles DEFER the covariance passes: every Kalman update of the
  * reference is P <- P - W1 W1^T (slam.h:260; the heading update slam.h:718 has the same shape), so the
  * updates of consecutive calls — the heading updates of the control steps and the sequential landmark
- * updates of a scan — accumulate as panel rows and ONE pass over the covariance applies up to 16 of them
+ * updates of a scan — accumulate as panel rows and ONE pass over the covariance applies up to 64 of them
+ * (32 sequential landmark updates; 32 rows from four GPUs on, 16 without room for a second covariance array;
+ * environment CSLAM_LAZY_BANK overrides)
  * (X, rows 0..2 of P and the landmarks' 2x2 diagonal blocks are always current; gains read the few other
  * entries of P they need through the pending terms).  Results are those of the eager sequence up to rounding.
  * cslam_ekf_flush applies everything that is pending (asynchronously, in stream order); accessors, augment,
