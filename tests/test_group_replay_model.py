@@ -125,3 +125,30 @@ def test_group_replay_equals_the_dense_sequence(flags, idf):
     assert np.max(np.abs(R3g - Ps[:3, :])) < 1e-10 * scale                                # rows 0..2 stayed current
     for l in range(N):
         assert np.max(np.abs(Dg[l] - Ps[3 + 2 * l:5 + 2 * l, 3 + 2 * l:5 + 2 * l])) < 1e-10 * scale
+
+
+def test_flagged_cell_protocol_model():
+    """k_col_push_ll / ll_wait: a double travels as {low word, epoch, high word, epoch}; each 8-byte half carries its
+    own tag, so whichever way a 16-byte store is split on its way, a reader that sees both tags equal to the epoch it
+    waits for holds exactly the value that was sent for that epoch."""
+    rng = np.random.default_rng(7)
+
+    def pack(v, epoch):
+        bits = np.array([v], dtype=np.float64).view(np.uint64)[0]
+        return np.array([bits & 0xFFFFFFFF, epoch, bits >> 32, epoch], dtype=np.uint64)
+
+    def ready(cell, epoch):
+        return cell[1] == epoch and cell[3] == epoch
+
+    def unpack(cell):
+        return np.array([(int(cell[2]) << 32) | int(cell[0])], dtype=np.uint64).view(np.float64)[0]
+
+    for _ in range(200):
+        old, new = rng.normal() * 1e3, rng.normal() * 1e-3
+        e = int(rng.integers(3, 1 << 31))
+        cell_old, cell_new = pack(old, e - 2), pack(new, e)      # cells are reused two snapshots later
+        assert ready(cell_new, e) and unpack(cell_new) == new
+        # a reader that polls while only ONE half of the new cell has landed must not accept the mixture
+        for torn in (np.concatenate([cell_new[:2], cell_old[2:]]), np.concatenate([cell_old[:2], cell_new[2:]])):
+            assert not ready(torn, e)
+        assert not ready(cell_old, e)
